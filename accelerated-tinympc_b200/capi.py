@@ -1,0 +1,174 @@
+"""ctypes binding of the C ABI in include/tmpc.h (lib/libtmpc_cuda.so).
+
+This is what a foreign-language caller of the reference would bind (the reference's own FFI surface is
+tiny_wrapper.hpp:14-23, one global instance; here it is batched).  No torch types: raw addresses only.
+The library has no CPU fallback: `load()` raises if the shared object is missing, `Solver()` raises if
+no B200-class device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtmpc_cuda.so")
+
+TMPC_F32, TMPC_F64 = 0, 1
+TMPC_ORDER_PARITY, TMPC_ORDER_FAST = 0, 1
+TMPC_MEM_HOST, TMPC_MEM_DEVICE = 0, 1
+
+EXPORTS = ["tmpc_create", "tmpc_destroy", "tmpc_set_model", "tmpc_set_settings", "tmpc_solve", "tmpc_get_stats",
+           "tmpc_host_alloc", "tmpc_host_free", "tmpc_last_error", "tmpc_version"]
+
+
+class TmpcWarm(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d", "y", "g", "v", "z")]
+
+
+class TmpcSolveArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("x0", C.c_void_p), ("Xref", C.c_void_p), ("xref_shared", C.c_int32),
+                ("mem", C.c_int32), ("warm", C.POINTER(TmpcWarm)), ("x", C.c_void_p), ("u", C.c_void_p),
+                ("iter", C.c_void_p), ("status", C.c_void_p), ("resid", C.c_void_p), ("stream", C.c_void_p)]
+
+
+class TmpcStats(C.Structure):
+    _fields_ = [("instances", C.c_int64), ("iterations", C.c_int64), ("solved", C.c_int64), ("trips", C.c_int64),
+                ("launches", C.c_int32), ("lanes", C.c_int32), ("kernel_ms", C.c_float), ("parity_pinned", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: build it with `make -C accelerated-tinympc_b200` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.tmpc_create.restype = C.c_int
+    lib.tmpc_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.tmpc_destroy.restype = C.c_int
+    lib.tmpc_destroy.argtypes = [C.c_void_p]
+    lib.tmpc_set_model.restype = C.c_int
+    lib.tmpc_set_model.argtypes = [C.c_void_p] + [C.c_void_p] * 7 + [C.c_double] + [C.c_void_p] * 4
+    lib.tmpc_set_settings.restype = C.c_int
+    lib.tmpc_set_settings.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.tmpc_solve.restype = C.c_int
+    lib.tmpc_solve.argtypes = [C.c_void_p, C.POINTER(TmpcSolveArgs)]
+    lib.tmpc_get_stats.restype = C.c_int
+    lib.tmpc_get_stats.argtypes = [C.c_void_p, C.POINTER(TmpcStats)]
+    lib.tmpc_host_alloc.restype = C.c_int
+    lib.tmpc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+    lib.tmpc_host_free.restype = C.c_int
+    lib.tmpc_host_free.argtypes = [C.c_void_p]
+    lib.tmpc_last_error.restype = C.c_char_p
+    lib.tmpc_last_error.argtypes = [C.c_void_p]
+    lib.tmpc_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+class TmpcError(RuntimeError):
+    pass
+
+
+def _addr(a):
+    """Address of a numpy array, a torch tensor, an int, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError("cannot take the address of %r" % type(a))
+
+
+class Solver:
+    """One tmpc_ctx: a problem shape + model on one device.  Mirrors TinySolver{settings, cache, work}
+    (types.hpp:102-107) for a batch."""
+
+    def __init__(self, prob, dtype=np.float32, policy="parity", device=0):
+        self.lib = load()
+        self.prob = prob
+        self.dtype = np.dtype(dtype)
+        self.nx, self.nu, self.N = prob.nx, prob.nu, prob.N
+        self._ctx = C.c_void_p()
+        pol = {"parity": TMPC_ORDER_PARITY, "fast": TMPC_ORDER_FAST}[policy]
+        rc = self.lib.tmpc_create(C.byref(self._ctx), device, prob.nx, prob.nu, prob.N,
+                                  TMPC_F32 if self.dtype == np.float32 else TMPC_F64, pol)
+        if rc != 0:
+            raise TmpcError("tmpc_create: %d %s" % (rc, self.lib.tmpc_last_error(None).decode()))
+        self.set_model(prob)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise TmpcError("%s: %d %s" % (what, rc, self.lib.tmpc_last_error(self._ctx).decode()))
+
+    def set_model(self, prob):
+        a = prob.cast(self.dtype)
+        self._model_keep = a
+        p = lambda k: _addr(a[k])
+        self._check(self.lib.tmpc_set_model(self._ctx, p("Kinf"), p("Pinf"), p("Quu_inv"), p("AmBKt"), p("Adyn"),
+                                            p("Bdyn"), p("Q"), float(prob.rho), p("x_min"), p("x_max"), p("u_min"),
+                                            p("u_max")), "tmpc_set_model")
+        self._check(self.lib.tmpc_set_settings(self._ctx, prob.abs_pri_tol, prob.abs_dua_tol, prob.max_iter,
+                                               prob.check_termination, prob.en_state_bound, prob.en_input_bound),
+                    "tmpc_set_settings")
+
+    def solve_raw(self, batch, x0, Xref, xref_shared, mem, x=None, u=None, it=None, status=None, resid=None,
+                  warm=None, stream=None):
+        """Thin call: every array argument is an address provider (numpy / torch / int) or None."""
+        args = TmpcSolveArgs()
+        args.batch = batch
+        args.x0 = _addr(x0)
+        args.Xref = _addr(Xref)
+        args.xref_shared = 1 if xref_shared else 0
+        args.mem = mem
+        w = None
+        if warm is not None:
+            w = TmpcWarm()
+            for k in ("d", "y", "g", "v", "z"):
+                setattr(w, k, _addr(warm[k]))
+            args.warm = C.pointer(w)
+        args.x, args.u, args.iter, args.status, args.resid = _addr(x), _addr(u), _addr(it), _addr(status), _addr(resid)
+        args.stream = stream
+        self._check(self.lib.tmpc_solve(self._ctx, C.byref(args)), "tmpc_solve")
+
+    def solve(self, x0, Xref, warm=None):
+        """Host-array convenience (numpy in, numpy out) through TMPC_MEM_HOST."""
+        dt = self.dtype
+        x0 = np.ascontiguousarray(x0, dtype=dt).reshape(-1, self.nx)
+        B = x0.shape[0]
+        Xref = np.ascontiguousarray(Xref, dtype=dt)
+        shared = Xref.size == self.N * self.nx
+        if not shared and Xref.size != B * self.N * self.nx:
+            raise ValueError("Xref must be [N,nx] or [B,N,nx]")
+        out = {"x": np.empty((B, self.N, self.nx), dt), "u": np.empty((B, self.N - 1, self.nu), dt),
+               "iter": np.empty(B, np.int32), "status": np.empty(B, np.int32), "resid": np.empty((B, 4), dt)}
+        if warm is not None:
+            warm = {k: np.ascontiguousarray(warm[k], dtype=dt) for k in ("d", "y", "g", "v", "z")}
+            out["warm"] = warm
+        self.solve_raw(B, x0, Xref, shared, TMPC_MEM_HOST, out["x"], out["u"], out["iter"], out["status"],
+                       out["resid"], warm=warm)
+        return out
+
+    def stats(self):
+        s = TmpcStats()
+        self._check(self.lib.tmpc_get_stats(self._ctx, C.byref(s)), "tmpc_get_stats")
+        return {f[0]: getattr(s, f[0]) for f in TmpcStats._fields_}
+
+    def close(self):
+        if self._ctx:
+            self.lib.tmpc_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

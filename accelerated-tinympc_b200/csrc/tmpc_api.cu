@@ -1,0 +1,597 @@
+// C ABI (include/tmpc.h) over the sm_100a kernels in tmpc_kernel.cuh.
+// Owns: device/model state per context, kernel dispatch by (shape, dtype, policy), the chunked
+// host<->device pipeline for TMPC_MEM_HOST callers, statistics.  No solver arithmetic runs on the host.
+#include "tmpc.h"
+#include "tmpc_kernel.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct KernelInfo {
+    const void *fn;
+    size_t smem;
+    int block;
+    size_t model_bytes;
+};
+
+struct tmpc_ctx_impl {
+    int device = 0;
+    int nx = 0, nu = 0, N = 0, dtype = 0, policy = 0;
+    bool has_model = false;
+    bool warm_variant_ready = false;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    // model image exactly as the kernel's Model<T,...> struct (built on the host, passed by value)
+    std::vector<unsigned char> model;
+    // settings
+    double pri = 1e-3, dua = 1e-3;
+    int max_iter = 100, check_term = 1, en_state = 1, en_input = 1;
+    // raw model copies (dtype of ctx) kept to rebuild the image when settings change
+    std::vector<unsigned char> Kinf, Pinf, Quu_inv, AmBKt, Adyn, Bdyn, Q, xmin, xmax, umin, umax;
+    double rho = 0;
+    bool has_xb = false, has_ub = false;
+    // device scratch
+    unsigned long long *d_counter = nullptr;  // [0] counter, [1..4] stats
+    // host staging (TMPC_MEM_HOST)
+    struct Stage {
+        void *h_in = nullptr, *h_out = nullptr;  // pinned
+        void *d_in = nullptr, *d_out = nullptr;
+        size_t in_bytes = 0, out_bytes = 0;
+        cudaStream_t s = nullptr;
+        cudaEvent_t done = nullptr;
+    } stage[3];
+    int64_t stage_chunk = 0;
+    // stats of the last solve
+    tmpc_stats stats{};
+    bool stats_pending = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
+};
+
+#define CTX(c) reinterpret_cast<tmpc_ctx_impl *>(c)
+
+int fail(tmpc_ctx_impl *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(c, call)                                                                            \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(c, TMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// kernel table
+// ---------------------------------------------------------------------------------------------
+template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool UNROLL>
+KernelInfo make_info()
+{
+    KernelInfo k;
+    k.fn = (const void *)&tmpc::admm_kernel<T, NX, NU, NH, BLOCK, FAST, WARM, UNROLL>;
+    k.smem = tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES;
+    k.block = BLOCK;
+    k.model_bytes = sizeof(tmpc::Model<T, NX, NU, NH>);
+    return k;
+}
+
+template <class T, int NX, int NU, int NH, int BLOCK, bool UNROLL>
+bool pick(int policy, bool warm, KernelInfo &out)
+{
+    if (policy == TMPC_ORDER_PARITY)
+        out = warm ? make_info<T, NX, NU, NH, BLOCK, false, true, UNROLL>()
+                   : make_info<T, NX, NU, NH, BLOCK, false, false, UNROLL>();
+    else
+        out = warm ? make_info<T, NX, NU, NH, BLOCK, true, true, UNROLL>()
+                   : make_info<T, NX, NU, NH, BLOCK, true, false, UNROLL>();
+    return true;
+}
+
+// Compiled shapes.  Thread-per-instance needs the per-instance state to fit shared memory:
+//   quadrotor 12/4/10: 360 scalars -> 128 threads (f32) / 64 threads (f64) per SM
+//   cartpole   4/1/10: 111 scalars -> 256 threads (f32) / 128 (f64)
+bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out)
+{
+    if (nx == 12 && nu == 4 && N == 10) {
+        if (dtype == TMPC_F32) return pick<float, 12, 4, 10, 128, false>(policy, warm, out);
+        return pick<double, 12, 4, 10, 64, false>(policy, warm, out);
+    }
+    if (nx == 4 && nu == 1 && N == 10) {
+        if (dtype == TMPC_F32) return pick<float, 4, 1, 10, 256, false>(policy, warm, out);
+        return pick<double, 4, 1, 10, 128, false>(policy, warm, out);
+    }
+    return false;
+}
+
+bool shape_parity_pinned(int nx, int nu)
+{
+    // evaluation orders verified bit-for-bit against the compiled reference (oracle/, tests/)
+    return (nx == 12 && nu == 4) || (nx == 4 && nu == 1) || (nx == 32 && nu == 8);
+}
+
+// ---------------------------------------------------------------------------------------------
+// model image
+// ---------------------------------------------------------------------------------------------
+template <class T, int NX, int NU, int NH> void build_model_t(tmpc_ctx_impl *c)
+{
+    using M = tmpc::Model<T, NX, NU, NH>;
+    c->model.assign(sizeof(M), 0);
+    M *m = reinterpret_cast<M *>(c->model.data());
+    auto cp = [](T *dst, const std::vector<unsigned char> &src, size_t n) { std::memcpy(dst, src.data(), n * sizeof(T)); };
+    cp(m->K, c->Kinf, NU * NX);
+    cp(m->A, c->Adyn, NX * NX);
+    cp(m->B, c->Bdyn, NX * NU);
+    cp(m->Qi, c->Quu_inv, NU * NU);
+    cp(m->M, c->AmBKt, NX * NX);
+    cp(m->Pf, c->Pinf, NX * NX);
+    cp(m->Qd, c->Q, NX);
+    const T inf = std::numeric_limits<T>::infinity();
+    // a disabled (or absent) bound becomes +-inf: min(+inf, max(-inf, v)) == v exactly, so the kernel
+    // needs no branch for en_state_bound / en_input_bound (admm.cpp:51,57)
+    const bool xs = c->en_state && c->has_xb, us = c->en_input && c->has_ub;
+    for (int k = 0; k < NH * NX; ++k) {
+        m->xmin[k] = xs ? reinterpret_cast<const T *>(c->xmin.data())[k] : -inf;
+        m->xmax[k] = xs ? reinterpret_cast<const T *>(c->xmax.data())[k] : inf;
+    }
+    for (int k = 0; k < (NH - 1) * NU; ++k) {
+        m->umin[k] = us ? reinterpret_cast<const T *>(c->umin.data())[k] : -inf;
+        m->umax[k] = us ? reinterpret_cast<const T *>(c->umax.data())[k] : inf;
+    }
+    m->rho = (T)c->rho;
+    m->nrho = -(T)c->rho;
+    m->pri_tol = (T)c->pri;
+    m->dua_tol = (T)c->dua;
+    m->max_iter = c->max_iter;
+    m->check_term = c->check_term;
+}
+
+bool build_model(tmpc_ctx_impl *c)
+{
+    const bool f32 = c->dtype == TMPC_F32;
+    if (c->nx == 12 && c->nu == 4 && c->N == 10) {
+        f32 ? build_model_t<float, 12, 4, 10>(c) : build_model_t<double, 12, 4, 10>(c);
+        return true;
+    }
+    if (c->nx == 4 && c->nu == 1 && c->N == 10) {
+        f32 ? build_model_t<float, 4, 1, 10>(c) : build_model_t<double, 4, 1, 10>(c);
+        return true;
+    }
+    return false;
+}
+
+size_t esize(const tmpc_ctx_impl *c) { return c->dtype == TMPC_F32 ? 4 : 8; }
+
+struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/double: pointers + int64)
+    long long batch;
+    const void *x0;
+    const void *Xref;
+    long long xref_stride;
+    void *wd, *wy, *wg, *wv, *wz;
+    void *x, *u;
+    int *iter, *status;
+    void *resid;
+    unsigned long long *counter;
+    unsigned long long *stats;
+};
+static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
+static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
+
+// Launch the persistent kernel for one device-resident batch on `s`.
+int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
+{
+    KernelInfo ki;
+    if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki))
+        return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
+    CUDA_TRY(c, cudaFuncSetAttribute(ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), s));
+    da.counter = c->d_counter;
+    da.stats = c->d_counter + 1;
+    long long blocks = (da.batch + ki.block - 1) / ki.block;
+    if (blocks > c->sm_count) blocks = c->sm_count;
+    if (blocks < 1) blocks = 1;
+    void *params[2] = {c->model.data(), &da};
+    if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev0, s));
+    CUDA_TRY(c, cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, s));
+    if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev1, s));
+    c->stats.launches += 1;
+    c->stats.lanes = (int32_t)(blocks * ki.block);
+    return TMPC_OK;
+}
+
+int ensure_stage(tmpc_ctx_impl *c, int k, size_t in_bytes, size_t out_bytes)
+{
+    auto &st = c->stage[k];
+    if (!st.s) CUDA_TRY(c, cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+    if (!st.done) CUDA_TRY(c, cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    if (st.in_bytes < in_bytes) {
+        if (st.h_in) cudaFreeHost(st.h_in);
+        if (st.d_in) cudaFree(st.d_in);
+        st.h_in = st.d_in = nullptr;
+        CUDA_TRY(c, cudaMallocHost(&st.h_in, in_bytes));
+        CUDA_TRY(c, cudaMalloc(&st.d_in, in_bytes));
+        st.in_bytes = in_bytes;
+    }
+    if (st.out_bytes < out_bytes) {
+        if (st.h_out) cudaFreeHost(st.h_out);
+        if (st.d_out) cudaFree(st.d_out);
+        st.h_out = st.d_out = nullptr;
+        CUDA_TRY(c, cudaMallocHost(&st.h_out, out_bytes));
+        CUDA_TRY(c, cudaMalloc(&st.d_out, out_bytes));
+        st.out_bytes = out_bytes;
+    }
+    return TMPC_OK;
+}
+
+bool is_pinned(const void *p)
+{
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tmpc_version(void) { return "tmpc 0.1 (sm_100a)"; }
+
+const char *tmpc_last_error(const tmpc_ctx *ctx)
+{
+    return ctx ? reinterpret_cast<const tmpc_ctx_impl *>(ctx)->err.c_str() : g_create_error.c_str();
+}
+
+int tmpc_create(tmpc_ctx **out, int device, int nx, int nu, int N, int dtype, int order_policy)
+{
+    if (!out) return fail(nullptr, TMPC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (dtype != TMPC_F32 && dtype != TMPC_F64) return fail(nullptr, TMPC_ERR_INVALID, "bad dtype");
+    if (order_policy != TMPC_ORDER_PARITY && order_policy != TMPC_ORDER_FAST)
+        return fail(nullptr, TMPC_ERR_INVALID, "bad order policy");
+    KernelInfo ki;
+    if (!lookup_kernel(nx, nu, N, dtype, order_policy, false, ki)) {
+        char b[160];
+        snprintf(b, sizeof b, "shape nx=%d nu=%d N=%d has no compiled sm_100a kernel (have 12/4/10, 4/1/10)", nx, nu, N);
+        return fail(nullptr, TMPC_ERR_UNSUPPORTED, b);
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TMPC_ERR_CUDA,
+                    std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, TMPC_ERR_INVALID, "bad device index");
+    tmpc_ctx_impl *c = new tmpc_ctx_impl;
+    c->device = device; c->nx = nx; c->nu = nu; c->N = N; c->dtype = dtype; c->policy = order_policy;
+    auto bail = [&](const char *what, cudaError_t er) {
+        std::string msg = std::string(what) + ": " + cudaGetErrorString(er);
+        delete c;
+        return fail(nullptr, TMPC_ERR_CUDA, msg);
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete c;
+        return fail(nullptr, TMPC_ERR_UNSUPPORTED, "device is not sm_100-class; kernels are built for sm_100a only");
+    }
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaMalloc(&c->d_counter, 5 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    c->stats.parity_pinned = shape_parity_pinned(nx, nu) && order_policy == TMPC_ORDER_PARITY;
+    *out = reinterpret_cast<tmpc_ctx *>(c);
+    return TMPC_OK;
+}
+
+int tmpc_destroy(tmpc_ctx *ctx)
+{
+    if (!ctx) return TMPC_OK;
+    tmpc_ctx_impl *c = CTX(ctx);
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &st : c->stage) {
+        if (st.s) { cudaStreamSynchronize(st.s); cudaStreamDestroy(st.s); }
+        if (st.done) cudaEventDestroy(st.done);
+        if (st.h_in) cudaFreeHost(st.h_in);
+        if (st.h_out) cudaFreeHost(st.h_out);
+        if (st.d_in) cudaFree(st.d_in);
+        if (st.d_out) cudaFree(st.d_out);
+    }
+    if (c->d_counter) cudaFree(c->d_counter);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return TMPC_OK;
+}
+
+int tmpc_set_model(tmpc_ctx *ctx, const void *Kinf, const void *Pinf, const void *Quu_inv, const void *AmBKt,
+                   const void *Adyn, const void *Bdyn, const void *Q, double rho, const void *x_min,
+                   const void *x_max, const void *u_min, const void *u_max)
+{
+    if (!ctx) return TMPC_ERR_INVALID;
+    tmpc_ctx_impl *c = CTX(ctx);
+    if (!Kinf || !Pinf || !Quu_inv || !AmBKt || !Adyn || !Bdyn || !Q)
+        return fail(c, TMPC_ERR_INVALID, "model pointers must not be NULL");
+    if ((x_min == nullptr) != (x_max == nullptr) || (u_min == nullptr) != (u_max == nullptr))
+        return fail(c, TMPC_ERR_INVALID, "bounds must be given as min/max pairs");
+    const size_t es = esize(c);
+    const int nx = c->nx, nu = c->nu, N = c->N;
+    auto cp = [&](std::vector<unsigned char> &dst, const void *src, size_t n) {
+        dst.resize(n * es);
+        if (src) std::memcpy(dst.data(), src, n * es);
+    };
+    cp(c->Kinf, Kinf, nu * nx); cp(c->Pinf, Pinf, nx * nx); cp(c->Quu_inv, Quu_inv, nu * nu);
+    cp(c->AmBKt, AmBKt, nx * nx); cp(c->Adyn, Adyn, nx * nx); cp(c->Bdyn, Bdyn, nx * nu); cp(c->Q, Q, nx);
+    c->has_xb = x_min != nullptr;
+    c->has_ub = u_min != nullptr;
+    cp(c->xmin, x_min, nx * N); cp(c->xmax, x_max, nx * N);
+    cp(c->umin, u_min, nu * (N - 1)); cp(c->umax, u_max, nu * (N - 1));
+    c->rho = rho;
+    c->has_model = true;
+    if (!build_model(c)) return fail(c, TMPC_ERR_UNSUPPORTED, "shape not compiled");
+    return TMPC_OK;
+}
+
+int tmpc_set_settings(tmpc_ctx *ctx, double abs_pri_tol, double abs_dua_tol, int max_iter, int check_termination,
+                      int en_state_bound, int en_input_bound)
+{
+    if (!ctx) return TMPC_ERR_INVALID;
+    tmpc_ctx_impl *c = CTX(ctx);
+    if (check_termination < 1)
+        return fail(c, TMPC_ERR_INVALID, "check_termination must be >= 1 (0 is undefined behaviour in the reference)");
+    if (max_iter < 1) return fail(c, TMPC_ERR_INVALID, "max_iter must be >= 1");
+    c->pri = abs_pri_tol; c->dua = abs_dua_tol; c->max_iter = max_iter; c->check_term = check_termination;
+    c->en_state = en_state_bound; c->en_input = en_input_bound;
+    if (c->has_model && !build_model(c)) return fail(c, TMPC_ERR_UNSUPPORTED, "shape not compiled");
+    return TMPC_OK;
+}
+
+int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
+{
+    if (!ctx || !a) return TMPC_ERR_INVALID;
+    tmpc_ctx_impl *c = CTX(ctx);
+    if (!c->has_model) return fail(c, TMPC_ERR_STATE, "tmpc_set_model has not been called");
+    if (a->batch < 0) return fail(c, TMPC_ERR_INVALID, "negative batch");
+    if (a->batch > 0 && (!a->x0 || !a->Xref)) return fail(c, TMPC_ERR_INVALID, "x0 / Xref must not be NULL");
+    if (a->warm && (!a->warm->d || !a->warm->y || !a->warm->g || !a->warm->v || !a->warm->z))
+        return fail(c, TMPC_ERR_INVALID, "warm state needs all of d, y, g, v, z");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->stats.instances = a->batch;
+    c->stats.iterations = c->stats.solved = c->stats.trips = 0;
+    c->stats.launches = 0;
+    c->stats.lanes = 0;
+    c->stats.kernel_ms = 0.f;
+    c->stats_pending = false;
+    if (a->batch == 0) return TMPC_OK;
+
+    const size_t es = esize(c);
+    const int nx = c->nx, nu = c->nu, N = c->N;
+    const size_t xrow = (size_t)nx * N, urow = (size_t)nu * (N - 1);
+    const bool warm = a->warm != nullptr;
+
+    if (a->mem == TMPC_MEM_DEVICE) {
+        auto mis = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
+        if (mis(a->x0) || mis(a->Xref) || mis(a->x) || mis(a->u) ||
+            (warm && (mis(a->warm->d) || mis(a->warm->y) || mis(a->warm->g) || mis(a->warm->v) || mis(a->warm->z))))
+            return fail(c, TMPC_ERR_INVALID, "device buffers must be 16-byte aligned");
+        DevArgs da{};
+        da.batch = a->batch; da.x0 = a->x0; da.Xref = a->Xref;
+        da.xref_stride = a->xref_shared ? 0 : (long long)xrow;
+        if (warm) { da.wd = a->warm->d; da.wy = a->warm->y; da.wg = a->warm->g; da.wv = a->warm->v; da.wz = a->warm->z; }
+        da.x = a->x; da.u = a->u; da.iter = a->iter; da.status = a->status; da.resid = a->resid;
+        cudaStream_t s = a->stream ? (cudaStream_t)a->stream : c->stream;
+        int rc = launch_device(c, da, warm, s, true);
+        if (rc != TMPC_OK) return rc;
+        c->stats_pending = true;
+        return TMPC_OK;
+    }
+    if (a->mem != TMPC_MEM_HOST) return fail(c, TMPC_ERR_INVALID, "bad mem kind");
+
+    // ---- host buffers: chunked 3-deep pipeline  H2D(k+1) | solve(k) | D2H(k-1) on three streams
+    // input chunk image : x0 | [Xref per instance] | [warm d y z g v]
+    // output chunk image: x | u | iter | status | resid | [warm d y z g v]
+    const size_t in_per = nx * es + (a->xref_shared ? 0 : xrow * es) + (warm ? (3 * urow + 2 * xrow) * es : 0);
+    const size_t out_per = (xrow + urow) * es + 8 + 4 * es;
+    int64_t chunk = std::min<int64_t>(a->batch, 131072);
+    if (a->batch > chunk) chunk = (int64_t)((a->batch + ((a->batch + chunk - 1) / chunk) - 1) / ((a->batch + chunk - 1) / chunk));
+    chunk = (chunk + 3) & ~int64_t(3);  // keep every sub-array 16-byte aligned
+    const size_t xref_sh_bytes = xrow * es;
+    void *d_xref_shared = nullptr;
+    if (a->xref_shared) {
+        CUDA_TRY(c, cudaMalloc(&d_xref_shared, xref_sh_bytes));
+        CUDA_TRY(c, cudaMemcpyAsync(d_xref_shared, a->Xref, xref_sh_bytes, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    const int nchunks = (int)((a->batch + chunk - 1) / chunk);
+    const int depth = nchunks < 3 ? nchunks : 3;
+    for (int k = 0; k < depth; ++k) {
+        int rc = ensure_stage(c, k, in_per * chunk, out_per * chunk + (warm ? (3 * urow + 2 * xrow) * es * chunk : 0));
+        if (rc != TMPC_OK) { if (d_xref_shared) cudaFree(d_xref_shared); return rc; }
+    }
+    // direct DMA from/to user memory when it is pinned, else bounce through the pinned staging buffers
+    const bool direct = is_pinned(a->x0) && is_pinned(a->x) && is_pinned(a->u) && is_pinned(a->iter) &&
+                        is_pinned(a->status) && is_pinned(a->resid) && (a->xref_shared || is_pinned(a->Xref)) &&
+                        (!warm || (is_pinned(a->warm->d) && is_pinned(a->warm->y) && is_pinned(a->warm->g) &&
+                                   is_pinned(a->warm->v) && is_pinned(a->warm->z)));
+    float total_ms = 0.f;
+    std::vector<cudaEvent_t> kev(2 * nchunks, nullptr);
+    int rc_all = TMPC_OK;
+    auto cleanup = [&]() {
+        for (auto e : kev) if (e) cudaEventDestroy(e);
+        if (d_xref_shared) cudaFree(d_xref_shared);
+    };
+    struct OutPtrs { char *x, *u, *iter, *status, *resid, *wd, *wy, *wz, *wg, *wv; };
+    std::vector<int64_t> cb(nchunks), cn(nchunks);
+    auto drain = [&](int k) -> int {  // copy chunk k's outputs from staging to user memory (bounce mode)
+        auto &st = c->stage[k % 3];
+        CUDA_TRY(c, cudaStreamSynchronize(st.s));
+        if (!direct) {
+            const int64_t b0 = cb[k], n = cn[k];
+            char *h = (char *)st.h_out;
+            size_t off = 0;
+            auto take = [&](void *dst, size_t per) {
+                if (dst) std::memcpy((char *)dst + b0 * per, h + off, n * per);
+                off += chunk * per;
+            };
+            take(a->x, xrow * es); take(a->u, urow * es); take(a->iter, 4); take(a->status, 4); take(a->resid, 4 * es);
+            if (warm) {
+                take(a->warm->d, urow * es); take(a->warm->y, urow * es); take(a->warm->z, urow * es);
+                take(a->warm->g, xrow * es); take(a->warm->v, xrow * es);
+            }
+        }
+        return TMPC_OK;
+    };
+    for (int k = 0; k < nchunks && rc_all == TMPC_OK; ++k) {
+        auto &st = c->stage[k % 3];
+        if (k >= 3) { rc_all = drain(k - 3); if (rc_all != TMPC_OK) break; }
+        const int64_t b0 = (int64_t)k * chunk, n = std::min<int64_t>(chunk, a->batch - b0);
+        cb[k] = b0; cn[k] = n;
+        // ---- H2D
+        char *din = (char *)st.d_in;
+        size_t off = 0;
+        char *hin = (char *)st.h_in;
+        auto put = [&](const void *src, size_t per) -> char * {
+            char *d = din + off;
+            if (direct) cudaMemcpyAsync(d, (const char *)src + b0 * per, n * per, cudaMemcpyHostToDevice, st.s);
+            else std::memcpy(hin + off, (const char *)src + b0 * per, n * per);
+            off += chunk * per;
+            return d;
+        };
+        DevArgs da{};
+        da.batch = n;
+        da.x0 = put(a->x0, nx * es);
+        if (a->xref_shared) { da.Xref = d_xref_shared; da.xref_stride = 0; }
+        else { da.Xref = put(a->Xref, xrow * es); da.xref_stride = (long long)xrow; }
+        char *dout = (char *)st.d_out;
+        size_t oo = 0;
+        auto outp = [&](size_t per) { char *p = dout + oo; oo += chunk * per; return p; };
+        da.x = outp(xrow * es); da.u = outp(urow * es);
+        da.iter = (int *)outp(4); da.status = (int *)outp(4); da.resid = outp(4 * es);
+        char *w_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (warm) {
+            // warm state is in place on the device: stage it straight into the OUTPUT image, solve there
+            da.wd = outp(urow * es); da.wy = outp(urow * es); da.wz = outp(urow * es);
+            da.wg = outp(xrow * es); da.wv = outp(xrow * es);
+            const void *src[5] = {a->warm->d, a->warm->y, a->warm->z, a->warm->g, a->warm->v};
+            void *dst[5] = {da.wd, da.wy, da.wz, da.wg, da.wv};
+            const size_t per[5] = {urow * es, urow * es, urow * es, xrow * es, xrow * es};
+            for (int q = 0; q < 5; ++q) {
+                if (direct) cudaMemcpyAsync(dst[q], (const char *)src[q] + b0 * per[q], n * per[q], cudaMemcpyHostToDevice, st.s);
+                else {
+                    w_in[q] = hin + off;
+                    std::memcpy(hin + off, (const char *)src[q] + b0 * per[q], n * per[q]);
+                    off += chunk * per[q];
+                }
+            }
+        }
+        if (!direct) {
+            const size_t plain = chunk * (nx * es + (a->xref_shared ? 0 : xrow * es));
+            cudaMemcpyAsync(din, hin, plain, cudaMemcpyHostToDevice, st.s);
+            if (warm) {
+                void *dst[5] = {da.wd, da.wy, da.wz, da.wg, da.wv};
+                const size_t per[5] = {urow * es, urow * es, urow * es, xrow * es, xrow * es};
+                for (int q = 0; q < 5; ++q) cudaMemcpyAsync(dst[q], w_in[q], n * per[q], cudaMemcpyHostToDevice, st.s);
+            }
+        }
+        // ---- solve (kernels of different chunks serialise on the device through the shared work counter,
+        //      so each chunk gets its own counter slot: reuse the ctx counter but order launches on st.s
+        //      after the previous chunk's kernel)
+        if (k > 0) cudaStreamWaitEvent(st.s, kev[2 * (k - 1) + 1], 0);
+        cudaEventCreate(&kev[2 * k]);
+        cudaEventCreate(&kev[2 * k + 1]);
+        {
+            KernelInfo ki;
+            lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki);
+            cudaFuncSetAttribute(ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem);
+            // stats accumulate over chunks; only the work counter is reset per chunk
+            cudaMemsetAsync(c->d_counter, 0, (k == 0 ? 5 : 1) * sizeof(unsigned long long), st.s);
+            da.counter = c->d_counter;
+            da.stats = c->d_counter + 1;
+            long long blocks = std::min<long long>((n + ki.block - 1) / ki.block, c->sm_count);
+            void *params[2] = {c->model.data(), &da};
+            cudaEventRecord(kev[2 * k], st.s);
+            cudaError_t e = cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, st.s);
+            cudaEventRecord(kev[2 * k + 1], st.s);
+            if (e != cudaSuccess) { rc_all = fail(c, TMPC_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e)); break; }
+            c->stats.launches += 1;
+            c->stats.lanes = (int32_t)(blocks * ki.block);
+        }
+        // ---- D2H
+        {
+            size_t o2 = 0;
+            char *hout = (char *)st.h_out;
+            auto get = [&](void *dst, size_t per) {
+                if (direct) { if (dst) cudaMemcpyAsync((char *)dst + b0 * per, dout + o2, n * per, cudaMemcpyDeviceToHost, st.s); }
+                else if (dst) cudaMemcpyAsync(hout + o2, dout + o2, n * per, cudaMemcpyDeviceToHost, st.s);
+                o2 += chunk * per;
+            };
+            get(a->x, xrow * es); get(a->u, urow * es); get(a->iter, 4); get(a->status, 4); get(a->resid, 4 * es);
+            if (warm) {
+                get(a->warm->d, urow * es); get(a->warm->y, urow * es); get(a->warm->z, urow * es);
+                get(a->warm->g, xrow * es); get(a->warm->v, xrow * es);
+            }
+        }
+    }
+    if (rc_all == TMPC_OK)
+        for (int k = std::max(0, nchunks - 3); k < nchunks && rc_all == TMPC_OK; ++k) rc_all = drain(k);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc_all == TMPC_OK && e != cudaSuccess) rc_all = fail(c, TMPC_ERR_CUDA, std::string("solve: ") + cudaGetErrorString(e));
+    if (rc_all == TMPC_OK) {
+        for (int k = 0; k < nchunks; ++k) {
+            float ms = 0.f;
+            if (kev[2 * k] && cudaEventElapsedTime(&ms, kev[2 * k], kev[2 * k + 1]) == cudaSuccess) total_ms += ms;
+        }
+        c->stats.kernel_ms = total_ms;
+        unsigned long long h[5];
+        if (cudaMemcpy(h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            c->stats.iterations = (int64_t)h[1]; c->stats.solved = (int64_t)h[2]; c->stats.trips = (int64_t)h[3];
+        }
+    }
+    cleanup();
+    return rc_all;
+}
+
+int tmpc_get_stats(tmpc_ctx *ctx, tmpc_stats *out)
+{
+    if (!ctx || !out) return TMPC_ERR_INVALID;
+    tmpc_ctx_impl *c = CTX(ctx);
+    if (c->stats_pending) {
+        CUDA_TRY(c, cudaSetDevice(c->device));
+        CUDA_TRY(c, cudaEventSynchronize(c->ev1));
+        float ms = 0.f;
+        CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->stats.kernel_ms = ms;
+        unsigned long long h[5];
+        CUDA_TRY(c, cudaMemcpy(h, c->d_counter, sizeof h, cudaMemcpyDeviceToHost));
+        c->stats.iterations = (int64_t)h[1]; c->stats.solved = (int64_t)h[2]; c->stats.trips = (int64_t)h[3];
+        c->stats_pending = false;
+    }
+    *out = c->stats;
+    return TMPC_OK;
+}
+
+int tmpc_host_alloc(void **ptr, uint64_t bytes)
+{
+    if (!ptr) return TMPC_ERR_INVALID;
+    return cudaMallocHost(ptr, bytes) == cudaSuccess ? TMPC_OK : TMPC_ERR_CUDA;
+}
+int tmpc_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? TMPC_OK : TMPC_ERR_CUDA; }
+
+}  // extern "C"

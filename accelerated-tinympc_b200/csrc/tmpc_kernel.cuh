@@ -1,0 +1,590 @@
+// Persistent thread-per-instance ADMM kernel for sm_100a.
+//
+// One CUDA thread owns one MPC instance at a time and runs the reference's whole tiny_solve loop
+// (/root/reference/src/tinympc/admm.cpp:111-152) on it; when the instance terminates the lane emits its
+// trajectory and claims the next instance from a global work counter (per-lane early exit + refill), so
+// lanes of a warp sit at different ADMM iterations of different instances while executing the same code.
+//
+//   * shared model/cache (Kinf, Adyn, Bdyn, Quu_inv, AmBKt, Pinf, Q, bounds, rho, tolerances) lives in the
+//     kernel-parameter constant bank (__grid_constant__): every mat-vec coefficient is a warp-uniform
+//     c[0][imm] operand of FMUL/FFMA and costs no load instruction and no register;
+//   * the state that survives an iteration {d, y, z, g, v} (+ p_N seed) sits in shared memory, laid out
+//     [16-byte chunk][thread] so a warp's LDS.128/STS.128 is conflict-free; x, u, q, r, p, vnew, znew are
+//     transient registers (q, r are recomputed bit-identically in the backward sweep);
+//   * forward_pass + update_slack + update_dual + the four residual maxima are fused into one sweep over
+//     the horizon; update_linear_cost + backward_pass_grad into the reverse sweep.
+//
+// Arithmetic policy (template FAST): false = products rounded individually and summed in the reference's
+// exact order (orders.h) with FMA contraction disabled -> bit-identical to the "-O3" SSE2 reference build;
+// true = FMA chains.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tmpc {
+
+// ------------------------------------------------------------------------------------------------
+// scalar traits: explicitly rounded ops (never contracted by the compiler)
+// ------------------------------------------------------------------------------------------------
+template <class T> struct Num;
+template <> struct Num<float> {
+    static constexpr int PK = 4;  // SSE packet width of the reference build for this scalar
+    using vec_t = float4;
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+};
+template <> struct Num<double> {
+    static constexpr int PK = 2;
+    using vec_t = double2;
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// evaluation orders of the reference build (restated and pinned in oracle/tinympc_oracle.c)
+// ------------------------------------------------------------------------------------------------
+enum { ORD_SEQ = 0, ORD_VECREDUX = 1, ORD_TREE = 2, ORD_GEMV_ROW = 5 };
+
+template <class T, int NX, int NU> struct Orders {
+    static constexpr int PK = Num<T>::PK;
+    static constexpr int LARGE = 8;
+    static constexpr int Kx = (NU == 1) ? ORD_VECREDUX : (NU % PK == 0 ? ORD_SEQ : ORD_TREE);
+    static constexpr int Ax = (NX % PK == 0) ? ORD_SEQ : ORD_TREE;
+    static constexpr int Bu = (NX % PK == 0) ? ORD_SEQ : ORD_TREE;
+    static constexpr int Btp = (NU >= LARGE && NX >= LARGE) ? ORD_GEMV_ROW : ORD_VECREDUX;
+    static constexpr int Qs = (NU >= LARGE || NU % PK == 0 || NU == 1) ? ORD_SEQ : ORD_TREE;
+    static constexpr int Mp = (NU == 1 && NX % PK == 0) ? ORD_SEQ : ORD_TREE;
+    static constexpr int Ktr = ORD_VECREDUX;
+    static constexpr int XtP = ORD_VECREDUX;
+};
+
+// e(k) = k-th individually rounded product.  All recursion is resolved at compile time.
+template <class T, int S, int LEN, class E> __device__ __forceinline__ T red_tree(const E &e)
+{
+    if constexpr (LEN == 1) {
+        return e(S);
+    } else {
+        constexpr int H = LEN / 2;
+        T a = red_tree<T, S, H>(e);
+        T b = red_tree<T, S + H, LEN - H>(e);
+        return Num<T>::add(a, b);
+    }
+}
+// tree over packets [S, S+LEN) for SIMD lane L of the reference's packet
+template <class T, int S, int LEN, int L, class E> __device__ __forceinline__ T red_ptree(const E &e)
+{
+    constexpr int PK = Num<T>::PK;
+    if constexpr (LEN == 1) {
+        return e(S * PK + L);
+    } else {
+        constexpr int H = LEN / 2;
+        T a = red_ptree<T, S, H, L>(e);
+        T b = red_ptree<T, S + H, LEN - H, L>(e);
+        return Num<T>::add(a, b);
+    }
+}
+template <class T> __device__ __forceinline__ T predux(const T (&l)[Num<T>::PK])
+{
+    if constexpr (Num<T>::PK == 4) return Num<T>::add(Num<T>::add(l[0], l[2]), Num<T>::add(l[1], l[3]));
+    else return Num<T>::add(l[0], l[1]);
+}
+template <class T, int K, int L, class E> __device__ __forceinline__ T red_lane_seq(const E &e)
+{
+    constexpr int PK = Num<T>::PK;
+    T acc = e(L);
+#pragma unroll
+    for (int j = PK; j + PK <= K; j += PK) acc = Num<T>::add(e(j + L), acc);
+    return acc;
+}
+
+// sum_k c(k)*x(k) in the named order (PARITY) or as one FMA chain (FAST)
+template <class T, int ORD, int K, bool FAST, class C, class X>
+__device__ __forceinline__ T dot(const C &c, const X &x)
+{
+    using N = Num<T>;
+    constexpr int PK = N::PK;
+    if constexpr (FAST) {
+        T acc = N::mul(c(0), x(0));
+#pragma unroll
+        for (int k = 1; k < K; ++k) acc = N::fma(c(k), x(k), acc);
+        return acc;
+    } else {
+        auto e = [&](int k) -> T { return N::mul(c(k), x(k)); };
+        if constexpr (ORD == ORD_SEQ) {
+            T acc = e(0);
+#pragma unroll
+            for (int k = 1; k < K; ++k) acc = N::add(e(k), acc);
+            return acc;
+        } else if constexpr (ORD == ORD_TREE) {
+            return red_tree<T, 0, K>(e);
+        } else if constexpr (ORD == ORD_VECREDUX) {
+            constexpr int NP = K / PK;
+            if constexpr (NP == 0) {
+                return red_tree<T, 0, K>(e);
+            } else {
+                T l[PK];
+                l[0] = red_ptree<T, 0, NP, 0>(e);
+                l[1] = red_ptree<T, 0, NP, 1>(e);
+                if constexpr (PK == 4) {
+                    l[2] = red_ptree<T, 0, NP, 2>(e);
+                    l[3] = red_ptree<T, 0, NP, 3>(e);
+                }
+                T r = predux<T>(l);
+                if constexpr (NP * PK != K) r = N::add(r, red_tree<T, NP * PK, K - NP * PK>(e));
+                return r;
+            }
+        } else {  // ORD_GEMV_ROW
+            constexpr int FULL = (K / PK) * PK;
+            static_assert(FULL > 0, "row-major GEMV order needs K >= packet");
+            T l[PK];
+            l[0] = red_lane_seq<T, K, 0>(e);
+            l[1] = red_lane_seq<T, K, 1>(e);
+            if constexpr (PK == 4) {
+                l[2] = red_lane_seq<T, K, 2>(e);
+                l[3] = red_lane_seq<T, K, 3>(e);
+            }
+            T r = predux<T>(l);
+#pragma unroll
+            for (int j = FULL; j < K; ++j) r = N::add(r, e(j));
+            return r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameters (constant bank)
+// ------------------------------------------------------------------------------------------------
+template <class T, int NX, int NU, int NH> struct alignas(16) Model {
+    T K[NU * NX];   // Kinf     (nu x nx) col-major: K[r + k*NU]
+    T A[NX * NX];   // Adyn                          A[r + k*NX]
+    T B[NX * NU];   // Bdyn     (nx x nu)            B[r + k*NX]
+    T Qi[NU * NU];  // Quu_inv
+    T M[NX * NX];   // AmBKt
+    T Pf[NX * NX];  // Pinf
+    T Qd[NX];       // work.Q
+    T xmin[NH * NX], xmax[NH * NX];
+    T umin[(NH - 1) * NU], umax[(NH - 1) * NU];
+    T rho, nrho, pri_tol, dua_tol;
+    int max_iter, check_term;
+};
+
+template <class T> struct SolveArgs {
+    long long batch;
+    const T *x0;
+    const T *Xref;
+    long long xref_stride;  // elements between instances (0 = shared)
+    T *wd, *wy, *wg, *wv, *wz;  // warm state, in place (all or none)
+    T *x, *u;
+    int *iter, *status;
+    T *resid;
+    unsigned long long *counter;  // next unclaimed instance
+    unsigned long long *stats;    // [0] iterations [1] solved [2] lane-trips [3] instances
+};
+
+// per-thread array of STAGES vectors of D scalars in shared memory.
+//  D % VEC == 0: [chunk][thread] with 16-byte chunks (conflict-free 128-bit access);
+//  otherwise   : [element][thread] (conflict-free 32/64-bit access).
+template <class T, int D, int STAGES, int BLOCK> struct SVec {
+    using vec_t = typename Num<T>::vec_t;
+    static constexpr int VEC = 16 / sizeof(T);
+    static constexpr bool CHUNK = (D % VEC == 0);
+    static constexpr int LEN = D * STAGES;
+    static constexpr size_t BYTES =
+        CHUNK ? size_t(LEN / VEC) * BLOCK * 16 : ((size_t(LEN) * BLOCK * sizeof(T) + 15) / 16) * 16;
+    unsigned char *base;
+    __device__ __forceinline__ SVec(unsigned char *b, int tid) : base(b + (CHUNK ? tid * 16 : tid * int(sizeof(T)))) {}
+    __device__ __forceinline__ void load(int i, T (&o)[D]) const
+    {
+        if constexpr (CHUNK) {
+#pragma unroll
+            for (int c = 0; c < D / VEC; ++c) {
+                vec_t t = *reinterpret_cast<const vec_t *>(base + size_t(i * (D / VEC) + c) * BLOCK * 16);
+                o[c * VEC + 0] = t.x;
+                o[c * VEC + 1] = t.y;
+                if constexpr (VEC == 4) {
+                    o[c * VEC + 2] = ((const T *)&t)[2];
+                    o[c * VEC + 3] = ((const T *)&t)[3];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                o[j] = *reinterpret_cast<const T *>(base + size_t(i * D + j) * BLOCK * sizeof(T));
+        }
+    }
+    __device__ __forceinline__ void store(int i, const T (&o)[D], bool pred = true) const
+    {
+        if (!pred) return;
+        if constexpr (CHUNK) {
+#pragma unroll
+            for (int c = 0; c < D / VEC; ++c) {
+                vec_t t;
+                t.x = o[c * VEC + 0];
+                t.y = o[c * VEC + 1];
+                if constexpr (VEC == 4) {
+                    ((T *)&t)[2] = o[c * VEC + 2];
+                    ((T *)&t)[3] = o[c * VEC + 3];
+                }
+                *reinterpret_cast<vec_t *>(base + size_t(i * (D / VEC) + c) * BLOCK * 16) = t;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                *reinterpret_cast<T *>(base + size_t(i * D + j) * BLOCK * sizeof(T)) = o[j];
+        }
+    }
+};
+
+// global [instance][stage][dim] rows; 16-byte vector access when D is a multiple of the vector width
+template <class T, int D> __device__ __forceinline__ void gload(const T *p, T (&o)[D])
+{
+    using vec_t = typename Num<T>::vec_t;
+    constexpr int VEC = 16 / sizeof(T);
+    if constexpr (D % VEC == 0) {
+#pragma unroll
+        for (int c = 0; c < D / VEC; ++c) {
+            vec_t t = __ldg(reinterpret_cast<const vec_t *>(p) + c);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) o[c * VEC + e] = ((const T *)&t)[e];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) o[j] = __ldg(p + j);
+    }
+}
+template <class T, int D> __device__ __forceinline__ void gstore(T *p, const T (&o)[D])
+{
+    using vec_t = typename Num<T>::vec_t;
+    constexpr int VEC = 16 / sizeof(T);
+    if constexpr (D % VEC == 0) {
+#pragma unroll
+        for (int c = 0; c < D / VEC; ++c) {
+            vec_t t;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) ((T *)&t)[e] = o[c * VEC + e];
+            reinterpret_cast<vec_t *>(p)[c] = t;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) p[j] = o[j];
+    }
+}
+
+template <class T, int NX, int NU, int NH, int BLOCK> struct SmemLayout {
+    using SU = SVec<T, NU, NH - 1, BLOCK>;
+    using SX = SVec<T, NX, NH, BLOCK>;
+    using SP = SVec<T, NX, 1, BLOCK>;
+    static constexpr size_t BYTES = 3 * SU::BYTES + 2 * SX::BYTES + SP::BYTES;
+};
+
+enum { PH_FREE = 0, PH_RUN = 1, PH_EMIT = 2 };
+
+template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool UNROLL>
+__global__ void __launch_bounds__(BLOCK, 1)
+admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constant__ SolveArgs<T> a)
+{
+    using N = Num<T>;
+    using O = Orders<T, NX, NU>;
+    using L = SmemLayout<T, NX, NU, NH, BLOCK>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31;
+    constexpr unsigned FULLM = 0xffffffffu;
+    constexpr int XROW = NX * NH, UROW = NU * (NH - 1);
+
+    unsigned char *sp = smem;
+    typename L::SU sd(sp, tid); sp += L::SU::BYTES;
+    typename L::SU sy(sp, tid); sp += L::SU::BYTES;
+    typename L::SU sz(sp, tid); sp += L::SU::BYTES;
+    typename L::SX sg(sp, tid); sp += L::SX::BYTES;
+    typename L::SX sv(sp, tid); sp += L::SX::BYTES;
+    typename L::SP spn(sp, tid);
+
+    long long inst = -1;
+    int it = 0;
+    int phase = PH_FREE;
+    bool exhausted = false;
+    bool hit_max = false;  // terminated by max_iter without converging (backward of that iteration still runs)
+    T x0[NX];
+    T res[4] = {T(0), T(0), T(0), T(0)};
+    unsigned long long n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x0[j] = T(0);
+
+    for (;;) {
+        // ------------------------------------------------------------------ lane refill
+        const bool need = (phase == PH_FREE) && !exhausted;
+        const unsigned m = __ballot_sync(FULLM, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(m));
+            base = __shfl_sync(FULLM, base, leader);
+            if (need) {
+                const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
+                if (idx < a.batch) {
+                    inst = idx;
+                    phase = PH_RUN;
+                    it = 0;
+                    hit_max = false;
+                    res[0] = res[1] = res[2] = res[3] = T(0);
+                    gload<T, NX>(a.x0 + inst * NX, x0);
+                    // p_N seed: -(Xref_{N-1}^T * Pinf)   (admm.cpp:83)
+                    {
+                        T xr[NX], pn[NX];
+                        gload<T, NX>(a.Xref + inst * a.xref_stride + (NH - 1) * NX, xr);
+#pragma unroll
+                        for (int j = 0; j < NX; ++j)
+                            pn[j] = -dot<T, O::XtP, NX, FAST>([&](int k) { return P.Pf[k + j * NX]; },
+                                                              [&](int k) { return xr[k]; });
+                        spn.store(0, pn);
+                    }
+                    if (WARM && a.wd) {
+#pragma unroll 1
+                        for (int i = 0; i < NH - 1; ++i) {
+                            T t[NU];
+                            gload<T, NU>(a.wd + inst * UROW + i * NU, t); sd.store(i, t);
+                            gload<T, NU>(a.wy + inst * UROW + i * NU, t); sy.store(i, t);
+                            gload<T, NU>(a.wz + inst * UROW + i * NU, t); sz.store(i, t);
+                        }
+#pragma unroll 1
+                        for (int i = 0; i < NH; ++i) {
+                            T t[NX];
+                            gload<T, NX>(a.wg + inst * XROW + i * NX, t); sg.store(i, t);
+                            gload<T, NX>(a.wv + inst * XROW + i * NX, t); sv.store(i, t);
+                        }
+                    } else {
+                        T zu[NU], zx[NX];
+#pragma unroll
+                        for (int j = 0; j < NU; ++j) zu[j] = T(0);
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) zx[j] = T(0);
+#pragma unroll 1
+                        for (int i = 0; i < NH - 1; ++i) { sd.store(i, zu); sy.store(i, zu); sz.store(i, zu); }
+#pragma unroll 1
+                        for (int i = 0; i < NH; ++i) { sg.store(i, zx); sv.store(i, zx); }
+                    }
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (__all_sync(FULLM, phase == PH_FREE)) break;
+        ++n_trips;
+
+        const bool emit = (phase == PH_EMIT);
+        if (phase == PH_RUN) ++it;
+
+        // ------------------------------------------------------------------ forward sweep
+        // forward_pass (admm.cpp:27-37) + update_slack (:45-61) + update_dual (:67-71) + residual maxima (:95-98)
+        T pri_x = T(0), dua_x = T(0), pri_u = T(0), dua_u = T(0);
+        {
+            T x[NX];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) x[j] = x0[j];
+            T *xo = (emit && a.x) ? a.x + inst * XROW : nullptr;
+            T *uo = (emit && a.u) ? a.u + inst * UROW : nullptr;
+            T *go = (WARM && emit && a.wg) ? a.wg + inst * XROW : nullptr;
+            T *yo = (WARM && emit && a.wy) ? a.wy + inst * UROW : nullptr;
+
+            auto stage = [&](int i, bool last) {
+                T g[NX], v[NX], vn[NX];
+                sg.load(i, g);
+                sv.load(i, v);
+                if (WARM && go) gstore<T, NX>(go + i * NX, g);
+#pragma unroll
+                for (int j = 0; j < NX; ++j) {
+                    vn[j] = N::add(x[j], g[j]);                                                  // :48
+                    vn[j] = N::mn(P.xmax[i * NX + j], N::mx(P.xmin[i * NX + j], vn[j]));         // :59
+                    pri_x = N::mx(pri_x, N::abs(N::sub(x[j], vn[j])));                           // :95
+                    dua_x = N::mx(dua_x, N::abs(N::sub(v[j], vn[j])));                           // :96
+                    g[j] = N::sub(N::add(g[j], x[j]), vn[j]);                                    // :70
+                }
+                sg.store(i, g);
+                sv.store(i, vn);
+                if (xo) gstore<T, NX>(xo + i * NX, x);
+                if (!last) {
+                    T d[NU], y[NU], z[NU], u[NU], zn[NU];
+                    sd.load(i, d);
+                    sy.load(i, y);
+                    sz.load(i, z);
+                    if (WARM && yo) gstore<T, NU>(yo + i * NU, y);
+#pragma unroll
+                    for (int r = 0; r < NU; ++r) {
+                        T kx = dot<T, O::Kx, NX, FAST>([&](int k) { return P.K[r + k * NU]; },
+                                                       [&](int k) { return x[k]; });
+                        u[r] = N::sub(-kx, d[r]);                                                // :31
+                        zn[r] = N::add(u[r], y[r]);                                              // :47
+                        zn[r] = N::mn(P.umax[i * NU + r], N::mx(P.umin[i * NU + r], zn[r]));     // :53
+                        pri_u = N::mx(pri_u, N::abs(N::sub(u[r], zn[r])));                       // :97
+                        dua_u = N::mx(dua_u, N::abs(N::sub(z[r], zn[r])));                       // :98
+                        y[r] = N::sub(N::add(y[r], u[r]), zn[r]);                                // :69
+                    }
+                    sy.store(i, y);
+                    sz.store(i, zn);
+                    if (uo) gstore<T, NU>(uo + i * NU, u);
+                    T xn[NX];
+#pragma unroll
+                    for (int r = 0; r < NX; ++r) {
+                        T ax = dot<T, O::Ax, NX, FAST>([&](int k) { return P.A[r + k * NX]; },
+                                                       [&](int k) { return x[k]; });
+                        if constexpr (FAST) {
+                            T acc = ax;
+#pragma unroll
+                            for (int k = 0; k < NU; ++k) acc = N::fma(P.B[r + k * NX], u[k], acc);
+                            xn[r] = acc;
+                        } else {
+                            T bu = dot<T, O::Bu, NU, FAST>([&](int k) { return P.B[r + k * NX]; },
+                                                           [&](int k) { return u[k]; });
+                            xn[r] = N::add(ax, bu);                                              // :35
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) x[j] = xn[j];
+                }
+            };
+            if constexpr (UNROLL) {
+#pragma unroll
+                for (int i = 0; i < NH - 1; ++i) stage(i, false);
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < NH - 1; ++i) stage(i, false);
+            }
+            stage(NH - 1, true);
+        }
+
+        // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
+        bool final_bwd = false;  // WARM: max_iter exit still runs the backward pass of its last iteration
+        if (phase == PH_RUN) {
+            const bool chk = (it % P.check_term) == 0;
+            if (chk) {
+                res[0] = pri_x;
+                res[1] = N::mul(dua_x, P.rho);
+                res[2] = pri_u;
+                res[3] = N::mul(dua_u, P.rho);
+            }
+            const bool conv = chk && res[0] < P.pri_tol && res[2] < P.pri_tol && res[1] < P.dua_tol &&
+                              res[3] < P.dua_tol;
+            if (conv || it >= P.max_iter) {
+                if (a.iter) a.iter[inst] = it;
+                if (a.status) a.status[inst] = conv ? 1 : 11;
+                if (a.resid) {
+                    a.resid[inst * 4 + 0] = res[0];
+                    a.resid[inst * 4 + 1] = res[1];
+                    a.resid[inst * 4 + 2] = res[2];
+                    a.resid[inst * 4 + 3] = res[3];
+                }
+                n_iter += (unsigned)it;
+                n_solved += conv ? 1u : 0u;
+                ++n_inst;
+                hit_max = !conv;
+                final_bwd = !conv;
+                phase = PH_EMIT;
+            }
+        } else if (phase == PH_EMIT) {
+            phase = PH_FREE;  // trajectory was written by this trip's forward sweep
+        }
+
+        // ------------------------------------------------------------------ backward sweep
+        // update_linear_cost (admm.cpp:77-85) recomputed per stage + backward_pass_grad (:15-22)
+        const bool cont = (phase == PH_RUN);
+        const bool wout = WARM && (cont || final_bwd) && a.wd;
+        if (__any_sync(FULLM, cont || wout)) {
+            T p[NX];
+            const T *xr_base = a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
+            T *wdo = wout ? a.wd + inst * UROW : nullptr;
+            T *wvo = wout ? a.wv + inst * XROW : nullptr;
+            T *wzo = wout ? a.wz + inst * UROW : nullptr;
+            {
+                T v[NX], g[NX], pn[NX];
+                sv.load(NH - 1, v);
+                sg.load(NH - 1, g);
+                spn.load(0, pn);
+                if (WARM && wvo) gstore<T, NX>(wvo + (NH - 1) * NX, v);
+#pragma unroll
+                for (int j = 0; j < NX; ++j) {
+                    if constexpr (FAST) p[j] = N::fma(P.nrho, N::sub(v[j], g[j]), pn[j]);
+                    else p[j] = N::sub(pn[j], N::mul(P.rho, N::sub(v[j], g[j])));                // :84
+                }
+            }
+            auto bstage = [&](int i) {
+                T z[NU], y[NU], r[NU], v[NX], g[NX], xr[NX], q[NX];
+                sz.load(i, z);
+                sy.load(i, y);
+                sv.load(i, v);
+                sg.load(i, g);
+                gload<T, NX>(xr_base + i * NX, xr);
+                if (WARM && wvo) { gstore<T, NX>(wvo + i * NX, v); gstore<T, NU>(wzo + i * NU, z); }
+#pragma unroll
+                for (int j = 0; j < NU; ++j) r[j] = N::mul(P.nrho, N::sub(z[j], y[j]));          // :80
+#pragma unroll
+                for (int j = 0; j < NX; ++j) {
+                    T cq = -N::mul(xr[j], P.Qd[j]);                                              // :81
+                    if constexpr (FAST) q[j] = N::fma(P.nrho, N::sub(v[j], g[j]), cq);
+                    else q[j] = N::sub(cq, N::mul(P.rho, N::sub(v[j], g[j])));                   // :82
+                }
+                T s[NU], d[NU];
+#pragma unroll
+                for (int r_ = 0; r_ < NU; ++r_) {
+                    T bp = dot<T, O::Btp, NX, FAST>([&](int k) { return P.B[k + r_ * NX]; },
+                                                    [&](int k) { return p[k]; });
+                    s[r_] = N::add(bp, r[r_]);
+                }
+#pragma unroll
+                for (int r_ = 0; r_ < NU; ++r_)
+                    d[r_] = dot<T, O::Qs, NU, FAST>([&](int k) { return P.Qi[r_ + k * NU]; },
+                                                    [&](int k) { return s[k]; });                // :19
+                sd.store(i, d, cont);
+                if (WARM && wdo) gstore<T, NU>(wdo + i * NU, d);
+                T pn[NX];
+#pragma unroll
+                for (int r_ = 0; r_ < NX; ++r_) {
+                    T mp = dot<T, O::Mp, NX, FAST>([&](int k) { return P.M[r_ + k * NX]; },
+                                                   [&](int k) { return p[k]; });
+                    T kr = dot<T, O::Ktr, NU, FAST>([&](int k) { return P.K[k + r_ * NU]; },
+                                                    [&](int k) { return r[k]; });
+                    pn[r_] = N::sub(N::add(q[r_], mp), kr);                                      // :20
+                }
+#pragma unroll
+                for (int j = 0; j < NX; ++j) p[j] = pn[j];
+            };
+            if constexpr (UNROLL) {
+#pragma unroll
+                for (int i = NH - 2; i >= 0; --i) bstage(i);
+            } else {
+#pragma unroll 1
+                for (int i = NH - 2; i >= 0; --i) bstage(i);
+            }
+        }
+        (void)hit_max;
+    }
+
+    // ---------------------------------------------------------------------- statistics
+    if (a.stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_iter += __shfl_down_sync(FULLM, n_iter, o);
+            n_solved += __shfl_down_sync(FULLM, n_solved, o);
+            n_trips += __shfl_down_sync(FULLM, n_trips, o);
+            n_inst += __shfl_down_sync(FULLM, n_inst, o);
+        }
+        if (lane == 0) {
+            atomicAdd(a.stats + 0, n_iter);
+            atomicAdd(a.stats + 1, n_solved);
+            atomicAdd(a.stats + 2, n_trips);
+            atomicAdd(a.stats + 3, n_inst);
+        }
+    }
+}
+
+}  // namespace tmpc

@@ -1,0 +1,133 @@
+/* tmpc.h -- C ABI of the B200-native batched TinyMPC solver (libtmpc_cuda.so).
+ *
+ * This is the drop-in boundary for the cached-Riccati ADMM hot path of ucb-bar/Accelerated-TinyMPC:
+ * one tmpc_solve() call runs the reference's whole `tiny_solve` loop (src/tinympc/admm.cpp:111-152:
+ * forward_pass :27-37, update_slack :45-61, update_dual :67-71, update_linear_cost :77-85,
+ * termination_condition :91-109, backward_pass_grad :15-22) for `batch` independent instances that share
+ * one model/cache, inside one persistent sm_100a kernel.  Plain pointers and sizes only: no C++/Eigen/torch
+ * types cross this boundary.  The reference has no FFI for a batch; the per-call pieces it does expose are
+ * cited on each entry point.  Host-side C++ mirrors of TinySolver/TinyCache/TinyWorkspace/TinySettings and
+ * tiny_setup/tiny_precompute/tiny_solve live in include/tinympc/ and call only this header.
+ *
+ * Conventions (identical to the reference's wire layout):
+ *   - matrices are COLUMN-MAJOR (Eigen default, types.hpp:13-21; tiny_codegen inputs, codegen.cpp:245-252);
+ *   - trajectories are [instance][stage][dim] (= column-major nx x N per instance, tiny_wrapper.cpp:27,154);
+ *   - scalar type is float (TMPC_F32, what tiny_codegen emits, codegen.cpp:152) or double (TMPC_F64, the
+ *     shipped glob_opts.hpp:3); every array of a ctx uses that one scalar type.
+ * Every function returns TMPC_OK (0) or a negative tmpc_status; tmpc_last_error() gives the text.
+ * There is NO CPU fallback: without a CUDA device every call that needs one fails with TMPC_ERR_CUDA.
+ */
+#ifndef TMPC_H
+#define TMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMPC_VERSION_MAJOR 0
+#define TMPC_VERSION_MINOR 1
+
+typedef enum {
+    TMPC_OK = 0,
+    TMPC_ERR_INVALID = -1,     /* bad argument (null pointer, check_termination < 1, ...) */
+    TMPC_ERR_UNSUPPORTED = -2, /* shape / dtype / policy has no compiled kernel */
+    TMPC_ERR_CUDA = -3,        /* CUDA runtime error (see tmpc_last_error) */
+    TMPC_ERR_STATE = -4        /* call order (solve before set_model, ...) */
+} tmpc_status;
+
+typedef enum { TMPC_F32 = 0, TMPC_F64 = 1 } tmpc_dtype;
+
+/* Arithmetic policy.
+ *  PARITY: individually rounded products summed in the exact order of the reference's "-O3" SSE2 build
+ *           -> per-instance iteration counts, status and x/u are bit-identical to tiny_solve.
+ *  FAST:   the same recurrences with FMA contraction and sequential accumulation; agrees with the reference
+ *          as well as the reference agrees with itself across compiler flags. */
+typedef enum { TMPC_ORDER_PARITY = 0, TMPC_ORDER_FAST = 1 } tmpc_order;
+
+typedef enum { TMPC_MEM_HOST = 0, TMPC_MEM_DEVICE = 1 } tmpc_mem;
+
+/* status values written per instance: the reference's work->status (admm.cpp:114,136) */
+#define TMPC_STATUS_SOLVED 1
+#define TMPC_STATUS_UNSOLVED 11
+
+typedef struct tmpc_ctx tmpc_ctx;
+
+/* Create a solver context bound to one CUDA device for one problem shape.
+ * Replaces the compile-time NSTATES/NINPUTS/NHORIZON/tinytype macros (glob_opts.hpp:3-9). */
+int tmpc_create(tmpc_ctx **out, int device, int nx, int nu, int N, int dtype, int order_policy);
+int tmpc_destroy(tmpc_ctx *ctx);
+
+/* Shared model + cache + bounds: what the examples put into TinyCache and the parameter half of
+ * TinyWorkspace (types.hpp:26-34,83-91; quadrotor_hovering.cpp:33-47).  Host pointers, ctx dtype.
+ *   Kinf [nu x nx], Pinf [nx x nx], Quu_inv [nu x nu], AmBKt [nx x nx], Adyn [nx x nx], Bdyn [nx x nu]: col-major
+ *   Q [nx] (used as given by update_linear_cost, admm.cpp:81);
+ *   x_min,x_max [N][nx], u_min,u_max [N-1][nu]; a NULL pair leaves that bound unconstrained. */
+int tmpc_set_model(tmpc_ctx *ctx, const void *Kinf, const void *Pinf, const void *Quu_inv, const void *AmBKt,
+                   const void *Adyn, const void *Bdyn, const void *Q, double rho, const void *x_min,
+                   const void *x_max, const void *u_min, const void *u_max);
+
+/* TinySettings (types.hpp:39-47).  check_termination < 1 is rejected (it is `% 0` UB in admm.cpp:93);
+ * max_iter < 1 is rejected. */
+int tmpc_set_settings(tmpc_ctx *ctx, double abs_pri_tol, double abs_dua_tol, int max_iter,
+                      int check_termination, int en_state_bound, int en_input_bound);
+
+/* State that is live across tiny_solve calls (read before written: admm.cpp:31,47-48,69-70,96,98), per
+ * instance, IN PLACE: read at the start of the solve, left exactly as the reference leaves its workspace
+ * (d from the last executed backward pass, v/z one iteration behind vnew/znew on an early exit).
+ * Cold start = these arrays zero-filled (quadrotor_hovering.cpp:49-71).  All five must be given. */
+typedef struct {
+    void *d; /* [batch][N-1][nu] */
+    void *y; /* [batch][N-1][nu] */
+    void *g; /* [batch][N][nx]   */
+    void *v; /* [batch][N][nx]   */
+    void *z; /* [batch][N-1][nu] */
+} tmpc_warm;
+
+typedef struct {
+    int64_t batch;
+    const void *x0;      /* [batch][nx]  -> work.x.col(0) (quadrotor_hovering.cpp:95, set_x0 tiny_wrapper.cpp:5) */
+    const void *Xref;    /* [N][nx] shared, or [batch][N][nx] (set_xref, tiny_wrapper.cpp:21-41) */
+    int32_t xref_shared; /* 1: one Xref for every instance */
+    int32_t mem;         /* tmpc_mem: where x0/Xref/warm/outputs live */
+    tmpc_warm *warm;     /* NULL = cold start, nothing written back */
+    void *x;             /* out [batch][N][nx]    (get_x, tiny_wrapper.cpp:152-163); NULL = skip */
+    void *u;             /* out [batch][N-1][nu]  (get_u, tiny_wrapper.cpp:165-176); NULL = skip */
+    int32_t *iter;       /* out [batch] work->iter   (admm.cpp:120); NULL = skip */
+    int32_t *status;     /* out [batch] work->status (1 solved / 11 not); NULL = skip */
+    void *resid;         /* out [batch][4]: primal_state, dual_state, primal_input, dual_input (admm.cpp:95-98) */
+    void *stream;        /* cudaStream_t (TMPC_MEM_DEVICE); NULL = the ctx's own stream */
+} tmpc_solve_args;
+
+/* Run tiny_solve for every instance of the batch.  With TMPC_MEM_DEVICE the call is asynchronous on
+ * `stream`; with TMPC_MEM_HOST it stages through pinned buffers in chunks (H2D / solve / D2H overlapped)
+ * and returns when the outputs are in host memory.  Returns TMPC_OK even if some instances stop at
+ * max_iter (their status is 11, as in the reference). */
+int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *args);
+
+typedef struct {
+    int64_t instances;        /* instances solved by the last tmpc_solve */
+    int64_t iterations;       /* sum of per-instance iteration counts */
+    int64_t solved;           /* instances with status 1 */
+    int64_t trips;            /* lane-trips executed by the persistent kernel (iterations + emission + idle) */
+    int32_t launches;         /* kernels launched by the last tmpc_solve */
+    int32_t lanes;            /* resident instance slots (threads) the kernel ran with */
+    float kernel_ms;          /* device time of those kernels (CUDA events on the launching stream) */
+    int32_t parity_pinned;    /* 1 if this shape's evaluation order is verified against the reference */
+} tmpc_stats;
+
+/* Statistics of the last tmpc_solve on this ctx (synchronises the ctx's stream). */
+int tmpc_get_stats(tmpc_ctx *ctx, tmpc_stats *out);
+
+/* Pinned host allocation helpers for TMPC_MEM_HOST callers that want full PCIe speed. */
+int tmpc_host_alloc(void **ptr, uint64_t bytes);
+int tmpc_host_free(void *ptr);
+
+const char *tmpc_last_error(const tmpc_ctx *ctx); /* ctx may be NULL: last error of tmpc_create */
+const char *tmpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMPC_H */

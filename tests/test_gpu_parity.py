@@ -1,0 +1,65 @@
+"""GPU parity: the sm_100a kernel (through the C ABI, include/tmpc.h) against the CPU oracle on the same
+seeded inputs.  PARITY policy must be bit-exact: per-instance iteration counts, status, residuals, x and u.
+Tolerance for the FAST policy (fp32): x/u within 1e-4 relative on instances whose iteration count agrees,
+and iteration-count mismatches no more frequent than the reference's own flag-to-flag spread (<= 2.5 %)."""
+import numpy as np
+import pytest
+
+from conftest import assert_same
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp_exact(out, ref):
+    assert_same(out["iter"], ref.iter, "iter")
+    assert_same(out["status"], ref.status, "status")
+    assert_same(out["x"], ref.x, "x")
+    assert_same(out["u"], ref.u, "u")
+    assert_same(out["resid"], ref.resid, "resid")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mult", [0.1, 0.25, 1.0])
+def test_quadrotor_hover_batch_bit_exact(pkg, oracle, dtype, mult):
+    prob = pkg.problems.quadrotor(20)
+    B = 6000
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=mult)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=dtype, nthreads=8)
+    s = pkg.capi.Solver(prob, dtype=dtype, policy="parity")
+    out = s.solve(x0, xref)
+    _cmp_exact(out, ref)
+    st = s.stats()
+    assert st["instances"] == B and st["iterations"] == int(ref.iter.sum())
+    assert st["solved"] == int((ref.status == 1).sum()) and st["launches"] >= 1 and st["parity_pinned"] == 1
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_quadrotor_tracking_per_instance_xref_bit_exact(pkg, oracle, dtype):
+    prob = pkg.problems.quadrotor(20)
+    x0, xref = pkg.workloads.quadrotor_tracking_batch(0, 3000)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=dtype, nthreads=8)
+    out = pkg.capi.Solver(prob, dtype=dtype, policy="parity").solve(x0, xref)
+    _cmp_exact(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cartpole_bit_exact(pkg, oracle, dtype):
+    prob = pkg.problems.cartpole()
+    x0, xref = pkg.workloads.cartpole_batch(0, 8000)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=dtype, nthreads=8)
+    out = pkg.capi.Solver(prob, dtype=dtype, policy="parity").solve(x0, xref)
+    _cmp_exact(out, ref)
+
+
+def test_fast_policy_statistical_parity(pkg, oracle):
+    prob = pkg.problems.quadrotor(20)
+    B = 20000
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=np.float32, nthreads=8)
+    out = pkg.capi.Solver(prob, dtype=np.float32, policy="fast").solve(x0, xref)
+    same = out["iter"] == ref.iter
+    assert (~same).mean() <= 0.025, "iteration mismatch rate %.4f" % (~same).mean()
+    assert np.abs(out["iter"].astype(int) - ref.iter).max() <= 12
+    scale = np.maximum(np.abs(ref.x[same]).max(), 1.0)
+    assert np.abs(out["x"][same] - ref.x[same]).max() / scale <= 1e-4
+    assert np.abs(out["u"][same] - ref.u[same]).max() <= 1e-4
