@@ -174,6 +174,8 @@ int ref_step(const ref_problem *P, int32_t which, void *ws_, int32_t iter)
     get(w.z, pz, 0, NUN); get(w.znew, pzn, 0, NUN); get(w.g, pg, 0, NXN); get(w.y, py, 0, NUN);
     get(w.Xref, pxr, 0, NXN);
     w.iter = iter;
+    w.primal_residual_state = pres[0]; w.dual_residual_state = pres[1];
+    w.primal_residual_input = pres[2]; w.dual_residual_input = pres[3];
     int rc = 0;
     switch (which) {
     case 0: forward_pass(&I->solver); break;
