@@ -3,9 +3,11 @@
 // host<->device pipeline for TMPC_MEM_HOST callers, statistics.  No solver arithmetic runs on the host.
 #include "tmpc.h"
 #include "tmpc_kernel.cuh"
+#include "tmpc_kernel_f32.cuh"
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -20,6 +22,7 @@ struct KernelInfo {
     size_t smem;
     int block;
     size_t model_bytes;
+    int model_kind;  // 0: tmpc::Model<T,...> (generic kernel)   1: tmpc::ModelF32<...> (packed fp32 kernel)
 };
 
 struct tmpc_ctx_impl {
@@ -32,7 +35,8 @@ struct tmpc_ctx_impl {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     // model image exactly as the kernel's Model<T,...> struct (built on the host, passed by value)
-    std::vector<unsigned char> model;
+    std::vector<unsigned char> model;      // tmpc::Model<T,...> image
+    std::vector<unsigned char> model_f32;  // tmpc::ModelF32<...> image (packed fp32 kernel)
     // settings
     double pri = 1e-3, dua = 1e-3;
     int max_iter = 100, check_term = 1, en_state = 1, en_input = 1;
@@ -84,7 +88,40 @@ KernelInfo make_info()
     k.smem = tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES;
     k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::Model<T, NX, NU, NH>);
+    k.model_kind = 0;
     return k;
+}
+
+template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM>
+KernelInfo make_info_f32()
+{
+    KernelInfo k;
+    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM>;
+    k.smem = tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES;
+    k.block = BLOCK;
+    k.model_bytes = sizeof(tmpc::ModelF32<NX, NU, NH>);
+    k.model_kind = 1;
+    return k;
+}
+
+template <int NX, int NU, int NH, int BLOCK, bool TM>
+bool pick_f32(int policy, bool warm, KernelInfo &out)
+{
+    if (policy == TMPC_ORDER_PARITY)
+        out = warm ? make_info_f32<NX, NU, NH, BLOCK, false, true, TM>() : make_info_f32<NX, NU, NH, BLOCK, false, false, TM>();
+    else
+        out = warm ? make_info_f32<NX, NU, NH, BLOCK, true, true, TM>() : make_info_f32<NX, NU, NH, BLOCK, true, false, TM>();
+    return true;
+}
+
+// development switch: TMPC_KERNEL=generic | f32_smem | f32_tmem (default) selects the fp32 12/4/10 kernel
+int kernel_variant()
+{
+    const char *e = getenv("TMPC_KERNEL");
+    if (!e) return 2;
+    if (!strcmp(e, "generic")) return 0;
+    if (!strcmp(e, "f32_smem")) return 1;
+    return 2;
 }
 
 template <class T, int NX, int NU, int NH, int BLOCK, bool UNROLL>
@@ -105,7 +142,12 @@ bool pick(int policy, bool warm, KernelInfo &out)
 bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out)
 {
     if (nx == 12 && nu == 4 && N == 10) {
-        if (dtype == TMPC_F32) return pick<float, 12, 4, 10, 128, false>(policy, warm, out);
+        if (dtype == TMPC_F32) {
+            const int v = kernel_variant();
+            if (v == 2) return pick_f32<12, 4, 10, 256, true>(policy, warm, out);   // g,v in TMEM: 256 instances / SM
+            if (v == 1) return pick_f32<12, 4, 10, 128, false>(policy, warm, out);  // all state in shared memory
+            return pick<float, 12, 4, 10, 128, false>(policy, warm, out);
+        }
         return pick<double, 12, 4, 10, 64, false>(policy, warm, out);
     }
     if (nx == 4 && nu == 1 && N == 10) {
@@ -157,8 +199,52 @@ template <class T, int NX, int NU, int NH> void build_model_t(tmpc_ctx_impl *c)
     m->check_term = c->check_term;
 }
 
+template <int NX, int NU, int NH> void build_model_f32(tmpc_ctx_impl *c, std::vector<unsigned char> &img)
+{
+    using M = tmpc::ModelF32<NX, NU, NH>;
+    constexpr int RS = NU + NX;
+    img.assign(sizeof(M), 0);
+    M *m = reinterpret_cast<M *>(img.data());
+    const float *K = reinterpret_cast<const float *>(c->Kinf.data());     // [r + k*NU]
+    const float *A = reinterpret_cast<const float *>(c->Adyn.data());     // [r + k*NX]
+    const float *B = reinterpret_cast<const float *>(c->Bdyn.data());     // [r + k*NX]
+    const float *Qi = reinterpret_cast<const float *>(c->Quu_inv.data());
+    const float *Mm = reinterpret_cast<const float *>(c->AmBKt.data());
+    const float *Pf = reinterpret_cast<const float *>(c->Pinf.data());
+    for (int k = 0; k < NX; ++k) {
+        for (int r = 0; r < NU; ++r) m->KA[k * RS + r] = K[r + k * NU];
+        for (int r = 0; r < NX; ++r) m->KA[k * RS + NU + r] = A[r + k * NX];
+        for (int r = 0; r < NU; ++r) m->BM[k * RS + r] = B[k + r * NX];       // (B^T)(r,k)
+        for (int r = 0; r < NX; ++r) m->BM[k * RS + NU + r] = Mm[r + k * NX];
+        for (int j = 0; j < NX; ++j) m->Pt[k * NX + j] = Pf[k + j * NX];      // Pinf(k,j)
+    }
+    for (int k = 0; k < NU; ++k) {
+        for (int r = 0; r < NX; ++r) m->Bc[k * NX + r] = B[r + k * NX];
+        for (int r = 0; r < NU; ++r) m->Qi[k * NU + r] = Qi[r + k * NU];
+        for (int j = 0; j < NX; ++j) m->Kr[k * NX + j] = K[k + j * NU];       // (K^T)(j,k)
+    }
+    std::memcpy(m->Qd, c->Q.data(), NX * sizeof(float));
+    const float inf = std::numeric_limits<float>::infinity();
+    const bool xs = c->en_state && c->has_xb, us = c->en_input && c->has_ub;
+    for (int k = 0; k < NH * NX; ++k) {
+        m->xmin[k] = xs ? reinterpret_cast<const float *>(c->xmin.data())[k] : -inf;
+        m->xmax[k] = xs ? reinterpret_cast<const float *>(c->xmax.data())[k] : inf;
+    }
+    for (int k = 0; k < (NH - 1) * NU; ++k) {
+        m->umin[k] = us ? reinterpret_cast<const float *>(c->umin.data())[k] : -inf;
+        m->umax[k] = us ? reinterpret_cast<const float *>(c->umax.data())[k] : inf;
+    }
+    m->rho = (float)c->rho;
+    m->nrho = -(float)c->rho;
+    m->pri_tol = (float)c->pri;
+    m->dua_tol = (float)c->dua;
+    m->max_iter = c->max_iter;
+    m->check_term = c->check_term;
+}
+
 bool build_model(tmpc_ctx_impl *c)
 {
+    if (c->dtype == TMPC_F32 && c->nx == 12 && c->nu == 4 && c->N == 10) build_model_f32<12, 4, 10>(c, c->model_f32);
     const bool f32 = c->dtype == TMPC_F32;
     if (c->nx == 12 && c->nu == 4 && c->N == 10) {
         f32 ? build_model_t<float, 12, 4, 10>(c) : build_model_t<double, 12, 4, 10>(c);
@@ -201,7 +287,7 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
     long long blocks = (da.batch + ki.block - 1) / ki.block;
     if (blocks > c->sm_count) blocks = c->sm_count;
     if (blocks < 1) blocks = 1;
-    void *params[2] = {c->model.data(), &da};
+    void *params[2] = {ki.model_kind == 1 ? (void *)c->model_f32.data() : (void *)c->model.data(), &da};
     if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev0, s));
     CUDA_TRY(c, cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, s));
     if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev1, s));
@@ -525,7 +611,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
             da.counter = c->d_counter;
             da.stats = c->d_counter + 1;
             long long blocks = std::min<long long>((n + ki.block - 1) / ki.block, c->sm_count);
-            void *params[2] = {c->model.data(), &da};
+            void *params[2] = {ki.model_kind == 1 ? (void *)c->model_f32.data() : (void *)c->model.data(), &da};
             cudaEventRecord(kev[2 * k], st.s);
             cudaError_t e = cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, st.s);
             cudaEventRecord(kev[2 * k + 1], st.s);

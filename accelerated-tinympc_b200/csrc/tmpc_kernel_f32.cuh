@@ -1,0 +1,542 @@
+// fp32 production kernel for sm_100a: same algorithm and bit-exact results as tmpc_kernel.cuh, re-engineered
+// around what the B200 SM actually offers (numbers: profiles/r01_*):
+//
+//  * 2 warps per scheduler instead of 1.  The per-instance state {d,y,z,g,v,p_N} is 1440 B, so shared memory
+//    alone holds 128-160 instances per SM = one warp per SMSP, and every LDS / constant-load latency is exposed
+//    (v1: 50 % issue utilisation, stall = short scoreboard).  Here g and v (2/3 of the state) live in TENSOR
+//    MEMORY, used as a per-thread scratchpad through tcgen05.st / tcgen05.ld (.32x32b: thread t of a warp owns
+//    TMEM lane 32*(warp%4)+t; 240 of the 256 columns of its half), d/y/z/p_N stay in shared memory: 256
+//    instances per SM.  Measured TMEM scratch bandwidth: 351 B/clk/SM load, 256 B/clk/SM store (tools/ubench_tmem.cu).
+//  * packed fp32: accumulations and element-wise work run as FADD2 / FFMA2 on pairs of output rows, which
+//    halves the issue slots of the FMA pipe's work (the pipe itself still does 128 lane-ops/clk/SM).  In PARITY
+//    mode the PRODUCTS stay scalar FMUL: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even with -fmad=false.
+//  * stacked coefficient matrices [K;A] and [B^T;AmBKt], stored so that the coefficients of consecutive output rows
+//    for one input column are adjacent in the constant bank: one LDCU.128 feeds 4 rows (8 FP instructions).
+#pragma once
+#include "tmpc_kernel.cuh"
+
+namespace tmpc {
+
+template <int NX, int NU, int NH> struct alignas(16) ModelF32 {
+    static constexpr int RS = NU + NX;  // stacked rows
+    float KA[NX * RS];   // column k: [Kinf(:,k) ; Adyn(:,k)]
+    float Bc[NU * NX];   // column k: Bdyn(:,k)
+    float BM[NX * RS];   // column k: [Bdyn(k,:)^T ; AmBKt(:,k)]     (B^T p and AmBKt p share p_k)
+    float Qi[NU * NU];   // column k: Quu_inv(:,k)
+    float Kr[NU * NX];   // column k: Kinf(k,:)^T                     (Kinf^T r)
+    float Pt[NX * NX];   // column k: Pinf(k,:)^T                     (Xref^T Pinf)
+    float Qd[NX];
+    float xmin[NH * NX], xmax[NH * NX];
+    float umin[(NH - 1) * NU], umax[(NH - 1) * NU];
+    float rho, nrho, pri_tol, dua_tol;
+    int max_iter, check_term;
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+
+// ---- TMEM scratch (per-thread columns) -------------------------------------------------------------
+__device__ __forceinline__ void tm_ld8(uint32_t a, float *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tm_ld4(uint32_t a, float *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t a, const float *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(a), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tm_st4(uint32_t a, const float *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 :: "r"(a), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]) : "memory");
+}
+// The loaded registers are only valid after tcgen05.wait::ld; passing them through the wait as in/out operands
+// gives the compiler the data dependence (it must not schedule a use above the wait).
+template <int N> __device__ __forceinline__ void tm_wait_ld(float (&r)[N])
+{
+    static_assert(N == 12 || N == 24, "wait helper sized for one or two 12-vectors");
+    if constexpr (N == 12) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                       "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]) :: "memory");
+    } else {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                       "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]),
+                       "+f"(r[15]), "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]),
+                       "+f"(r[22]), "+f"(r[23]) :: "memory");
+    }
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// g and v for one thread: NX*NH columns each.  TM = tensor memory, else shared memory (same interface).
+template <int NX, int NH, int BLOCK, bool TM> struct XStore;
+template <int NX, int NH, int BLOCK> struct XStore<NX, NH, BLOCK, true> {
+    static_assert(NX == 12, "TMEM path is laid out for 12-vectors (x8 + x4)");
+    uint32_t gbase, vbase;
+    __device__ __forceinline__ XStore(uint32_t tmem_base, int warp)
+    {
+        const uint32_t my = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
+        gbase = my;
+        vbase = my + NX * NH;
+    }
+    // issue loads of g_i and v_i into gv[0..11], gv[12..23]; valid after wait()
+    __device__ __forceinline__ void load_issue(int i, float (&gv)[24]) const
+    {
+        tm_ld8(gbase + i * NX, gv); tm_ld4(gbase + i * NX + 8, gv + 8);
+        tm_ld8(vbase + i * NX, gv + 12); tm_ld4(vbase + i * NX + 8, gv + 20);
+    }
+    __device__ __forceinline__ void wait(float (&gv)[24]) const { tm_wait_ld<24>(gv); }
+    __device__ __forceinline__ void store(int i, const float (&g)[12], const float (&v)[12]) const
+    {
+        tm_st8(gbase + i * NX, g); tm_st4(gbase + i * NX + 8, g + 8);
+        tm_st8(vbase + i * NX, v); tm_st4(vbase + i * NX + 8, v + 8);
+    }
+    __device__ __forceinline__ void fence_st() const { tm_wait_st(); }
+};
+template <int NX, int NH, int BLOCK> struct XStore<NX, NH, BLOCK, false> {
+    SVec<float, NX, NH, BLOCK> sg, sv;
+    static constexpr size_t BYTES = 2 * SVec<float, NX, NH, BLOCK>::BYTES;
+    __device__ __forceinline__ XStore(unsigned char *p, int tid) : sg(p, tid), sv(p + SVec<float, NX, NH, BLOCK>::BYTES, tid) {}
+    __device__ __forceinline__ void load_issue(int i, float (&gv)[2 * NX]) const
+    {
+        float g[NX], v[NX];
+        sg.load(i, g); sv.load(i, v);
+#pragma unroll
+        for (int j = 0; j < NX; ++j) { gv[j] = g[j]; gv[NX + j] = v[j]; }
+    }
+    __device__ __forceinline__ void wait(float (&)[2 * NX]) const {}
+    __device__ __forceinline__ void store(int i, const float (&g)[NX], const float (&v)[NX]) const { sg.store(i, g); sv.store(i, v); }
+    __device__ __forceinline__ void fence_st() const {}
+};
+
+// ---- packed row-pair reductions -----------------------------------------------------------------------
+// e(k) returns the float2 of products for one row pair at input index k.
+template <int S, int LEN, class E> __device__ __forceinline__ float2 tree2(const E &e)
+{
+    if constexpr (LEN == 1) return e(S);
+    else {
+        constexpr int H = LEN / 2;
+        float2 a = tree2<S, H>(e);
+        float2 b = tree2<S + H, LEN - H>(e);
+        return add2(a, b);
+    }
+}
+template <int S, int LEN, int L, class E> __device__ __forceinline__ float2 ptree2(const E &e)
+{
+    if constexpr (LEN == 1) return e(S * 4 + L);
+    else {
+        constexpr int H = LEN / 2;
+        float2 a = ptree2<S, H, L>(e);
+        float2 b = ptree2<S + H, LEN - H, L>(e);
+        return add2(a, b);
+    }
+}
+template <int ORD, int K, class E> __device__ __forceinline__ float2 reduce2(const E &e)
+{
+    if constexpr (ORD == ORD_SEQ) {
+        float2 acc = e(0);
+#pragma unroll
+        for (int k = 1; k < K; ++k) acc = add2(e(k), acc);
+        return acc;
+    } else if constexpr (ORD == ORD_TREE) {
+        return tree2<0, K>(e);
+    } else {
+        static_assert(ORD == ORD_VECREDUX && K % 4 == 0, "packed path supports K % 4 == 0 vector reductions");
+        float2 l0 = ptree2<0, K / 4, 0>(e), l1 = ptree2<0, K / 4, 1>(e), l2 = ptree2<0, K / 4, 2>(e), l3 = ptree2<0, K / 4, 3>(e);
+        return add2(add2(l0, l2), add2(l1, l3));
+    }
+}
+
+// out2[j] (row pair j of R rows) = sum_k c[k*RS + R0 + 2j .. +1] * x[k], rows R0..R0+R-1 of a stacked matrix
+template <int ORD, int R, int K, int RS, int R0, bool FAST>
+__device__ __forceinline__ void matvec2(const float *c, const float (&x)[K], float2 (&out)[R / 2])
+{
+    static_assert(R % 2 == 0, "row pairs");
+    if constexpr (FAST) {
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) out[j] = __fmul2_rn(f2(c[R0 + 2 * j], c[R0 + 2 * j + 1]), f2(x[0], x[0]));
+#pragma unroll
+        for (int k = 1; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < R / 2; ++j)
+                out[j] = __ffma2_rn(f2(c[k * RS + R0 + 2 * j], c[k * RS + R0 + 2 * j + 1]), f2(x[k], x[k]), out[j]);
+    } else if constexpr (ORD == ORD_SEQ) {
+        // column sweep: all rows advance together, one coefficient column (R adjacent values) per step
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) out[j] = f2(__fmul_rn(c[R0 + 2 * j], x[0]), __fmul_rn(c[R0 + 2 * j + 1], x[0]));
+#pragma unroll
+        for (int k = 1; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < R / 2; ++j)
+                out[j] = add2(f2(__fmul_rn(c[k * RS + R0 + 2 * j], x[k]), __fmul_rn(c[k * RS + R0 + 2 * j + 1], x[k])), out[j]);
+    } else {
+        // tree orders need all K products of a row before the first add: go 2 row pairs (4 rows = one LDCU.128 per k) at a time
+#pragma unroll
+        for (int j0 = 0; j0 < R / 2; j0 += 2) {
+#pragma unroll
+            for (int jj = 0; jj < 2 && j0 + jj < R / 2; ++jj) {
+                const int j = j0 + jj;
+                auto e = [&](int k) { return f2(__fmul_rn(c[k * RS + R0 + 2 * j], x[k]), __fmul_rn(c[k * RS + R0 + 2 * j + 1], x[k])); };
+                out[j] = reduce2<ORD, K>(e);
+            }
+        }
+    }
+}
+
+template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
+    using SU = SVec<float, NU, NH - 1, BLOCK>;
+    using SP = SVec<float, NX, 1, BLOCK>;
+    static constexpr size_t XBYTES = TM ? 0 : 2 * SVec<float, NX, NH, BLOCK>::BYTES;
+    static constexpr size_t BYTES = 3 * SU::BYTES + SP::BYTES + XBYTES + 16;
+};
+
+template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM>
+__global__ void __launch_bounds__(BLOCK, 1)
+admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_constant__ SolveArgs<float> a)
+{
+    static_assert(NX % 4 == 0 && NU % 4 == 0, "packed kernel: 16-byte vectors of x and u");
+    using O = Orders<float, NX, NU>;
+    using L = SmemLayoutF32<NX, NU, NH, BLOCK, TM>;
+    constexpr int RS = NU + NX;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const unsigned lane = tid & 31;
+    constexpr unsigned FULLM = 0xffffffffu;
+    constexpr int XROW = NX * NH, UROW = NU * (NH - 1);
+
+    unsigned char *sp = smem;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sp); sp += 16;
+    typename L::SU sd(sp, tid); sp += L::SU::BYTES;
+    typename L::SU sy(sp, tid); sp += L::SU::BYTES;
+    typename L::SU sz(sp, tid); sp += L::SU::BYTES;
+    typename L::SP spn(sp, tid); sp += L::SP::BYTES;
+
+    uint32_t tmem_base = 0;
+    if constexpr (TM) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_base = *tmem_slot;
+    }
+    auto make_xs = [&]() {
+        if constexpr (TM) return XStore<NX, NH, BLOCK, true>(tmem_base, warp);
+        else return XStore<NX, NH, BLOCK, false>(sp, tid);
+    };
+    auto xs = make_xs();
+
+    long long inst = -1;
+    int it = 0;
+    int phase = PH_FREE;
+    bool exhausted = false;
+    float x0[NX];
+    float res[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned long long n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x0[j] = 0.f;
+
+    for (;;) {
+        // ------------------------------------------------------------------ lane refill (warp-uniform branch)
+        const bool need = (phase == PH_FREE) && !exhausted;
+        const unsigned m = __ballot_sync(FULLM, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(m));
+            base = __shfl_sync(FULLM, base, leader);
+            bool fill = false;
+            if (need) {
+                const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
+                if (idx < a.batch) {
+                    inst = idx; phase = PH_RUN; it = 0; fill = true;
+                    res[0] = res[1] = res[2] = res[3] = 0.f;
+                    gload<float, NX>(a.x0 + inst * NX, x0);
+                    float xr[NX], pn[NX];
+                    gload<float, NX>(a.Xref + inst * a.xref_stride + (NH - 1) * NX, xr);
+#pragma unroll
+                    for (int j = 0; j < NX; ++j)   // p_N seed: -(Xref_{N-1}^T Pinf)  (admm.cpp:83)
+                        pn[j] = -dot<float, O::XtP, NX, FAST>([&](int k) { return P.Pt[k * NX + j]; }, [&](int k) { return xr[k]; });
+                    spn.store(0, pn);
+                    if (WARM && a.wd) {
+#pragma unroll 1
+                        for (int i = 0; i < NH - 1; ++i) {
+                            float t[NU];
+                            gload<float, NU>(a.wd + inst * UROW + i * NU, t); sd.store(i, t);
+                            gload<float, NU>(a.wy + inst * UROW + i * NU, t); sy.store(i, t);
+                            gload<float, NU>(a.wz + inst * UROW + i * NU, t); sz.store(i, t);
+                        }
+                    } else {
+                        float zu[NU];
+#pragma unroll
+                        for (int j = 0; j < NU; ++j) zu[j] = 0.f;
+#pragma unroll 1
+                        for (int i = 0; i < NH - 1; ++i) { sd.store(i, zu); sy.store(i, zu); sz.store(i, zu); }
+                    }
+                } else {
+                    exhausted = true;
+                }
+            }
+            // g, v: every lane of the warp takes part (tcgen05 is warp-collective); lanes that are not being
+            // refilled write back what they hold
+            const bool wfill = WARM && a.wd;
+#pragma unroll 1
+            for (int i = 0; i < NH; ++i) {
+                float gv[2 * NX];
+                xs.load_issue(i, gv);
+                xs.wait(gv);
+                if (fill) {
+                    if (wfill) {
+                        gload<float, NX>(a.wg + inst * XROW + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
+                        gload<float, NX>(a.wv + inst * XROW + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2 * NX; ++j) gv[j] = 0.f;
+                    }
+                }
+                xs.store(i, *reinterpret_cast<float(*)[NX]>(gv), *reinterpret_cast<float(*)[NX]>(gv + NX));
+            }
+            xs.fence_st();
+        }
+        if (__all_sync(FULLM, phase == PH_FREE)) break;
+        ++n_trips;
+
+        const bool emit = (phase == PH_EMIT);
+        if (phase == PH_RUN) ++it;
+
+        // ------------------------------------------------------------------ forward sweep
+        // forward_pass (admm.cpp:27-37) + update_slack (:45-61) + update_dual (:67-71) + residual maxima (:95-98)
+        float pri_x = 0.f, dua_x = 0.f, pri_u = 0.f, dua_u = 0.f;
+        {
+            float x[NX];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) x[j] = x0[j];
+            float *xo = (emit && a.x) ? a.x + inst * XROW : nullptr;
+            float *uo = (emit && a.u) ? a.u + inst * UROW : nullptr;
+            float *go = (WARM && emit && a.wg) ? a.wg + inst * XROW : nullptr;
+            float *yo = (WARM && emit && a.wy) ? a.wy + inst * UROW : nullptr;
+
+            auto xpart = [&](int i, float (&gv)[2 * NX]) {
+                // state slack / dual / residuals for stage i (uses x_i)
+                xs.wait(gv);
+                float g[NX], vn[NX];
+                if (WARM && go) gstore<float, NX>(go + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
+#pragma unroll
+                for (int j = 0; j < NX; j += 2) {
+                    const float2 x2 = f2(x[j], x[j + 1]), g2 = f2(gv[j], gv[j + 1]), v2 = f2(gv[NX + j], gv[NX + j + 1]);
+                    float2 t = add2(x2, g2);                                                         // :48
+                    t.x = fminf(P.xmax[i * NX + j], fmaxf(P.xmin[i * NX + j], t.x));               // :59
+                    t.y = fminf(P.xmax[i * NX + j + 1], fmaxf(P.xmin[i * NX + j + 1], t.y));
+                    const float2 rp = sub2(x2, t), rd = sub2(v2, t);
+                    pri_x = fmaxf(pri_x, fmaxf(fabsf(rp.x), fabsf(rp.y)));                           // :95
+                    dua_x = fmaxf(dua_x, fmaxf(fabsf(rd.x), fabsf(rd.y)));                           // :96
+                    const float2 gn = sub2(add2(g2, x2), t);                                         // :70
+                    g[j] = gn.x; g[j + 1] = gn.y; vn[j] = t.x; vn[j + 1] = t.y;
+                }
+                xs.store(i, g, vn);
+                if (xo) gstore<float, NX>(xo + i * NX, x);
+            };
+
+#pragma unroll 1
+            for (int i = 0; i < NH - 1; ++i) {
+                float gv[2 * NX];
+                xs.load_issue(i, gv);
+                float d[NU], y[NU], z[NU];
+                sd.load(i, d); sy.load(i, y); sz.load(i, z);
+                // [K;A] x_i in one column sweep
+                float2 ka[RS / 2];
+                if constexpr (O::Kx == ORD_SEQ && O::Ax == ORD_SEQ) {
+                    matvec2<ORD_SEQ, RS, NX, RS, 0, FAST>(P.KA, x, ka);
+                } else {
+                    float2 kk[NU / 2], aa[NX / 2];
+                    matvec2<O::Kx, NU, NX, RS, 0, FAST>(P.KA, x, kk);
+                    matvec2<O::Ax, NX, NX, RS, NU, FAST>(P.KA, x, aa);
+#pragma unroll
+                    for (int j = 0; j < NU / 2; ++j) ka[j] = kk[j];
+#pragma unroll
+                    for (int j = 0; j < NX / 2; ++j) ka[NU / 2 + j] = aa[j];
+                }
+                float u[NU], zn[NU];
+                if (WARM && yo) gstore<float, NU>(yo + i * NU, y);
+#pragma unroll
+                for (int r = 0; r < NU; r += 2) {
+                    const float2 d2 = f2(d[r], d[r + 1]), y2 = f2(y[r], y[r + 1]), z2 = f2(z[r], z[r + 1]);
+                    const float2 u2 = sub2(neg2(ka[r / 2]), d2);                                     // :31
+                    float2 t = add2(u2, y2);                                                         // :47
+                    t.x = fminf(P.umax[i * NU + r], fmaxf(P.umin[i * NU + r], t.x));               // :53
+                    t.y = fminf(P.umax[i * NU + r + 1], fmaxf(P.umin[i * NU + r + 1], t.y));
+                    const float2 rp = sub2(u2, t), rd = sub2(z2, t);
+                    pri_u = fmaxf(pri_u, fmaxf(fabsf(rp.x), fabsf(rp.y)));                           // :97
+                    dua_u = fmaxf(dua_u, fmaxf(fabsf(rd.x), fabsf(rd.y)));                           // :98
+                    const float2 yn = sub2(add2(y2, u2), t);                                         // :69
+                    u[r] = u2.x; u[r + 1] = u2.y; zn[r] = t.x; zn[r + 1] = t.y; y[r] = yn.x; y[r + 1] = yn.y;
+                }
+                sy.store(i, y);
+                sz.store(i, zn);
+                if (uo) gstore<float, NU>(uo + i * NU, u);
+                // x_{i+1} = A x_i + B u_i                                                            :35
+                float2 xn[NX / 2];
+                if constexpr (FAST) {
+#pragma unroll
+                    for (int j = 0; j < NX / 2; ++j) xn[j] = ka[NU / 2 + j];
+#pragma unroll
+                    for (int k = 0; k < NU; ++k)
+#pragma unroll
+                        for (int j = 0; j < NX / 2; ++j)
+                            xn[j] = __ffma2_rn(f2(P.Bc[k * NX + 2 * j], P.Bc[k * NX + 2 * j + 1]), f2(u[k], u[k]), xn[j]);
+                } else {
+                    float2 bu[NX / 2];
+                    matvec2<O::Bu, NX, NU, NX, 0, false>(P.Bc, u, bu);
+#pragma unroll
+                    for (int j = 0; j < NX / 2; ++j) xn[j] = add2(ka[NU / 2 + j], bu[j]);
+                }
+                xpart(i, gv);
+#pragma unroll
+                for (int j = 0; j < NX / 2; ++j) { x[2 * j] = xn[j].x; x[2 * j + 1] = xn[j].y; }
+            }
+            {
+                float gv[2 * NX];
+                xs.load_issue(NH - 1, gv);
+                xpart(NH - 1, gv);
+            }
+            xs.fence_st();
+        }
+
+        // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
+        bool final_bwd = false;
+        if (phase == PH_RUN) {
+            const bool chk = (it % P.check_term) == 0;
+            if (chk) {
+                res[0] = pri_x; res[1] = __fmul_rn(dua_x, P.rho); res[2] = pri_u; res[3] = __fmul_rn(dua_u, P.rho);
+            }
+            const bool conv = chk && res[0] < P.pri_tol && res[2] < P.pri_tol && res[1] < P.dua_tol && res[3] < P.dua_tol;
+            if (conv || it >= P.max_iter) {
+                if (a.iter) a.iter[inst] = it;
+                if (a.status) a.status[inst] = conv ? 1 : 11;
+                if (a.resid) *reinterpret_cast<float4 *>(a.resid + inst * 4) = make_float4(res[0], res[1], res[2], res[3]);
+                n_iter += (unsigned)it; n_solved += conv ? 1u : 0u; ++n_inst;
+                final_bwd = !conv;
+                phase = PH_EMIT;
+            }
+        } else if (phase == PH_EMIT) {
+            phase = PH_FREE;
+        }
+
+        // ------------------------------------------------------------------ backward sweep
+        // update_linear_cost (admm.cpp:77-85) recomputed per stage + backward_pass_grad (:15-22)
+        const bool cont = (phase == PH_RUN);
+        const bool wout = WARM && (cont || final_bwd) && a.wd;
+        if (__any_sync(FULLM, cont || wout)) {
+            float p[NX];
+            const float *xr_base = a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
+            float *wdo = wout ? a.wd + inst * UROW : nullptr;
+            float *wvo = wout ? a.wv + inst * XROW : nullptr;
+            float *wzo = wout ? a.wz + inst * UROW : nullptr;
+            {
+                float gv[2 * NX], pn[NX];
+                xs.load_issue(NH - 1, gv);
+                spn.load(0, pn);
+                xs.wait(gv);
+                if (WARM && wvo) gstore<float, NX>(wvo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
+#pragma unroll
+                for (int j = 0; j < NX; ++j) {
+                    const float dvg = __fsub_rn(gv[NX + j], gv[j]);
+                    if constexpr (FAST) p[j] = __fmaf_rn(P.nrho, dvg, pn[j]);
+                    else p[j] = __fsub_rn(pn[j], __fmul_rn(P.rho, dvg));                             // :84
+                }
+            }
+#pragma unroll 1
+            for (int i = NH - 2; i >= 0; --i) {
+                float gv[2 * NX];
+                xs.load_issue(i, gv);
+                float z[NU], y[NU], r[NU], xr[NX];
+                sz.load(i, z);
+                sy.load(i, y);
+                gload<float, NX>(xr_base + i * NX, xr);
+#pragma unroll
+                for (int j = 0; j < NU; ++j) r[j] = __fmul_rn(P.nrho, __fsub_rn(z[j], y[j]));        // :80
+                // [B^T ; AmBKt] p_{i+1}
+                float2 bm[RS / 2];
+                if constexpr (FAST) {
+                    matvec2<ORD_SEQ, RS, NX, RS, 0, true>(P.BM, p, bm);
+                } else {
+                    float2 bb[NU / 2], mm[NX / 2];
+                    matvec2<O::Btp, NU, NX, RS, 0, false>(P.BM, p, bb);
+                    matvec2<O::Mp, NX, NX, RS, NU, false>(P.BM, p, mm);
+#pragma unroll
+                    for (int j = 0; j < NU / 2; ++j) bm[j] = bb[j];
+#pragma unroll
+                    for (int j = 0; j < NX / 2; ++j) bm[NU / 2 + j] = mm[j];
+                }
+                float s[NU];
+#pragma unroll
+                for (int j = 0; j < NU; j += 2) {
+                    const float2 t = add2(bm[j / 2], f2(r[j], r[j + 1]));
+                    s[j] = t.x; s[j + 1] = t.y;
+                }
+                float2 d2[NU / 2];
+                matvec2<O::Qs, NU, NU, NU, 0, FAST>(P.Qi, s, d2);                                    // :19
+                float d[NU];
+#pragma unroll
+                for (int j = 0; j < NU / 2; ++j) { d[2 * j] = d2[j].x; d[2 * j + 1] = d2[j].y; }
+                sd.store(i, d, cont);
+                if (WARM && wdo) gstore<float, NU>(wdo + i * NU, d);
+                float2 kr[NX / 2];
+                matvec2<O::Ktr, NX, NU, NX, 0, FAST>(P.Kr, r, kr);
+                xs.wait(gv);
+                if (WARM && wvo) {
+                    gstore<float, NX>(wvo + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                    gstore<float, NU>(wzo + i * NU, z);
+                }
+#pragma unroll
+                for (int j = 0; j < NX; j += 2) {
+                    const float2 cq = f2(-__fmul_rn(xr[j], P.Qd[j]), -__fmul_rn(xr[j + 1], P.Qd[j + 1]));          // :81
+                    const float2 dvg = sub2(f2(gv[NX + j], gv[NX + j + 1]), f2(gv[j], gv[j + 1]));
+                    float2 q;
+                    if constexpr (FAST) q = __ffma2_rn(f2(P.nrho, P.nrho), dvg, cq);
+                    else q = sub2(cq, f2(__fmul_rn(P.rho, dvg.x), __fmul_rn(P.rho, dvg.y)));                       // :82
+                    const float2 pn = sub2(add2(q, bm[NU / 2 + j / 2]), kr[j / 2]);                                // :20
+                    p[j] = pn.x; p[j + 1] = pn.y;
+                }
+            }
+        }
+    }
+
+    if (a.stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_iter += __shfl_down_sync(FULLM, n_iter, o);
+            n_solved += __shfl_down_sync(FULLM, n_solved, o);
+            n_trips += __shfl_down_sync(FULLM, n_trips, o);
+            n_inst += __shfl_down_sync(FULLM, n_inst, o);
+        }
+        if (lane == 0) {
+            atomicAdd(a.stats + 0, n_iter);
+            atomicAdd(a.stats + 1, n_solved);
+            atomicAdd(a.stats + 2, n_trips);
+            atomicAdd(a.stats + 3, n_inst);
+        }
+    }
+    if constexpr (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
+    }
+}
+
+}  // namespace tmpc

@@ -51,6 +51,6 @@ if __name__ == "__main__":
     for mult in (0.1, 0.25, 1.0):
         run("parity", np.float32, B, mult)
         run("fast", np.float32, B, mult)
-    run("parity", np.float64, B // 8, 0.25)
-    run("parity", np.float32, B * 4, None, shape="c")
-    run("fast", np.float32, B * 4, None, shape="c")
+    pass
+    pass
+    pass
