@@ -18,7 +18,7 @@ TMPC_F32, TMPC_F64 = 0, 1
 TMPC_ORDER_PARITY, TMPC_ORDER_FAST = 0, 1
 TMPC_MEM_HOST, TMPC_MEM_DEVICE = 0, 1
 
-EXPORTS = ["tmpc_create", "tmpc_destroy", "tmpc_set_model", "tmpc_set_settings", "tmpc_solve", "tmpc_get_stats",
+EXPORTS = ["tmpc_create", "tmpc_destroy", "tmpc_set_model", "tmpc_set_settings", "tmpc_solve", "tmpc_get_stats", "tmpc_step",
            "tmpc_host_alloc", "tmpc_host_free", "tmpc_last_error", "tmpc_version"]
 
 
@@ -30,6 +30,11 @@ class TmpcSolveArgs(C.Structure):
     _fields_ = [("batch", C.c_int64), ("x0", C.c_void_p), ("Xref", C.c_void_p), ("xref_shared", C.c_int32),
                 ("mem", C.c_int32), ("warm", C.POINTER(TmpcWarm)), ("x", C.c_void_p), ("u", C.c_void_p),
                 ("iter", C.c_void_p), ("status", C.c_void_p), ("resid", C.c_void_p), ("stream", C.c_void_p)]
+
+
+class TmpcWorkspace(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x", "u", "q", "r", "p", "d", "v", "vnew", "z", "znew", "g", "y", "Xref")] + \
+               [("xref_shared", C.c_int32), ("resid", C.c_void_p), ("term", C.c_void_p)]
 
 
 class TmpcStats(C.Structure):
@@ -60,6 +65,8 @@ def load():
     lib.tmpc_solve.argtypes = [C.c_void_p, C.POINTER(TmpcSolveArgs)]
     lib.tmpc_get_stats.restype = C.c_int
     lib.tmpc_get_stats.argtypes = [C.c_void_p, C.POINTER(TmpcStats)]
+    lib.tmpc_step.restype = C.c_int
+    lib.tmpc_step.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(TmpcWorkspace), C.c_int32, C.c_int32, C.c_void_p]
     lib.tmpc_host_alloc.restype = C.c_int
     lib.tmpc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     lib.tmpc_host_free.restype = C.c_int
@@ -156,6 +163,22 @@ class Solver:
         self.solve_raw(B, x0, Xref, shared, TMPC_MEM_HOST, out["x"], out["u"], out["iter"], out["status"],
                        out["resid"], warm=warm)
         return out
+
+    def step(self, which, ws, it=1):
+        """One reference step function on host workspaces.  `ws`: dict of numpy arrays x,u,q,r,p,d,v,vnew,z,znew,g,y
+        ([B,N,nx] / [B,N-1,nu]), Xref ([N,nx] or [B,N,nx]), resid [B,4]; modified in place.  Returns term[B]."""
+        dt = self.dtype
+        B = ws["x"].shape[0]
+        w = TmpcWorkspace()
+        for k in ("x", "u", "q", "r", "p", "d", "v", "vnew", "z", "znew", "g", "y", "Xref", "resid"):
+            a = ws[k]
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"], k
+            setattr(w, k, _addr(a))
+        w.xref_shared = 1 if ws["Xref"].size == self.N * self.nx else 0
+        term = np.zeros(B, np.int32)
+        w.term = _addr(term)
+        self._check(self.lib.tmpc_step(self._ctx, which, B, C.byref(w), it, TMPC_MEM_HOST, None), "tmpc_step")
+        return term
 
     def stats(self):
         s = TmpcStats()

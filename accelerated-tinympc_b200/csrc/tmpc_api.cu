@@ -4,6 +4,7 @@
 #include "tmpc.h"
 #include "tmpc_kernel.cuh"
 #include "tmpc_kernel_f32.cuh"
+#include "tmpc_steps.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -11,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -329,6 +331,17 @@ bool is_pinned(const void *p)
         return false;
     }
     return at.type == cudaMemoryTypeHost;
+}
+
+template <class T, int NX, int NU, int NH>
+cudaError_t launch_step(tmpc_ctx_impl *c, const tmpc::StepArgs<T> &sa, int which, cudaStream_t s)
+{
+    const int threads = 64;
+    const unsigned blocks = (unsigned)((sa.batch + threads - 1) / threads);
+    const tmpc::Model<T, NX, NU, NH> *m = reinterpret_cast<const tmpc::Model<T, NX, NU, NH> *>(c->model.data());
+    if (c->policy == TMPC_ORDER_PARITY) tmpc::step_kernel<T, NX, NU, NH, false><<<blocks, threads, 0, s>>>(*m, sa, which);
+    else tmpc::step_kernel<T, NX, NU, NH, true><<<blocks, threads, 0, s>>>(*m, sa, which);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -652,6 +665,81 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
     }
     cleanup();
     return rc_all;
+}
+
+int tmpc_step(tmpc_ctx *ctx, int which, int64_t batch, const tmpc_workspace *ws, int32_t iter, int32_t mem, void *stream)
+{
+    if (!ctx || !ws) return TMPC_ERR_INVALID;
+    tmpc_ctx_impl *c = CTX(ctx);
+    if (!c->has_model) return fail(c, TMPC_ERR_STATE, "tmpc_set_model has not been called");
+    if (which < 0 || which > 5) return fail(c, TMPC_ERR_INVALID, "bad step index");
+    if (batch <= 0) return batch == 0 ? TMPC_OK : fail(c, TMPC_ERR_INVALID, "negative batch");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t es = esize(c);
+    const size_t xrow = (size_t)c->nx * c->N, urow = (size_t)c->nu * (c->N - 1);
+    void *arr[12] = {ws->x, ws->u, ws->q, ws->r, ws->p, ws->d, ws->v, ws->vnew, ws->z, ws->znew, ws->g, ws->y};
+    const size_t per[12] = {xrow, urow, xrow, urow, xrow, urow, xrow, xrow, urow, urow, xrow, urow};
+    for (void *p : arr) if (!p) return fail(c, TMPC_ERR_INVALID, "workspace arrays must not be NULL");
+    if (!ws->Xref) return fail(c, TMPC_ERR_INVALID, "Xref must not be NULL");
+    cudaStream_t s = (mem == TMPC_MEM_DEVICE && stream) ? (cudaStream_t)stream : c->stream;
+    void *dev[12];
+    void *d_xref = nullptr, *d_res = nullptr;
+    int *d_term = nullptr;
+    const size_t xref_n = ws->xref_shared ? xrow : xrow * batch;
+    if (mem == TMPC_MEM_HOST) {
+        for (int k = 0; k < 12; ++k) {
+            CUDA_TRY(c, cudaMalloc(&dev[k], per[k] * batch * es));
+            CUDA_TRY(c, cudaMemcpyAsync(dev[k], arr[k], per[k] * batch * es, cudaMemcpyHostToDevice, s));
+        }
+        CUDA_TRY(c, cudaMalloc(&d_xref, xref_n * es));
+        CUDA_TRY(c, cudaMemcpyAsync(d_xref, ws->Xref, xref_n * es, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMalloc(&d_res, 4 * batch * es));
+        if (ws->resid) CUDA_TRY(c, cudaMemcpyAsync(d_res, ws->resid, 4 * batch * es, cudaMemcpyHostToDevice, s));
+        else CUDA_TRY(c, cudaMemsetAsync(d_res, 0, 4 * batch * es, s));
+        CUDA_TRY(c, cudaMalloc((void **)&d_term, sizeof(int) * batch));
+    } else {
+        for (int k = 0; k < 12; ++k) dev[k] = arr[k];
+        d_xref = const_cast<void *>(ws->Xref);
+        d_res = ws->resid;
+        d_term = ws->term;
+        if (which == 4 && !d_res) return fail(c, TMPC_ERR_INVALID, "step 4 needs resid");
+    }
+    cudaError_t e = cudaErrorInvalidValue;
+    auto go = [&](auto tag, auto nx_, auto nu_, auto nh_) {
+        using T = decltype(tag);
+        tmpc::StepArgs<T> sa;
+        sa.batch = batch;
+        T **dst[12] = {&sa.x, &sa.u, &sa.q, &sa.r, &sa.p, &sa.d, &sa.v, &sa.vnew, &sa.z, &sa.znew, &sa.g, &sa.y};
+        for (int k = 0; k < 12; ++k) *dst[k] = (T *)dev[k];
+        sa.Xref = (const T *)d_xref;
+        sa.xref_stride = ws->xref_shared ? 0 : (long long)xrow;
+        sa.resid = (T *)d_res;
+        sa.term = d_term;
+        sa.iter = iter;
+        e = launch_step<T, decltype(nx_)::value, decltype(nu_)::value, decltype(nh_)::value>(c, sa, which, s);
+    };
+    using I = std::integral_constant<int, 0>;
+    (void)sizeof(I);
+    const bool f32 = c->dtype == TMPC_F32;
+    if (c->nx == 12 && c->nu == 4 && c->N == 10) {
+        if (f32) go(float(), std::integral_constant<int, 12>(), std::integral_constant<int, 4>(), std::integral_constant<int, 10>());
+        else go(double(), std::integral_constant<int, 12>(), std::integral_constant<int, 4>(), std::integral_constant<int, 10>());
+    } else if (c->nx == 4 && c->nu == 1 && c->N == 10) {
+        if (f32) go(float(), std::integral_constant<int, 4>(), std::integral_constant<int, 1>(), std::integral_constant<int, 10>());
+        else go(double(), std::integral_constant<int, 4>(), std::integral_constant<int, 1>(), std::integral_constant<int, 10>());
+    } else {
+        return fail(c, TMPC_ERR_UNSUPPORTED, "no step kernels for this shape");
+    }
+    if (e != cudaSuccess) return fail(c, TMPC_ERR_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
+    if (mem == TMPC_MEM_HOST) {
+        for (int k = 0; k < 12; ++k) CUDA_TRY(c, cudaMemcpyAsync(arr[k], dev[k], per[k] * batch * es, cudaMemcpyDeviceToHost, s));
+        if (ws->resid) CUDA_TRY(c, cudaMemcpyAsync(ws->resid, d_res, 4 * batch * es, cudaMemcpyDeviceToHost, s));
+        if (ws->term) CUDA_TRY(c, cudaMemcpyAsync(ws->term, d_term, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+        for (int k = 0; k < 12; ++k) cudaFree(dev[k]);
+        cudaFree(d_xref); cudaFree(d_res); cudaFree(d_term);
+    }
+    return TMPC_OK;
 }
 
 int tmpc_get_stats(tmpc_ctx *ctx, tmpc_stats *out)

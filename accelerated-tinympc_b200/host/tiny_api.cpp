@@ -1,0 +1,311 @@
+// Host C++ layer: the reference's entry points (include/tinympc/*.hpp) on top of the C ABI (include/tmpc.h).
+// Nothing numerical from the solver loop runs here; tiny_precompute is the only host-side math (the cold,
+// once-per-model Riccati recursion the reference performs inside tiny_codegen, codegen.cpp:254-292).
+#include "tinympc/tiny_api.hpp"
+#include "tmpc.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string &m) { g_err = m; return -1; }
+
+constexpr int kDtype = sizeof(tinytype) == 4 ? TMPC_F32 : TMPC_F64;
+
+struct Backend {
+    tmpc_ctx *ctx = nullptr;
+    int policy = TMPC_ORDER_PARITY;
+};
+
+Backend *backend(TinySolver *s)
+{
+    if (!s->backend) s->backend = new Backend;
+    return static_cast<Backend *>(s->backend);
+}
+
+// (re)create the device context if needed and push model + settings (cheap: a few KB; done on every call because
+// the reference lets callers edit cache/work/settings fields freely between solves)
+int sync_model(TinySolver *s)
+{
+    Backend *b = backend(s);
+    if (!b->ctx) {
+        int rc = tmpc_create(&b->ctx, 0, s->nx, s->nu, s->N, kDtype, b->policy);
+        if (rc != TMPC_OK) return fail(std::string("tmpc_create: ") + tmpc_last_error(nullptr));
+    }
+    const TinyWorkspace &w = *s->work;
+    const TinyCache &c = *s->cache;
+    int rc = tmpc_set_model(b->ctx, c.Kinf.data(), c.Pinf.data(), c.Quu_inv.data(), c.AmBKt.data(), w.Adyn.data(),
+                            w.Bdyn.data(), w.Q.data(), (double)c.rho, w.x_min.data(), w.x_max.data(), w.u_min.data(),
+                            w.u_max.data());
+    if (rc != TMPC_OK) return fail(std::string("tmpc_set_model: ") + tmpc_last_error(b->ctx));
+    const TinySettings &t = *s->settings;
+    rc = tmpc_set_settings(b->ctx, (double)t.abs_pri_tol, (double)t.abs_dua_tol, t.max_iter, t.check_termination,
+                           t.en_state_bound, t.en_input_bound);
+    if (rc != TMPC_OK) return fail(std::string("tmpc_set_settings: ") + tmpc_last_error(b->ctx));
+    return 0;
+}
+
+// ---- small dense helpers in double, row-major std::vector (cold path only)
+typedef std::vector<double> Mat;
+Mat mul(const Mat &A, int ar, int ac, const Mat &B, int bc)
+{
+    Mat C((size_t)ar * bc, 0.0);
+    for (int i = 0; i < ar; ++i)
+        for (int k = 0; k < ac; ++k) {
+            const double a = A[(size_t)i * ac + k];
+            for (int j = 0; j < bc; ++j) C[(size_t)i * bc + j] += a * B[(size_t)k * bc + j];
+        }
+    return C;
+}
+Mat transpose(const Mat &A, int r, int c)
+{
+    Mat T((size_t)r * c);
+    for (int i = 0; i < r; ++i)
+        for (int j = 0; j < c; ++j) T[(size_t)j * r + i] = A[(size_t)i * c + j];
+    return T;
+}
+bool inverse(Mat A, int n, Mat &inv)  // Gauss-Jordan with partial pivoting
+{
+    inv.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r)
+            if (std::fabs(A[(size_t)r * n + c]) > std::fabs(A[(size_t)piv * n + c])) piv = r;
+        if (A[(size_t)piv * n + c] == 0.0) return false;
+        if (piv != c)
+            for (int j = 0; j < n; ++j) {
+                std::swap(A[(size_t)piv * n + j], A[(size_t)c * n + j]);
+                std::swap(inv[(size_t)piv * n + j], inv[(size_t)c * n + j]);
+            }
+        const double d = 1.0 / A[(size_t)c * n + c];
+        for (int j = 0; j < n; ++j) { A[(size_t)c * n + j] *= d; inv[(size_t)c * n + j] *= d; }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const double f = A[(size_t)r * n + c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < n; ++j) { A[(size_t)r * n + j] -= f * A[(size_t)c * n + j]; inv[(size_t)r * n + j] -= f * inv[(size_t)c * n + j]; }
+        }
+    }
+    return true;
+}
+Mat to_rowmajor(const tiny_Matrix &m)
+{
+    Mat A((size_t)m.rows() * m.cols());
+    for (int i = 0; i < m.rows(); ++i)
+        for (int j = 0; j < m.cols(); ++j) A[(size_t)i * m.cols() + j] = (double)m(i, j);
+    return A;
+}
+void from_rowmajor(tiny_Matrix &m, const Mat &A, int r, int c)
+{
+    m.resize(r, c);
+    for (int i = 0; i < r; ++i)
+        for (int j = 0; j < c; ++j) m(i, j) = (tinytype)A[(size_t)i * c + j];
+}
+
+// single-instance step through tmpc_step on the host workspace
+int run_step(TinySolver *s, int which, int *term)
+{
+    if (sync_model(s) != 0) return -1;
+    TinyWorkspace &w = *s->work;
+    tinytype res[4] = {w.primal_residual_state, w.dual_residual_state, w.primal_residual_input, w.dual_residual_input};
+    tmpc_workspace ws;
+    ws.x = w.x.data(); ws.u = w.u.data(); ws.q = w.q.data(); ws.r = w.r.data(); ws.p = w.p.data(); ws.d = w.d.data();
+    ws.v = w.v.data(); ws.vnew = w.vnew.data(); ws.z = w.z.data(); ws.znew = w.znew.data(); ws.g = w.g.data(); ws.y = w.y.data();
+    ws.Xref = w.Xref.data(); ws.xref_shared = 1; ws.resid = res;
+    int32_t t = 0;
+    ws.term = &t;
+    int rc = tmpc_step(backend(s)->ctx, which, 1, &ws, w.iter, TMPC_MEM_HOST, nullptr);
+    if (rc != TMPC_OK) return fail(std::string("tmpc_step: ") + tmpc_last_error(backend(s)->ctx));
+    w.primal_residual_state = res[0]; w.dual_residual_state = res[1];
+    w.primal_residual_input = res[2]; w.dual_residual_input = res[3];
+    if (term) *term = t;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tiny_last_error(void) { return g_err.c_str(); }
+
+int tiny_setup(TinySolver **out, int nx, int nu, int N, const tinytype *Adyn, const tinytype *Bdyn, const tinytype *Q,
+               const tinytype *R, tinytype rho, const tinytype *x_min, const tinytype *x_max, const tinytype *u_min,
+               const tinytype *u_max, int verbose)
+{
+    if (!out || !Adyn || !Bdyn || !Q || !R || nx < 1 || nu < 1 || N < 2) return fail("tiny_setup: bad argument");
+    TinySolver *s = new TinySolver;
+    s->settings = new TinySettings;
+    s->cache = new TinyCache;
+    s->work = new TinyWorkspace;
+    s->nx = nx; s->nu = nu; s->N = N; s->backend = nullptr;
+    TinyWorkspace &w = *s->work;
+    TinyCache &c = *s->cache;
+    // zero every work array, as examples/quadrotor_hovering.cpp:49-71
+    for (tiny_Matrix *m : {&w.x, &w.q, &w.p, &w.v, &w.vnew, &w.g, &w.x_min, &w.x_max, &w.Xref}) m->resize(nx, N);
+    for (tiny_Matrix *m : {&w.u, &w.r, &w.d, &w.z, &w.znew, &w.y, &w.u_min, &w.u_max, &w.Uref}) m->resize(nu, N - 1);
+    w.primal_residual_state = w.primal_residual_input = w.dual_residual_state = w.dual_residual_input = 0;
+    w.status = 0; w.iter = 0;
+    w.Q.resize(nx, 1); w.R.resize(nu, 1); w.Qu.resize(nu, 1);
+    w.Adyn.resize(nx, nx); w.Bdyn.resize(nx, nu);
+    std::memcpy(w.Adyn.data(), Adyn, sizeof(tinytype) * nx * nx);   // column-major in, column-major stored
+    std::memcpy(w.Bdyn.data(), Bdyn, sizeof(tinytype) * nx * nu);
+    std::memcpy(w.Q.data(), Q, sizeof(tinytype) * nx);
+    std::memcpy(w.R.data(), R, sizeof(tinytype) * nu);
+    c.rho = rho;
+    c.Kinf.resize(nu, nx); c.Pinf.resize(nx, nx); c.Quu_inv.resize(nu, nu); c.AmBKt.resize(nx, nx); c.coeff_d2p.resize(nx, nu);
+    TinySettings &t = *s->settings;
+    t.abs_pri_tol = (tinytype)1e-3; t.abs_dua_tol = (tinytype)1e-3; t.max_iter = 100; t.check_termination = 1;
+    t.en_state_bound = (x_min && x_max) ? 1 : 0;   // codegen.cpp:227-243
+    t.en_input_bound = (u_min && u_max) ? 1 : 0;
+    if (t.en_state_bound) {
+        std::memcpy(w.x_min.data(), x_min, sizeof(tinytype) * nx * N);
+        std::memcpy(w.x_max.data(), x_max, sizeof(tinytype) * nx * N);
+    }
+    if (t.en_input_bound) {
+        std::memcpy(w.u_min.data(), u_min, sizeof(tinytype) * nu * (N - 1));
+        std::memcpy(w.u_max.data(), u_max, sizeof(tinytype) * nu * (N - 1));
+    }
+    if (verbose) printf("tiny_setup: nx=%d nu=%d N=%d rho=%g state bounds %s, input bounds %s\n", nx, nu, N, (double)rho,
+                        t.en_state_bound ? "on" : "off", t.en_input_bound ? "on" : "off");
+    *out = s;
+    return 0;
+}
+
+int tiny_precompute(TinySolver *s)
+{
+    if (!s) return fail("tiny_precompute: NULL solver");
+    const int n = s->nx, m = s->nu;
+    const double rho = (double)s->cache->rho;
+    const Mat A = to_rowmajor(s->work->Adyn), B = to_rowmajor(s->work->Bdyn);
+    const Mat At = transpose(A, n, n), Bt = transpose(B, n, m);
+    Mat Q1((size_t)n * n, 0.0), R1((size_t)m * m, 0.0);
+    for (int i = 0; i < n; ++i) Q1[(size_t)i * n + i] = (double)s->work->Q(i) + rho;      // codegen.cpp:255-258
+    for (int i = 0; i < m; ++i) R1[(size_t)i * m + i] = (double)s->work->R(i) + rho;
+    Mat Ktp1((size_t)m * n, 0.0), Ptp1((size_t)n * n, 0.0), Kinf((size_t)m * n, 0.0), Pinf((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) Ptp1[(size_t)i * n + i] = rho;
+    int sweeps = 1000;
+    for (int it = 0; it < 1000; ++it) {                                                   // codegen.cpp:273-285
+        Mat BtP = mul(Bt, m, n, Ptp1, n);
+        Mat S = mul(BtP, m, n, B, m);
+        for (size_t k = 0; k < S.size(); ++k) S[k] += R1[k];
+        Mat Sinv;
+        if (!inverse(S, m, Sinv)) return fail("tiny_precompute: R + B'PB is singular");
+        Kinf = mul(mul(Sinv, m, m, BtP, n), m, n, A, n);
+        Mat BK = mul(B, n, m, Kinf, n);
+        Mat AmBK(A);
+        for (size_t k = 0; k < AmBK.size(); ++k) AmBK[k] -= BK[k];
+        Pinf = mul(mul(At, n, n, Ptp1, n), n, n, AmBK, n);
+        for (size_t k = 0; k < Pinf.size(); ++k) Pinf[k] += Q1[k];
+        double dmax = 0.0;
+        for (size_t k = 0; k < Kinf.size(); ++k) dmax = std::fmax(dmax, std::fabs(Kinf[k] - Ktp1[k]));
+        if (dmax < 1e-5) { sweeps = it + 1; break; }
+        Ktp1 = Kinf;
+        Ptp1 = Pinf;
+    }
+    Mat S = mul(mul(Bt, m, n, Pinf, n), m, n, B, m);                                       // codegen.cpp:290-292
+    for (size_t k = 0; k < S.size(); ++k) S[k] += R1[k];
+    Mat Quu_inv;
+    if (!inverse(S, m, Quu_inv)) return fail("tiny_precompute: R + B'PB is singular");
+    Mat BK = mul(B, n, m, Kinf, n);
+    Mat AmBK(A);
+    for (size_t k = 0; k < AmBK.size(); ++k) AmBK[k] -= BK[k];
+    Mat AmBKt = transpose(AmBK, n, n);
+    Mat d2p = mul(transpose(Kinf, m, n), n, m, R1, m);
+    Mat t2 = mul(mul(AmBKt, n, n, Pinf, n), n, n, B, m);
+    for (size_t k = 0; k < d2p.size(); ++k) d2p[k] -= t2[k];
+    from_rowmajor(s->cache->Kinf, Kinf, m, n);
+    from_rowmajor(s->cache->Pinf, Pinf, n, n);
+    from_rowmajor(s->cache->Quu_inv, Quu_inv, m, m);
+    from_rowmajor(s->cache->AmBKt, AmBKt, n, n);
+    from_rowmajor(s->cache->coeff_d2p, d2p, n, m);
+    return sweeps;
+}
+
+int tiny_set_order_policy(TinySolver *s, int policy)
+{
+    if (!s || (policy != TMPC_ORDER_PARITY && policy != TMPC_ORDER_FAST)) return fail("tiny_set_order_policy: bad argument");
+    Backend *b = backend(s);
+    if (b->ctx && b->policy != policy) { tmpc_destroy(b->ctx); b->ctx = nullptr; }
+    b->policy = policy;
+    return 0;
+}
+
+int tiny_solve(TinySolver *s)
+{
+    if (!s) return fail("tiny_solve: NULL solver");
+    if (sync_model(s) != 0) return -1;
+    TinyWorkspace &w = *s->work;
+    tmpc_warm warm = {w.d.data(), w.y.data(), w.g.data(), w.v.data(), w.z.data()};
+    tinytype res[4];
+    int32_t it = 0, st = 0;
+    tmpc_solve_args a;
+    std::memset(&a, 0, sizeof a);
+    a.batch = 1;
+    a.x0 = w.x.col(0);          // work.x.col(0) = x0 (quadrotor_hovering.cpp:95)
+    std::vector<tinytype> x0(w.x.col(0), w.x.col(0) + s->nx);   // x is also an output: keep the input separate
+    a.x0 = x0.data();
+    a.Xref = w.Xref.data();
+    a.xref_shared = 1;
+    a.mem = TMPC_MEM_HOST;
+    a.warm = &warm;
+    a.x = w.x.data(); a.u = w.u.data(); a.iter = &it; a.status = &st; a.resid = res;
+    int rc = tmpc_solve(backend(s)->ctx, &a);
+    if (rc != TMPC_OK) return fail(std::string("tmpc_solve: ") + tmpc_last_error(backend(s)->ctx));
+    w.iter = it; w.status = st;
+    w.primal_residual_state = res[0]; w.dual_residual_state = res[1];
+    w.primal_residual_input = res[2]; w.dual_residual_input = res[3];
+    return st == TMPC_STATUS_SOLVED ? 0 : 1;    // admm.cpp:137,151
+}
+
+int tiny_solve_batch(TinySolver *s, const TinyBatchIn *in, TinyBatchOut *out)
+{
+    if (!s || !in || !out) return fail("tiny_solve_batch: NULL argument");
+    if (sync_model(s) != 0) return -1;
+    tmpc_warm warm = {in->d, in->y, in->g, in->v, in->z};
+    const bool any = in->d || in->y || in->g || in->v || in->z;
+    tmpc_solve_args a;
+    std::memset(&a, 0, sizeof a);
+    a.batch = in->batch; a.x0 = in->x0; a.Xref = in->Xref; a.xref_shared = in->xref_shared;
+    a.mem = in->on_device ? TMPC_MEM_DEVICE : TMPC_MEM_HOST;
+    a.warm = any ? &warm : nullptr;
+    a.x = out->x; a.u = out->u; a.iter = out->iter; a.status = out->status; a.resid = out->resid;
+    a.stream = in->stream;
+    int rc = tmpc_solve(backend(s)->ctx, &a);
+    if (rc != TMPC_OK) return fail(std::string("tmpc_solve: ") + tmpc_last_error(backend(s)->ctx));
+    return 0;
+}
+
+void forward_pass(TinySolver *s) { run_step(s, 0, nullptr); }
+void update_slack(TinySolver *s) { run_step(s, 1, nullptr); }
+void update_dual(TinySolver *s) { run_step(s, 2, nullptr); }
+void update_linear_cost(TinySolver *s) { run_step(s, 3, nullptr); }
+bool termination_condition(TinySolver *s)
+{
+    int t = 0;
+    run_step(s, 4, &t);
+    return t != 0;
+}
+void backward_pass_grad(TinySolver *s) { run_step(s, 5, nullptr); }
+
+void tiny_free(TinySolver *s)
+{
+    if (!s) return;
+    if (s->backend) {
+        Backend *b = static_cast<Backend *>(s->backend);
+        if (b->ctx) tmpc_destroy(b->ctx);
+        delete b;
+    }
+    delete s->settings;
+    delete s->cache;
+    delete s->work;
+    delete s;
+}
+
+}  // extern "C"

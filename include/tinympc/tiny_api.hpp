@@ -1,0 +1,57 @@
+// Set-up / precompute / batched solve entry points named by the project brief.  The reference has no
+// tiny_setup or tiny_precompute: "setup" is the hand-written initialisation block of each example
+// (examples/quadrotor_hovering.cpp:33-78) and the cache math lives inside tiny_codegen (codegen.cpp:254-292);
+// these functions package exactly those two pieces.
+#pragma once
+#include <stdint.h>
+#include "admm.hpp"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Allocate a solver for an nx/nu/N problem and fill it like the examples do: model (column-major inputs, as
+ * tiny_codegen takes them, codegen.cpp:245-252), raw Q and R, rho, bounds (a NULL min/max pair disables that
+ * bound: en_*_bound = 0, codegen.cpp:227-243), all work arrays zero, settings tol 1e-3 / max_iter 100 /
+ * check_termination 1.  The cache is NOT computed here: call tiny_precompute or fill solver->cache yourself. */
+int tiny_setup(TinySolver **out, int nx, int nu, int N, const tinytype *Adyn, const tinytype *Bdyn,
+               const tinytype *Q, const tinytype *R, tinytype rho, const tinytype *x_min, const tinytype *x_max,
+               const tinytype *u_min, const tinytype *u_max, int verbose);
+
+/* Kinf, Pinf, Quu_inv, AmBKt, coeff_d2p by the reference's recursion (codegen.cpp:254-292): Riccati fixed point
+ * on Q+rho, R+rho from P = rho*I, at most 1000 sweeps, stop when max|dKinf| < 1e-5; computed in double, stored
+ * as tinytype.  Returns the number of sweeps (the reference never reports non-convergence; neither do we).
+ * work.Q keeps the value the caller gave (the examples pass raw Q; generated code passes Q+rho). */
+int tiny_precompute(TinySolver *solver);
+
+typedef struct {
+    int64_t batch;
+    const tinytype *x0;    /* [batch][nx] */
+    const tinytype *Xref;  /* [N][nx] if xref_shared, else [batch][N][nx] */
+    int xref_shared;
+    int on_device;         /* 0: host pointers, 1: device pointers (then `stream` is a cudaStream_t) */
+    void *stream;
+    tinytype *d, *y, *g, *v, *z; /* warm state in place, all or none (NULL = cold start) */
+} TinyBatchIn;
+
+typedef struct {
+    tinytype *x;      /* [batch][N][nx]   */
+    tinytype *u;      /* [batch][N-1][nu] */
+    int32_t *iter;    /* [batch] */
+    int32_t *status;  /* [batch] 1 solved / 11 max_iter */
+    tinytype *resid;  /* [batch][4] primal_state, dual_state, primal_input, dual_input; nullable */
+} TinyBatchOut;
+
+/* tiny_solve for `batch` instances sharing solver's model, cache, bounds and settings.  0 = the call worked
+ * (instances that stop at max_iter have status 11), negative = error. */
+int tiny_solve_batch(TinySolver *solver, const TinyBatchIn *in, TinyBatchOut *out);
+
+/* policy 0 = bit-exact order of the reference's -O3 SSE2 build (default), 1 = FMA-contracted */
+int tiny_set_order_policy(TinySolver *solver, int policy);
+
+void tiny_free(TinySolver *solver);
+const char *tiny_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif

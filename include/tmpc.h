@@ -120,6 +120,21 @@ typedef struct {
 /* Statistics of the last tmpc_solve on this ctx (synchronises the ctx's stream). */
 int tmpc_get_stats(tmpc_ctx *ctx, tmpc_stats *out);
 
+/* Full per-instance workspace (every array of TinyWorkspace that the step functions touch, types.hpp:55-76),
+ * [batch][stage][dim]; all pointers required except resid/term. */
+typedef struct {
+    void *x, *u, *q, *r, *p, *d, *v, *vnew, *z, *znew, *g, *y;
+    const void *Xref;    /* [N][nx] shared or [batch][N][nx] */
+    int32_t xref_shared;
+    void *resid;         /* [batch][4], read and written by step 4 */
+    int32_t *term;       /* [batch] out: termination_condition() result (step 4) */
+} tmpc_workspace;
+
+/* One of the reference's step functions (admm.hpp:13-18) on every instance of a batch, as its own kernel:
+ * which = 0 forward_pass, 1 update_slack, 2 update_dual, 3 update_linear_cost, 4 termination_condition (uses
+ * `iter` for the check_termination test), 5 backward_pass_grad.  Unit-test surface; synchronous for host memory. */
+int tmpc_step(tmpc_ctx *ctx, int which, int64_t batch, const tmpc_workspace *ws, int32_t iter, int32_t mem, void *stream);
+
 /* Pinned host allocation helpers for TMPC_MEM_HOST callers that want full PCIe speed. */
 int tmpc_host_alloc(void **ptr, uint64_t bytes);
 int tmpc_host_free(void *ptr);
