@@ -4,6 +4,6 @@ The directory name carries a hyphen, so import it through `__graft_entry__.load_
 registers it as `accelerated_tinympc_b200`).  PyTorch is plumbing only (device buffers, streams,
 torch.distributed); every numerical result comes from the hand-written sm_100a kernels in csrc/.
 """
-from . import capi, problems, workloads  # noqa: F401
+from . import capi, problems, sharding, workloads  # noqa: F401
 
-__all__ = ["capi", "problems", "workloads"]
+__all__ = ["capi", "problems", "sharding", "workloads"]

@@ -174,8 +174,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     capi = pkg.capi
     B = args.batch
-    b0 = rank * B
-    x0_np, xref_np = pkg.workloads.quadrotor_hover_batch(b0, b0 + B, mult=args.mult)
+    b0, b1 = pkg.sharding.shard_range(rank, world, per_rank=B)
+    x0_np, xref_np = pkg.workloads.quadrotor_hover_batch(b0, b1, mult=args.mult)
     solver = capi.Solver(prob, dtype=np.float32, policy=args.policy, device=local)
     x0 = torch.from_numpy(x0_np).to(dev)
     xref = torch.from_numpy(xref_np).to(dev)
@@ -218,16 +218,12 @@ def main():
     launches = stats["launches"] * args.steps
 
     # whole-job numbers: max time over ranks, totals over ranks (NCCL only for this statistics gather)
-    tot = torch.tensor([float(stats["iterations"]), float(stats["solved"]), float(stats["instances"])],
-                       dtype=torch.float64, device=dev)
-    tmax = torch.tensor([ms, kernel_ms], dtype=torch.float64, device=dev)
-    hist = torch.bincount(it.to(torch.int64), minlength=prob.max_iter + 1).to(torch.float64)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    vec = pkg.sharding.local_stats(it.cpu().numpy(), st.cpu().numpy(), prob.max_iter)
+    assert vec[0] == stats["iterations"] and vec[1] == stats["solved"], "kernel statistics disagree with the outputs"
+    vec, tmax = pkg.sharding.gather_stats(vec, [ms, kernel_ms], dist if world > 1 else None, dev)
     ms, kernel_ms = float(tmax[0]), float(tmax[1])
-    total_iters, total_solved, total_inst = [float(v) for v in tot]
+    total_iters, total_solved, total_inst = float(vec[0]), float(vec[1]), float(vec[2])
+    hist = vec[3:]
     value = total_inst * args.steps / (ms * 1e-3)
 
     # ---- roofline of the one kernel (per GPU, per launch; kernel time by CUDA events inside the library,
