@@ -33,7 +33,7 @@ BYTES_PER_SOLVE = {"q": 680, "c": 220}      # algorithmic HBM bytes per solve, f
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="instances per GPU per step")
@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -241,8 +241,15 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = stats["instances"] * BYTES_PER_SOLVE["q"] / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:   # DRAM bytes (read + write) of this kernel at this workload, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        if tj.get("batch") == args.batch and tj.get("policy") == args.policy and abs(tj.get("mult", -1) - args.mult) < 1e-9:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_fp32_max, "unit": "TFLOP/s",
-                "frac": achieved / peak_fp32_max, "traffic": None,
+                "frac": achieved / peak_fp32_max, "traffic": traffic,
                 "peak_source": "SMs x 128 FMA lanes x 2 x clocks.max.sm (%d SMs, %d MHz); at the median clock under load "
                                "(%s MHz) the peak is %.1f TFLOP/s -> frac %.3f" % (prop.multi_processor_count,
                                                                                  clocks["sm_max_mhz"] or 1965, sm_mhz,
