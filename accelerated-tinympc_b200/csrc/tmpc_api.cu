@@ -57,6 +57,13 @@ struct tmpc_ctx_impl {
         cudaEvent_t done = nullptr;
     } stage[3];
     int64_t stage_chunk = 0;
+    // gated host pipeline (cold solves): full-batch device image + per-chunk completion counters
+    void *g_in = nullptr, *g_out = nullptr;
+    size_t g_in_bytes = 0, g_out_bytes = 0;
+    unsigned *g_done = nullptr;
+    size_t g_done_n = 0;
+    cudaStream_t g_copy = nullptr;
+    cudaEvent_t g_h2d = nullptr;
     // stats of the last solve
     tmpc_stats stats{};
     bool stats_pending = false;
@@ -272,6 +279,8 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     void *resid;
     unsigned long long *counter;
     unsigned long long *stats;
+    unsigned *done;
+    int done_shift;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
@@ -319,6 +328,107 @@ int ensure_stage(tmpc_ctx_impl *c, int k, size_t in_bytes, size_t out_bytes)
         CUDA_TRY(c, cudaMalloc(&st.d_out, out_bytes));
         st.out_bytes = out_bytes;
     }
+    return TMPC_OK;
+}
+
+
+typedef int (*wait_value32_fn)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned, unsigned);
+
+// Cold solve from/to HOST memory: ONE persistent-kernel launch over the whole batch, outputs copied back while the
+// kernel is still running.  The kernel bumps done[inst >> shift] after the last store of each instance; the copy
+// stream waits on those counters with stream memory operations (cuStreamWaitValue32 GEQ) and then DMAs that
+// chunk's slices straight into the caller's buffers.  No host thread is involved between launch and the final sync.
+int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it);
+
+int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
+{
+    const size_t es = esize(c);
+    const int nx = c->nx, nu = c->nu, N = c->N;
+    const size_t xrow = (size_t)nx * N, urow = (size_t)nu * (N - 1);
+    const int64_t B = a->batch;
+    static wait_value32_fn wait32 = nullptr;
+    static bool wait32_probed = false;
+    if (!wait32_probed) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
+            qr == cudaDriverEntryPointSuccess)
+            wait32 = reinterpret_cast<wait_value32_fn>(fn);
+        else
+            cudaGetLastError();
+        wait32_probed = true;
+    }
+    int shift = 16;                                   // 65,536 instances per D2H chunk
+    while (shift > 10 && (B >> shift) < 8) --shift;   // small batches: at least ~8 chunks, >= 1024 instances each
+    const int64_t CH = (int64_t)1 << shift;
+    const int nch = (int)((B + CH - 1) / CH);
+    // device image: in = x0 | [Xref];  out = x | u | iter | status | resid
+    const size_t in_bytes = (size_t)B * nx * es + (a->xref_shared ? xrow * es : (size_t)B * xrow * es);
+    const size_t out_bytes = (size_t)B * ((xrow + urow + 4) * es + 8) + 64;
+    if (c->g_in_bytes < in_bytes) {
+        if (c->g_in) cudaFree(c->g_in);
+        c->g_in = nullptr; c->g_in_bytes = 0;
+        CUDA_TRY(c, cudaMalloc(&c->g_in, in_bytes));
+        c->g_in_bytes = in_bytes;
+    }
+    if (c->g_out_bytes < out_bytes) {
+        if (c->g_out) cudaFree(c->g_out);
+        c->g_out = nullptr; c->g_out_bytes = 0;
+        CUDA_TRY(c, cudaMalloc(&c->g_out, out_bytes));
+        c->g_out_bytes = out_bytes;
+    }
+    if (c->g_done_n < (size_t)nch) {
+        if (c->g_done) cudaFree(c->g_done);
+        c->g_done = nullptr; c->g_done_n = 0;
+        CUDA_TRY(c, cudaMalloc((void **)&c->g_done, sizeof(unsigned) * nch));
+        c->g_done_n = nch;
+    }
+    if (!c->g_copy) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->g_copy, cudaStreamNonBlocking));
+    if (!c->g_h2d) CUDA_TRY(c, cudaEventCreateWithFlags(&c->g_h2d, cudaEventDisableTiming));
+    cudaStream_t s = c->stream;
+    char *din = (char *)c->g_in;
+    char *d_x0 = din, *d_xref = din + (size_t)B * nx * es;
+    CUDA_TRY(c, cudaMemcpyAsync(d_x0, a->x0, (size_t)B * nx * es, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(d_xref, a->Xref, a->xref_shared ? xrow * es : (size_t)B * xrow * es, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemsetAsync(c->g_done, 0, sizeof(unsigned) * nch, s));
+    // the copy stream must not evaluate its waits against counters left by a previous solve
+    CUDA_TRY(c, cudaEventRecord(c->g_h2d, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->g_copy, c->g_h2d, 0));
+    char *dout = (char *)c->g_out;
+    auto a16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+    size_t o = 0;
+    char *d_x = dout + o; o = a16(o + (size_t)B * xrow * es);
+    char *d_u = dout + o; o = a16(o + (size_t)B * urow * es);
+    char *d_it = dout + o; o = a16(o + (size_t)B * 4);
+    char *d_st = dout + o; o = a16(o + (size_t)B * 4);
+    char *d_rs = dout + o;
+    DevArgs da{};
+    da.batch = B; da.x0 = d_x0; da.Xref = d_xref; da.xref_stride = a->xref_shared ? 0 : (long long)xrow;
+    da.x = d_x; da.u = d_u; da.iter = (int *)d_it; da.status = (int *)d_st; da.resid = d_rs;
+    da.done = wait32 ? c->g_done : nullptr;
+    da.done_shift = shift;
+    int rc = launch_device(c, da, false, s, true);
+    if (rc != TMPC_OK) return rc;
+    cudaStream_t cs = c->g_copy;
+    if (!wait32) {                                      // no stream mem-ops available: plain copy after the kernel
+        CUDA_TRY(c, cudaEventRecord(c->g_h2d, s));
+        CUDA_TRY(c, cudaStreamWaitEvent(cs, c->g_h2d, 0));
+    }
+    for (int k = 0; k < nch; ++k) {
+        const int64_t b0 = (int64_t)k * CH, n = std::min<int64_t>(CH, B - b0);
+        if (wait32) {
+            int e = wait32(cs, (unsigned long long)(uintptr_t)(c->g_done + k), (unsigned)n, 0u /*CU_STREAM_WAIT_VALUE_GEQ*/);
+            if (e != 0) return fail(c, TMPC_ERR_CUDA, "cuStreamWaitValue32 failed");
+        }
+        auto back = [&](void *dst, const char *src, size_t per) {
+            if (dst) cudaMemcpyAsync((char *)dst + b0 * per, src + b0 * per, n * per, cudaMemcpyDeviceToHost, cs);
+        };
+        back(a->x, d_x, xrow * es); back(a->u, d_u, urow * es); back(a->iter, d_it, 4); back(a->status, d_st, 4);
+        back(a->resid, d_rs, 4 * es);
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(cs));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    c->stats_pending = true;
     return TMPC_OK;
 }
 
@@ -412,6 +522,11 @@ int tmpc_destroy(tmpc_ctx *ctx)
         if (st.d_in) cudaFree(st.d_in);
         if (st.d_out) cudaFree(st.d_out);
     }
+    if (c->g_in) cudaFree(c->g_in);
+    if (c->g_out) cudaFree(c->g_out);
+    if (c->g_done) cudaFree(c->g_done);
+    if (c->g_copy) cudaStreamDestroy(c->g_copy);
+    if (c->g_h2d) cudaEventDestroy(c->g_h2d);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -502,6 +617,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
         return TMPC_OK;
     }
     if (a->mem != TMPC_MEM_HOST) return fail(c, TMPC_ERR_INVALID, "bad mem kind");
+    if (!warm && !getenv("TMPC_HOST_CHUNKED")) return solve_host_gated(c, a);
 
     // ---- host buffers: chunked 3-deep pipeline  H2D(k+1) | solve(k) | D2H(k-1) on three streams
     // input chunk image : x0 | [Xref per instance] | [warm d y z g v]

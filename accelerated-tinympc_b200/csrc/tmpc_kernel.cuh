@@ -189,6 +189,8 @@ template <class T> struct SolveArgs {
     T *resid;
     unsigned long long *counter;  // next unclaimed instance
     unsigned long long *stats;    // [0] iterations [1] solved [2] lane-trips [3] instances
+    unsigned *done;               // nullable: done[inst >> done_shift] += 1 when every output of inst is written
+    int done_shift;
 };
 
 // per-thread array of STAGES vectors of D scalars in shared memory.
@@ -493,6 +495,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             }
         } else if (phase == PH_EMIT) {
             phase = PH_FREE;  // trajectory was written by this trip's forward sweep
+            if (a.done) { __threadfence(); atomicAdd(a.done + (inst >> a.done_shift), 1u); }
         }
 
         // ------------------------------------------------------------------ backward sweep

@@ -433,7 +433,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 phase = PH_EMIT;
             }
         } else if (phase == PH_EMIT) {
-            phase = PH_FREE;
+            phase = PH_FREE;   // every output of this instance is written: signal the host-side D2H pipeline
+            if (a.done) { __threadfence(); atomicAdd(a.done + (inst >> a.done_shift), 1u); }
         }
 
         // ------------------------------------------------------------------ backward sweep
