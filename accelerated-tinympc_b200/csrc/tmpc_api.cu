@@ -160,7 +160,7 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
         return pick<double, 12, 4, 10, 64, false>(policy, warm, out);
     }
     if (nx == 4 && nu == 1 && N == 10) {
-        if (dtype == TMPC_F32) return pick<float, 4, 1, 10, 256, false>(policy, warm, out);
+        if (dtype == TMPC_F32) return pick<float, 4, 1, 10, 512, false>(policy, warm, out);   // 444 B of state: 512 instances / SM
         return pick<double, 4, 1, 10, 128, false>(policy, warm, out);
     }
     return false;

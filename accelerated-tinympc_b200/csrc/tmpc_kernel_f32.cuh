@@ -244,6 +244,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
     int it = 0;
     int phase = PH_FREE;
     bool exhausted = false;
+    bool spec = false;   // speculative emission: this trip's x,u go straight to the output because the lane is
+                         // expected to terminate in it (residuals within SPEC_FACTOR of tolerance, or last iteration)
     float x0[NX];
     float res[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned long long n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
@@ -264,6 +266,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
                 if (idx < a.batch) {
                     inst = idx; phase = PH_RUN; it = 0; fill = true;
+                    spec = (P.max_iter <= 1);
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);
                     float xr[NX], pn[NX];
@@ -325,16 +328,17 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             float x[NX];
 #pragma unroll
             for (int j = 0; j < NX; ++j) x[j] = x0[j];
-            float *xo = (emit && a.x) ? a.x + inst * XROW : nullptr;
-            float *uo = (emit && a.u) ? a.u + inst * UROW : nullptr;
-            float *go = (WARM && emit && a.wg) ? a.wg + inst * XROW : nullptr;
-            float *yo = (WARM && emit && a.wy) ? a.wy + inst * UROW : nullptr;
+            const bool wr = emit || (spec && phase == PH_RUN);
+            float *xo = (wr && a.x) ? a.x + inst * XROW : nullptr;
+            float *uo = (wr && a.u) ? a.u + inst * UROW : nullptr;
+            float *go = (WARM && wr && a.wg) ? a.wg + inst * XROW : nullptr;
+            float *yo = (WARM && wr && a.wy) ? a.wy + inst * UROW : nullptr;
 
             auto xpart = [&](int i, float (&gv)[2 * NX]) {
                 // state slack / dual / residuals for stage i (uses x_i)
                 xs.wait(gv);
                 float g[NX], vn[NX];
-                if (WARM && go) gstore<float, NX>(go + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
+                if (WARM && go && emit) gstore<float, NX>(go + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
 #pragma unroll
                 for (int j = 0; j < NX; j += 2) {
                     const float2 x2 = f2(x[j], x[j + 1]), g2 = f2(gv[j], gv[j + 1]), v2 = f2(gv[NX + j], gv[NX + j + 1]);
@@ -348,6 +352,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     g[j] = gn.x; g[j + 1] = gn.y; vn[j] = t.x; vn[j + 1] = t.y;
                 }
                 xs.store(i, g, vn);
+                if (WARM && go && !emit) gstore<float, NX>(go + i * NX, g);
                 if (xo) gstore<float, NX>(xo + i * NX, x);
             };
 
@@ -371,7 +376,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     for (int j = 0; j < NX / 2; ++j) ka[NU / 2 + j] = aa[j];
                 }
                 float u[NU], zn[NU];
-                if (WARM && yo) gstore<float, NU>(yo + i * NU, y);
+                if (WARM && yo && emit) gstore<float, NU>(yo + i * NU, y);
 #pragma unroll
                 for (int r = 0; r < NU; r += 2) {
                     const float2 d2 = f2(d[r], d[r + 1]), y2 = f2(y[r], y[r + 1]), z2 = f2(z[r], z[r + 1]);
@@ -387,6 +392,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 }
                 sy.store(i, y);
                 sz.store(i, zn);
+                if (WARM && yo && !emit) gstore<float, NU>(yo + i * NU, y);
                 if (uo) gstore<float, NU>(uo + i * NU, u);
                 // x_{i+1} = A x_i + B u_i                                                            :35
                 float2 xn[NX / 2];
@@ -418,6 +424,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
 
         // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
         bool final_bwd = false;
+        bool finished = false;   // every output of this lane's instance is (or will be, after this trip's backward) written
         if (phase == PH_RUN) {
             const bool chk = (it % P.check_term) == 0;
             if (chk) {
@@ -430,11 +437,20 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 if (a.resid) *reinterpret_cast<float4 *>(a.resid + inst * 4) = make_float4(res[0], res[1], res[2], res[3]);
                 n_iter += (unsigned)it; n_solved += conv ? 1u : 0u; ++n_inst;
                 final_bwd = !conv;
-                phase = PH_EMIT;
+                if (spec) { phase = PH_FREE; finished = true; }   // x,u of this very trip are already in the output
+                else phase = PH_EMIT;
+                spec = false;
+            } else {
+                // predict termination in the next trip: last allowed iteration, or every residual within 25 % of its
+                // tolerance at a check (ADMM crawls across the threshold); a wrong guess only costs stores
+                constexpr float SF = 1.25f;
+                const bool next_chk = ((it + 1) % P.check_term) == 0;
+                spec = (it + 1 >= P.max_iter) ||
+                       (next_chk && res[0] < SF * P.pri_tol && res[2] < SF * P.pri_tol && res[1] < SF * P.dua_tol && res[3] < SF * P.dua_tol);
             }
         } else if (phase == PH_EMIT) {
-            phase = PH_FREE;   // every output of this instance is written: signal the host-side D2H pipeline
-            if (a.done) { __threadfence(); atomicAdd(a.done + (inst >> a.done_shift), 1u); }
+            phase = PH_FREE;
+            finished = true;
         }
 
         // ------------------------------------------------------------------ backward sweep
@@ -515,6 +531,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 }
             }
         }
+        // signal the host-side D2H pipeline: all stores of this instance (incl. warm state of a final backward) are issued
+        if (finished && a.done) { __threadfence(); atomicAdd(a.done + (inst >> a.done_shift), 1u); }
     }
 
     if (a.stats) {
