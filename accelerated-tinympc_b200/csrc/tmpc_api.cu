@@ -4,6 +4,7 @@
 #include "tmpc.h"
 #include "tmpc_kernel.cuh"
 #include "tmpc_kernel_f32.cuh"
+#include "tmpc_kernel_warp.cuh"
 #include "tmpc_steps.cuh"
 
 #include <algorithm>
@@ -25,6 +26,8 @@ struct KernelInfo {
     int block;
     size_t model_bytes;
     int model_kind;  // 0: tmpc::Model<T,...> (generic kernel)   1: tmpc::ModelF32<...> (packed fp32 kernel)
+                     // 2: tmpc::ModelWarp (warp-per-instance kernel; pointers into the ctx's device model image)
+    int per_block;   // instances resident per block (threads for the thread-per-instance kernels, warps for kind 2)
 };
 
 struct tmpc_ctx_impl {
@@ -39,6 +42,9 @@ struct tmpc_ctx_impl {
     // model image exactly as the kernel's Model<T,...> struct (built on the host, passed by value)
     std::vector<unsigned char> model;      // tmpc::Model<T,...> image
     std::vector<unsigned char> model_f32;  // tmpc::ModelF32<...> image (packed fp32 kernel)
+    tmpc::ModelWarp model_w{};             // warp-per-instance kernel: scalars + pointers into d_model_w
+    float *d_model_w = nullptr;            // device image: fwd4 | bwd4 | Pt | Qd | xmin | xmax | umin | umax
+    size_t d_model_w_floats = 0;
     // settings
     double pri = 1e-3, dua = 1e-3;
     int max_iter = 100, check_term = 1, en_state = 1, en_input = 1;
@@ -98,6 +104,7 @@ KernelInfo make_info()
     k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::Model<T, NX, NU, NH>);
     k.model_kind = 0;
+    k.per_block = BLOCK;
     return k;
 }
 
@@ -110,7 +117,30 @@ KernelInfo make_info_f32()
     k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::ModelF32<NX, NU, NH>);
     k.model_kind = 1;
+    k.per_block = BLOCK;
     return k;
+}
+
+template <int NH, int WARPS, bool FAST, bool WARM>
+KernelInfo make_info_warp()
+{
+    KernelInfo k;
+    k.fn = (const void *)&tmpc::admm_kernel_warp<NH, WARPS, FAST, WARM>;
+    k.smem = tmpc::WarpSmem<NH>::BYTES * WARPS;
+    k.block = WARPS * 32;
+    k.model_bytes = sizeof(tmpc::ModelWarp);
+    k.model_kind = 2;
+    k.per_block = WARPS;
+    return k;
+}
+
+template <int NH, int WARPS>
+bool pick_warp(int policy, bool warm, KernelInfo &out)
+{
+    static_assert(tmpc::WarpSmem<NH>::BYTES * WARPS <= 232448, "per-block shared memory limit of sm_100");
+    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_warp<NH, WARPS, false, true>() : make_info_warp<NH, WARPS, false, false>();
+    else out = warm ? make_info_warp<NH, WARPS, true, true>() : make_info_warp<NH, WARPS, true, false>();
+    return true;
 }
 
 template <int NX, int NU, int NH, int BLOCK, bool TM>
@@ -163,6 +193,8 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
         if (dtype == TMPC_F32) return pick<float, 4, 1, 10, 512, false>(policy, warm, out);   // 444 B of state: 512 instances / SM
         return pick<double, 4, 1, 10, 128, false>(policy, warm, out);
     }
+    // large shape: one warp per instance, 17.8 KB of shared memory each -> 12 instances / SM
+    if (nx == 32 && nu == 8 && N == 50 && dtype == TMPC_F32) return pick_warp<50, 12>(policy, warm, out);
     return false;
 }
 
@@ -251,8 +283,81 @@ template <int NX, int NU, int NH> void build_model_f32(tmpc_ctx_impl *c, std::ve
     m->check_term = c->check_term;
 }
 
+// lane-major coefficient image of the warp-per-instance kernel (layout: tmpc_kernel_warp.cuh ModelWarp)
+bool build_model_warp(tmpc_ctx_impl *c)
+{
+    constexpr int NX = tmpc::WNX, NU = tmpc::WNU;
+    const int NH = c->N;
+    const float *K = reinterpret_cast<const float *>(c->Kinf.data());     // [r + k*NU]
+    const float *A = reinterpret_cast<const float *>(c->Adyn.data());     // [r + k*NX]
+    const float *B = reinterpret_cast<const float *>(c->Bdyn.data());     // [r + k*NX]
+    const float *Qi = reinterpret_cast<const float *>(c->Quu_inv.data()); // [r + k*NU]
+    const float *Mm = reinterpret_cast<const float *>(c->AmBKt.data());
+    const float *Pf = reinterpret_cast<const float *>(c->Pinf.data());
+    const size_t n_fwd = (size_t)tmpc::WARP_FWD4 * 32 * 4, n_bwd = (size_t)tmpc::WARP_BWD4 * 32 * 4;
+    const size_t n_x = (size_t)NH * NX, n_u = (size_t)(NH - 1) * NU;
+    const size_t total = n_fwd + n_bwd + NX * NX + NX + 2 * n_x + 2 * n_u;
+    std::vector<float> h(total, 0.f);
+    float *fwd = h.data(), *bwd = fwd + n_fwd, *Pt = bwd + n_bwd, *Qd = Pt + NX * NX;
+    float *xmin = Qd + NX, *xmax = xmin + n_x, *umin = xmax + n_x, *umax = umin + n_u;
+    auto at4 = [](float *base, int group, int lane, int t) -> float & { return base[((size_t)group * 32 + lane) * 4 + t]; };
+    for (int lane = 0; lane < 32; ++lane) {
+        const int ur = lane >> 2, sl = lane & 3;
+        for (int k = 0; k < NX; ++k) {
+            at4(fwd, k / 4, lane, k % 4) = A[lane + k * NX];
+            at4(fwd, 8 + k / 4, lane, k % 4) = K[ur + k * NU];
+            at4(bwd, k / 4, lane, k % 4) = Mm[lane + k * NX];
+        }
+        for (int k = 0; k < NU; ++k) {
+            at4(fwd, 16 + k / 4, lane, k % 4) = B[lane + k * NX];
+            at4(bwd, 8 + k / 4, lane, k % 4) = B[(4 * k + sl) + ur * NX];   // (B^T)(ur, 4k + sl): packet k of SIMD lane sl
+            at4(bwd, 10 + k / 4, lane, k % 4) = Qi[ur + k * NU];
+            at4(bwd, 12 + k / 4, lane, k % 4) = K[k + lane * NU];           // (K^T)(lane, k)
+        }
+    }
+    for (int k = 0; k < NX; ++k)
+        for (int j = 0; j < NX; ++j) Pt[k * NX + j] = Pf[k + j * NX];
+    std::memcpy(Qd, c->Q.data(), NX * sizeof(float));
+    const float inf = std::numeric_limits<float>::infinity();
+    const bool xs = c->en_state && c->has_xb, us = c->en_input && c->has_ub;
+    for (size_t k = 0; k < n_x; ++k) {
+        xmin[k] = xs ? reinterpret_cast<const float *>(c->xmin.data())[k] : -inf;
+        xmax[k] = xs ? reinterpret_cast<const float *>(c->xmax.data())[k] : inf;
+    }
+    for (size_t k = 0; k < n_u; ++k) {
+        umin[k] = us ? reinterpret_cast<const float *>(c->umin.data())[k] : -inf;
+        umax[k] = us ? reinterpret_cast<const float *>(c->umax.data())[k] : inf;
+    }
+    if (c->d_model_w_floats < total) {
+        if (c->d_model_w) cudaFree(c->d_model_w);
+        c->d_model_w = nullptr; c->d_model_w_floats = 0;
+        if (cudaMalloc((void **)&c->d_model_w, total * sizeof(float)) != cudaSuccess) return false;
+        c->d_model_w_floats = total;
+    }
+    // a solve still in flight on the ctx stream may be reading the old image
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+    if (cudaMemcpy(c->d_model_w, h.data(), total * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    float *d = c->d_model_w;
+    tmpc::ModelWarp &m = c->model_w;
+    m.fwd4 = reinterpret_cast<const float4 *>(d);
+    m.bwd4 = reinterpret_cast<const float4 *>(d + n_fwd);
+    m.Pt = d + n_fwd + n_bwd;
+    m.Qd = m.Pt + NX * NX;
+    m.xmin = m.Qd + NX; m.xmax = m.xmin + n_x; m.umin = m.xmax + n_x; m.umax = m.umin + n_u;
+    m.rho = (float)c->rho; m.nrho = -(float)c->rho;
+    m.pri_tol = (float)c->pri; m.dua_tol = (float)c->dua;
+    m.max_iter = c->max_iter; m.check_term = c->check_term;
+    return true;
+}
+
 bool build_model(tmpc_ctx_impl *c)
 {
+    if (c->nx == 32 && c->nu == 8 && c->dtype == TMPC_F32) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return false;
+        if (!build_model_warp(c)) return false;
+        build_model_t<float, 32, 8, 50>(c);   // step kernels
+        return true;
+    }
     if (c->dtype == TMPC_F32 && c->nx == 12 && c->nu == 4 && c->N == 10) build_model_f32<12, 4, 10>(c, c->model_f32);
     const bool f32 = c->dtype == TMPC_F32;
     if (c->nx == 12 && c->nu == 4 && c->N == 10) {
@@ -285,6 +390,12 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
 
+void *model_param(tmpc_ctx_impl *c, const KernelInfo &ki)
+{
+    if (ki.model_kind == 2) return (void *)&c->model_w;
+    return ki.model_kind == 1 ? (void *)c->model_f32.data() : (void *)c->model.data();
+}
+
 // Launch the persistent kernel for one device-resident batch on `s`.
 int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
 {
@@ -295,15 +406,15 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
     CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), s));
     da.counter = c->d_counter;
     da.stats = c->d_counter + 1;
-    long long blocks = (da.batch + ki.block - 1) / ki.block;
+    long long blocks = (da.batch + ki.per_block - 1) / ki.per_block;
     if (blocks > c->sm_count) blocks = c->sm_count;
     if (blocks < 1) blocks = 1;
-    void *params[2] = {ki.model_kind == 1 ? (void *)c->model_f32.data() : (void *)c->model.data(), &da};
+    void *params[2] = {model_param(c, ki), &da};
     if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev0, s));
     CUDA_TRY(c, cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, s));
     if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev1, s));
     c->stats.launches += 1;
-    c->stats.lanes = (int32_t)(blocks * ki.block);
+    c->stats.lanes = (int32_t)(blocks * ki.per_block);
     return TMPC_OK;
 }
 
@@ -475,7 +586,7 @@ int tmpc_create(tmpc_ctx **out, int device, int nx, int nu, int N, int dtype, in
     KernelInfo ki;
     if (!lookup_kernel(nx, nu, N, dtype, order_policy, false, ki)) {
         char b[160];
-        snprintf(b, sizeof b, "shape nx=%d nu=%d N=%d has no compiled sm_100a kernel (have 12/4/10, 4/1/10)", nx, nu, N);
+        snprintf(b, sizeof b, "shape nx=%d nu=%d N=%d has no compiled sm_100a kernel (have 12/4/10, 4/1/10 in f32/f64 and 32/8/50 in f32)", nx, nu, N);
         return fail(nullptr, TMPC_ERR_UNSUPPORTED, b);
     }
     int ndev = 0;
@@ -528,6 +639,7 @@ int tmpc_destroy(tmpc_ctx *ctx)
     if (c->g_copy) cudaStreamDestroy(c->g_copy);
     if (c->g_h2d) cudaEventDestroy(c->g_h2d);
     if (c->d_counter) cudaFree(c->d_counter);
+    if (c->d_model_w) cudaFree(c->d_model_w);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -739,14 +851,14 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
             cudaMemsetAsync(c->d_counter, 0, (k == 0 ? 5 : 1) * sizeof(unsigned long long), st.s);
             da.counter = c->d_counter;
             da.stats = c->d_counter + 1;
-            long long blocks = std::min<long long>((n + ki.block - 1) / ki.block, c->sm_count);
-            void *params[2] = {ki.model_kind == 1 ? (void *)c->model_f32.data() : (void *)c->model.data(), &da};
+            long long blocks = std::min<long long>((n + ki.per_block - 1) / ki.per_block, c->sm_count);
+            void *params[2] = {model_param(c, ki), &da};
             cudaEventRecord(kev[2 * k], st.s);
             cudaError_t e = cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, st.s);
             cudaEventRecord(kev[2 * k + 1], st.s);
             if (e != cudaSuccess) { rc_all = fail(c, TMPC_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e)); break; }
             c->stats.launches += 1;
-            c->stats.lanes = (int32_t)(blocks * ki.block);
+            c->stats.lanes = (int32_t)(blocks * ki.per_block);
         }
         // ---- D2H
         {
@@ -843,6 +955,8 @@ int tmpc_step(tmpc_ctx *ctx, int which, int64_t batch, const tmpc_workspace *ws,
     } else if (c->nx == 4 && c->nu == 1 && c->N == 10) {
         if (f32) go(float(), std::integral_constant<int, 4>(), std::integral_constant<int, 1>(), std::integral_constant<int, 10>());
         else go(double(), std::integral_constant<int, 4>(), std::integral_constant<int, 1>(), std::integral_constant<int, 10>());
+    } else if (c->nx == 32 && c->nu == 8 && c->N == 50 && f32) {
+        go(float(), std::integral_constant<int, 32>(), std::integral_constant<int, 8>(), std::integral_constant<int, 50>());
     } else {
         return fail(c, TMPC_ERR_UNSUPPORTED, "no step kernels for this shape");
     }
