@@ -139,14 +139,15 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                     Bc[4 * g4] = t.x; Bc[4 * g4 + 1] = t.y; Bc[4 * g4 + 2] = t.z; Bc[4 * g4 + 3] = t.w;
                 }
                 float x = x0;
+                // stage operands are fetched one stage ahead (shared-memory state and the global bound rows), so
+                // their latency overlaps the previous stage's Bdyn u chain instead of heading the dependent chain
+                float xmn = __ldg(P.xmin + lane), xmx = __ldg(P.xmax + lane);
+                float umn = __ldg(P.umin + ur), umx = __ldg(P.umax + ur);
+                float g = sg[lane], v = sv[lane], d = sd[ur], y = sy[ur], z = sz[ur];
 #pragma unroll 1
                 for (int i = 0; i < NH - 1; ++i) {
                     xb[lane] = x;
                     __syncwarp();
-                    const float xmn = __ldg(P.xmin + i * WNX + lane), xmx = __ldg(P.xmax + i * WNX + lane);
-                    const float umn = __ldg(P.umin + i * WNU + ur), umx = __ldg(P.umax + i * WNU + ur);
-                    const float g = sg[i * WNX + lane], v = sv[i * WNX + lane];
-                    const float d = sd[i * WNU + ur], y = sy[i * WNU + ur], z = sz[i * WNU + ur];
                     if (xo) xo[i * WNX + lane] = x;
                     // [Kinf(ur,:) ; Adyn(lane,:)] x_i : two sequential chains advancing together as one float2
                     float2 ka;
@@ -186,6 +187,13 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                         if (uo) uo[i * WNU + ur] = u;
                     }
                     __syncwarp();
+                    {   // operands of stage i+1 (the nu-rows of the last stage do not exist: re-read stage i's)
+                        const int in = i + 1, iu = (in < NH - 1) ? in : i;
+                        xmn = __ldg(P.xmin + in * WNX + lane); xmx = __ldg(P.xmax + in * WNX + lane);
+                        umn = __ldg(P.umin + iu * WNU + ur); umx = __ldg(P.umax + iu * WNU + ur);
+                        g = sg[in * WNX + lane]; v = sv[in * WNX + lane];
+                        d = sd[iu * WNU + ur]; y = sy[iu * WNU + ur]; z = sz[iu * WNU + ur];
+                    }
                     // x_{i+1} = Adyn x_i + Bdyn u_i                                                     :35
                     const float4 u0 = ub4[0], u1 = ub4[1];
                     const float us[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
@@ -204,8 +212,6 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                 }
                 {   // last stage: state slack / dual only
                     constexpr int i = NH - 1;
-                    const float xmn = __ldg(P.xmin + i * WNX + lane), xmx = __ldg(P.xmax + i * WNX + lane);
-                    const float g = sg[i * WNX + lane], v = sv[i * WNX + lane];
                     if (xo) xo[i * WNX + lane] = x;
                     float t = __fadd_rn(x, g);
                     t = fminf(xmx, fmaxf(xmn, t));
@@ -257,11 +263,12 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                     if constexpr (FAST) p = __fmaf_rn(P.nrho, dvg, pn);
                     else p = __fsub_rn(pn, __fmul_rn(P.rho, dvg));                                     // :84
                 }
+                // stage operands one stage ahead, as in the forward sweep
+                float z = sz[(NH - 2) * WNU + ur], y = sy[(NH - 2) * WNU + ur];
+                float v = sv[(NH - 2) * WNX + lane], g = sg[(NH - 2) * WNX + lane];
+                float xr = __ldg(xref + (NH - 2) * WNX + lane);
 #pragma unroll 1
                 for (int i = NH - 2; i >= 0; --i) {
-                    const float z = sz[i * WNU + ur], y = sy[i * WNU + ur];
-                    const float v = sv[i * WNX + lane], g = sg[i * WNX + lane];
-                    const float xr = __ldg(xref + i * WNX + lane);
                     const float r = __fmul_rn(P.nrho, __fsub_rn(z, y));                                // :80
                     xb[lane] = p;
                     if (uw) ub[ur] = r;
@@ -302,6 +309,12 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                     if constexpr (FAST) q = __fmaf_rn(P.nrho, dvg, cq);
                     else q = __fsub_rn(cq, __fmul_rn(P.rho, dvg));                                     // :82
                     __syncwarp();
+                    {   // operands of stage i-1
+                        const int ip = (i > 0) ? i - 1 : 0;
+                        z = sz[ip * WNU + ur]; y = sy[ip * WNU + ur];
+                        v = sv[ip * WNX + lane]; g = sg[ip * WNX + lane];
+                        xr = __ldg(xref + ip * WNX + lane);
+                    }
                     // d_i = Quu_inv (Bdyn^T p_{i+1} + r_i)                                              :19
                     const float4 s0 = sb4[0], s1 = sb4[1];
                     const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};

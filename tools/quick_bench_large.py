@@ -1,3 +1,5 @@
+"""Quick device-resident timing of the warp-per-instance kernel on BASELINE config 5 (development helper).
+usage: quick_bench_large.py [B] [parity,fast] [cold,warm]"""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, "/root/repo")
@@ -32,6 +34,8 @@ def run(policy, B, warm_pass):
     ms, iters = best["kernel_ms"], best["iterations"]
     print("%-6s large %s B=%d: %.3f ms  %.3e solves/s  %.3e it/s  mean it %.2f solved %.3f  %.2f TFLOP/s" % (policy, "warm" if warm_pass else "cold", B, ms, B / ms * 1e3, iters / ms * 1e3, iters / B, best["solved"] / B, iters * 344058 / ms * 1e3 / 1e12), flush=True)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
-for pol in ("parity", "fast"):
-    run(pol, B, False)
-    run(pol, B, True)
+pols = sys.argv[2].split(",") if len(sys.argv) > 2 else ("parity", "fast")
+modes = sys.argv[3].split(",") if len(sys.argv) > 3 else ("cold", "warm")
+for pol in pols:
+    for m in modes:
+        run(pol, B, m == "warm")
