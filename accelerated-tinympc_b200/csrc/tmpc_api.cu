@@ -34,6 +34,7 @@ struct tmpc_ctx_impl {
     int device = 0;
     int nx = 0, nu = 0, N = 0, dtype = 0, policy = 0;
     bool has_model = false;
+    int pattern = 0;  // structural-sparsity specialisation the current model conforms to (0 = dense)
     bool warm_variant_ready = false;
     std::string err;
     cudaStream_t stream = nullptr;
@@ -108,11 +109,11 @@ KernelInfo make_info()
     return k;
 }
 
-template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM>
+template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT>
 KernelInfo make_info_f32()
 {
     KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM>;
+    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM, PAT>;
     k.smem = tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES;
     k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::ModelF32<NX, NU, NH>);
@@ -143,13 +144,13 @@ bool pick_warp(int policy, bool warm, KernelInfo &out)
     return true;
 }
 
-template <int NX, int NU, int NH, int BLOCK, bool TM>
+template <int NX, int NU, int NH, int BLOCK, bool TM, class PAT = tmpc::PatDense<NX>>
 bool pick_f32(int policy, bool warm, KernelInfo &out)
 {
     if (policy == TMPC_ORDER_PARITY)
-        out = warm ? make_info_f32<NX, NU, NH, BLOCK, false, true, TM>() : make_info_f32<NX, NU, NH, BLOCK, false, false, TM>();
+        out = warm ? make_info_f32<NX, NU, NH, BLOCK, false, true, TM, PAT>() : make_info_f32<NX, NU, NH, BLOCK, false, false, TM, PAT>();
     else
-        out = warm ? make_info_f32<NX, NU, NH, BLOCK, true, true, TM>() : make_info_f32<NX, NU, NH, BLOCK, true, false, TM>();
+        out = warm ? make_info_f32<NX, NU, NH, BLOCK, true, true, TM, PAT>() : make_info_f32<NX, NU, NH, BLOCK, true, false, TM, PAT>();
     return true;
 }
 
@@ -178,11 +179,14 @@ bool pick(int policy, bool warm, KernelInfo &out)
 // Compiled shapes.  Thread-per-instance needs the per-instance state to fit shared memory:
 //   quadrotor 12/4/10: 360 scalars -> 128 threads (f32) / 64 threads (f64) per SM
 //   cartpole   4/1/10: 111 scalars -> 256 threads (f32) / 128 (f64)
-bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out)
+bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out, int pattern = 0)
 {
     if (nx == 12 && nu == 4 && N == 10) {
         if (dtype == TMPC_F32) {
             const int v = kernel_variant();
+            // model-structure specialisation (tmpc_kernel_f32.cuh PatQuadrotor): chosen by build_model when the
+            // actual matrices conform
+            if (v == 2 && pattern == tmpc::PatQuadrotor::id) return pick_f32<12, 4, 10, 256, true, tmpc::PatQuadrotor>(policy, warm, out);
             if (v == 2) return pick_f32<12, 4, 10, 256, true>(policy, warm, out);   // g,v in TMEM: 256 instances / SM
             if (v == 1) return pick_f32<12, 4, 10, 128, false>(policy, warm, out);  // all state in shared memory
             return pick<float, 12, 4, 10, 128, false>(policy, warm, out);
@@ -281,6 +285,21 @@ template <int NX, int NU, int NH> void build_model_f32(tmpc_ctx_impl *c, std::ve
     m->dua_tol = (float)c->dua;
     m->max_iter = c->max_iter;
     m->check_term = c->check_term;
+    // does the model conform to a compiled structural pattern?  Every coefficient the pattern drops must be an
+    // exact zero, every multiply it skips an exact one.  TMPC_DENSE=1 forces the dense instance.
+    c->pattern = 0;
+    if constexpr (NX == 12 && NU == 4) {
+        using PQ = tmpc::PatQuadrotor;
+        bool ok = !getenv("TMPC_DENSE");
+        for (int r = 0; r < NX && ok; ++r)
+            for (int k = 0; k < NX && ok; ++k) {
+                const float a = A[r + k * NX], mm = Mm[r + k * NX];
+                if (!((PQ::a_nz[r] >> k) & 1u) && a != 0.f) ok = false;
+                if (((PQ::a_one[r] >> k) & 1u) && a != 1.f) ok = false;
+                if (!((PQ::m_nz[r] >> k) & 1u) && mm != 0.f) ok = false;
+            }
+        if (ok) c->pattern = PQ::id;
+    }
 }
 
 // lane-major coefficient image of the warp-per-instance kernel (layout: tmpc_kernel_warp.cuh ModelWarp)
@@ -400,7 +419,7 @@ void *model_param(tmpc_ctx_impl *c, const KernelInfo &ki)
 int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
 {
     KernelInfo ki;
-    if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki))
+    if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern))
         return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
     CUDA_TRY(c, cudaFuncSetAttribute(ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
     CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), s));
@@ -415,6 +434,7 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
     if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev1, s));
     c->stats.launches += 1;
     c->stats.lanes = (int32_t)(blocks * ki.per_block);
+    c->stats.pattern = c->pattern;
     return TMPC_OK;
 }
 
@@ -845,7 +865,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
         cudaEventCreate(&kev[2 * k + 1]);
         {
             KernelInfo ki;
-            lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki);
+            lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern);
             cudaFuncSetAttribute(ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem);
             // stats accumulate over chunks; only the work counter is reset per chunk
             cudaMemsetAsync(c->d_counter, 0, (k == 0 ? 5 : 1) * sizeof(unsigned long long), st.s);
@@ -859,6 +879,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
             if (e != cudaSuccess) { rc_all = fail(c, TMPC_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e)); break; }
             c->stats.launches += 1;
             c->stats.lanes = (int32_t)(blocks * ki.per_block);
+            c->stats.pattern = c->pattern;
         }
         // ---- D2H
         {

@@ -193,6 +193,90 @@ __device__ __forceinline__ void matvec2(const float *c, const float (&x)[K], flo
     }
 }
 
+
+// ---- structural sparsity of the model, known at compile time -------------------------------------------------
+// A term whose coefficient is exactly zero contributes +-0 to its sum, and adding +-0 is the identity on every
+// non-zero partial sum, so dropping it leaves every VALUE of the reference computation unchanged (only the sign of
+// an exactly-zero result can differ; finite data, as everywhere on this path).  A coefficient that is exactly 1
+// needs no multiply.  The pattern is a compile-time property of the kernel instance; tmpc_set_model() checks the
+// actual matrices against it and falls back to the dense instance when they do not conform.
+//   a_nz[r] bit k : Adyn(r,k) may be non-zero      a_one[r] bit k : Adyn(r,k) == 1 exactly
+//   m_nz[r] bit k : AmBKt(r,k) may be non-zero
+template <int NX> struct PatDense {
+    static constexpr bool sparse = false;
+    static constexpr int id = 0;
+};
+// Linearised quadrotor of the reference's examples (problem_data/quadrotor_*hz_params.hpp): Adyn = I + 14 couplings;
+// the shipped 7-decimal AmBKt has the z / vz rows and columns decoupled.
+struct PatQuadrotor {
+    static constexpr bool sparse = true;
+    static constexpr int id = 1;
+    static constexpr uint32_t a_nz[12] = {0x451, 0x28a, 0x104, 0x208, 0x410, 0x820, 0x450, 0x288, 0x100, 0x200, 0x400, 0x800};
+    static constexpr uint32_t a_one[12] = {0x001, 0x002, 0x004, 0x008, 0x010, 0x020, 0x040, 0x080, 0x100, 0x200, 0x400, 0x800};
+    static constexpr uint32_t m_nz[12] = {0xefb, 0xefb, 0x104, 0xefb, 0xefb, 0xefb, 0xefb, 0xefb, 0x104, 0xefb, 0xefb, 0xefb};
+};
+
+__host__ __device__ constexpr bool bits_any(uint32_t m, int s, int len) { return ((m >> s) & ((len >= 32) ? 0xffffffffu : ((1u << len) - 1u))) != 0; }
+
+// sequential order (acc = e_0; acc = e_k + acc) over the non-zero terms of one row
+template <uint32_t NZ, uint32_t ONE, int K, int KEND, bool STARTED, bool FAST, class C, class X>
+__device__ __forceinline__ float sp_seq(const C &c, const X &x, float acc)
+{
+    if constexpr (K == KEND) {
+        return STARTED ? acc : 0.f;
+    } else if constexpr (((NZ >> K) & 1u) == 0u) {
+        return sp_seq<NZ, ONE, K + 1, KEND, STARTED, FAST>(c, x, acc);
+    } else {
+        constexpr bool one = ((ONE >> K) & 1u) != 0u;
+        if constexpr (!STARTED) acc = one ? x(K) : __fmul_rn(c(K), x(K));
+        else if constexpr (one) acc = __fadd_rn(x(K), acc);
+        else if constexpr (FAST) acc = __fmaf_rn(c(K), x(K), acc);
+        else acc = __fadd_rn(__fmul_rn(c(K), x(K)), acc);
+        return sp_seq<NZ, ONE, K + 1, KEND, true, FAST>(c, x, acc);
+    }
+}
+// scalar tree order (recursive half split) over the non-zero terms of one row; precondition: some bit of NZ in [S, S+LEN)
+template <uint32_t NZ, int S, int LEN, class E> __device__ __forceinline__ float sp_tree(const E &e)
+{
+    if constexpr (LEN == 1) {
+        return e(S);
+    } else {
+        constexpr int H = LEN / 2;
+        constexpr bool la = bits_any(NZ, S, H), lb = bits_any(NZ, S + H, LEN - H);
+        if constexpr (la && lb) return __fadd_rn(sp_tree<NZ, S, H>(e), sp_tree<NZ, S + H, LEN - H>(e));
+        else if constexpr (la) return sp_tree<NZ, S, H>(e);
+        else return sp_tree<NZ, S + H, LEN - H>(e);
+    }
+}
+// row R of a sparse mat-vec: c(k) coefficient, x(k) input
+template <int ORD, uint32_t NZ, uint32_t ONE, int K, bool FAST, class C, class X>
+__device__ __forceinline__ float sp_row(const C &c, const X &x)
+{
+    if constexpr (!bits_any(NZ, 0, K)) return 0.f;
+    else if constexpr (FAST || ORD == ORD_SEQ) return sp_seq<NZ, ONE, 0, K, false, FAST>(c, x, 0.f);
+    else {
+        static_assert(ORD == ORD_TREE, "sparse rows: sequential or scalar-tree order");
+        return sp_tree<NZ, 0, K>([&](int k) { return __fmul_rn(c(k), x(k)); });
+    }
+}
+// all rows of a sparse mat-vec, resolved at compile time
+template <int ORD, class MASKS, int R, int NR, int K, bool FAST, class CF, class X>
+__device__ __forceinline__ void sp_rows(const CF &cf, const X &x, float (&out)[NR])
+{
+    if constexpr (R < NR) {
+        out[R] = sp_row<ORD, MASKS::nz(R), MASKS::one(R), K, FAST>([&](int k) { return cf(R, k); }, x);
+        sp_rows<ORD, MASKS, R + 1, NR, K, FAST>(cf, x, out);
+    }
+}
+template <class PAT> struct MaskA {
+    __host__ __device__ static constexpr uint32_t nz(int r) { return PAT::a_nz[r]; }
+    __host__ __device__ static constexpr uint32_t one(int r) { return PAT::a_one[r]; }
+};
+template <class PAT> struct MaskM {
+    __host__ __device__ static constexpr uint32_t nz(int r) { return PAT::m_nz[r]; }
+    __host__ __device__ static constexpr uint32_t one(int) { return 0u; }
+};
+
 template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
     using SU = SVec<float, NU, NH - 1, BLOCK>;
     using SP = SVec<float, NX, 1, BLOCK>;
@@ -200,7 +284,7 @@ template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
     static constexpr size_t BYTES = 3 * SU::BYTES + SP::BYTES + XBYTES + 16;
 };
 
-template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM>
+template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT = PatDense<NX>>
 __global__ void __launch_bounds__(BLOCK, 1)
 admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_constant__ SolveArgs<float> a)
 {
@@ -364,7 +448,18 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 sd.load(i, d); sy.load(i, y); sz.load(i, z);
                 // [K;A] x_i in one column sweep
                 float2 ka[RS / 2];
-                if constexpr (O::Kx == ORD_SEQ && O::Ax == ORD_SEQ) {
+                if constexpr (PAT::sparse) {
+                    // Kinf x_i dense (packed row pairs), Adyn x_i over its non-zero terms only
+                    float2 kk[NU / 2];
+                    float aa[NX];
+                    matvec2<O::Kx, NU, NX, RS, 0, FAST>(P.KA, x, kk);
+                    sp_rows<O::Ax, MaskA<PAT>, 0, NX, NX, FAST>([&](int r, int k) { return P.KA[k * RS + NU + r]; },
+                                                                  [&](int k) { return x[k]; }, aa);
+#pragma unroll
+                    for (int j = 0; j < NU / 2; ++j) ka[j] = kk[j];
+#pragma unroll
+                    for (int j = 0; j < NX / 2; ++j) ka[NU / 2 + j] = f2(aa[2 * j], aa[2 * j + 1]);
+                } else if constexpr (O::Kx == ORD_SEQ && O::Ax == ORD_SEQ) {
                     matvec2<ORD_SEQ, RS, NX, RS, 0, FAST>(P.KA, x, ka);
                 } else {
                     float2 kk[NU / 2], aa[NX / 2];
@@ -488,7 +583,17 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 for (int j = 0; j < NU; ++j) r[j] = __fmul_rn(P.nrho, __fsub_rn(z[j], y[j]));        // :80
                 // [B^T ; AmBKt] p_{i+1}
                 float2 bm[RS / 2];
-                if constexpr (FAST) {
+                if constexpr (PAT::sparse) {
+                    float2 bb[NU / 2];
+                    float mm[NX];
+                    matvec2<O::Btp, NU, NX, RS, 0, FAST>(P.BM, p, bb);
+                    sp_rows<O::Mp, MaskM<PAT>, 0, NX, NX, FAST>([&](int r, int k) { return P.BM[k * RS + NU + r]; },
+                                                                  [&](int k) { return p[k]; }, mm);
+#pragma unroll
+                    for (int j = 0; j < NU / 2; ++j) bm[j] = bb[j];
+#pragma unroll
+                    for (int j = 0; j < NX / 2; ++j) bm[NU / 2 + j] = f2(mm[2 * j], mm[2 * j + 1]);
+                } else if constexpr (FAST) {
                     matvec2<ORD_SEQ, RS, NX, RS, 0, true>(P.BM, p, bm);
                 } else {
                     float2 bb[NU / 2], mm[NX / 2];

@@ -115,6 +115,9 @@ typedef struct {
     int32_t lanes;            /* resident instance slots (threads) the kernel ran with */
     float kernel_ms;          /* device time of those kernels (CUDA events on the launching stream) */
     int32_t parity_pinned;    /* 1 if this shape's evaluation order is verified against the reference */
+    int32_t pattern;          /* model-structure specialisation the kernel ran with: 0 dense, 1 quadrotor (exact zeros
+                                 and ones of Adyn / AmBKt dropped; value-identical results) */
+    int32_t reserved_;
 } tmpc_stats;
 
 /* Statistics of the last tmpc_solve on this ctx (synchronises the ctx's stream). */

@@ -66,3 +66,43 @@ def test_fast_policy_statistical_parity(pkg, oracle):
     scale = np.maximum(np.abs(ref.x[same]).max(), 1.0)
     assert np.abs(out["x"][same] - ref.x[same]).max() / scale <= 1e-4
     assert np.abs(out["u"][same] - ref.u[same]).max() <= 1e-4
+
+
+def test_structure_specialisation_and_dense_fallback(pkg, oracle, monkeypatch):
+    """The quadrotor model conforms to the compiled structural pattern (exact zeros / ones of Adyn and AmBKt are
+    dropped): results must equal the oracle's, the dense instance's, and a model that does not conform must fall
+    back to the dense instance on its own."""
+    import copy
+    prob = pkg.problems.quadrotor(20)
+    B = 4000
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.5)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=np.float32, nthreads=8)
+    for policy in ("parity", "fast"):
+        s = pkg.capi.Solver(prob, dtype=np.float32, policy=policy)
+        out = s.solve(x0, xref)
+        assert s.stats()["pattern"] == 1
+        monkeypatch.setenv("TMPC_DENSE", "1")
+        sd = pkg.capi.Solver(prob, dtype=np.float32, policy=policy)
+        outd = sd.solve(x0, xref)
+        monkeypatch.delenv("TMPC_DENSE")
+        assert sd.stats()["pattern"] == 0
+        if policy == "parity":
+            _cmp_exact(out, ref)
+            _cmp_exact(outd, ref)
+        else:
+            same = out["iter"] == outd["iter"]
+            assert same.mean() >= 0.95
+            assert np.abs(out["x"][same] - outd["x"][same]).max() <= 1e-4
+    p2 = copy.deepcopy(prob)
+    p2.Adyn = p2.Adyn.copy(); p2.Adyn[0, 1] = 1e-3          # breaks the pattern (cache kept: still a valid ADMM run)
+    ref2 = oracle.solve_batch(p2, x0[:1500], xref, dtype=np.float32, nthreads=8)
+    s2 = pkg.capi.Solver(p2, dtype=np.float32, policy="parity")
+    out2 = s2.solve(x0[:1500], xref)
+    assert s2.stats()["pattern"] == 0
+    _cmp_exact(out2, ref2)
+    # warm-start variant of the specialised instance
+    warm = {k: np.zeros((B, prob.N - 1, prob.nu) if k in "dyz" else (B, prob.N, prob.nx), np.float32) for k in ("d", "y", "g", "v", "z")}
+    r1 = oracle.solve_batch(prob, x0, xref, dtype=np.float32, want_state=True, nthreads=8)
+    o1 = pkg.capi.Solver(prob, dtype=np.float32, policy="parity").solve(x0, xref, warm=warm)
+    for k in warm:
+        assert_same(o1["warm"][k], r1.state[k], "warm." + k)
