@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtmpc_cuda.so")
+LIB_PATH = os.environ.get("TMPC_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtmpc_cuda.so")
 
 TMPC_F32, TMPC_F64 = 0, 1
 TMPC_ORDER_PARITY, TMPC_ORDER_FAST = 0, 1

@@ -256,11 +256,35 @@ template <int NX, int NU, int NH> void build_model_f32(tmpc_ctx_impl *c, std::ve
     const float *Qi = reinterpret_cast<const float *>(c->Quu_inv.data());
     const float *Mm = reinterpret_cast<const float *>(c->AmBKt.data());
     const float *Pf = reinterpret_cast<const float *>(c->Pinf.data());
+    // does the model conform to a compiled structural pattern?  Every coefficient the pattern drops must be an
+    // exact zero, every multiply it skips an exact one.  TMPC_DENSE=1 forces the dense instance.
+    c->pattern = 0;
+    int mperm[NX];
+    for (int r = 0; r < NX; ++r) mperm[r] = r;
+    if constexpr (NX == 12 && NU == 4) {
+        using PQ = tmpc::PatQuadrotor;
+        bool ok = !getenv("TMPC_DENSE");
+        for (int r = 0; r < NX && ok; ++r)
+            for (int k = 0; k < NX && ok; ++k) {
+                const float a = A[r + k * NX], mm = Mm[r + k * NX];
+                if (!((PQ::a_nz[r] >> k) & 1u) && a != 0.f) ok = false;
+                if (((PQ::a_one[r] >> k) & 1u) && a != 1.f) ok = false;
+                if (!((PQ::m_nz[r] >> k) & 1u) && mm != 0.f) ok = false;
+            }
+        for (int j = 0; j < NX / 2 && ok; ++j)   // the pair masks must cover both rows of each pair
+            for (int h = 0; h < 2; ++h)
+                if (PQ::m_nz[PQ::m_perm[2 * j + h]] & ~PQ::m_pair_nz[j]) ok = false;
+        if (ok) {
+            c->pattern = PQ::id;
+            for (int r = 0; r < NX; ++r) mperm[r] = PQ::m_perm[r];   // AmBKt rows stored in pair order
+        }
+    }
+    m->nz2 = make_float2(-0.0f, -0.0f);
     for (int k = 0; k < NX; ++k) {
         for (int r = 0; r < NU; ++r) m->KA[k * RS + r] = K[r + k * NU];
         for (int r = 0; r < NX; ++r) m->KA[k * RS + NU + r] = A[r + k * NX];
         for (int r = 0; r < NU; ++r) m->BM[k * RS + r] = B[k + r * NX];       // (B^T)(r,k)
-        for (int r = 0; r < NX; ++r) m->BM[k * RS + NU + r] = Mm[r + k * NX];
+        for (int r = 0; r < NX; ++r) m->BM[k * RS + NU + r] = Mm[mperm[r] + k * NX];
         for (int j = 0; j < NX; ++j) m->Pt[k * NX + j] = Pf[k + j * NX];      // Pinf(k,j)
     }
     for (int k = 0; k < NU; ++k) {
@@ -285,21 +309,6 @@ template <int NX, int NU, int NH> void build_model_f32(tmpc_ctx_impl *c, std::ve
     m->dua_tol = (float)c->dua;
     m->max_iter = c->max_iter;
     m->check_term = c->check_term;
-    // does the model conform to a compiled structural pattern?  Every coefficient the pattern drops must be an
-    // exact zero, every multiply it skips an exact one.  TMPC_DENSE=1 forces the dense instance.
-    c->pattern = 0;
-    if constexpr (NX == 12 && NU == 4) {
-        using PQ = tmpc::PatQuadrotor;
-        bool ok = !getenv("TMPC_DENSE");
-        for (int r = 0; r < NX && ok; ++r)
-            for (int k = 0; k < NX && ok; ++k) {
-                const float a = A[r + k * NX], mm = Mm[r + k * NX];
-                if (!((PQ::a_nz[r] >> k) & 1u) && a != 0.f) ok = false;
-                if (((PQ::a_one[r] >> k) & 1u) && a != 1.f) ok = false;
-                if (!((PQ::m_nz[r] >> k) & 1u) && mm != 0.f) ok = false;
-            }
-        if (ok) c->pattern = PQ::id;
-    }
 }
 
 // lane-major coefficient image of the warp-per-instance kernel (layout: tmpc_kernel_warp.cuh ModelWarp)

@@ -30,12 +30,43 @@ template <int NX, int NU, int NH> struct alignas(16) ModelF32 {
     float umin[(NH - 1) * NU], umax[(NH - 1) * NU];
     float rho, nrho, pri_tol, dua_tol;
     int max_iter, check_term;
+    float2 nz2;          // (-0.f, -0.f), opaque to the compiler: addend of the exactly-rounded packed product (prod2)
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+// Exactly rounded PAIR of products in one FMA-pipe instruction.  sm_100 has no packed multiply that survives ptxas:
+// mul.rn.f32x2 followed by add.rn.f32x2 is contracted into FFMA2 (tools/ubench_fp32.cu), which would break the
+// reference's "round the product, then round the sum".  fma(a, b, -0) rounds the exact product once and adding -0
+// changes neither value nor sign, so with Z = (-0, -0) read from the kernel parameters (unknown to the compiler, hence
+// neither folded nor contracted into the following add) FFMA2 R, R.F32, UR.F32x2, Z IS the packed multiply.
+__device__ __forceinline__ float2 prod2(float2 a, float2 b, float2 Z) { return __ffma2_rn(a, b, Z); }
+// Where the packed product is used (tuning switches).  Measured on B200, 1,048,576 hover instances, PARITY, quadrotor
+// pattern (gpurun_out/variants_v6.log): DENSE/M/ELT = 1/1/1 12.69 ms, 0/0/0 11.40, 0/0/1 11.36, 0/1/0 11.28, 0/1/1 11.37.
+// FFMA2 occupies the FMA pipe for two cycles like the two FMULs it replaces, and its coefficient PAIR has to come
+// through LDC.64 into registers where FMUL takes the coefficient straight from the constant bank (FMUL R,R,c[][] /
+// UR), so the packed product does not pay for the dense mat-vecs; it does for the paired AmBKt rows.
+#ifndef TMPC_PROD2_DENSE
+#define TMPC_PROD2_DENSE 0   // dense row-pair mat-vecs
+#endif
+#ifndef TMPC_PROD2_M
+#define TMPC_PROD2_M 1       // AmBKt rows of a structural pattern evaluated as pairs (else row by row, scalar)
+#endif
+#ifndef TMPC_PROD2_ELT
+#define TMPC_PROD2_ELT 0     // element-wise products of update_linear_cost
+#endif
+__device__ __forceinline__ float2 prodd(float2 c, float x, float2 Z)
+{
+    if constexpr (TMPC_PROD2_DENSE) return prod2(c, f2(x, x), Z);
+    else return f2(__fmul_rn(c.x, x), __fmul_rn(c.y, x));
+}
+__device__ __forceinline__ float2 prode(float2 a, float2 b, float2 Z)
+{
+    if constexpr (TMPC_PROD2_ELT) return prod2(a, b, Z);
+    else return f2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+}
 
 // ---- TMEM scratch (per-thread columns) -------------------------------------------------------------
 __device__ __forceinline__ void tm_ld8(uint32_t a, float *r)
@@ -159,7 +190,7 @@ template <int ORD, int K, class E> __device__ __forceinline__ float2 reduce2(con
 
 // out2[j] (row pair j of R rows) = sum_k c[k*RS + R0 + 2j .. +1] * x[k], rows R0..R0+R-1 of a stacked matrix
 template <int ORD, int R, int K, int RS, int R0, bool FAST>
-__device__ __forceinline__ void matvec2(const float *c, const float (&x)[K], float2 (&out)[R / 2])
+__device__ __forceinline__ void matvec2(const float *c, const float (&x)[K], float2 (&out)[R / 2], const float2 Z)
 {
     static_assert(R % 2 == 0, "row pairs");
     if constexpr (FAST) {
@@ -173,12 +204,12 @@ __device__ __forceinline__ void matvec2(const float *c, const float (&x)[K], flo
     } else if constexpr (ORD == ORD_SEQ) {
         // column sweep: all rows advance together, one coefficient column (R adjacent values) per step
 #pragma unroll
-        for (int j = 0; j < R / 2; ++j) out[j] = f2(__fmul_rn(c[R0 + 2 * j], x[0]), __fmul_rn(c[R0 + 2 * j + 1], x[0]));
+        for (int j = 0; j < R / 2; ++j) out[j] = prodd(f2(c[R0 + 2 * j], c[R0 + 2 * j + 1]), x[0], Z);
 #pragma unroll
         for (int k = 1; k < K; ++k)
 #pragma unroll
             for (int j = 0; j < R / 2; ++j)
-                out[j] = add2(f2(__fmul_rn(c[k * RS + R0 + 2 * j], x[k]), __fmul_rn(c[k * RS + R0 + 2 * j + 1], x[k])), out[j]);
+                out[j] = add2(prodd(f2(c[k * RS + R0 + 2 * j], c[k * RS + R0 + 2 * j + 1]), x[k], Z), out[j]);
     } else {
         // tree orders need all K products of a row before the first add: go 2 row pairs (4 rows = one LDCU.128 per k) at a time
 #pragma unroll
@@ -186,7 +217,7 @@ __device__ __forceinline__ void matvec2(const float *c, const float (&x)[K], flo
 #pragma unroll
             for (int jj = 0; jj < 2 && j0 + jj < R / 2; ++jj) {
                 const int j = j0 + jj;
-                auto e = [&](int k) { return f2(__fmul_rn(c[k * RS + R0 + 2 * j], x[k]), __fmul_rn(c[k * RS + R0 + 2 * j + 1], x[k])); };
+                auto e = [&](int k) { return prodd(f2(c[k * RS + R0 + 2 * j], c[k * RS + R0 + 2 * j + 1]), x[k], Z); };
                 out[j] = reduce2<ORD, K>(e);
             }
         }
@@ -214,6 +245,10 @@ struct PatQuadrotor {
     static constexpr uint32_t a_nz[12] = {0x451, 0x28a, 0x104, 0x208, 0x410, 0x820, 0x450, 0x288, 0x100, 0x200, 0x400, 0x800};
     static constexpr uint32_t a_one[12] = {0x001, 0x002, 0x004, 0x008, 0x010, 0x020, 0x040, 0x080, 0x100, 0x200, 0x400, 0x800};
     static constexpr uint32_t m_nz[12] = {0xefb, 0xefb, 0x104, 0xefb, 0xefb, 0xefb, 0xefb, 0xefb, 0x104, 0xefb, 0xefb, 0xefb};
+    // AmBKt rows are evaluated as PAIRS (one FFMA2 + one FADD2 per term for two rows): m_perm lists the rows in pair
+    // order (the host stores the AmBKt part of the stacked image in this row order), rows of a pair share a mask
+    static constexpr int m_perm[12] = {0, 1, 3, 9, 4, 5, 6, 7, 10, 11, 2, 8};
+    static constexpr uint32_t m_pair_nz[6] = {0xefb, 0xefb, 0xefb, 0xefb, 0xefb, 0x104};
 };
 
 __host__ __device__ constexpr bool bits_any(uint32_t m, int s, int len) { return ((m >> s) & ((len >= 32) ? 0xffffffffu : ((1u << len) - 1u))) != 0; }
@@ -268,9 +303,66 @@ __device__ __forceinline__ void sp_rows(const CF &cf, const X &x, float (&out)[N
         sp_rows<ORD, MASKS, R + 1, NR, K, FAST>(cf, x, out);
     }
 }
+// the same for a PAIR of rows that share a mask: e(k) = float2 of exactly rounded products
+template <uint32_t NZ, int S, int LEN, class E> __device__ __forceinline__ float2 sp_tree2(const E &e)
+{
+    if constexpr (LEN == 1) {
+        return e(S);
+    } else {
+        constexpr int H = LEN / 2;
+        constexpr bool la = bits_any(NZ, S, H), lb = bits_any(NZ, S + H, LEN - H);
+        if constexpr (la && lb) return add2(sp_tree2<NZ, S, H>(e), sp_tree2<NZ, S + H, LEN - H>(e));
+        else if constexpr (la) return sp_tree2<NZ, S, H>(e);
+        else return sp_tree2<NZ, S + H, LEN - H>(e);
+    }
+}
+template <uint32_t NZ, int K, int KEND, bool STARTED, bool FAST, class C2, class X>
+__device__ __forceinline__ float2 sp_seq2(const C2 &c2, const X &x, float2 acc, const float2 Z)
+{
+    if constexpr (K == KEND) {
+        return STARTED ? acc : f2(0.f, 0.f);
+    } else if constexpr (((NZ >> K) & 1u) == 0u) {
+        return sp_seq2<NZ, K + 1, KEND, STARTED, FAST>(c2, x, acc, Z);
+    } else {
+        if constexpr (!STARTED) acc = FAST ? __fmul2_rn(c2(K), f2(x(K), x(K))) : prod2(c2(K), f2(x(K), x(K)), Z);
+        else if constexpr (FAST) acc = __ffma2_rn(c2(K), f2(x(K), x(K)), acc);
+        else acc = add2(prod2(c2(K), f2(x(K), x(K)), Z), acc);
+        return sp_seq2<NZ, K + 1, KEND, true, FAST>(c2, x, acc, Z);
+    }
+}
+// AmBKt p over row pairs in PAT::m_perm order; out[] in NATURAL row order.  c2(j, k) = coefficient pair of pair j
+template <int ORD, class PAT, int J, int NX, bool FAST, class CF2, class X>
+__device__ __forceinline__ void sp_pairs_m(const CF2 &cf2, const X &x, float (&out)[NX], const float2 Z)
+{
+    if constexpr (J < NX / 2) {
+        constexpr uint32_t NZ = PAT::m_pair_nz[J];
+        float2 r;
+        if constexpr (!bits_any(NZ, 0, NX)) r = f2(0.f, 0.f);
+        else if constexpr (FAST || ORD == ORD_SEQ)
+            r = sp_seq2<NZ, 0, NX, false, FAST>([&](int k) { return cf2(J, k); }, x, f2(0.f, 0.f), Z);
+        else {
+            static_assert(ORD == ORD_TREE, "sparse row pairs: sequential or scalar-tree order");
+            r = sp_tree2<NZ, 0, NX>([&](int k) { return prod2(cf2(J, k), f2(x(k), x(k)), Z); });
+        }
+        out[PAT::m_perm[2 * J]] = r.x;
+        out[PAT::m_perm[2 * J + 1]] = r.y;
+        sp_pairs_m<ORD, PAT, J + 1, NX, FAST>(cf2, x, out, Z);
+    }
+}
 template <class PAT> struct MaskA {
     __host__ __device__ static constexpr uint32_t nz(int r) { return PAT::a_nz[r]; }
     __host__ __device__ static constexpr uint32_t one(int r) { return PAT::a_one[r]; }
+};
+template <class PAT, int R, int NX> __device__ __forceinline__ void unpermute_m(const float (&in)[NX], float (&out)[NX])
+{
+    if constexpr (R < NX) {
+        out[PAT::m_perm[R]] = in[R];
+        unpermute_m<PAT, R + 1, NX>(in, out);
+    }
+}
+template <class PAT> struct MaskMP {   // AmBKt rows in the stored (pair) order
+    __host__ __device__ static constexpr uint32_t nz(int r) { return PAT::m_nz[PAT::m_perm[r]]; }
+    __host__ __device__ static constexpr uint32_t one(int) { return 0u; }
 };
 template <class PAT> struct MaskM {
     __host__ __device__ static constexpr uint32_t nz(int r) { return PAT::m_nz[r]; }
@@ -292,6 +384,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
     using O = Orders<float, NX, NU>;
     using L = SmemLayoutF32<NX, NU, NH, BLOCK, TM>;
     constexpr int RS = NU + NX;
+    const float2 Z = P.nz2;   // (-0, -0): see prod2
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -452,7 +545,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     // Kinf x_i dense (packed row pairs), Adyn x_i over its non-zero terms only
                     float2 kk[NU / 2];
                     float aa[NX];
-                    matvec2<O::Kx, NU, NX, RS, 0, FAST>(P.KA, x, kk);
+                    matvec2<O::Kx, NU, NX, RS, 0, FAST>(P.KA, x, kk, Z);
                     sp_rows<O::Ax, MaskA<PAT>, 0, NX, NX, FAST>([&](int r, int k) { return P.KA[k * RS + NU + r]; },
                                                                   [&](int k) { return x[k]; }, aa);
 #pragma unroll
@@ -460,11 +553,11 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
 #pragma unroll
                     for (int j = 0; j < NX / 2; ++j) ka[NU / 2 + j] = f2(aa[2 * j], aa[2 * j + 1]);
                 } else if constexpr (O::Kx == ORD_SEQ && O::Ax == ORD_SEQ) {
-                    matvec2<ORD_SEQ, RS, NX, RS, 0, FAST>(P.KA, x, ka);
+                    matvec2<ORD_SEQ, RS, NX, RS, 0, FAST>(P.KA, x, ka, Z);
                 } else {
                     float2 kk[NU / 2], aa[NX / 2];
-                    matvec2<O::Kx, NU, NX, RS, 0, FAST>(P.KA, x, kk);
-                    matvec2<O::Ax, NX, NX, RS, NU, FAST>(P.KA, x, aa);
+                    matvec2<O::Kx, NU, NX, RS, 0, FAST>(P.KA, x, kk, Z);
+                    matvec2<O::Ax, NX, NX, RS, NU, FAST>(P.KA, x, aa, Z);
 #pragma unroll
                     for (int j = 0; j < NU / 2; ++j) ka[j] = kk[j];
 #pragma unroll
@@ -501,7 +594,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                             xn[j] = __ffma2_rn(f2(P.Bc[k * NX + 2 * j], P.Bc[k * NX + 2 * j + 1]), f2(u[k], u[k]), xn[j]);
                 } else {
                     float2 bu[NX / 2];
-                    matvec2<O::Bu, NX, NU, NX, 0, false>(P.Bc, u, bu);
+                    matvec2<O::Bu, NX, NU, NX, 0, false>(P.Bc, u, bu, Z);
 #pragma unroll
                     for (int j = 0; j < NX / 2; ++j) xn[j] = add2(ka[NU / 2 + j], bu[j]);
                 }
@@ -580,25 +673,38 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 sy.load(i, y);
                 gload<float, NX>(xr_base + i * NX, xr);
 #pragma unroll
-                for (int j = 0; j < NU; ++j) r[j] = __fmul_rn(P.nrho, __fsub_rn(z[j], y[j]));        // :80
+                for (int j = 0; j < NU; j += 2) {                                                    // :80
+                    float2 t = sub2(f2(z[j], z[j + 1]), f2(y[j], y[j + 1]));
+                    if constexpr (FAST) t = __fmul2_rn(t, f2(P.nrho, P.nrho));
+                    else t = prode(t, f2(P.nrho, P.nrho), Z);
+                    r[j] = t.x; r[j + 1] = t.y;
+                }
                 // [B^T ; AmBKt] p_{i+1}
                 float2 bm[RS / 2];
                 if constexpr (PAT::sparse) {
                     float2 bb[NU / 2];
                     float mm[NX];
-                    matvec2<O::Btp, NU, NX, RS, 0, FAST>(P.BM, p, bb);
-                    sp_rows<O::Mp, MaskM<PAT>, 0, NX, NX, FAST>([&](int r, int k) { return P.BM[k * RS + NU + r]; },
-                                                                  [&](int k) { return p[k]; }, mm);
+                    matvec2<O::Btp, NU, NX, RS, 0, FAST>(P.BM, p, bb, Z);
+                    if constexpr (TMPC_PROD2_M || FAST) {
+                        sp_pairs_m<O::Mp, PAT, 0, NX, FAST>(
+                            [&](int j, int k) { return f2(P.BM[k * RS + NU + 2 * j], P.BM[k * RS + NU + 2 * j + 1]); },
+                            [&](int k) { return p[k]; }, mm, Z);
+                    } else {   // row by row (scalar FMUL with the coefficient as a direct constant-bank operand)
+                        float mt[NX];
+                        sp_rows<O::Mp, MaskMP<PAT>, 0, NX, NX, FAST>([&](int r, int k) { return P.BM[k * RS + NU + r]; },
+                                                                       [&](int k) { return p[k]; }, mt);
+                        unpermute_m<PAT, 0, NX>(mt, mm);
+                    }
 #pragma unroll
                     for (int j = 0; j < NU / 2; ++j) bm[j] = bb[j];
 #pragma unroll
                     for (int j = 0; j < NX / 2; ++j) bm[NU / 2 + j] = f2(mm[2 * j], mm[2 * j + 1]);
                 } else if constexpr (FAST) {
-                    matvec2<ORD_SEQ, RS, NX, RS, 0, true>(P.BM, p, bm);
+                    matvec2<ORD_SEQ, RS, NX, RS, 0, true>(P.BM, p, bm, Z);
                 } else {
                     float2 bb[NU / 2], mm[NX / 2];
-                    matvec2<O::Btp, NU, NX, RS, 0, false>(P.BM, p, bb);
-                    matvec2<O::Mp, NX, NX, RS, NU, false>(P.BM, p, mm);
+                    matvec2<O::Btp, NU, NX, RS, 0, false>(P.BM, p, bb, Z);
+                    matvec2<O::Mp, NX, NX, RS, NU, false>(P.BM, p, mm, Z);
 #pragma unroll
                     for (int j = 0; j < NU / 2; ++j) bm[j] = bb[j];
 #pragma unroll
@@ -611,14 +717,14 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     s[j] = t.x; s[j + 1] = t.y;
                 }
                 float2 d2[NU / 2];
-                matvec2<O::Qs, NU, NU, NU, 0, FAST>(P.Qi, s, d2);                                    // :19
+                matvec2<O::Qs, NU, NU, NU, 0, FAST>(P.Qi, s, d2, Z);                                    // :19
                 float d[NU];
 #pragma unroll
                 for (int j = 0; j < NU / 2; ++j) { d[2 * j] = d2[j].x; d[2 * j + 1] = d2[j].y; }
                 sd.store(i, d, cont);
                 if (WARM && wdo) gstore<float, NU>(wdo + i * NU, d);
                 float2 kr[NX / 2];
-                matvec2<O::Ktr, NX, NU, NX, 0, FAST>(P.Kr, r, kr);
+                matvec2<O::Ktr, NX, NU, NX, 0, FAST>(P.Kr, r, kr, Z);
                 xs.wait(gv);
                 if (WARM && wvo) {
                     gstore<float, NX>(wvo + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
@@ -626,11 +732,11 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 }
 #pragma unroll
                 for (int j = 0; j < NX; j += 2) {
-                    const float2 cq = f2(-__fmul_rn(xr[j], P.Qd[j]), -__fmul_rn(xr[j + 1], P.Qd[j + 1]));          // :81
+                    const float2 cq = neg2(prode(f2(xr[j], xr[j + 1]), f2(P.Qd[j], P.Qd[j + 1]), Z));              // :81
                     const float2 dvg = sub2(f2(gv[NX + j], gv[NX + j + 1]), f2(gv[j], gv[j + 1]));
                     float2 q;
                     if constexpr (FAST) q = __ffma2_rn(f2(P.nrho, P.nrho), dvg, cq);
-                    else q = sub2(cq, f2(__fmul_rn(P.rho, dvg.x), __fmul_rn(P.rho, dvg.y)));                       // :82
+                    else q = sub2(cq, prode(dvg, f2(P.rho, P.rho), Z));                                            // :82
                     const float2 pn = sub2(add2(q, bm[NU / 2 + j / 2]), kr[j / 2]);                                // :20
                     p[j] = pn.x; p[j + 1] = pn.y;
                 }

@@ -248,15 +248,23 @@ def main():
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
+    # With the quadrotor structure specialisation (stats.pattern == 1) the kernel drops the terms whose coefficient is an
+    # exact zero (118 of Adyn's 144, 40 of AmBKt's 144) and the multiplies by exact ones (Adyn's diagonal): per stage
+    # 28 instead of 276 FLOP for Adyn x and 196 instead of 276 for AmBKt p.  `achieved` keeps SURVEY 8d's ALGORITHMIC
+    # (dense) FLOP count; `executed_*` is what the FMA pipe really performs.
+    exec_flop = FLOP_PER_ITER["q"] - (9 * (276 - 28) + 9 * (276 - 196) if stats.get("pattern") == 1 else 0)
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_fp32_max, "unit": "TFLOP/s",
                 "frac": achieved / peak_fp32_max, "traffic": traffic,
+                "structure_pattern": stats.get("pattern"), "executed_flop_per_iteration": exec_flop,
+                "executed_tflops": stats["iterations"] * exec_flop / (kernel_ms * 1e-3) / 1e12,
+                "executed_frac": stats["iterations"] * exec_flop / (kernel_ms * 1e-3) / 1e12 / peak_fp32_max,
                 "peak_source": "SMs x 128 FMA lanes x 2 x clocks.max.sm (%d SMs, %d MHz); at the median clock under load "
                                "(%s MHz) the peak is %.1f TFLOP/s -> frac %.3f" % (prop.multi_processor_count,
                                                                                  clocks["sm_max_mhz"] or 1965, sm_mhz,
                                                                                  peak_fp32, achieved / peak_fp32),
-                "kernel": "tmpc::admm_kernel<float,12,4,10>", "kernel_ms_per_launch": kernel_ms,
+                "kernel": "tmpc::admm_kernel_f32<12,4,10,256,%s,cold,TMEM,%s>" % (args.policy.upper(), "PatQuadrotor" if stats.get("pattern") == 1 else "PatDense"), "kernel_ms_per_launch": kernel_ms,
                 "algorithmic_flop_per_iteration": FLOP_PER_ITER["q"], "iterations_per_launch": stats["iterations"],
-                "fp32_instr_slot_util": (stats["iterations"] * FLOP_PER_ITER["q"]) / (kernel_ms * 1e-3) /
+                "fp32_instr_slot_util": (stats["iterations"] * exec_flop) / (kernel_ms * 1e-3) /
                                         (prop.multi_processor_count * 128 * sm_mhz * 1e6) if args.policy == "parity" else None,
                 "hbm": {"achieved_gbs": hbm_ach, "peak_gbs": hbm_peak, "frac": hbm_ach / hbm_peak,
                         "algorithmic_bytes_per_solve": BYTES_PER_SOLVE["q"],
@@ -291,7 +299,7 @@ def main():
         assert int(hit.sum()) == int(it.sum().item()), "host-path results differ from device-path results"
         e2e = {"value": total_inst * esteps / float(et[0]), "unit": "solves/s",
                "h2d_bytes_per_step": int(B * 48 + 480), "d2h_bytes_per_step": int(B * (480 + 144 + 4 + 4 + 16)),
-               "steps": esteps, "how": "tmpc_solve(TMPC_MEM_HOST) on pinned host buffers; chunked H2D | solve | D2H pipeline"}
+               "steps": esteps, "how": "tmpc_solve(TMPC_MEM_HOST) on pinned host buffers: H2D, one persistent-kernel launch, D2H of 65,536-instance chunks gated by in-kernel completion counters (cuStreamWaitValue32)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -20,9 +20,12 @@ __global__ void __launch_bounds__(1024) k(const __grid_constant__ Coef P, float 
     for (int i = 0; i < NCH; ++i) a[i] = x + i;
 #pragma unroll
     for (int i = 0; i < NCH / 2; ++i) PACK(a[2 * i], a[2 * i + 1], a2[i]);
-    unsigned long long x2, y2;
+    unsigned long long x2, y2, z2, t2[NCH / 2];
     PACK(x, x, x2);
     PACK(y, y, y2);
+    PACK(P.c[30] * 0.f - 0.f, P.c[31] * 0.f - 0.f, z2);   // opaque to the compiler
+#pragma unroll
+    for (int i = 0; i < NCH / 2; ++i) t2[i] = 0;
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -74,6 +77,24 @@ __global__ void __launch_bounds__(1024) k(const __grid_constant__ Coef P, float 
 #pragma unroll
                 for (int i = 0; i < NCH / 2; ++i)
                     asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(a2[i]) : "l"(x2), "l"(a2[i]));
+            } else if (MODE == 11) {  // exact packed product: FFMA2(x.F32, c2 from const, Z = (-0,-0) opaque) + FADD2 accumulate
+#pragma unroll
+                for (int i = 0; i < NCH / 2; ++i) {
+                    unsigned long long c2, t;
+                    PACK(P.c[(2 * i + rep * 4) & 31], P.c[(2 * i + 1 + rep * 4) & 31], c2);
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(x2), "l"(c2), "l"(z2));
+                    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(a2[i]) : "l"(t), "l"(a2[i]));
+                }
+            } else if (MODE == 12) {  // same, but the product feeds a DIFFERENT accumulator pair's add one step later (more ILP)
+#pragma unroll
+                for (int i = 0; i < NCH / 2; ++i) {
+                    unsigned long long c2;
+                    PACK(P.c[(2 * i + rep * 4) & 31], P.c[(2 * i + 1 + rep * 4) & 31], c2);
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t2[i]) : "l"(x2), "l"(c2), "l"(z2));
+                }
+#pragma unroll
+                for (int i = 0; i < NCH / 2; ++i)
+                    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(a2[i]) : "l"(t2[i]), "l"(a2[i]));
             } else if (MODE == 8) {  // FMNMX + FADD mix (alu + fma pipes)
 #pragma unroll
                 for (int i = 0; i < NCH; i += 2) { a[i] = fmaxf(a[i], a[i + 1]); a[i + 1] = __fadd_rn(a[i + 1], y); }
@@ -81,7 +102,7 @@ __global__ void __launch_bounds__(1024) k(const __grid_constant__ Coef P, float 
         }
     }
     float s = 0.f;
-    if (MODE == 3 || MODE == 4 || MODE == 7 || MODE == 9 || MODE == 10) {
+    if (MODE == 3 || MODE == 4 || MODE == 7 || MODE == 9 || MODE == 10 || MODE == 11 || MODE == 12) {
 #pragma unroll
         for (int i = 0; i < NCH / 2; ++i) { float lo, hi; UNPACK(a2[i], lo, hi); s += lo + hi; }
     } else {
@@ -117,8 +138,8 @@ template <int MODE> void run(const char *name, int lane_ops_per_inner, int threa
 
 int main()
 {
-    for (int cfg = 0; cfg < 2; ++cfg) {
-        int threads = cfg == 0 ? 128 : 1024, bps = 1;
+    for (int cfg = 0; cfg < 3; ++cfg) {
+        int threads = cfg == 0 ? 128 : (cfg == 1 ? 256 : 1024), bps = 1;
         run<0>("FFMA R,R,R,R", 16, threads, bps);
         run<1>("FFMA R,R,UR,R", 16, threads, bps);
         run<2>("FMUL R,R,UR + FADD", 32, threads, bps);
@@ -130,6 +151,8 @@ int main()
         run<8>("FMNMX + FADD mix", 16, threads, bps);
         run<9>("2xFMUL R,R,UR + FADD2", 32, threads, bps);
         run<10>("FADD2", 16, threads, bps);
+        run<11>("FFMA2(x,c2,-0) + FADD2 same acc", 32, threads, bps);
+        run<12>("FFMA2(x,c2,-0) x8 then FADD2 x8", 32, threads, bps);
     }
     return 0;
 }
