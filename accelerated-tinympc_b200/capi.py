@@ -19,7 +19,12 @@ TMPC_ORDER_PARITY, TMPC_ORDER_FAST = 0, 1
 TMPC_MEM_HOST, TMPC_MEM_DEVICE = 0, 1
 
 EXPORTS = ["tmpc_create", "tmpc_destroy", "tmpc_set_model", "tmpc_set_settings", "tmpc_solve", "tmpc_get_stats", "tmpc_step",
-           "tmpc_host_alloc", "tmpc_host_free", "tmpc_last_error", "tmpc_version"]
+           "tmpc_host_alloc", "tmpc_host_free", "tmpc_last_error", "tmpc_version",
+           "tmpc_batch_create", "tmpc_batch_destroy", "tmpc_batch_set_x0", "tmpc_batch_set_xref", "tmpc_batch_set_xref_table",
+           "tmpc_batch_reset_dual_variables", "tmpc_batch_reset", "tmpc_batch_solve", "tmpc_batch_get", "tmpc_batch_rollout",
+           "tmpc_batch_last_rollout_ms", "tmpc_batch_last_error"]
+
+GET = {"x": 0, "u": 1, "iter": 2, "status": 3, "resid": 4, "x0": 5, "d": 6, "y": 7, "z": 8, "g": 9, "v": 10}
 
 
 class TmpcWarm(C.Structure):
@@ -75,6 +80,27 @@ def load():
     lib.tmpc_last_error.restype = C.c_char_p
     lib.tmpc_last_error.argtypes = [C.c_void_p]
     lib.tmpc_version.restype = C.c_char_p
+    lib.tmpc_batch_create.restype = C.c_int
+    lib.tmpc_batch_create.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+    lib.tmpc_batch_destroy.restype = C.c_int
+    lib.tmpc_batch_destroy.argtypes = [C.c_void_p]
+    lib.tmpc_batch_set_x0.restype = C.c_int
+    lib.tmpc_batch_set_x0.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.tmpc_batch_set_xref.restype = C.c_int
+    lib.tmpc_batch_set_xref.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.tmpc_batch_set_xref_table.restype = C.c_int
+    lib.tmpc_batch_set_xref_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
+    for fn in ("tmpc_batch_reset_dual_variables", "tmpc_batch_reset", "tmpc_batch_solve"):
+        getattr(lib, fn).restype = C.c_int
+        getattr(lib, fn).argtypes = [C.c_void_p]
+    lib.tmpc_batch_get.restype = C.c_int
+    lib.tmpc_batch_get.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    lib.tmpc_batch_rollout.restype = C.c_int
+    lib.tmpc_batch_rollout.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.tmpc_batch_last_rollout_ms.restype = C.c_float
+    lib.tmpc_batch_last_rollout_ms.argtypes = [C.c_void_p]
+    lib.tmpc_batch_last_error.restype = C.c_char_p
+    lib.tmpc_batch_last_error.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -190,6 +216,91 @@ class Solver:
         if self._ctx:
             self.lib.tmpc_destroy(self._ctx)
             self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """tmpc_batch: device-resident workspaces of `batch` instances of a Solver -- the reference's wrapper calls
+    (tiny_wrapper.hpp:14-23) with a leading batch dimension, and the examples' closed loop on the device."""
+
+    def __init__(self, solver: Solver, batch: int):
+        self.s = solver
+        self.lib = solver.lib
+        self.B = int(batch)
+        self._b = C.c_void_p()
+        solver._check(self.lib.tmpc_batch_create(solver._ctx, self.B, C.byref(self._b)), "tmpc_batch_create")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise TmpcError("%s: %d %s" % (what, rc, self.lib.tmpc_batch_last_error(self._b).decode()))
+
+    def _host(self, a, shape=None):
+        a = np.ascontiguousarray(a, dtype=self.s.dtype)
+        return a if shape is None else a.reshape(shape)
+
+    def set_x0(self, x0):
+        if hasattr(x0, "data_ptr"):
+            return self._check(self.lib.tmpc_batch_set_x0(self._b, x0.data_ptr(), TMPC_MEM_DEVICE), "tmpc_batch_set_x0")
+        a = self._host(x0, (self.B, self.s.nx))
+        self._check(self.lib.tmpc_batch_set_x0(self._b, a.ctypes.data, TMPC_MEM_HOST), "tmpc_batch_set_x0")
+
+    def set_xref(self, xref):
+        a = self._host(xref)
+        shared = a.size == self.s.N * self.s.nx
+        if not shared and a.size != self.B * self.s.N * self.s.nx:
+            raise ValueError("Xref must be [N,nx] or [B,N,nx]")
+        self._check(self.lib.tmpc_batch_set_xref(self._b, a.ctypes.data, 1 if shared else 0, TMPC_MEM_HOST), "tmpc_batch_set_xref")
+
+    def set_xref_table(self, table, start=None):
+        t = self._host(table).reshape(-1, self.s.nx)
+        st = None if start is None else np.ascontiguousarray(start, dtype=np.int32).reshape(self.B)
+        self._check(self.lib.tmpc_batch_set_xref_table(self._b, t.ctypes.data, t.shape[0], None if st is None else st.ctypes.data,
+                                                       TMPC_MEM_HOST), "tmpc_batch_set_xref_table")
+
+    def reset_dual_variables(self):
+        self._check(self.lib.tmpc_batch_reset_dual_variables(self._b), "tmpc_batch_reset_dual_variables")
+
+    def reset(self):
+        self._check(self.lib.tmpc_batch_reset(self._b), "tmpc_batch_reset")
+
+    def solve(self):
+        self._check(self.lib.tmpc_batch_solve(self._b), "tmpc_batch_solve")
+
+    def get(self, what):
+        s = self.s
+        shape = {"x": (self.B, s.N, s.nx), "u": (self.B, s.N - 1, s.nu), "iter": (self.B,), "status": (self.B,), "resid": (self.B, 4),
+                 "x0": (self.B, s.nx), "d": (self.B, s.N - 1, s.nu), "y": (self.B, s.N - 1, s.nu), "z": (self.B, s.N - 1, s.nu),
+                 "g": (self.B, s.N, s.nx), "v": (self.B, s.N, s.nx)}[what]
+        out = np.empty(shape, np.int32 if what in ("iter", "status") else s.dtype)
+        self._check(self.lib.tmpc_batch_get(self._b, GET[what], out.ctypes.data, TMPC_MEM_HOST), "tmpc_batch_get")
+        return out
+
+    def rollout(self, steps, reset_duals=True, history=True):
+        """`steps` closed-loop MPC steps on the device.  Returns dict(x0 [steps+1,B,nx], u0 [steps,B,nu], iter, status
+        [steps,B]) when history is requested, else None."""
+        s = self.s
+        if not history:
+            self._check(self.lib.tmpc_batch_rollout(self._b, steps, 1 if reset_duals else 0, None, None, None, None, TMPC_MEM_HOST),
+                        "tmpc_batch_rollout")
+            return None
+        h = {"x0": np.empty((steps + 1, self.B, s.nx), s.dtype), "u0": np.empty((steps, self.B, s.nu), s.dtype),
+             "iter": np.empty((steps, self.B), np.int32), "status": np.empty((steps, self.B), np.int32)}
+        self._check(self.lib.tmpc_batch_rollout(self._b, steps, 1 if reset_duals else 0, h["x0"].ctypes.data, h["u0"].ctypes.data,
+                                                h["iter"].ctypes.data, h["status"].ctypes.data, TMPC_MEM_HOST), "tmpc_batch_rollout")
+        return h
+
+    def last_rollout_ms(self):
+        return float(self.lib.tmpc_batch_last_rollout_ms(self._b))
+
+    def close(self):
+        if self._b:
+            self.lib.tmpc_batch_destroy(self._b)
+            self._b = C.c_void_p()
 
     def __del__(self):
         try:

@@ -34,6 +34,7 @@ struct tmpc_ctx_impl {
     int device = 0;
     int nx = 0, nu = 0, N = 0, dtype = 0, policy = 0;
     bool has_model = false;
+    float rollout_ms = 0.f;  // device time of the last tmpc_batch_rollout
     int pattern = 0;  // structural-sparsity specialisation the current model conforms to (0 = dense)
     bool warm_variant_ready = false;
     std::string err;
@@ -1029,3 +1030,5 @@ int tmpc_host_alloc(void **ptr, uint64_t bytes)
 int tmpc_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? TMPC_OK : TMPC_ERR_CUDA; }
 
 }  // extern "C"
+
+#include "tmpc_batch.cuh"

@@ -1,0 +1,393 @@
+// Device-resident batch of workspaces (include/tmpc.h "tmpc_batch_*"): the reference's wrapper API
+// (/root/reference/src/tinympc/tiny_wrapper.cpp:5-176: set_x0 / set_xref / reset_dual_variables / call_tiny_solve /
+// get_x / get_u on ONE global workspace) with a leading batch dimension, and the closed loop of its examples
+// (examples/quadrotor_hovering.cpp:90-114, quadrotor_tracking.cpp:93-118) run entirely on the device:
+//
+//     per MPC step:  Xref window from a table  ->  y = g = 0  ->  tiny_solve (warm: d, v, z carried)  ->  x0 <- A x0 + B u_0
+//
+// as three kernels per step on one stream (window gather, the persistent ADMM kernel, plant step) with no host
+// round trip, no H2D/D2H and the warm-start state {d,y,g,v,z} never leaving HBM.  Included by tmpc_api.cu.
+#pragma once
+
+namespace tmpc {
+
+// Xref[b][i][:] = table[w0 + i][:], w0 = min(start[b] + step, rows - N)   (tracking.cpp:101: Xref_total.block(0, k); the
+// window stops moving at the end of the table, which the reference's loop bound k < NTOTAL-NHORIZON-1 never reaches)
+template <class T>
+__global__ void xref_window_kernel(long long batch, int nx, int N, const T *table, long long rows, const int *start, int step, T *Xref)
+{
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long per = (long long)N * nx;
+    if (idx >= batch * per) return;
+    const long long b = idx / per;
+    const int i = (int)((idx - b * per) / nx), j = (int)(idx % nx);
+    long long w0 = (start ? start[b] : 0) + step;
+    if (w0 > rows - N) w0 = rows - N;
+    Xref[idx] = table[(w0 + i) * nx + j];
+}
+
+// The examples' plant step x1 = Adyn * x0 + Bdyn * u.col(0) (quadrotor_hovering.cpp:108).  It evaluates like one stage of
+// forward_pass (admm.cpp:35): both products in their own order, one add per row -- pinned against the compiled
+// reference by tests/test_oracle_vs_ref.py::test_plant_step.  Also records the step's u0 / iter / status histories.
+template <class T, int NX, int NU, int NH, bool FAST>
+__global__ void plant_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, long long batch, T *x0, const T *u, T *x_next_hist,
+                             T *u0_hist, const int *iter, const int *status, int *iter_hist, int *status_hist)
+{
+    using N = Num<T>;
+    using O = Orders<T, NX, NU>;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    T x[NX], u0[NU];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x[j] = x0[b * NX + j];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) u0[j] = u[b * (long long)(NU * (NH - 1)) + j];
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+        T v;
+        if constexpr (FAST) {
+            v = dot<T, O::Ax, NX, true>([&](int k) { return P.A[r + k * NX]; }, [&](int k) { return x[k]; });
+#pragma unroll
+            for (int k = 0; k < NU; ++k) v = N::fma(P.B[r + k * NX], u0[k], v);
+        } else {
+            const T ax = dot<T, O::Ax, NX, false>([&](int k) { return P.A[r + k * NX]; }, [&](int k) { return x[k]; });
+            const T bu = dot<T, O::Bu, NU, false>([&](int k) { return P.B[r + k * NX]; }, [&](int k) { return u0[k]; });
+            v = N::add(ax, bu);
+        }
+        x0[b * NX + r] = v;
+        if (x_next_hist) x_next_hist[b * NX + r] = v;
+    }
+    if (u0_hist) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) u0_hist[b * NU + j] = u0[j];
+    }
+    if (iter_hist) iter_hist[b] = iter[b];
+    if (status_hist) status_hist[b] = status[b];
+}
+
+}  // namespace tmpc
+
+struct tmpc_batch_impl {
+    tmpc_ctx_impl *c = nullptr;
+    int64_t B = 0;
+    char *base = nullptr;          // one device allocation
+    void *x0 = nullptr, *xref = nullptr, *d = nullptr, *y = nullptr, *g = nullptr, *v = nullptr, *z = nullptr;
+    void *x = nullptr, *u = nullptr, *resid = nullptr;
+    int *iter = nullptr, *status = nullptr;
+    bool xref_shared = true;
+    void *table = nullptr;         // [rows][nx]
+    int64_t table_rows = 0;
+    int *start = nullptr;          // [B] or null
+    int64_t steps_done = 0;        // window offset of the next rollout step
+    std::string err;
+};
+#define BAT(b) reinterpret_cast<tmpc_batch_impl *>(b)
+
+namespace {
+
+int bfail(tmpc_batch_impl *b, int code, const std::string &msg)
+{
+    if (b) { b->err = msg; if (b->c) b->c->err = msg; }
+    return code;
+}
+#define BCUDA_TRY(b, call)                                                                         \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return bfail(b, TMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T, int NX, int NU, int NH>
+cudaError_t launch_plant(tmpc_ctx_impl *c, tmpc_batch_impl *b, void *x_next_hist, void *u0_hist, int *iter_hist, int *status_hist, cudaStream_t s)
+{
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((b->B + threads - 1) / threads);
+    const tmpc::Model<T, NX, NU, NH> *m = reinterpret_cast<const tmpc::Model<T, NX, NU, NH> *>(c->model.data());
+    if (c->policy == TMPC_ORDER_PARITY)
+        tmpc::plant_kernel<T, NX, NU, NH, false><<<blocks, threads, 0, s>>>(*m, b->B, (T *)b->x0, (const T *)b->u, (T *)x_next_hist,
+                                                                               (T *)u0_hist, b->iter, b->status, iter_hist, status_hist);
+    else
+        tmpc::plant_kernel<T, NX, NU, NH, true><<<blocks, threads, 0, s>>>(*m, b->B, (T *)b->x0, (const T *)b->u, (T *)x_next_hist,
+                                                                              (T *)u0_hist, b->iter, b->status, iter_hist, status_hist);
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch_plant(tmpc_ctx_impl *c, tmpc_batch_impl *b, void *xh, void *uh, int *ih, int *sh, cudaStream_t s)
+{
+    const bool f32 = c->dtype == TMPC_F32;
+    if (c->nx == 12 && c->nu == 4 && c->N == 10)
+        return f32 ? launch_plant<float, 12, 4, 10>(c, b, xh, uh, ih, sh, s) : launch_plant<double, 12, 4, 10>(c, b, xh, uh, ih, sh, s);
+    if (c->nx == 4 && c->nu == 1 && c->N == 10)
+        return f32 ? launch_plant<float, 4, 1, 10>(c, b, xh, uh, ih, sh, s) : launch_plant<double, 4, 1, 10>(c, b, xh, uh, ih, sh, s);
+    if (c->nx == 32 && c->nu == 8 && c->N == 50 && f32) return launch_plant<float, 32, 8, 50>(c, b, xh, uh, ih, sh, s);
+    return cudaErrorInvalidValue;
+}
+
+int batch_copy_in(tmpc_batch_impl *b, void *dst, const void *src, size_t bytes, int mem)
+{
+    if (!src) return bfail(b, TMPC_ERR_INVALID, "NULL source");
+    BCUDA_TRY(b, cudaSetDevice(b->c->device));
+    BCUDA_TRY(b, cudaMemcpyAsync(dst, src, bytes, mem == TMPC_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, b->c->stream));
+    if (mem != TMPC_MEM_DEVICE) BCUDA_TRY(b, cudaStreamSynchronize(b->c->stream));   // the caller may reuse its buffer
+    return TMPC_OK;
+}
+int batch_copy_out(tmpc_batch_impl *b, void *dst, const void *src, size_t bytes, int mem)
+{
+    if (!dst) return bfail(b, TMPC_ERR_INVALID, "NULL destination");
+    BCUDA_TRY(b, cudaSetDevice(b->c->device));
+    BCUDA_TRY(b, cudaMemcpyAsync(dst, src, bytes, mem == TMPC_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, b->c->stream));
+    if (mem != TMPC_MEM_DEVICE) BCUDA_TRY(b, cudaStreamSynchronize(b->c->stream));
+    return TMPC_OK;
+}
+
+int batch_solve_async(tmpc_batch_impl *b)
+{
+    tmpc_ctx_impl *c = b->c;
+    DevArgs da{};
+    da.batch = b->B; da.x0 = b->x0; da.Xref = b->xref;
+    da.xref_stride = b->xref_shared ? 0 : (long long)c->nx * c->N;
+    da.wd = b->d; da.wy = b->y; da.wg = b->g; da.wv = b->v; da.wz = b->z;
+    da.x = b->x; da.u = b->u; da.iter = b->iter; da.status = b->status; da.resid = b->resid;
+    c->stats.instances = b->B;
+    c->stats.launches = 0;
+    int rc = launch_device(c, da, true, c->stream, true);
+    if (rc == TMPC_OK) c->stats_pending = true;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tmpc_batch_create(tmpc_ctx *ctx, int64_t batch, tmpc_batch **out)
+{
+    if (!ctx || !out) return TMPC_ERR_INVALID;
+    *out = nullptr;
+    tmpc_ctx_impl *c = CTX(ctx);
+    if (batch < 1) return fail(c, TMPC_ERR_INVALID, "batch must be >= 1");
+    if (!c->has_model) return fail(c, TMPC_ERR_STATE, "tmpc_set_model has not been called");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t es = esize(c), xrow = (size_t)c->nx * c->N, urow = (size_t)c->nu * (c->N - 1);
+    auto a256 = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t sz_x0 = a256(batch * c->nx * es), sz_xr = a256(batch * xrow * es), sz_u = a256(batch * urow * es),
+                 sz_i = a256(batch * 4), sz_r = a256(batch * 4 * es);
+    const size_t total = sz_x0 + 4 * sz_xr /*xref g v x*/ + 4 * sz_u /*d y z u*/ + 2 * sz_i + sz_r;
+    tmpc_batch_impl *b = new tmpc_batch_impl;
+    b->c = c; b->B = batch;
+    cudaError_t e = cudaMalloc((void **)&b->base, total);
+    if (e != cudaSuccess) { delete b; return fail(c, TMPC_ERR_CUDA, std::string("tmpc_batch_create: cudaMalloc: ") + cudaGetErrorString(e)); }
+    char *p = b->base;
+    auto take = [&](size_t n) { char *q = p; p += n; return (void *)q; };
+    b->x0 = take(sz_x0); b->xref = take(sz_xr); b->g = take(sz_xr); b->v = take(sz_xr); b->x = take(sz_xr);
+    b->d = take(sz_u); b->y = take(sz_u); b->z = take(sz_u); b->u = take(sz_u);
+    b->iter = (int *)take(sz_i); b->status = (int *)take(sz_i); b->resid = take(sz_r);
+    e = cudaMemsetAsync(b->base, 0, total, c->stream);     // the zeroing block of the examples (hovering.cpp:49-71)
+    if (e != cudaSuccess) { cudaFree(b->base); delete b; return fail(c, TMPC_ERR_CUDA, "tmpc_batch_create: memset failed"); }
+    *out = reinterpret_cast<tmpc_batch *>(b);
+    return TMPC_OK;
+}
+
+int tmpc_batch_destroy(tmpc_batch *bt)
+{
+    if (!bt) return TMPC_OK;
+    tmpc_batch_impl *b = BAT(bt);
+    cudaSetDevice(b->c->device);
+    cudaStreamSynchronize(b->c->stream);
+    if (b->base) cudaFree(b->base);
+    if (b->table) cudaFree(b->table);
+    if (b->start) cudaFree(b->start);
+    delete b;
+    return TMPC_OK;
+}
+
+int tmpc_batch_set_x0(tmpc_batch *bt, const void *x0, int32_t mem)
+{
+    if (!bt) return TMPC_ERR_INVALID;
+    tmpc_batch_impl *b = BAT(bt);
+    return batch_copy_in(b, b->x0, x0, (size_t)b->B * b->c->nx * esize(b->c), mem);
+}
+
+int tmpc_batch_set_xref(tmpc_batch *bt, const void *xref, int32_t shared, int32_t mem)
+{
+    if (!bt) return TMPC_ERR_INVALID;
+    tmpc_batch_impl *b = BAT(bt);
+    const size_t xrow = (size_t)b->c->nx * b->c->N * esize(b->c);
+    int rc = batch_copy_in(b, b->xref, xref, shared ? xrow : (size_t)b->B * xrow, mem);
+    if (rc == TMPC_OK) b->xref_shared = shared != 0;
+    return rc;
+}
+
+int tmpc_batch_set_xref_table(tmpc_batch *bt, const void *table, int64_t rows, const int32_t *start, int32_t mem)
+{
+    if (!bt) return TMPC_ERR_INVALID;
+    tmpc_batch_impl *b = BAT(bt);
+    tmpc_ctx_impl *c = b->c;
+    if (!table || rows < c->N) return bfail(b, TMPC_ERR_INVALID, "the reference table needs at least N rows");
+    BCUDA_TRY(b, cudaSetDevice(c->device));
+    BCUDA_TRY(b, cudaStreamSynchronize(c->stream));
+    if (b->table) { cudaFree(b->table); b->table = nullptr; }
+    if (b->start) { cudaFree(b->start); b->start = nullptr; }
+    const size_t bytes = (size_t)rows * c->nx * esize(c);
+    BCUDA_TRY(b, cudaMalloc(&b->table, bytes));
+    int rc = batch_copy_in(b, b->table, table, bytes, mem);
+    if (rc != TMPC_OK) return rc;
+    if (start) {
+        BCUDA_TRY(b, cudaMalloc((void **)&b->start, (size_t)b->B * sizeof(int)));
+        rc = batch_copy_in(b, b->start, start, (size_t)b->B * sizeof(int), mem);
+        if (rc != TMPC_OK) return rc;
+    }
+    b->table_rows = rows;
+    b->steps_done = 0;
+    b->xref_shared = false;
+    return TMPC_OK;
+}
+
+int tmpc_batch_reset_dual_variables(tmpc_batch *bt)
+{
+    if (!bt) return TMPC_ERR_INVALID;
+    tmpc_batch_impl *b = BAT(bt);
+    tmpc_ctx_impl *c = b->c;
+    const size_t es = esize(c);
+    BCUDA_TRY(b, cudaSetDevice(c->device));
+    BCUDA_TRY(b, cudaMemsetAsync(b->y, 0, (size_t)b->B * c->nu * (c->N - 1) * es, c->stream));
+    BCUDA_TRY(b, cudaMemsetAsync(b->g, 0, (size_t)b->B * c->nx * c->N * es, c->stream));
+    return TMPC_OK;
+}
+
+int tmpc_batch_reset(tmpc_batch *bt)
+{
+    if (!bt) return TMPC_ERR_INVALID;
+    tmpc_batch_impl *b = BAT(bt);
+    tmpc_ctx_impl *c = b->c;
+    const size_t es = esize(c), xb = (size_t)b->B * c->nx * c->N * es, ub = (size_t)b->B * c->nu * (c->N - 1) * es;
+    BCUDA_TRY(b, cudaSetDevice(c->device));
+    BCUDA_TRY(b, cudaMemsetAsync(b->d, 0, ub, c->stream));
+    BCUDA_TRY(b, cudaMemsetAsync(b->y, 0, ub, c->stream));
+    BCUDA_TRY(b, cudaMemsetAsync(b->z, 0, ub, c->stream));
+    BCUDA_TRY(b, cudaMemsetAsync(b->g, 0, xb, c->stream));
+    BCUDA_TRY(b, cudaMemsetAsync(b->v, 0, xb, c->stream));
+    b->steps_done = 0;
+    return TMPC_OK;
+}
+
+int tmpc_batch_solve(tmpc_batch *bt)
+{
+    if (!bt) return TMPC_ERR_INVALID;
+    tmpc_batch_impl *b = BAT(bt);
+    BCUDA_TRY(b, cudaSetDevice(b->c->device));
+    return batch_solve_async(b);
+}
+
+int tmpc_batch_get(tmpc_batch *bt, int32_t what, void *dst, int32_t mem)
+{
+    if (!bt) return TMPC_ERR_INVALID;
+    tmpc_batch_impl *b = BAT(bt);
+    tmpc_ctx_impl *c = b->c;
+    const size_t es = esize(c), xrow = (size_t)c->nx * c->N, urow = (size_t)c->nu * (c->N - 1);
+    const void *src = nullptr;
+    size_t per = 0;
+    switch (what) {
+    case TMPC_GET_X: src = b->x; per = xrow * es; break;
+    case TMPC_GET_U: src = b->u; per = urow * es; break;
+    case TMPC_GET_ITER: src = b->iter; per = 4; break;
+    case TMPC_GET_STATUS: src = b->status; per = 4; break;
+    case TMPC_GET_RESID: src = b->resid; per = 4 * es; break;
+    case TMPC_GET_X0: src = b->x0; per = c->nx * es; break;
+    case TMPC_GET_D: src = b->d; per = urow * es; break;
+    case TMPC_GET_Y: src = b->y; per = urow * es; break;
+    case TMPC_GET_Z: src = b->z; per = urow * es; break;
+    case TMPC_GET_G: src = b->g; per = xrow * es; break;
+    case TMPC_GET_V: src = b->v; per = xrow * es; break;
+    default: return bfail(b, TMPC_ERR_INVALID, "bad tmpc_batch_get selector");
+    }
+    return batch_copy_out(b, dst, src, (size_t)b->B * per, mem);
+}
+
+int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void *x0_hist, void *u0_hist, int32_t *iter_hist,
+                       int32_t *status_hist, int32_t mem)
+{
+    if (!bt) return TMPC_ERR_INVALID;
+    tmpc_batch_impl *b = BAT(bt);
+    tmpc_ctx_impl *c = b->c;
+    if (steps < 0) return bfail(b, TMPC_ERR_INVALID, "negative step count");
+    if (steps == 0) return TMPC_OK;
+    BCUDA_TRY(b, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t es = esize(c);
+    const int64_t B = b->B;
+    const size_t nxb = (size_t)B * c->nx * es, nub = (size_t)B * c->nu * es, ib = (size_t)B * 4;
+    // histories: device buffers when the caller's are on the host
+    const bool host = mem != TMPC_MEM_DEVICE;
+    char *dx = nullptr, *du = nullptr;
+    int *di = nullptr, *ds = nullptr;
+    auto cleanup = [&]() {
+        if (host) { if (dx) cudaFree(dx); if (du) cudaFree(du); if (di) cudaFree(di); if (ds) cudaFree(ds); }
+    };
+    auto dev_hist = [&](void *user, size_t bytes, void **dptr) -> cudaError_t {
+        *dptr = nullptr;
+        if (!user) return cudaSuccess;
+        if (!host) { *dptr = user; return cudaSuccess; }
+        return cudaMalloc(dptr, bytes);
+    };
+    cudaError_t e;
+    if ((e = dev_hist(x0_hist, nxb * (steps + 1), (void **)&dx)) != cudaSuccess || (e = dev_hist(u0_hist, nub * steps, (void **)&du)) != cudaSuccess ||
+        (e = dev_hist(iter_hist, ib * steps, (void **)&di)) != cudaSuccess || (e = dev_hist(status_hist, ib * steps, (void **)&ds)) != cudaSuccess) {
+        cleanup();
+        return bfail(b, TMPC_ERR_CUDA, std::string("tmpc_batch_rollout: history allocation: ") + cudaGetErrorString(e));
+    }
+    if (dx) BCUDA_TRY(b, cudaMemcpyAsync(dx, b->x0, nxb, cudaMemcpyDeviceToDevice, s));
+    cudaEvent_t r0, r1;
+    BCUDA_TRY(b, cudaEventCreate(&r0));
+    BCUDA_TRY(b, cudaEventCreate(&r1));
+    float kernel_ms = 0.f;
+    BCUDA_TRY(b, cudaEventRecord(r0, s));
+    int rc = TMPC_OK;
+    for (int k = 0; k < steps && rc == TMPC_OK; ++k) {
+        if (b->table) {   // 2. reference window (tracking.cpp:101)
+            const long long n = (long long)B * c->nx * c->N;
+            const unsigned blocks = (unsigned)((n + 255) / 256);
+            if (c->dtype == TMPC_F32)
+                tmpc::xref_window_kernel<float><<<blocks, 256, 0, s>>>(B, c->nx, c->N, (const float *)b->table, b->table_rows, b->start,
+                                                                         (int)(b->steps_done), (float *)b->xref);
+            else
+                tmpc::xref_window_kernel<double><<<blocks, 256, 0, s>>>(B, c->nx, c->N, (const double *)b->table, b->table_rows, b->start,
+                                                                          (int)(b->steps_done), (double *)b->xref);
+        }
+        if (reset_duals) {   // 3. y = 0, g = 0 (hovering.cpp:100-101)
+            cudaMemsetAsync(b->y, 0, (size_t)B * c->nu * (c->N - 1) * es, s);
+            cudaMemsetAsync(b->g, 0, (size_t)B * c->nx * c->N * es, s);
+        }
+        rc = batch_solve_async(b);   // 4. tiny_solve
+        if (rc != TMPC_OK) break;
+        // 5. plant step + histories
+        e = dispatch_plant(c, b, dx ? dx + nxb * (k + 1) : nullptr, du ? du + nub * k : nullptr, di ? di + (size_t)B * k : nullptr,
+                           ds ? ds + (size_t)B * k : nullptr, s);
+        if (e != cudaSuccess) { rc = bfail(b, TMPC_ERR_CUDA, std::string("plant step: ") + cudaGetErrorString(e)); break; }
+        b->steps_done += 1;
+    }
+    if (rc == TMPC_OK) {
+        cudaEventRecord(r1, s);
+        if (host) {
+            if (dx) cudaMemcpyAsync(x0_hist, dx, nxb * (steps + 1), cudaMemcpyDeviceToHost, s);
+            if (du) cudaMemcpyAsync(u0_hist, du, nub * steps, cudaMemcpyDeviceToHost, s);
+            if (di) cudaMemcpyAsync(iter_hist, di, ib * steps, cudaMemcpyDeviceToHost, s);
+            if (ds) cudaMemcpyAsync(status_hist, ds, ib * steps, cudaMemcpyDeviceToHost, s);
+        }
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = bfail(b, TMPC_ERR_CUDA, std::string("tmpc_batch_rollout: ") + cudaGetErrorString(e));
+        else cudaEventElapsedTime(&kernel_ms, r0, r1);
+    }
+    cudaEventDestroy(r0);
+    cudaEventDestroy(r1);
+    cleanup();
+    if (rc == TMPC_OK) {
+        c->stats.launches = steps * (2 + (b->table ? 1 : 0));
+        c->rollout_ms = kernel_ms;
+    }
+    return rc;
+}
+
+float tmpc_batch_last_rollout_ms(const tmpc_batch *bt) { return bt ? reinterpret_cast<const tmpc_batch_impl *>(bt)->c->rollout_ms : 0.f; }
+
+const char *tmpc_batch_last_error(const tmpc_batch *bt) { return bt ? reinterpret_cast<const tmpc_batch_impl *>(bt)->err.c_str() : ""; }
+
+}  // extern "C"

@@ -138,6 +138,48 @@ typedef struct {
  * `iter` for the check_termination test), 5 backward_pass_grad.  Unit-test surface; synchronous for host memory. */
 int tmpc_step(tmpc_ctx *ctx, int which, int64_t batch, const tmpc_workspace *ws, int32_t iter, int32_t mem, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Device-resident batch of workspaces: the reference's wrapper API (tiny_wrapper.hpp:14-23 -- set_x0, set_xref,
+ * reset_dual_variables, call_tiny_solve, get_x, get_u on ONE global workspace) with a leading batch dimension,
+ * and the closed loop of the reference's examples kept on the device.  A tmpc_batch owns, in HBM, what
+ * TinyWorkspace holds per instance: x(:,0), Xref, the warm state d y g v z, and the results x u iter status
+ * residuals.  Every solve is a warm start from whatever the workspace holds (exactly like tiny_solve); a new
+ * batch is zero-filled like the examples' init block (quadrotor_hovering.cpp:49-71).
+ * `mem` says where the caller's array lives (tmpc_mem).  Bounds and model are the ctx's (tmpc_set_model /
+ * tmpc_set_settings: set_umin/set_umax/set_xmin/set_xmax of the wrapper apply to every instance of the ctx).
+ * All work is queued on the ctx's stream; calls with host arrays return when the copy is complete. */
+typedef struct tmpc_batch tmpc_batch;
+int tmpc_batch_create(tmpc_ctx *ctx, int64_t batch, tmpc_batch **out);
+int tmpc_batch_destroy(tmpc_batch *b);
+int tmpc_batch_set_x0(tmpc_batch *b, const void *x0, int32_t mem);                    /* [batch][nx]  set_x0, tiny_wrapper.cpp:5-19 */
+int tmpc_batch_set_xref(tmpc_batch *b, const void *xref, int32_t shared, int32_t mem); /* [N][nx] or [batch][N][nx]  set_xref :21-41 */
+/* Reference trajectory table [rows][nx] (examples/quadrotor_tracking.cpp:84) + per-instance first row start[batch]
+ * (NULL = 0): at rollout step k instance b tracks rows w0..w0+N-1, w0 = min(start[b] + k, rows - N) (tracking.cpp:101). */
+int tmpc_batch_set_xref_table(tmpc_batch *b, const void *table, int64_t rows, const int32_t *start, int32_t mem);
+int tmpc_batch_reset_dual_variables(tmpc_batch *b);                                    /* y = 0, g = 0  reset_dual_variables :131-140 */
+int tmpc_batch_reset(tmpc_batch *b);                                                   /* d y g v z = 0: cold start */
+int tmpc_batch_solve(tmpc_batch *b);                                                   /* call_tiny_solve :142-150 for every instance (async) */
+typedef enum {
+    TMPC_GET_X = 0,      /* [batch][N][nx]    get_x, tiny_wrapper.cpp:152-163 */
+    TMPC_GET_U = 1,      /* [batch][N-1][nu]  get_u :165-176 */
+    TMPC_GET_ITER = 2,   /* int32 [batch] */
+    TMPC_GET_STATUS = 3, /* int32 [batch] */
+    TMPC_GET_RESID = 4,  /* [batch][4] */
+    TMPC_GET_X0 = 5,     /* [batch][nx]: the current measurement (after a rollout: the plant state) */
+    TMPC_GET_D = 6, TMPC_GET_Y = 7, TMPC_GET_Z = 8, /* [batch][N-1][nu] */
+    TMPC_GET_G = 9, TMPC_GET_V = 10                 /* [batch][N][nx] */
+} tmpc_batch_field;
+int tmpc_batch_get(tmpc_batch *b, int32_t what, void *dst, int32_t mem);
+/* The examples' closed loop (quadrotor_hovering.cpp:90-114, quadrotor_tracking.cpp:93-118) for `steps` MPC steps,
+ * entirely on the device: [reference window from the table] -> [y = g = 0 if reset_duals] -> tiny_solve ->
+ * x0 <- Adyn x0 + Bdyn u(:,0) (the examples' plant step, same evaluation order).  Histories are optional (NULL):
+ * x0_hist [steps+1][batch][nx] (entry 0 = the initial state), u0_hist [steps][batch][nu], iter_hist / status_hist
+ * [steps][batch].  Synchronous. */
+int tmpc_batch_rollout(tmpc_batch *b, int32_t steps, int32_t reset_duals, void *x0_hist, void *u0_hist, int32_t *iter_hist,
+                       int32_t *status_hist, int32_t mem);
+float tmpc_batch_last_rollout_ms(const tmpc_batch *b);   /* device time of the last rollout (CUDA events on the ctx stream) */
+const char *tmpc_batch_last_error(const tmpc_batch *b);
+
 /* Pinned host allocation helpers for TMPC_MEM_HOST callers that want full PCIe speed. */
 int tmpc_host_alloc(void **ptr, uint64_t bytes);
 int tmpc_host_free(void *ptr);

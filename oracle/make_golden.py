@@ -69,6 +69,62 @@ def gen_closed_loops():
     print("cartpole f32 iter hist:", np.bincount(rec["iter"]))
 
 
+def rollout(ref, prob, x0s, table, starts, steps, dtype):
+    """The examples' closed loop, verbatim, for a few instances: measurement, reference window from a table
+    (quadrotor_tracking.cpp:101; a one-window table = hovering), duals reset, tiny_solve, plant step on the
+    reference's own Eigen expression (ref_plant_step).  Everything in `dtype`, nothing computed in numpy."""
+    nx, nu, N = prob.nx, prob.nu, prob.N
+    B = len(x0s)
+    rec = {k: [] for k in ("x0", "iter", "status", "u0", "err")}
+    for b in range(B):
+        warm = {k: np.zeros((1, N - 1, nu) if k in "dyz" else (1, N, nx), dtype) for k in ("d", "y", "g", "v", "z")}
+        x0 = np.asarray(x0s[b], dtype)
+        xs, its, sts, u0s, errs = [x0.copy()], [], [], [], []
+        for k in range(steps):
+            w0 = min(starts[b] + k, table.shape[0] - N)
+            xr = np.ascontiguousarray(table[w0:w0 + N], dtype)
+            warm["y"][:] = 0
+            warm["g"][:] = 0
+            r = ref.solve_batch(prob, x0[None, :], xr, warm=warm, want_state=True)
+            warm = {kk: r.state[kk].copy() for kk in ("d", "y", "g", "v", "z")}
+            x1, err = ref.plant_step(prob, x0, r.u[0], xref=xr)
+            its.append(r.iter[0]); sts.append(r.status[0]); u0s.append(r.u[0, 0].copy()); errs.append(err)
+            x0 = x1
+            xs.append(x0.copy())
+        rec["x0"].append(np.array(xs)); rec["iter"].append(np.array(its)); rec["status"].append(np.array(sts))
+        rec["u0"].append(np.array(u0s)); rec["err"].append(np.array(errs))
+    out = {k: np.array(v) for k, v in rec.items()}          # [B][steps(+1)][...]
+    out["starts"] = np.asarray(starts, np.int32)
+    out["x0_init"] = np.asarray(x0s, dtype)
+    return out
+
+
+def gen_rollouts():
+    """Closed loops INCLUDING the reference's plant step: what tmpc_batch_rollout must reproduce on the device."""
+    q = P.quadrotor(20)
+    hover_tab = np.tile(W.QUAD_HOVER[None, :], (q.N, 1))           # one window: Xref never moves
+    table = P.quadrotor_trajectory().T                              # [301][12]
+    for tag, dt in DT.items():
+        ref = RefLib("q_" + tag)
+        x0s = np.concatenate([np.array([[0, 1, 0, 0.2, 0, 0, 0.1, 0, 0, 0, 0, 0]], np.float64),   # hovering.cpp:88
+                              W.quadrotor_hover_batch(0, 7, mult=0.5)[0].astype(np.float64)])
+        rec = rollout(ref, q, x0s, hover_tab, [0] * 8, 70, dt)
+        np.savez_compressed(os.path.join(OUT, "rollout_hover_%s.npz" % tag), **rec)
+        print("rollout hover", tag, "instance 0 iters:", " ".join(str(i) for i in rec["iter"][0][:16]), "err0 %.4f" % rec["err"][0][0])
+        starts = [0, 17, 100, 250]
+        x0s = np.array([table[s0] for s0 in starts], np.float64)
+        x0s[1:] += 0.05 * W.QUAD_SCALE[None, :] * W._noise(4321, 0, 3, 12)
+        rec = rollout(ref, q, x0s, table, starts, 60, dt)
+        np.savez_compressed(os.path.join(OUT, "rollout_tracking_%s.npz" % tag), **rec)
+        print("rollout tracking", tag, "iters[0][:8]:", rec["iter"][0][:8])
+    c = P.cartpole(max_iter=150)
+    ref = RefLib("c_f32")
+    x0s = np.concatenate([np.array([[0.0, 0, 0.1, 0]]), W.cartpole_batch(0, 5)[0].astype(np.float64)])
+    rec = rollout(ref, c, x0s, np.zeros((c.N, 4)), [0] * 6, 80, np.float32)
+    np.savez_compressed(os.path.join(OUT, "rollout_cartpole_f32.npz"), **rec)
+    print("rollout cartpole f32 iter hist:", np.bincount(rec["iter"].reshape(-1)))
+
+
 def gen_batches():
     q, c, l = P.quadrotor(20), P.cartpole(), P.random_system()
     rng = np.random.default_rng(7)
@@ -113,7 +169,13 @@ def gen_steps():
 
 
 if __name__ == "__main__":
-    gen_closed_loops()
-    gen_batches()
-    gen_steps()
+    which = sys.argv[1:] or ["closed_loops", "batches", "steps", "rollouts"]
+    if "closed_loops" in which:
+        gen_closed_loops()
+    if "batches" in which:
+        gen_batches()
+    if "steps" in which:
+        gen_steps()
+    if "rollouts" in which:
+        gen_rollouts()
     print("fixtures:", sorted(os.listdir(OUT)))

@@ -121,6 +121,8 @@ class RefLib(_Base):
                                              C.c_int32]
         self.lib.ref_step.restype = C.c_int
         self.lib.ref_step.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+        self.lib.ref_plant_step.restype = C.c_int
+        self.lib.ref_plant_step.argtypes = [C.c_void_p] * 6
 
     @staticmethod
     def available(cfg: str) -> bool:
@@ -147,6 +149,18 @@ class RefLib(_Base):
         ws = np.ascontiguousarray(ws, dtype=self.dtype).copy()
         rc = self.lib.ref_step(C.byref(P), which, _ptr(ws), it)
         return rc, ws
+
+    def plant_step(self, prob, x0, u, xref=None):
+        """The examples' `x1 = Adyn * x0 + Bdyn * u.col(0)` on the reference's Eigen types, one instance.
+        u: [N-1, nu] trajectory.  Returns x1 (and the printed tracking error if xref [N, nx] is given)."""
+        P, keep = self._problem(prob)
+        x0 = np.ascontiguousarray(x0, dtype=self.dtype).reshape(-1)
+        u = np.ascontiguousarray(u, dtype=self.dtype).reshape(self.N - 1, self.nu)
+        x1 = np.zeros(self.nx, self.dtype)
+        err = np.zeros(1, self.dtype)
+        xr = None if xref is None else np.ascontiguousarray(xref, dtype=self.dtype)
+        self.lib.ref_plant_step(C.byref(P), _ptr(x0), _ptr(u), _ptr(x1), _ptr(xr), _ptr(err) if xr is not None else None)
+        return (x1, err[0]) if xr is not None else x1
 
 
 class OracleLib(_Base):
@@ -183,6 +197,19 @@ class OracleLib(_Base):
         ws = np.ascontiguousarray(ws, dtype=dtype).copy()
         rc = self.lib.oracle_step(C.byref(P), which, _ptr(ws), it)
         return rc, ws
+
+    def plant_step(self, prob, x0, u0, dtype=np.float32):
+        """Batched plant step x1 = Adyn x0 + Bdyn u0 in the reference's evaluation order.  x0 [B, nx], u0 [B, nu]."""
+        P, keep = self._problem(prob, dtype)
+        x0 = np.ascontiguousarray(x0, dtype=dtype).reshape(-1, prob.nx)
+        u0 = np.ascontiguousarray(u0, dtype=dtype).reshape(-1, prob.nu)
+        x1 = np.empty_like(x0)
+        self.lib.oracle_plant_step.restype = C.c_int
+        self.lib.oracle_plant_step.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        rc = self.lib.oracle_plant_step(C.byref(P), x0.shape[0], _ptr(x0), _ptr(u0), prob.nu, _ptr(x1))
+        if rc != 0:
+            raise RuntimeError("oracle_plant_step failed")
+        return x1
 
 
 def ws_size(nx, nu, N):

@@ -194,4 +194,26 @@ int ref_step(const ref_problem *P, int32_t which, void *ws_, int32_t iter)
     return rc;
 }
 
+// The plant step of the reference's closed-loop examples, the verbatim expression of
+// examples/quadrotor_hovering.cpp:108 and quadrotor_tracking.cpp:112 on the same Eigen types:
+//     x1 = work.Adyn * x0 + work.Bdyn * work.u.col(0);
+// u = the [N-1][nu] input trajectory of the workspace (col(0) is used).  Also returns the tracking error the
+// examples print before each solve, (x0 - work.Xref.col(1)).norm() (hovering.cpp:92), when xref/err are given.
+int ref_plant_step(const ref_problem *P, const void *x0_, const void *u_, void *x1_, const void *xref_, void *err_)
+{
+    std::unique_ptr<Inst> I(new Inst);
+    load_problem(*I, P);
+    TinyWorkspace &work = I->work;
+    tiny_VectorNx x0, x1;
+    std::memcpy(x0.data(), x0_, sizeof(T) * NSTATES);
+    get(work.u, u_, 0, NUN);
+    x1 = work.Adyn * x0 + work.Bdyn * work.u.col(0);
+    std::memcpy(x1_, x1.data(), sizeof(T) * NSTATES);
+    if (xref_ && err_) {
+        get(work.Xref, xref_, 0, NXN);
+        *(T *)err_ = (x0 - work.Xref.col(1)).norm();
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -147,3 +147,11 @@ int oracle_step(const oracle_problem *in, int32_t which, void *ws, int32_t iter)
     if (in->scalar_bytes == 8) return oracle_step_f64(in, which, ws, iter);
     return -1;
 }
+
+/* batched plant step x1 = Adyn x0 + Bdyn u0; u0 of instance b = u0[b * u_stride .. + nu) */
+int oracle_plant_step(const oracle_problem *in, int64_t B, const void *x0, const void *u0, int64_t u_stride, void *x1)
+{
+    if (in->scalar_bytes == 4) return oracle_plant_step_f32(in, B, x0, u0, u_stride, x1);
+    if (in->scalar_bytes == 8) return oracle_plant_step_f64(in, B, x0, u0, u_stride, x1);
+    return -1;
+}

@@ -410,5 +410,27 @@ int SFX(oracle_step)(const oracle_problem *in, int32_t which, void *ws_, int32_t
     return rc;
 }
 
+/* The plant step of the reference's closed-loop examples (quadrotor_hovering.cpp:108, quadrotor_tracking.cpp:112):
+ *     x1 = work.Adyn * x0 + work.Bdyn * work.u.col(0)
+ * evaluates exactly like one stage of forward_pass (admm.cpp:35): (Adyn x0) and (Bdyn u0) each in their product
+ * order, then one add per row.  Pinned against oracle/_ref's ref_plant_step by tests/test_oracle_vs_ref.py. */
+int SFX(oracle_plant_step)(const oracle_problem *in, int64_t B, const void *x0_, const void *u0_, int64_t u_stride,
+                           void *x1_)
+{
+    SFX(prob) P;
+    SFX(load_prob)(&P, in);
+    const int n = P.nx, m = P.nu;
+    if (n > 64 || m > 64) return -1;
+    T Ax[64], Bu[64], e[64];
+    for (int64_t b = 0; b < B; ++b) {
+        const T *x0 = (const T *)x0_ + b * n, *u0 = (const T *)u0_ + b * u_stride;
+        T *x1 = (T *)x1_ + b * n;
+        SFX(matvec)(Ax, P.Adyn, 1, n, x0, n, n, P.ord.Ax, e);
+        SFX(matvec)(Bu, P.Bdyn, 1, n, u0, n, m, P.ord.Bu, e);
+        for (int r = 0; r < n; ++r) x1[r] = Ax[r] + Bu[r];
+    }
+    return 0;
+}
+
 #undef GETV
 #undef PUTV

@@ -109,3 +109,48 @@ def test_step_function_vectors(pkg, oracle, shape, tag):
             rc, out = oracle.step(prob, which, ws, it=1, dtype=DT[tag])
             assert rc == g["rc%d" % which][t]
             assert_same(out, g["out%d" % which][t], "step %d trial %d" % (which, t))
+
+
+ROLLOUTS = [("hover", "f32"), ("hover", "f64"), ("tracking", "f32"), ("tracking", "f64"), ("cartpole", "f32")]
+
+
+def rollout_setup(pkg, name):
+    """(problem, reference table [rows, nx]) of a rollout fixture (oracle/make_golden.py gen_rollouts)."""
+    if name == "cartpole":
+        prob = pkg.problems.cartpole(max_iter=150)
+        return prob, np.zeros((prob.N, 4))
+    prob = pkg.problems.quadrotor(20)
+    if name == "hover":
+        return prob, np.tile(pkg.workloads.QUAD_HOVER[None, :], (prob.N, 1))
+    return prob, pkg.problems.quadrotor_trajectory().T
+
+
+@pytest.mark.parametrize("name,tag", ROLLOUTS)
+def test_rollouts_with_reference_plant(pkg, oracle, name, tag):
+    """The examples' closed loop INCLUDING the reference's own plant step (x1 = Adyn*x0 + Bdyn*u.col(0) on its Eigen
+    types, ref_plant_step): the oracle's solve + plant step reproduce every state, input and iteration count."""
+    rec = np.load(os.path.join(G, "rollout_%s_%s.npz" % (name, tag)))
+    prob, table = rollout_setup(pkg, name)
+    dt = DT[tag]
+    nx, nu, N = prob.nx, prob.nu, prob.N
+    B, steps = rec["iter"].shape
+    x0 = rec["x0_init"].astype(dt)
+    assert_same(x0, rec["x0"][:, 0], "initial state")
+    warm = {k: np.zeros((B, N - 1, nu) if k in "dyz" else (B, N, nx), dt) for k in ("d", "y", "g", "v", "z")}
+    for k in range(steps):
+        w0 = np.minimum(rec["starts"] + k, table.shape[0] - N)
+        xref = np.stack([table[w:w + N] for w in w0]).astype(dt)
+        warm["y"][:] = 0
+        warm["g"][:] = 0
+        r = oracle.solve_batch(prob, x0, xref, dtype=dt, warm=warm, want_state=True, nthreads=4)
+        warm = {kk: r.state[kk] for kk in warm}
+        assert_same(r.iter, rec["iter"][:, k], "iter step %d" % k)
+        assert_same(r.u[:, 0], rec["u0"][:, k], "u0 step %d" % k)
+        x0 = oracle.plant_step(prob, x0, r.u[:, 0], dtype=dt)
+        assert_same(x0, rec["x0"][:, k + 1], "x0 after step %d" % k)
+    if name == "hover" and tag == "f64":   # G1/G2: the printed tracking error and iteration sequence of the reference binary
+        assert ["%.4f" % e for e in rec["err"][0, :5]] == ["2.2472", "2.9549", "2.5478", "2.6331", "3.1375"]   # SURVEY 4.2 G1
+        assert "%.4f" % rec["err"][0, 9] == "4.6282" and "%.4f" % rec["err"][0, 35] == "0.0217" and "%.4f" % rec["err"][0, 69] == "0.0052"
+        g2 = "100 100 100 100 100 100 100 100 31 19 21 38 38 31 20 12 12 11 11 10 9 9 9 9 8 8 7 6 7 7 7 7 7 6 6 6 6 6 5 5 5 4 4 3 2 2 " \
+             "3 3 3 3 3 3 3 3 2 2 2 2 2 2 2 2 2 2 2 2 2 2 1 2"
+        assert list(rec["iter"][0]) == [int(t) for t in g2.split()]                                               # SURVEY 4.2 G2

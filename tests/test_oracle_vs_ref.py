@@ -81,3 +81,22 @@ def test_step_functions(pkg, oracle, shape, tag):
             rc_o, out_o = oracle.step(prob, which, ws, it=1, dtype=DT[tag])
             assert rc_r == rc_o
             assert_same(out_o, out_r, "step %d" % which)
+
+
+@pytest.mark.parametrize("tag", list(DT))
+@pytest.mark.parametrize("shape", SHAPES)
+def test_plant_step(pkg, oracle, shape, tag):
+    """The examples' plant step `x1 = Adyn * x0 + Bdyn * u.col(0)` (quadrotor_hovering.cpp:108) on the reference's
+    Eigen types against the oracle's restatement (= one forward_pass stage)."""
+    cfg = "%s_%s" % (shape, tag)
+    if not RefLib.available(cfg):
+        pytest.skip("oracle/_ref/libref_%s.so not built" % cfg)
+    prob = _prob(pkg, shape)
+    ref = RefLib(cfg)
+    rng = np.random.default_rng(11)
+    B = 64
+    x0 = rng.uniform(-2, 2, (B, prob.nx)).astype(DT[tag])
+    u = rng.uniform(-1, 1, (B, prob.N - 1, prob.nu)).astype(DT[tag])
+    exp = np.stack([ref.plant_step(prob, x0[b], u[b]) for b in range(B)])
+    got = oracle.plant_step(prob, x0, u[:, 0], dtype=DT[tag])
+    assert_same(got, exp, "plant step")
