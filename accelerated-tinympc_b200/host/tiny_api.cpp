@@ -131,6 +131,8 @@ int run_step(TinySolver *s, int which, int *term)
 
 }  // namespace
 
+namespace tinyhost { int set_error(const std::string &m) { return fail(m); } }   // for the other host translation units
+
 extern "C" {
 
 const char *tiny_last_error(void) { return g_err.c_str(); }

@@ -297,8 +297,22 @@ def main():
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         assert int(hit.sum()) == int(it.sum().item()), "host-path results differ from device-path results"
+        # the PCIe floor of this step: the same D2H bytes as one plain pinned-memory copy (explains e2e vs value)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(3):
+            hx.copy_(x, non_blocking=True); hu.copy_(u, non_blocking=True); hit.copy_(it, non_blocking=True)
+            hst.copy_(st, non_blocking=True); hrs.copy_(rs, non_blocking=True)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        d2h_ms = c0.elapsed_time(c1) / 3
+        d2h_bytes = int(B * (480 + 144 + 4 + 4 + 16))
         e2e = {"value": total_inst * esteps / float(et[0]), "unit": "solves/s",
-               "h2d_bytes_per_step": int(B * 48 + 480), "d2h_bytes_per_step": int(B * (480 + 144 + 4 + 4 + 16)),
+               "h2d_bytes_per_step": int(B * 48 + 480), "d2h_bytes_per_step": d2h_bytes,
+               "ms_per_step": 1e3 * float(et[0]) / esteps,
+               "pcie_floor": {"d2h_ms_plain_copy": d2h_ms, "d2h_gbs": d2h_bytes / (d2h_ms * 1e-3) / 1e9,
+                              "solves_per_s_if_only_d2h": B / (d2h_ms * 1e-3) * world},
                "steps": esteps, "how": "tmpc_solve(TMPC_MEM_HOST) on pinned host buffers: H2D, one persistent-kernel launch, D2H of 65,536-instance chunks gated by in-kernel completion counters (cuStreamWaitValue32)"}
 
     cpu = None

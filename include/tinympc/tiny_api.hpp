@@ -49,6 +49,15 @@ int tiny_solve_batch(TinySolver *solver, const TinyBatchIn *in, TinyBatchOut *ou
 /* policy 0 = bit-exact order of the reference's -O3 SSE2 build (default), 1 = FMA-contracted */
 int tiny_set_order_policy(TinySolver *solver, int policy);
 
+/* Codegen-compatible data files (the reference's tiny_codegen output, codegen.cpp:322-477 and :131-160).
+ * export: write solver's settings, cache, model and bounds as a `tiny_data_workspace.cpp` / `glob_opts.hpp` that a
+ *         generated TinyMPC project compiles as is (work arrays zero, as the generator writes them; Q and R exactly as
+ *         stored in solver->work -- the generator stores Q+rho, R+rho, codegen.cpp:255-256,431-436).
+ * import: parse a generated `tiny_data_workspace.cpp` (sizes are inferred from the matrices) into a new solver. */
+int tiny_export_data_workspace(const TinySolver *solver, const char *path);
+int tiny_export_glob_opts(const TinySolver *solver, const char *path);
+int tiny_import_data_workspace(TinySolver **out, const char *path);
+
 void tiny_free(TinySolver *solver);
 const char *tiny_last_error(void);
 

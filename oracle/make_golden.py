@@ -125,6 +125,34 @@ def gen_rollouts():
     print("rollout cartpole f32 iter hist:", np.bincount(rec["iter"].reshape(-1)))
 
 
+def gen_codegen():
+    """What the reference's tiny_codegen (codegen.cpp:218) emits for the cartpole model of examples/codegen_cartpole.cpp
+    and for the 20 Hz quadrotor model: src/tiny_data_workspace.cpp and tinympc/glob_opts.hpp, timestamp line removed."""
+    import shutil
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "codegen_ref")
+    cs, cm = P.cartpole_model()
+    q = P.quadrotor(20)
+    jobs = {"cartpole": (4, 1, 10, float(cs["rho"]), cm["Adyn"], cm["Bdyn"], cm["Q"].reshape(-1), cm["R"].reshape(-1), 5.0, 5.0, 100),
+            "quadrotor": (12, 4, 10, q.rho, q.Adyn, q.Bdyn, q.Q, q.R, 5.0, 0.5, 100)}
+    for name, (nx, nu, N, rho, A, B, Q, R, xb, ub, max_iter) in jobs.items():
+        tmp = tempfile.mkdtemp(prefix="tmpc_codegen_")
+        with open(os.path.join(tmp, "problem.txt"), "w") as f:
+            f.write("%d %d %d %.17g 1e-3 1e-3 %d 1\n" % (nx, nu, N, rho, max_iter))
+            for arr in (np.asarray(A).flatten(order="F"), np.asarray(B).flatten(order="F"), Q, R, np.full(nx * N, -xb), np.full(nx * N, xb),
+                        np.full(nu * (N - 1), -ub), np.full(nu * (N - 1), ub)):
+                f.write(" ".join("%.17g" % v for v in np.asarray(arr, np.float64).reshape(-1)) + "\n")
+        out = os.path.join(tmp, "generated")
+        subprocess.run([exe, os.path.join(tmp, "problem.txt"), "/root/reference", out], check=True, stdout=subprocess.DEVNULL)
+        for src, dst in (("src/tiny_data_workspace.cpp", "codegen_%s_tiny_data_workspace.cpp.txt" % name),
+                         ("tinympc/glob_opts.hpp", "codegen_%s_glob_opts.hpp.txt" % name)):
+            lines = [ln for ln in open(os.path.join(out, src)).read().split("\n") if "autogenerated by TinyMPC on" not in ln]
+            open(os.path.join(OUT, dst), "w").write("\n".join(lines))
+        shutil.rmtree(tmp)
+        print("codegen golden:", name)
+
+
 def gen_batches():
     q, c, l = P.quadrotor(20), P.cartpole(), P.random_system()
     rng = np.random.default_rng(7)
@@ -169,7 +197,7 @@ def gen_steps():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["closed_loops", "batches", "steps", "rollouts"]
+    which = sys.argv[1:] or ["closed_loops", "batches", "steps", "rollouts", "codegen"]
     if "closed_loops" in which:
         gen_closed_loops()
     if "batches" in which:
@@ -178,4 +206,6 @@ if __name__ == "__main__":
         gen_steps()
     if "rollouts" in which:
         gen_rollouts()
+    if "codegen" in which:
+        gen_codegen()
     print("fixtures:", sorted(os.listdir(OUT)))
