@@ -130,7 +130,20 @@ def cpu_reference(pkg, args, prob, quiet=False):
             "iters_per_s": float(r.iter.sum()) / dt, "mean_iters": float(r.iter.mean()), "seconds": dt}, n, dt
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything any library prints to fd 1 during the run
+    (torch.distributed's NCCL banner, for one) has been routed to stderr by main()."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -161,7 +174,7 @@ def main():
                "dtype": "f32", "data": "synthetic", "config": config,
                "cpu_baseline": {**base, "value": v},
                "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
+        emit(json.dumps(out))
         return 0
 
     import torch
@@ -308,7 +321,21 @@ def main():
         torch.cuda.synchronize()
         d2h_ms = c0.elapsed_time(c1) / 3
         d2h_bytes = int(B * (480 + 144 + 4 + 4 + 16))
+        # the same call when the caller only needs the controls (x = NULL: u, iter, status, resid come back: 168 B/solve)
+        def cstep():
+            solver.solve_raw(B, hx0, hxr, True, capi.TMPC_MEM_HOST, None, hu, hit, hst, hrs)
+        cstep()
+        barrier()
+        tc0 = time.perf_counter()
+        for _ in range(esteps):
+            cstep()
+        barrier()
+        ct = torch.tensor([time.perf_counter() - tc0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ct, op=dist.ReduceOp.MAX)
         e2e = {"value": total_inst * esteps / float(et[0]), "unit": "solves/s",
+               "controls_only": {"value": total_inst * esteps / float(ct[0]), "d2h_bytes_per_step": int(B * (144 + 4 + 4 + 16)),
+                                 "what": "same call with x = NULL (u, iter, status, resid returned)"},
                "h2d_bytes_per_step": int(B * 48 + 480), "d2h_bytes_per_step": d2h_bytes,
                "ms_per_step": 1e3 * float(et[0]) / esteps,
                "pcie_floor": {"d2h_ms_plain_copy": d2h_ms, "d2h_gbs": d2h_bytes / (d2h_ms * 1e-3) / 1e9,
@@ -331,7 +358,7 @@ def main():
                                                               float(hist[81:100].sum()), float(hist[100:].sum())],
                "lane_trips_per_iteration": stats["trips"] / max(stats["iterations"], 1),
                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
