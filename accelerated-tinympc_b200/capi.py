@@ -22,7 +22,10 @@ EXPORTS = ["tmpc_create", "tmpc_destroy", "tmpc_set_model", "tmpc_set_settings",
            "tmpc_host_alloc", "tmpc_host_free", "tmpc_last_error", "tmpc_version",
            "tmpc_batch_create", "tmpc_batch_destroy", "tmpc_batch_set_x0", "tmpc_batch_set_xref", "tmpc_batch_set_xref_table",
            "tmpc_batch_reset_dual_variables", "tmpc_batch_reset", "tmpc_batch_solve", "tmpc_batch_get", "tmpc_batch_rollout",
-           "tmpc_batch_last_rollout_ms", "tmpc_batch_last_error"]
+           "tmpc_batch_last_rollout_ms", "tmpc_batch_last_error",
+           "tmpc_systems_precompute", "tmpc_systems_destroy", "tmpc_systems_get", "tmpc_solve_systems"]
+
+SYS = {"Kinf": 0, "Pinf": 1, "Quu_inv": 2, "AmBKt": 3, "Adyn": 4, "Bdyn": 5, "Q": 6, "rho": 7, "sweeps": 8}
 
 GET = {"x": 0, "u": 1, "iter": 2, "status": 3, "resid": 4, "x0": 5, "d": 6, "y": 7, "z": 8, "g": 9, "v": 10}
 
@@ -101,6 +104,14 @@ def load():
     lib.tmpc_batch_last_rollout_ms.argtypes = [C.c_void_p]
     lib.tmpc_batch_last_error.restype = C.c_char_p
     lib.tmpc_batch_last_error.argtypes = [C.c_void_p]
+    lib.tmpc_systems_precompute.restype = C.c_int
+    lib.tmpc_systems_precompute.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.tmpc_systems_destroy.restype = C.c_int
+    lib.tmpc_systems_destroy.argtypes = [C.c_void_p]
+    lib.tmpc_systems_get.restype = C.c_int
+    lib.tmpc_systems_get.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.tmpc_solve_systems.restype = C.c_int
+    lib.tmpc_solve_systems.argtypes = [C.c_void_p, C.POINTER(TmpcSolveArgs), C.c_void_p]
     _lib = lib
     return lib
 
@@ -301,6 +312,72 @@ class Batch:
         if self._b:
             self.lib.tmpc_batch_destroy(self._b)
             self._b = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Systems:
+    """tmpc_systems: per-instance models + caches, precomputed on the device (codegen.cpp:254-292 per instance)."""
+
+    def __init__(self, solver: Solver, Adyn, Bdyn, Q, R, rho, q_plus_rho=False):
+        """Adyn [B, nx, nx], Bdyn [B, nx, nu] (numpy, natural row/col indexing), Q [B, nx], R [B, nu], rho [B]."""
+        self.s = solver
+        self.lib = solver.lib
+        dt = solver.dtype
+        A = np.ascontiguousarray(np.transpose(np.asarray(Adyn, dtype=np.float64), (0, 2, 1))).astype(dt)   # column-major per instance
+        Bm = np.ascontiguousarray(np.transpose(np.asarray(Bdyn, dtype=np.float64), (0, 2, 1))).astype(dt)
+        self.B = A.shape[0]
+        Qa = np.ascontiguousarray(Q, dtype=dt).reshape(self.B, solver.nx)
+        Ra = np.ascontiguousarray(R, dtype=dt).reshape(self.B, solver.nu)
+        rh = np.ascontiguousarray(rho, dtype=dt).reshape(self.B)
+        self.inputs = {"Adyn": A, "Bdyn": Bm, "Q": Qa, "R": Ra, "rho": rh}
+        self._p = C.c_void_p()
+        solver._check(self.lib.tmpc_systems_precompute(solver._ctx, self.B, A.ctypes.data, Bm.ctypes.data, Qa.ctypes.data, Ra.ctypes.data,
+                                                       rh.ctypes.data, 1 if q_plus_rho else 0, TMPC_MEM_HOST, C.byref(self._p)),
+                      "tmpc_systems_precompute")
+
+    def get(self, what):
+        """Cache matrices as [B, rows, cols] numpy arrays in natural indexing; sweeps / rho / Q as [B(, nx)]."""
+        s = self.s
+        nx, nu = s.nx, s.nu
+        shape = {"Kinf": (nu, nx), "Pinf": (nx, nx), "Quu_inv": (nu, nu), "AmBKt": (nx, nx), "Adyn": (nx, nx), "Bdyn": (nx, nu)}
+        if what == "sweeps":
+            out = np.empty(self.B, np.int32)
+        elif what == "rho":
+            out = np.empty(self.B, s.dtype)
+        elif what == "Q":
+            out = np.empty((self.B, nx), s.dtype)
+        else:
+            r, c = shape[what]
+            out = np.empty((self.B, c, r), s.dtype)      # column-major per instance
+        s._check(self.lib.tmpc_systems_get(self._p, SYS[what], out.ctypes.data), "tmpc_systems_get")
+        return np.transpose(out, (0, 2, 1)) if what in shape else out
+
+    def solve_raw(self, x0, Xref, xref_shared, x=None, u=None, it=None, status=None, resid=None, warm=None, stream=None):
+        """Device buffers (torch tensors / addresses) only."""
+        args = TmpcSolveArgs()
+        args.batch = self.B
+        args.x0, args.Xref = _addr(x0), _addr(Xref)
+        args.xref_shared = 1 if xref_shared else 0
+        args.mem = TMPC_MEM_DEVICE
+        w = None
+        if warm is not None:
+            w = TmpcWarm()
+            for k in ("d", "y", "g", "v", "z"):
+                setattr(w, k, _addr(warm[k]))
+            args.warm = C.pointer(w)
+        args.x, args.u, args.iter, args.status, args.resid = _addr(x), _addr(u), _addr(it), _addr(status), _addr(resid)
+        args.stream = stream
+        self.s._check(self.lib.tmpc_solve_systems(self.s._ctx, C.byref(args), self._p), "tmpc_solve_systems")
+
+    def close(self):
+        if self._p:
+            self.lib.tmpc_systems_destroy(self._p)
+            self._p = C.c_void_p()
 
     def __del__(self):
         try:

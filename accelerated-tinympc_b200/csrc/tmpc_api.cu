@@ -110,6 +110,19 @@ KernelInfo make_info()
     return k;
 }
 
+template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool PERSYS>
+KernelInfo make_info_g()
+{
+    KernelInfo k;
+    k.fn = (const void *)&tmpc::admm_kernel<T, NX, NU, NH, BLOCK, FAST, WARM, false, PERSYS>;
+    k.smem = tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES;
+    k.block = BLOCK;
+    k.model_bytes = sizeof(tmpc::Model<T, NX, NU, NH>);
+    k.model_kind = 0;
+    k.per_block = BLOCK;
+    return k;
+}
+
 template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT>
 KernelInfo make_info_f32()
 {
@@ -415,6 +428,7 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     unsigned long long *stats;
     unsigned *done;
     int done_shift;
+    const void *sys;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
@@ -425,12 +439,9 @@ void *model_param(tmpc_ctx_impl *c, const KernelInfo &ki)
     return ki.model_kind == 1 ? (void *)c->model_f32.data() : (void *)c->model.data();
 }
 
-// Launch the persistent kernel for one device-resident batch on `s`.
-int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
+// Launch one persistent kernel (already chosen) for one device-resident batch on `s`.
+int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cudaStream_t s, bool time_it)
 {
-    KernelInfo ki;
-    if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern))
-        return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
     CUDA_TRY(c, cudaFuncSetAttribute(ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
     CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), s));
     da.counter = c->d_counter;
@@ -446,6 +457,15 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
     c->stats.lanes = (int32_t)(blocks * ki.per_block);
     c->stats.pattern = c->pattern;
     return TMPC_OK;
+}
+
+// Launch the persistent kernel for one device-resident batch on `s`.
+int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
+{
+    KernelInfo ki;
+    if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern))
+        return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
+    return launch_kernel_info(c, ki, da, s, time_it);
 }
 
 int ensure_stage(tmpc_ctx_impl *c, int k, size_t in_bytes, size_t out_bytes)
@@ -1032,3 +1052,4 @@ int tmpc_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? TMPC_O
 }  // extern "C"
 
 #include "tmpc_batch.cuh"
+#include "tmpc_systems.cuh"

@@ -191,6 +191,14 @@ template <class T> struct SolveArgs {
     unsigned long long *stats;    // [0] iterations [1] solved [2] lane-trips [3] instances
     unsigned *done;               // nullable: done[inst >> done_shift] += 1 when every output of inst is written
     int done_shift;
+    const T *sys;                 // per-instance systems (PERSYS kernels): [instance][SysBlock::STRIDE], else null
+};
+
+// Per-instance system block (PERSYS: every instance brings its own model + cache; the "systems" batching axis).
+// Column-major matrices in the order below, then work.Q and rho; written by the batched precompute kernel.
+template <int NX, int NU> struct SysBlock {
+    static constexpr int K = 0, A = K + NU * NX, B = A + NX * NX, Qi = B + NX * NU, M = Qi + NU * NU, Pf = M + NX * NX,
+                         Qd = Pf + NX * NX, RHO = Qd + NX, LEN = RHO + 1, STRIDE = (LEN + 3) / 4 * 4;
 };
 
 // per-thread array of STAGES vectors of D scalars in shared memory.
@@ -291,10 +299,22 @@ template <class T, int NX, int NU, int NH, int BLOCK> struct SmemLayout {
 
 enum { PH_FREE = 0, PH_RUN = 1, PH_EMIT = 2 };
 
-template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool UNROLL>
+template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool UNROLL, bool PERSYS = false>
 __global__ void __launch_bounds__(BLOCK, 1)
 admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constant__ SolveArgs<T> a)
 {
+    // model source: the shared constant-bank image, or (PERSYS) this lane's own block in global memory, read through
+    // the read-only path every time it is used (the 2.2 KB of coefficients per instance do not fit registers)
+    using SB = SysBlock<NX, NU>;
+    const T *blk = PERSYS ? a.sys : nullptr;   // idle lanes keep a valid block (instance 0)
+    T rho_l = P.rho, nrho_l = P.nrho;
+    auto mK = [&](int i) -> T { if constexpr (PERSYS) return __ldg(blk + SB::K + i); else return P.K[i]; };
+    auto mA = [&](int i) -> T { if constexpr (PERSYS) return __ldg(blk + SB::A + i); else return P.A[i]; };
+    auto mB = [&](int i) -> T { if constexpr (PERSYS) return __ldg(blk + SB::B + i); else return P.B[i]; };
+    auto mQi = [&](int i) -> T { if constexpr (PERSYS) return __ldg(blk + SB::Qi + i); else return P.Qi[i]; };
+    auto mM = [&](int i) -> T { if constexpr (PERSYS) return __ldg(blk + SB::M + i); else return P.M[i]; };
+    auto mPf = [&](int i) -> T { if constexpr (PERSYS) return __ldg(blk + SB::Pf + i); else return P.Pf[i]; };
+    auto mQd = [&](int i) -> T { if constexpr (PERSYS) return __ldg(blk + SB::Qd + i); else return P.Qd[i]; };
     using N = Num<T>;
     using O = Orders<T, NX, NU>;
     using L = SmemLayout<T, NX, NU, NH, BLOCK>;
@@ -341,13 +361,18 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     hit_max = false;
                     res[0] = res[1] = res[2] = res[3] = T(0);
                     gload<T, NX>(a.x0 + inst * NX, x0);
+                    if constexpr (PERSYS) {
+                        blk = a.sys + inst * SB::STRIDE;
+                        rho_l = __ldg(blk + SB::RHO);
+                        nrho_l = -rho_l;
+                    }
                     // p_N seed: -(Xref_{N-1}^T * Pinf)   (admm.cpp:83)
                     {
                         T xr[NX], pn[NX];
                         gload<T, NX>(a.Xref + inst * a.xref_stride + (NH - 1) * NX, xr);
 #pragma unroll
                         for (int j = 0; j < NX; ++j)
-                            pn[j] = -dot<T, O::XtP, NX, FAST>([&](int k) { return P.Pf[k + j * NX]; },
+                            pn[j] = -dot<T, O::XtP, NX, FAST>([&](int k) { return mPf(k + j * NX); },
                                                               [&](int k) { return xr[k]; });
                         spn.store(0, pn);
                     }
@@ -423,7 +448,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     if (WARM && yo) gstore<T, NU>(yo + i * NU, y);
 #pragma unroll
                     for (int r = 0; r < NU; ++r) {
-                        T kx = dot<T, O::Kx, NX, FAST>([&](int k) { return P.K[r + k * NU]; },
+                        T kx = dot<T, O::Kx, NX, FAST>([&](int k) { return mK(r + k * NU); },
                                                        [&](int k) { return x[k]; });
                         u[r] = N::sub(-kx, d[r]);                                                // :31
                         zn[r] = N::add(u[r], y[r]);                                              // :47
@@ -438,15 +463,15 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     T xn[NX];
 #pragma unroll
                     for (int r = 0; r < NX; ++r) {
-                        T ax = dot<T, O::Ax, NX, FAST>([&](int k) { return P.A[r + k * NX]; },
+                        T ax = dot<T, O::Ax, NX, FAST>([&](int k) { return mA(r + k * NX); },
                                                        [&](int k) { return x[k]; });
                         if constexpr (FAST) {
                             T acc = ax;
 #pragma unroll
-                            for (int k = 0; k < NU; ++k) acc = N::fma(P.B[r + k * NX], u[k], acc);
+                            for (int k = 0; k < NU; ++k) acc = N::fma(mB(r + k * NX), u[k], acc);
                             xn[r] = acc;
                         } else {
-                            T bu = dot<T, O::Bu, NU, FAST>([&](int k) { return P.B[r + k * NX]; },
+                            T bu = dot<T, O::Bu, NU, FAST>([&](int k) { return mB(r + k * NX); },
                                                            [&](int k) { return u[k]; });
                             xn[r] = N::add(ax, bu);                                              // :35
                         }
@@ -471,9 +496,9 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             const bool chk = (it % P.check_term) == 0;
             if (chk) {
                 res[0] = pri_x;
-                res[1] = N::mul(dua_x, P.rho);
+                res[1] = N::mul(dua_x, rho_l);
                 res[2] = pri_u;
-                res[3] = N::mul(dua_u, P.rho);
+                res[3] = N::mul(dua_u, rho_l);
             }
             const bool conv = chk && res[0] < P.pri_tol && res[2] < P.pri_tol && res[1] < P.dua_tol &&
                               res[3] < P.dua_tol;
@@ -516,8 +541,8 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                 if (WARM && wvo) gstore<T, NX>(wvo + (NH - 1) * NX, v);
 #pragma unroll
                 for (int j = 0; j < NX; ++j) {
-                    if constexpr (FAST) p[j] = N::fma(P.nrho, N::sub(v[j], g[j]), pn[j]);
-                    else p[j] = N::sub(pn[j], N::mul(P.rho, N::sub(v[j], g[j])));                // :84
+                    if constexpr (FAST) p[j] = N::fma(nrho_l, N::sub(v[j], g[j]), pn[j]);
+                    else p[j] = N::sub(pn[j], N::mul(rho_l, N::sub(v[j], g[j])));                // :84
                 }
             }
             auto bstage = [&](int i) {
@@ -529,32 +554,32 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                 gload<T, NX>(xr_base + i * NX, xr);
                 if (WARM && wvo) { gstore<T, NX>(wvo + i * NX, v); gstore<T, NU>(wzo + i * NU, z); }
 #pragma unroll
-                for (int j = 0; j < NU; ++j) r[j] = N::mul(P.nrho, N::sub(z[j], y[j]));          // :80
+                for (int j = 0; j < NU; ++j) r[j] = N::mul(nrho_l, N::sub(z[j], y[j]));          // :80
 #pragma unroll
                 for (int j = 0; j < NX; ++j) {
-                    T cq = -N::mul(xr[j], P.Qd[j]);                                              // :81
-                    if constexpr (FAST) q[j] = N::fma(P.nrho, N::sub(v[j], g[j]), cq);
-                    else q[j] = N::sub(cq, N::mul(P.rho, N::sub(v[j], g[j])));                   // :82
+                    T cq = -N::mul(xr[j], mQd(j));                                              // :81
+                    if constexpr (FAST) q[j] = N::fma(nrho_l, N::sub(v[j], g[j]), cq);
+                    else q[j] = N::sub(cq, N::mul(rho_l, N::sub(v[j], g[j])));                   // :82
                 }
                 T s[NU], d[NU];
 #pragma unroll
                 for (int r_ = 0; r_ < NU; ++r_) {
-                    T bp = dot<T, O::Btp, NX, FAST>([&](int k) { return P.B[k + r_ * NX]; },
+                    T bp = dot<T, O::Btp, NX, FAST>([&](int k) { return mB(k + r_ * NX); },
                                                     [&](int k) { return p[k]; });
                     s[r_] = N::add(bp, r[r_]);
                 }
 #pragma unroll
                 for (int r_ = 0; r_ < NU; ++r_)
-                    d[r_] = dot<T, O::Qs, NU, FAST>([&](int k) { return P.Qi[r_ + k * NU]; },
+                    d[r_] = dot<T, O::Qs, NU, FAST>([&](int k) { return mQi(r_ + k * NU); },
                                                     [&](int k) { return s[k]; });                // :19
                 sd.store(i, d, cont);
                 if (WARM && wdo) gstore<T, NU>(wdo + i * NU, d);
                 T pn[NX];
 #pragma unroll
                 for (int r_ = 0; r_ < NX; ++r_) {
-                    T mp = dot<T, O::Mp, NX, FAST>([&](int k) { return P.M[r_ + k * NX]; },
+                    T mp = dot<T, O::Mp, NX, FAST>([&](int k) { return mM(r_ + k * NX); },
                                                    [&](int k) { return p[k]; });
-                    T kr = dot<T, O::Ktr, NU, FAST>([&](int k) { return P.K[k + r_ * NU]; },
+                    T kr = dot<T, O::Ktr, NU, FAST>([&](int k) { return mK(k + r_ * NU); },
                                                     [&](int k) { return r[k]; });
                     pn[r_] = N::sub(N::add(q[r_], mp), kr);                                      // :20
                 }

@@ -230,6 +230,22 @@ int tiny_precompute(TinySolver *s)
     return sweeps;
 }
 
+int tiny_precompute_raw(int nx, int nu, const tinytype *Adyn, const tinytype *Bdyn, const tinytype *Q, const tinytype *R, tinytype rho,
+                        tinytype *Kinf, tinytype *Pinf, tinytype *Quu_inv, tinytype *AmBKt)
+{
+    TinySolver *s = nullptr;
+    if (tiny_setup(&s, nx, nu, 2, Adyn, Bdyn, Q, R, rho, nullptr, nullptr, nullptr, nullptr, 0) != 0) return -1;
+    const int sweeps = tiny_precompute(s);
+    if (sweeps >= 0) {
+        if (Kinf) std::memcpy(Kinf, s->cache->Kinf.data(), sizeof(tinytype) * nu * nx);
+        if (Pinf) std::memcpy(Pinf, s->cache->Pinf.data(), sizeof(tinytype) * nx * nx);
+        if (Quu_inv) std::memcpy(Quu_inv, s->cache->Quu_inv.data(), sizeof(tinytype) * nu * nu);
+        if (AmBKt) std::memcpy(AmBKt, s->cache->AmBKt.data(), sizeof(tinytype) * nx * nx);
+    }
+    tiny_free(s);
+    return sweeps;
+}
+
 int tiny_set_order_policy(TinySolver *s, int policy)
 {
     if (!s || (policy != TMPC_ORDER_PARITY && policy != TMPC_ORDER_FAST)) return fail("tiny_set_order_policy: bad argument");

@@ -24,6 +24,11 @@ int tiny_setup(TinySolver **out, int nx, int nu, int N, const tinytype *Adyn, co
  * work.Q keeps the value the caller gave (the examples pass raw Q; generated code passes Q+rho). */
 int tiny_precompute(TinySolver *solver);
 
+/* The same recursion on plain column-major arrays (no solver object): what a foreign caller binds, and the host twin of
+ * the batched device precompute (tmpc_systems_precompute), which it matches bit for bit.  Returns the sweep count. */
+int tiny_precompute_raw(int nx, int nu, const tinytype *Adyn, const tinytype *Bdyn, const tinytype *Q, const tinytype *R, tinytype rho,
+                        tinytype *Kinf, tinytype *Pinf, tinytype *Quu_inv, tinytype *AmBKt);
+
 typedef struct {
     int64_t batch;
     const tinytype *x0;    /* [batch][nx] */

@@ -180,6 +180,32 @@ int tmpc_batch_rollout(tmpc_batch *b, int32_t steps, int32_t reset_duals, void *
 float tmpc_batch_last_rollout_ms(const tmpc_batch *b);   /* device time of the last rollout (CUDA events on the ctx stream) */
 const char *tmpc_batch_last_error(const tmpc_batch *b);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Per-instance SYSTEMS: every instance of the batch has its own model (Adyn, Bdyn, Q, R, rho) and therefore its own
+ * cache.  tmpc_systems_precompute runs the reference's cache recursion (tiny_codegen, codegen.cpp:254-292: Riccati
+ * fixed point on Q+rho, R+rho from P = rho*I, <= 1000 sweeps, stop at max|dKinf| < 1e-5; Quu_inv, AmBKt) for all
+ * instances on the device, one instance per thread, in double, bit-identical to the host tiny_precompute, and keeps
+ * the result device-resident; tmpc_solve_systems is tmpc_solve with those per-instance models.  Bounds, tolerances,
+ * max_iter and check_termination remain the ctx's (tmpc_set_model must have been called; its matrices are unused here).
+ *   Adyn [batch][nx*nx], Bdyn [batch][nx*nu] column-major; Q [batch][nx]; R [batch][nu]; rho [batch]; ctx dtype.
+ *   q_plus_rho: the Q used by update_linear_cost (admm.cpp:81) is Q+rho (as tiny_codegen stores it, codegen.cpp:255,433)
+ *               or Q as given (as the examples do, quadrotor_20hz_params.hpp:89). */
+typedef struct tmpc_systems tmpc_systems;
+int tmpc_systems_precompute(tmpc_ctx *ctx, int64_t batch, const void *Adyn, const void *Bdyn, const void *Q, const void *R,
+                            const void *rho, int32_t q_plus_rho, int32_t mem, tmpc_systems **out);
+int tmpc_systems_destroy(tmpc_systems *s);
+typedef enum {
+    TMPC_SYS_KINF = 0,    /* [batch][nu*nx] column-major */
+    TMPC_SYS_PINF = 1,    /* [batch][nx*nx] */
+    TMPC_SYS_QUU_INV = 2, /* [batch][nu*nu] */
+    TMPC_SYS_AMBKT = 3,   /* [batch][nx*nx] */
+    TMPC_SYS_ADYN = 4, TMPC_SYS_BDYN = 5, TMPC_SYS_Q = 6, TMPC_SYS_RHO = 7,
+    TMPC_SYS_SWEEPS = 8   /* int32 [batch]: Riccati sweeps (1000 = not converged, as silent as the reference; -1 = singular) */
+} tmpc_systems_field;
+int tmpc_systems_get(tmpc_systems *s, int32_t what, void *dst_host);
+/* tmpc_solve for a batch whose instance i uses system i.  Device buffers only (args->mem = TMPC_MEM_DEVICE). */
+int tmpc_solve_systems(tmpc_ctx *ctx, const tmpc_solve_args *args, const tmpc_systems *systems);
+
 /* Pinned host allocation helpers for TMPC_MEM_HOST callers that want full PCIe speed. */
 int tmpc_host_alloc(void **ptr, uint64_t bytes);
 int tmpc_host_free(void *ptr);
