@@ -115,21 +115,22 @@ __global__ void __launch_bounds__(64) precompute_kernel(const PrecomputeArgs<T> 
         for (int i = 0; i < n * n; ++i) AmBK[i] = __dsub_rn(A[i], BK[i]);
     }
     T *blk = a.blocks + b * SB::STRIDE;
+    for (int i = 0; i < SB::STRIDE; ++i) blk[i] = T(0);
     for (int i = 0; i < m; ++i)
-        for (int j = 0; j < n; ++j) blk[SB::K + i + j * m] = (T)Kinf[i * n + j];
+        for (int j = 0; j < n; ++j) { const T v = (T)Kinf[i * n + j]; blk[SB::K + i + j * m] = v; blk[SB::Krm + i * n + j] = v; }
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) {
-            blk[SB::A + i + j * n] = Ac[i + j * n];
-            blk[SB::M + i + j * n] = (T)AmBK[j * n + i];      // AmBKt = (A - B K)^T
+            const T av = Ac[i + j * n], mv = (T)AmBK[j * n + i];                                 // AmBKt = (A - B K)^T
+            blk[SB::A + i + j * n] = av; blk[SB::Arm + i * n + j] = av;
+            blk[SB::M + i + j * n] = mv; blk[SB::Mrm + i * n + j] = mv;
             blk[SB::Pf + i + j * n] = (T)Pinf[i * n + j];
         }
     for (int i = 0; i < n; ++i)
-        for (int j = 0; j < m; ++j) blk[SB::B + i + j * n] = Bc[i + j * n];
+        for (int j = 0; j < m; ++j) { const T v = Bc[i + j * n]; blk[SB::B + i + j * n] = v; blk[SB::Brm + i * m + j] = v; }
     for (int i = 0; i < m; ++i)
-        for (int j = 0; j < m; ++j) blk[SB::Qi + i + j * m] = (T)Sinv[i * m + j];
+        for (int j = 0; j < m; ++j) { const T v = (T)Sinv[i * m + j]; blk[SB::Qi + i + j * m] = v; blk[SB::Qirm + i * m + j] = v; }
     for (int i = 0; i < n; ++i) blk[SB::Qd + i] = a.q_plus_rho ? (T)q1[i] : a.Q[b * n + i];
     blk[SB::RHO] = a.rho[b];
-    for (int i = SB::LEN; i < SB::STRIDE; ++i) blk[i] = T(0);
     if (a.sweeps) a.sweeps[b] = singular ? -1 : sweeps;
 }
 
@@ -260,8 +261,9 @@ int tmpc_systems_get(tmpc_systems *sp, int32_t what, void *dst)
         return TMPC_OK;
     }
     int off = 0, len = 0;
-    const int oK = 0, oA = oK + nu * nx, oB = oA + nx * nx, oQi = oB + nx * nu, oM = oQi + nu * nu, oPf = oM + nx * nx, oQd = oPf + nx * nx,
-              oRho = oQd + nx;
+    int oK, oA, oB, oQi, oM, oPf, oQd, oRho;
+    if (nx == 12) { using SB = tmpc::SysBlock<12, 4>; oK = SB::K; oA = SB::A; oB = SB::B; oQi = SB::Qi; oM = SB::M; oPf = SB::Pf; oQd = SB::Qd; oRho = SB::RHO; }
+    else { using SB = tmpc::SysBlock<4, 1>; oK = SB::K; oA = SB::A; oB = SB::B; oQi = SB::Qi; oM = SB::M; oPf = SB::Pf; oQd = SB::Qd; oRho = SB::RHO; }
     switch (what) {
     case TMPC_SYS_KINF: off = oK; len = nu * nx; break;
     case TMPC_SYS_PINF: off = oPf; len = nx * nx; break;
