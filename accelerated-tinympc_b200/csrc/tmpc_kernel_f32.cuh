@@ -48,6 +48,9 @@ __device__ __forceinline__ float2 prod2(float2 a, float2 b, float2 Z) { return _
 // FFMA2 occupies the FMA pipe for two cycles like the two FMULs it replaces, and its coefficient PAIR has to come
 // through LDC.64 into registers where FMUL takes the coefficient straight from the constant bank (FMUL R,R,c[][] /
 // UR), so the packed product does not pay for the dense mat-vecs; it does for the paired AmBKt rows.
+#ifndef TMPC_SPEC_FACTOR
+#define TMPC_SPEC_FACTOR 2.0f    // speculative emission when every residual is within this factor of its tolerance (measured 1.25: 11.278 ms, 2: 11.216, 4: 11.227, always: 11.309; the remaining 6.6 % of extra lane-trips at 1M instances are the tail: exhausted lanes waiting for their warp)
+#endif
 #ifndef TMPC_PROD2_DENSE
 #define TMPC_PROD2_DENSE 0   // dense row-pair mat-vecs
 #endif
@@ -631,7 +634,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             } else {
                 // predict termination in the next trip: last allowed iteration, or every residual within 25 % of its
                 // tolerance at a check (ADMM crawls across the threshold); a wrong guess only costs stores
-                constexpr float SF = 1.25f;
+                constexpr float SF = TMPC_SPEC_FACTOR;
                 const bool next_chk = ((it + 1) % P.check_term) == 0;
                 spec = (it + 1 >= P.max_iter) ||
                        (next_chk && res[0] < SF * P.pri_tol && res[2] < SF * P.pri_tol && res[1] < SF * P.dua_tol && res[3] < SF * P.dua_tol);
