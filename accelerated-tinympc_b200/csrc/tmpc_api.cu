@@ -136,12 +136,12 @@ KernelInfo make_info_f32()
     return k;
 }
 
-template <int NH, int WARPS, bool FAST, bool WARM>
+template <int NH, int WARPS, bool FAST, bool WARM, bool TM>
 KernelInfo make_info_warp()
 {
     KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_warp<NH, WARPS, FAST, WARM>;
-    k.smem = tmpc::WarpSmem<NH>::BYTES * WARPS;
+    k.fn = (const void *)&tmpc::admm_kernel_warp<NH, WARPS, FAST, WARM, TM>;
+    k.smem = tmpc::WarpSmem<NH, TM>::total_bytes(WARPS);
     k.block = WARPS * 32;
     k.model_bytes = sizeof(tmpc::ModelWarp);
     k.model_kind = 2;
@@ -149,12 +149,12 @@ KernelInfo make_info_warp()
     return k;
 }
 
-template <int NH, int WARPS>
+template <int NH, int WARPS, bool TM>
 bool pick_warp(int policy, bool warm, KernelInfo &out)
 {
-    static_assert(tmpc::WarpSmem<NH>::BYTES * WARPS <= 232448, "per-block shared memory limit of sm_100");
-    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_warp<NH, WARPS, false, true>() : make_info_warp<NH, WARPS, false, false>();
-    else out = warm ? make_info_warp<NH, WARPS, true, true>() : make_info_warp<NH, WARPS, true, false>();
+    static_assert(tmpc::WarpSmem<NH, TM>::total_bytes(WARPS) <= 232448, "per-block shared memory limit of sm_100");
+    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_warp<NH, WARPS, false, true, TM>() : make_info_warp<NH, WARPS, false, false, TM>();
+    else out = warm ? make_info_warp<NH, WARPS, true, true, TM>() : make_info_warp<NH, WARPS, true, false, TM>();
     return true;
 }
 
@@ -211,8 +211,13 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
         if (dtype == TMPC_F32) return pick<float, 4, 1, 10, 512, false>(policy, warm, out);   // 444 B of state: 512 instances / SM
         return pick<double, 4, 1, 10, 128, false>(policy, warm, out);
     }
-    // large shape: one warp per instance, 17.8 KB of shared memory each -> 12 instances / SM
-    if (nx == 32 && nu == 8 && N == 50 && dtype == TMPC_F32) return pick_warp<50, 12>(policy, warm, out);
+    // large shape: one warp per instance.  g,v in tensor memory -> 16 instances / SM (TMPC_KERNEL=warp_smem: all state in
+    // shared memory, 17.8 KB each -> 12 instances / SM)
+    if (nx == 32 && nu == 8 && N == 50 && dtype == TMPC_F32) {
+        const char *e = getenv("TMPC_KERNEL");
+        if (e && !strcmp(e, "warp_smem")) return pick_warp<50, 12, false>(policy, warm, out);
+        return pick_warp<50, 16, true>(policy, warm, out);
+    }
     return false;
 }
 
@@ -389,6 +394,7 @@ bool build_model_warp(tmpc_ctx_impl *c)
     m.rho = (float)c->rho; m.nrho = -(float)c->rho;
     m.pri_tol = (float)c->pri; m.dua_tol = (float)c->dua;
     m.max_iter = c->max_iter; m.check_term = c->check_term;
+    m.nz2 = make_float2(-0.0f, -0.0f);
     return true;
 }
 

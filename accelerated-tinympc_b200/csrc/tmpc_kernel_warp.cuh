@@ -49,26 +49,70 @@ struct ModelWarp {
     const float *umin, *umax;   // [NH-1][8]
     float rho, nrho, pri_tol, dua_tol;
     int max_iter, check_term;
+    float2 nz2;                 // (-0, -0): addend of the exactly rounded packed product (prod2, tmpc_kernel_f32.cuh)
 };
 constexpr int WARP_FWD4 = 18, WARP_BWD4 = 14;
 
-template <int NH> struct WarpSmem {
-    static constexpr int G = 0, V = G + NH * WNX, D = V + NH * WNX, Y = D + (NH - 1) * WNU, Z = Y + (NH - 1) * WNU,
+// K individually rounded products c[k]*x[k].  TMPC_WARP_PROD2 = 1 forms them two per FFMA2 (prod2: here the coefficient
+// pairs sit in registers, so the packed product halves the multiply instructions of every mat-vec).  Measured on B200
+// (32,768 instances, PARITY, cold): 5.11e7 it/s with scalar FMUL, 4.97e7 it/s packed -- FFMA2 occupies the FMA pipe for two
+// cycles and lengthens the dependent chains, and this kernel is latency-bound, not issue-bound.  Default: scalar.
+#ifndef TMPC_WARP_PROD2
+#define TMPC_WARP_PROD2 0
+#endif
+template <int K> __device__ __forceinline__ void prod_pairs(const float (&c)[K], const float (&x)[K], float (&e)[K], const float2 Z)
+{
+    static_assert(K % 2 == 0, "pairs");
+#pragma unroll
+    for (int m = 0; m < K / 2; ++m) {
+        if constexpr (TMPC_WARP_PROD2) {
+            const float2 r = prod2(f2(c[2 * m], c[2 * m + 1]), f2(x[2 * m], x[2 * m + 1]), Z);
+            e[2 * m] = r.x; e[2 * m + 1] = r.y;
+        } else {
+            e[2 * m] = __fmul_rn(c[2 * m], x[2 * m]); e[2 * m + 1] = __fmul_rn(c[2 * m + 1], x[2 * m + 1]);
+        }
+    }
+}
+template <int K> __device__ __forceinline__ float sum_seq(const float (&e)[K])
+{
+    float acc = e[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) acc = __fadd_rn(e[k], acc);
+    return acc;
+}
+
+// TM = g and v (2 x NH x 32 floats, 73 % of the per-instance state) live in TENSOR MEMORY instead of shared memory:
+// lane j's TMEM lane holds row j, one column per horizon stage (tcgen05.ld/st.32x32b.x1), 2*NH columns per instance,
+// so the 4 warps that share a TMEM lane quadrant hold 4 instances in 400 of its 512 columns.  Shared memory then keeps
+// only d, y, z and the broadcast buffers (5 KB per instance): 16 warps = 16 instances per SM instead of 12, and room
+// for the bound rows and the coefficient images (read with LDS instead of LDG).
+template <int NH, bool TM = false> struct WarpSmem {
+    static constexpr int G = 0, V = G + (TM ? 0 : NH * WNX), D = V + (TM ? 0 : NH * WNX), Y = D + (NH - 1) * WNU, Z = Y + (NH - 1) * WNU,
                          PN = Z + (NH - 1) * WNU, XB = PN + WNX, UB = XB + WNX, SB = UB + WNU, FLOATS = SB + WNU;
     static constexpr size_t BYTES = size_t(FLOATS) * 4;
     static_assert(FLOATS % 4 == 0, "per-warp regions stay 16-byte aligned");
+    // CTA-shared staging (TM only): fwd4 | bwd4 | xmin | xmax | umin | umax, then the TMEM base slot
+    static constexpr int SH_FWD = 0, SH_BWD = SH_FWD + WARP_FWD4 * 32 * 4, SH_XMIN = SH_BWD + WARP_BWD4 * 32 * 4, SH_XMAX = SH_XMIN + NH * WNX,
+                         SH_UMIN = SH_XMAX + NH * WNX, SH_UMAX = SH_UMIN + (NH - 1) * WNU, SH_SLOT = SH_UMAX + (NH - 1) * WNU,
+                         SH_FLOATS = TM ? SH_SLOT + 4 : 0;
+    static constexpr size_t total_bytes(int warps) { return size_t(SH_FLOATS) * 4 + BYTES * warps; }
 };
+
+__device__ __forceinline__ void tm_ld1(uint32_t a, float &r) { asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(r) : "r"(a) : "memory"); }
+__device__ __forceinline__ void tm_st1(uint32_t a, float r) { asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(a), "f"(r) : "memory"); }
+__device__ __forceinline__ void tm_wait_ld2(float &a, float &b) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a), "+f"(b) :: "memory"); }
 
 __device__ __forceinline__ float warp_max_nonneg(float v)
 {
     return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
 }
 
-template <int NH, int WARPS, bool FAST, bool WARM>
+template <int NH, int WARPS, bool FAST, bool WARM, bool TM = false>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ SolveArgs<float> a)
 {
-    using S = WarpSmem<NH>;
+    using S = WarpSmem<NH, TM>;
+    static_assert(!TM || (WARPS % 4 == 0 && (WARPS / 4) * 2 * NH <= 512), "TMEM: WARPS/4 instances per lane quadrant, 2*NH columns each");
     constexpr unsigned FULLM = 0xffffffffu;
     constexpr int XROW = WNX * NH, UROW = WNU * (NH - 1);
     extern __shared__ __align__(16) unsigned char smem[];
@@ -76,15 +120,53 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
     const int ur = lane >> 2;            // the nu-row this lane carries (replicated over 4 lanes)
     const int sl = lane & 3;             // SIMD lane of the reference's packet in the row-major GEMV
     const bool uw = (sl == 0);           // the lane of each group that writes nu-vectors
-    float *ws = reinterpret_cast<float *>(smem) + size_t(warp) * S::FLOATS;
+    float *shr = reinterpret_cast<float *>(smem);                                   // CTA-shared staging (TM)
+    float *ws = shr + S::SH_FLOATS + size_t(warp) * S::FLOATS;
     float *sg = ws + S::G, *sv = ws + S::V, *sd = ws + S::D, *sy = ws + S::Y, *sz = ws + S::Z, *spn = ws + S::PN;
     float *xb = ws + S::XB, *ub = ws + S::UB, *sb = ws + S::SB;
     const float4 *xb4 = reinterpret_cast<const float4 *>(xb);
     const float4 *ub4 = reinterpret_cast<const float4 *>(ub);
     const float4 *sb4 = reinterpret_cast<const float4 *>(sb);
     const float Qd = __ldg(P.Qd + lane);
+    const float2 Z = P.nz2;
     const bool warm = WARM && a.wd;
     unsigned long long n_iter = 0, n_solved = 0, n_inst = 0;
+
+    // model sources: global memory (read-only path), or their shared-memory copies when TM leaves the room
+    const float4 *fwd4 = P.fwd4, *bwd4 = P.bwd4;
+    const float *bxmin = P.xmin, *bxmax = P.xmax, *bumin = P.umin, *bumax = P.umax;
+    uint32_t gcol = 0, vcol = 0;   // TMEM addresses of this warp's g / v columns (stage i at +i)
+    if constexpr (TM) {
+        uint32_t *slot = reinterpret_cast<uint32_t *>(shr + S::SH_SLOT);
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"((uint32_t)__cvta_generic_to_shared(slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        for (int k = threadIdx.x; k < WARP_FWD4 * 32; k += WARPS * 32) reinterpret_cast<float4 *>(shr + S::SH_FWD)[k] = __ldg(P.fwd4 + k);
+        for (int k = threadIdx.x; k < WARP_BWD4 * 32; k += WARPS * 32) reinterpret_cast<float4 *>(shr + S::SH_BWD)[k] = __ldg(P.bwd4 + k);
+        for (int k = threadIdx.x; k < NH * WNX; k += WARPS * 32) { shr[S::SH_XMIN + k] = __ldg(P.xmin + k); shr[S::SH_XMAX + k] = __ldg(P.xmax + k); }
+        for (int k = threadIdx.x; k < (NH - 1) * WNU; k += WARPS * 32) { shr[S::SH_UMIN + k] = __ldg(P.umin + k); shr[S::SH_UMAX + k] = __ldg(P.umax + k); }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = *slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 2 * NH);
+        gcol = base; vcol = base + NH;
+        fwd4 = reinterpret_cast<const float4 *>(shr + S::SH_FWD); bwd4 = reinterpret_cast<const float4 *>(shr + S::SH_BWD);
+        bxmin = shr + S::SH_XMIN; bxmax = shr + S::SH_XMAX; bumin = shr + S::SH_UMIN; bumax = shr + S::SH_UMAX;
+    }
+    // state rows g_i[lane], v_i[lane]: shared memory, or TMEM columns (loads complete at gv_wait)
+    auto gv_load = [&](int i, float &g, float &v) {
+        if constexpr (TM) { tm_ld1(gcol + i, g); tm_ld1(vcol + i, v); }
+        else { g = sg[i * WNX + lane]; v = sv[i * WNX + lane]; }
+    };
+    auto gv_wait = [&](float &g, float &v) { if constexpr (TM) tm_wait_ld2(g, v); };
+    auto gv_store = [&](int i, float g, float v) {
+        if constexpr (TM) { tm_st1(gcol + i, g); tm_st1(vcol + i, v); }
+        else { sg[i * WNX + lane] = g; sv[i * WNX + lane] = v; }
+    };
+    auto gv_fence = [&]() { if constexpr (TM) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); };
+    auto ld4 = [&](const float4 *p) -> float4 { if constexpr (TM) return *p; else return __ldg(p); };
+    auto ld1 = [&](const float *p) -> float { if constexpr (TM) return *p; else return __ldg(p); };
 
     for (;;) {
         long long inst;
@@ -107,11 +189,14 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
             const float *gd = a.wd + inst * UROW, *gy = a.wy + inst * UROW, *gz = a.wz + inst * UROW;
             const float *gg = a.wg + inst * XROW, *gv = a.wv + inst * XROW;
             for (int k = lane; k < UROW; k += 32) { sd[k] = gd[k]; sy[k] = gy[k]; sz[k] = gz[k]; }
-            for (int k = lane; k < XROW; k += 32) { sg[k] = gg[k]; sv[k] = gv[k]; }
+#pragma unroll 2
+            for (int i = 0; i < NH; ++i) gv_store(i, gg[i * WNX + lane], gv[i * WNX + lane]);
         } else {
             for (int k = lane; k < UROW; k += 32) { sd[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
-            for (int k = lane; k < XROW; k += 32) { sg[k] = 0.f; sv[k] = 0.f; }
+#pragma unroll 2
+            for (int i = 0; i < NH; ++i) gv_store(i, 0.f, 0.f);
         }
+        gv_fence();
         __syncwarp();
 
         float *xo = a.x ? a.x + inst * XROW : nullptr;
@@ -129,25 +214,27 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                 float Ac[WNX], Kc[WNX], Bc[WNU];
 #pragma unroll
                 for (int g4 = 0; g4 < 8; ++g4) {
-                    const float4 t = __ldg(P.fwd4 + g4 * 32 + lane), s = __ldg(P.fwd4 + (8 + g4) * 32 + lane);
+                    const float4 t = ld4(fwd4 + g4 * 32 + lane), s = ld4(fwd4 + (8 + g4) * 32 + lane);
                     Ac[4 * g4] = t.x; Ac[4 * g4 + 1] = t.y; Ac[4 * g4 + 2] = t.z; Ac[4 * g4 + 3] = t.w;
                     Kc[4 * g4] = s.x; Kc[4 * g4 + 1] = s.y; Kc[4 * g4 + 2] = s.z; Kc[4 * g4 + 3] = s.w;
                 }
 #pragma unroll
                 for (int g4 = 0; g4 < 2; ++g4) {
-                    const float4 t = __ldg(P.fwd4 + (16 + g4) * 32 + lane);
+                    const float4 t = ld4(fwd4 + (16 + g4) * 32 + lane);
                     Bc[4 * g4] = t.x; Bc[4 * g4 + 1] = t.y; Bc[4 * g4 + 2] = t.z; Bc[4 * g4 + 3] = t.w;
                 }
                 float x = x0;
                 // stage operands are fetched one stage ahead (shared-memory state and the global bound rows), so
                 // their latency overlaps the previous stage's Bdyn u chain instead of heading the dependent chain
-                float xmn = __ldg(P.xmin + lane), xmx = __ldg(P.xmax + lane);
-                float umn = __ldg(P.umin + ur), umx = __ldg(P.umax + ur);
-                float g = sg[lane], v = sv[lane], d = sd[ur], y = sy[ur], z = sz[ur];
+                float xmn = ld1(bxmin + lane), xmx = ld1(bxmax + lane);
+                float umn = ld1(bumin + ur), umx = ld1(bumax + ur);
+                float g, v, d = sd[ur], y = sy[ur], z = sz[ur];
+                gv_load(0, g, v);
 #pragma unroll 1
                 for (int i = 0; i < NH - 1; ++i) {
                     xb[lane] = x;
                     __syncwarp();
+                    gv_wait(g, v);
                     if (xo) xo[i * WNX + lane] = x;
                     // [Kinf(ur,:) ; Adyn(lane,:)] x_i : two sequential chains advancing together as one float2
                     float2 ka;
@@ -162,7 +249,8 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                                 if (k == 0) ka = __fmul2_rn(f2(Kc[0], Ac[0]), f2(xs[0], xs[0]));
                                 else ka = __ffma2_rn(f2(Kc[k], Ac[k]), f2(xs[t], xs[t]), ka);
                             } else {
-                                const float2 e = f2(__fmul_rn(Kc[k], xs[t]), __fmul_rn(Ac[k], xs[t]));
+                                const float2 e = TMPC_WARP_PROD2 ? prod2(f2(Kc[k], Ac[k]), f2(xs[t], xs[t]), Z)
+                                                                 : f2(__fmul_rn(Kc[k], xs[t]), __fmul_rn(Ac[k], xs[t]));
                                 if (k == 0) ka = e;
                                 else ka = add2(e, ka);
                             }
@@ -178,8 +266,7 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                     pri_x = fmaxf(pri_x, fabsf(rp.x)); pri_u = fmaxf(pri_u, fabsf(rp.y));              // :95,:97
                     dua_x = fmaxf(dua_x, fabsf(rd.x)); dua_u = fmaxf(dua_u, fabsf(rd.y));              // :96,:98
                     const float2 gyn = sub2(add2(gy, xu), t);                                          // :69-70
-                    sg[i * WNX + lane] = gyn.x;
-                    sv[i * WNX + lane] = t.x;
+                    gv_store(i, gyn.x, t.x);
                     if (uw) {
                         sy[i * WNU + ur] = gyn.y;
                         sz[i * WNU + ur] = t.y;
@@ -189,9 +276,9 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                     __syncwarp();
                     {   // operands of stage i+1 (the nu-rows of the last stage do not exist: re-read stage i's)
                         const int in = i + 1, iu = (in < NH - 1) ? in : i;
-                        xmn = __ldg(P.xmin + in * WNX + lane); xmx = __ldg(P.xmax + in * WNX + lane);
-                        umn = __ldg(P.umin + iu * WNU + ur); umx = __ldg(P.umax + iu * WNU + ur);
-                        g = sg[in * WNX + lane]; v = sv[in * WNX + lane];
+                        xmn = ld1(bxmin + in * WNX + lane); xmx = ld1(bxmax + in * WNX + lane);
+                        umn = ld1(bumin + iu * WNU + ur); umx = ld1(bumax + iu * WNU + ur);
+                        gv_load(in, g, v);
                         d = sd[iu * WNU + ur]; y = sy[iu * WNU + ur]; z = sz[iu * WNU + ur];
                     }
                     // x_{i+1} = Adyn x_i + Bdyn u_i                                                     :35
@@ -204,21 +291,22 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                         for (int k = 0; k < WNU; ++k) bu = __fmaf_rn(Bc[k], us[k], bu);
                         x = bu;
                     } else {
-                        bu = __fmul_rn(Bc[0], us[0]);
-#pragma unroll
-                        for (int k = 1; k < WNU; ++k) bu = __fadd_rn(__fmul_rn(Bc[k], us[k]), bu);
+                        float eb[WNU];
+                        prod_pairs<WNU>(Bc, us, eb, Z);
+                        bu = sum_seq<WNU>(eb);
                         x = __fadd_rn(ka.y, bu);
                     }
                 }
                 {   // last stage: state slack / dual only
                     constexpr int i = NH - 1;
+                    gv_wait(g, v);
                     if (xo) xo[i * WNX + lane] = x;
                     float t = __fadd_rn(x, g);
                     t = fminf(xmx, fmaxf(xmn, t));
                     pri_x = fmaxf(pri_x, fabsf(__fsub_rn(x, t)));
                     dua_x = fmaxf(dua_x, fabsf(__fsub_rn(v, t)));
-                    sg[i * WNX + lane] = __fsub_rn(__fadd_rn(g, x), t);
-                    sv[i * WNX + lane] = t;
+                    gv_store(i, __fsub_rn(__fadd_rn(g, x), t), t);
+                    gv_fence();
                 }
             }
             // -------------------------------------------------------------- termination (admm.cpp:91-109, :135-138)
@@ -241,13 +329,13 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                 float Mc[WNX], BTc[WNU], Qic[WNU], KTc[WNU];
 #pragma unroll
                 for (int g4 = 0; g4 < 8; ++g4) {
-                    const float4 t = __ldg(P.bwd4 + g4 * 32 + lane);
+                    const float4 t = ld4(bwd4 + g4 * 32 + lane);
                     Mc[4 * g4] = t.x; Mc[4 * g4 + 1] = t.y; Mc[4 * g4 + 2] = t.z; Mc[4 * g4 + 3] = t.w;
                 }
 #pragma unroll
                 for (int g4 = 0; g4 < 2; ++g4) {
-                    const float4 t = __ldg(P.bwd4 + (8 + g4) * 32 + lane), s = __ldg(P.bwd4 + (10 + g4) * 32 + lane),
-                                 w = __ldg(P.bwd4 + (12 + g4) * 32 + lane);
+                    const float4 t = ld4(bwd4 + (8 + g4) * 32 + lane), s = ld4(bwd4 + (10 + g4) * 32 + lane),
+                                 w = ld4(bwd4 + (12 + g4) * 32 + lane);
                     BTc[4 * g4] = t.x; BTc[4 * g4 + 1] = t.y; BTc[4 * g4 + 2] = t.z; BTc[4 * g4 + 3] = t.w;
                     Qic[4 * g4] = s.x; Qic[4 * g4 + 1] = s.y; Qic[4 * g4 + 2] = s.z; Qic[4 * g4 + 3] = s.w;
                     KTc[4 * g4] = w.x; KTc[4 * g4 + 1] = w.y; KTc[4 * g4 + 2] = w.z; KTc[4 * g4 + 3] = w.w;
@@ -257,7 +345,10 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                 float *wzo = warm ? a.wz + inst * UROW : nullptr;
                 float p;
                 {
-                    const float v = sv[(NH - 1) * WNX + lane], g = sg[(NH - 1) * WNX + lane], pn = spn[lane];
+                    float v, g;
+                    gv_load(NH - 1, g, v);
+                    const float pn = spn[lane];
+                    gv_wait(g, v);
                     if (WARM && wvo) wvo[(NH - 1) * WNX + lane] = v;
                     const float dvg = __fsub_rn(v, g);
                     if constexpr (FAST) p = __fmaf_rn(P.nrho, dvg, pn);
@@ -265,11 +356,13 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                 }
                 // stage operands one stage ahead, as in the forward sweep
                 float z = sz[(NH - 2) * WNU + ur], y = sy[(NH - 2) * WNU + ur];
-                float v = sv[(NH - 2) * WNX + lane], g = sg[(NH - 2) * WNX + lane];
+                float v, g;
+                gv_load(NH - 2, g, v);
                 float xr = __ldg(xref + (NH - 2) * WNX + lane);
 #pragma unroll 1
                 for (int i = NH - 2; i >= 0; --i) {
                     const float r = __fmul_rn(P.nrho, __fsub_rn(z, y));                                // :80
+                    gv_wait(g, v);
                     xb[lane] = p;
                     if (uw) ub[ur] = r;
                     if (WARM && wvo) {
@@ -284,9 +377,11 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
 #pragma unroll
                         for (int j = 1; j < 8; ++j) bp = __fmaf_rn(BTc[j], xb[4 * j + sl], bp);
                     } else {
-                        bp = __fmul_rn(BTc[0], xb[sl]);
+                        float pj[8], ej[8];
 #pragma unroll
-                        for (int j = 1; j < 8; ++j) bp = __fadd_rn(__fmul_rn(BTc[j], xb[4 * j + sl]), bp);
+                        for (int j = 0; j < 8; ++j) pj[j] = xb[4 * j + sl];
+                        prod_pairs<8>(BTc, pj, ej, Z);
+                        bp = sum_seq<8>(ej);
                     }
                     bp = __fadd_rn(bp, __shfl_xor_sync(FULLM, bp, 2));       // (l0+l2), (l1+l3)
                     bp = __fadd_rn(bp, __shfl_xor_sync(FULLM, bp, 1));       // (l0+l2)+(l1+l3)
@@ -299,10 +394,24 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                         const float4 t = xb4[g4];
                         pv[4 * g4] = t.x; pv[4 * g4 + 1] = t.y; pv[4 * g4 + 2] = t.z; pv[4 * g4 + 3] = t.w;
                     }
-                    const float mp = dot<float, ORD_TREE, WNX, FAST>([&](int k) { return Mc[k]; }, [&](int k) { return pv[k]; });
+                    float mp;
+                    if constexpr (FAST) mp = dot<float, ORD_TREE, WNX, true>([&](int k) { return Mc[k]; }, [&](int k) { return pv[k]; });
+                    else {
+                        float em[WNX];
+                        prod_pairs<WNX>(Mc, pv, em, Z);
+                        mp = red_tree<float, 0, WNX>([&](int k) { return em[k]; });
+                    }
                     const float4 r0 = ub4[0], r1 = ub4[1];
                     const float rs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                    const float kr = dot<float, ORD_VECREDUX, WNU, FAST>([&](int k) { return KTc[k]; }, [&](int k) { return rs[k]; });
+                    float kr;
+                    if constexpr (FAST) kr = dot<float, ORD_VECREDUX, WNU, true>([&](int k) { return KTc[k]; }, [&](int k) { return rs[k]; });
+                    else {
+                        float ek[WNU];
+                        prod_pairs<WNU>(KTc, rs, ek, Z);
+                        const float2 l01 = add2(f2(ek[0], ek[1]), f2(ek[4], ek[5])), l23 = add2(f2(ek[2], ek[3]), f2(ek[6], ek[7]));
+                        const float2 t = add2(l01, l23);                     // (l0+l2, l1+l3)
+                        kr = __fadd_rn(t.x, t.y);
+                    }
                     const float cq = -__fmul_rn(xr, Qd);                                               // :81
                     const float dvg = __fsub_rn(v, g);
                     float q;
@@ -312,13 +421,19 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                     {   // operands of stage i-1
                         const int ip = (i > 0) ? i - 1 : 0;
                         z = sz[ip * WNU + ur]; y = sy[ip * WNU + ur];
-                        v = sv[ip * WNX + lane]; g = sg[ip * WNX + lane];
+                        gv_load(ip, g, v);
                         xr = __ldg(xref + ip * WNX + lane);
                     }
                     // d_i = Quu_inv (Bdyn^T p_{i+1} + r_i)                                              :19
                     const float4 s0 = sb4[0], s1 = sb4[1];
                     const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                    const float d = dot<float, ORD_SEQ, WNU, FAST>([&](int k) { return Qic[k]; }, [&](int k) { return ss[k]; });
+                    float d;
+                    if constexpr (FAST) d = dot<float, ORD_SEQ, WNU, true>([&](int k) { return Qic[k]; }, [&](int k) { return ss[k]; });
+                    else {
+                        float ed[WNU];
+                        prod_pairs<WNU>(Qic, ss, ed, Z);
+                        d = sum_seq<WNU>(ed);
+                    }
                     if (uw) {
                         if (!last) sd[i * WNU + ur] = d;
                         if (WARM && wdo) wdo[i * WNU + ur] = d;
@@ -335,7 +450,13 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
             float *gy = a.wy + inst * UROW, *gg = a.wg + inst * XROW;
             __syncwarp();
             for (int k = lane; k < UROW; k += 32) gy[k] = sy[k];
-            for (int k = lane; k < XROW; k += 32) gg[k] = sg[k];
+#pragma unroll 2
+            for (int i = 0; i < NH; ++i) {
+                float g, v;
+                gv_load(i, g, v);
+                gv_wait(g, v);
+                gg[i * WNX + lane] = g;
+            }
         }
         if (lane == 0) {
             if (a.iter) a.iter[inst] = it;
@@ -355,6 +476,14 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
         atomicAdd(a.stats + 1, n_solved);
         atomicAdd(a.stats + 2, n_iter);   // lane-trips == iterations: no emission trip, no idle lanes
         atomicAdd(a.stats + 3, n_inst);
+    }
+    if constexpr (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t base = *reinterpret_cast<uint32_t *>(shr + S::SH_SLOT);
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(base) : "memory");
+        }
     }
 }
 
