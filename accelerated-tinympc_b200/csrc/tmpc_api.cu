@@ -526,6 +526,7 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
         wait32_probed = true;
     }
     int shift = 16;                                   // 65,536 instances per D2H chunk
+    if (const char *e = getenv("TMPC_D2H_SHIFT")) shift = std::max(10, std::min(20, atoi(e)));
     while (shift > 10 && (B >> shift) < 8) --shift;   // small batches: at least ~8 chunks, >= 1024 instances each
     const int64_t CH = (int64_t)1 << shift;
     const int nch = (int)((B + CH - 1) / CH);
