@@ -110,12 +110,12 @@ KernelInfo make_info()
     return k;
 }
 
-template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool PERSYS>
+template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, int SYS>
 KernelInfo make_info_g()
 {
     KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel<T, NX, NU, NH, BLOCK, FAST, WARM, false, PERSYS>;
-    k.smem = tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES;
+    k.fn = (const void *)&tmpc::admm_kernel<T, NX, NU, NH, BLOCK, FAST, WARM, false, SYS>;
+    k.smem = tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES + (SYS == 2 ? 16 : 0);   // + the TMEM base slot
     k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::Model<T, NX, NU, NH>);
     k.model_kind = 0;

@@ -200,20 +200,71 @@ template <class T> struct SolveArgs {
 // kernel fetches with vector loads (4x fewer L1 requests than element-wise access to a lane-private 2-4 KB block).
 __host__ __device__ constexpr int sys_al(int v) { return (v + 3) / 4 * 4; }
 template <int NX, int NU> struct SysBlock {
-    static constexpr int K = 0,                         // Kinf     col-major  (rows of Kinf^T)
-                         Krm = sys_al(K + NU * NX),     // Kinf     row-major
-                         A = sys_al(Krm + NU * NX),     // Adyn     col-major
-                         Arm = sys_al(A + NX * NX),     // Adyn     row-major
-                         B = sys_al(Arm + NX * NX),     // Bdyn     col-major  (rows of Bdyn^T)
-                         Brm = sys_al(B + NX * NU),     // Bdyn     row-major
-                         Qi = sys_al(Brm + NX * NU),    // Quu_inv  col-major
-                         Qirm = sys_al(Qi + NU * NU),   // Quu_inv  row-major
-                         M = sys_al(Qirm + NU * NU),    // AmBKt    col-major
-                         Mrm = sys_al(M + NX * NX),     // AmBKt    row-major
-                         Pf = sys_al(Mrm + NX * NX),    // Pinf     col-major  (columns = what Xref^T Pinf sweeps)
+    // the coefficients the ADMM loop sweeps, each dot product's vector contiguous; this prefix [0, TMLEN) is also the
+    // image a lane keeps in tensor memory (SYS == 2: TMEM column = block offset)
+    static constexpr int Krm = 0,                       // Kinf     row-major
+                         Arm = sys_al(Krm + NU * NX),   // Adyn     row-major
+                         Brm = sys_al(Arm + NX * NX),   // Bdyn     row-major
+                         B = sys_al(Brm + NX * NU),     // Bdyn     col-major  (rows of Bdyn^T)
+                         Qirm = sys_al(B + NX * NU),    // Quu_inv  row-major
+                         Mrm = sys_al(Qirm + NU * NU),  // AmBKt    row-major
+                         K = sys_al(Mrm + NX * NX),     // Kinf     col-major  (rows of Kinf^T)
+                         TMLEN = sys_al(K + NU * NX),
+                         // the rest: seed / getters
+                         A = TMLEN,                     // Adyn     col-major
+                         Qi = sys_al(A + NX * NX),      // Quu_inv  col-major
+                         M = sys_al(Qi + NU * NU),      // AmBKt    col-major
+                         Pf = sys_al(M + NX * NX),      // Pinf     col-major  (columns = what Xref^T Pinf sweeps)
                          Qd = sys_al(Pf + NX * NX),     // work.Q
                          RHO = sys_al(Qd + NX), LEN = RHO + 1, STRIDE = sys_al(LEN);
 };
+
+// ---- tensor memory as a per-thread scratchpad (tcgen05.ld/st.32x32b: thread t of a warp owns TMEM lane 32*(warp%4)+t) ----
+__device__ __forceinline__ void tm_ld8(uint32_t a, float *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tm_ld4(uint32_t a, float *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t a, const float *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(a), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tm_st4(uint32_t a, const float *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 :: "r"(a), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// The loaded registers are only valid after tcgen05.wait::ld; passing them through the wait as in/out operands
+// gives the compiler the data dependence (it must not schedule a use above the wait).
+__device__ __forceinline__ void tm_wait4(float *r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]) :: "memory");
+}
+__device__ __forceinline__ void tm_wait8(float *r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]) :: "memory");
+}
+__device__ __forceinline__ void tm_wait12(float *r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                   "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]) :: "memory");
+}
+__device__ __forceinline__ void tm_wait16(float *r, float *q)   // a 12-vector and a 4-vector in flight together
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                   "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(q[0]), "+f"(q[1]), "+f"(q[2]), "+f"(q[3]) :: "memory");
+}
 
 // per-thread array of STAGES vectors of D scalars in shared memory.
 //  D % VEC == 0: [chunk][thread] with 16-byte chunks (conflict-free 128-bit access);
@@ -313,10 +364,38 @@ template <class T, int NX, int NU, int NH, int BLOCK> struct SmemLayout {
 
 enum { PH_FREE = 0, PH_RUN = 1, PH_EMIT = 2 };
 
-template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool UNROLL, bool PERSYS = false>
+// coefficient vector of one dot product for the per-instance-systems kernels: `off` elements into the lane's block
+// (16-byte vector loads through the read-only path), or (TM) the same offset in the lane's tensor-memory columns.
+// issue() starts the fetch, ready() completes it, so the next row is in flight while the current one is consumed.
+template <class T, int K, bool TM> __device__ __forceinline__ void crow_issue(const T *blk, uint32_t tcol, int off, T (&c)[K])
+{
+    if constexpr (TM) {
+        static_assert(sizeof(T) == 4 && (K == 12 || K == 4), "TMEM rows: 12 or 4 floats");
+        if constexpr (K == 12) { tm_ld8(tcol + off, c); tm_ld4(tcol + off + 8, c + 8); }
+        else tm_ld4(tcol + off, c);
+    } else {
+        gload<T, K>(blk + off, c);
+    }
+}
+template <class T, int K, bool TM> __device__ __forceinline__ void crow_ready(T (&c)[K])
+{
+    if constexpr (TM) { if constexpr (K == 12) tm_wait12(c); else tm_wait4(c); }
+}
+template <class T, int K1, int K2, bool TM> __device__ __forceinline__ void crow_ready2(T (&c1)[K1], T (&c2)[K2])
+{
+    if constexpr (TM) { static_assert(K1 == 12 && K2 == 4, "12 + 4"); tm_wait16(c1, c2); }
+}
+
+// SYS: 0 = one shared model (constant bank); 1 = per-instance systems, coefficients fetched from the lane's global block;
+//      2 = per-instance systems, the lane's loop coefficients (SysBlock prefix, 496 floats at 12/4) resident in TENSOR
+//          MEMORY: 128 threads per SM, one TMEM lane (512 columns) each, rewritten warp-collectively when a lane refills
+template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool UNROLL, int SYS = 0>
 __global__ void __launch_bounds__(BLOCK, 1)
 admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constant__ SolveArgs<T> a)
 {
+    constexpr bool PERSYS = SYS != 0, SYSTM = SYS == 2;
+    static_assert(!SYSTM || (BLOCK == 128 && sizeof(T) == 4 && SysBlock<NX, NU>::TMLEN <= 512 && SysBlock<NX, NU>::TMLEN % 8 == 0),
+                  "TMEM-resident systems: 4 warps, one 512-column TMEM lane per thread, float");
     // model source: the shared constant-bank image, or (PERSYS) this lane's own block in global memory, read through
     // the read-only path every time it is used (the 2.2 KB of coefficients per instance do not fit registers)
     using SB = SysBlock<NX, NU>;
@@ -341,6 +420,18 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
     typename L::SX sg(sp, tid); sp += L::SX::BYTES;
     typename L::SX sv(sp, tid); sp += L::SX::BYTES;
     typename L::SP spn(sp, tid);
+    uint32_t tcol = 0;   // SYSTM: TMEM address of this thread's lane, column 0
+    if constexpr (SYSTM) {
+        uint32_t *slot = reinterpret_cast<uint32_t *>(smem + L::BYTES);
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"((uint32_t)__cvta_generic_to_shared(slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tcol = *slot + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
+    }
 
     long long inst = -1;
     int it = 0;
@@ -418,6 +509,22 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     exhausted = true;
                 }
             }
+            if constexpr (SYSTM) {
+                // tcgen05 is warp-collective: every lane rewrites its columns, lanes that were not refilled with what they hold
+                const bool fill = need && !exhausted;
+#pragma unroll 1
+                for (int c8 = 0; c8 < SB::TMLEN; c8 += 8) {
+                    float t[8];
+                    tm_ld8(tcol + c8, t);
+                    tm_wait8(t);
+                    if (fill) {
+                        const float4 lo = __ldg(reinterpret_cast<const float4 *>(blk + c8)), hi = __ldg(reinterpret_cast<const float4 *>(blk + c8 + 4));
+                        t[0] = lo.x; t[1] = lo.y; t[2] = lo.z; t[3] = lo.w; t[4] = hi.x; t[5] = hi.y; t[6] = hi.z; t[7] = hi.w;
+                    }
+                    tm_st8(tcol + c8, t);
+                }
+                tm_wait_st();
+            }
         }
         if (__all_sync(FULLM, phase == PH_FREE)) break;
         ++n_trips;
@@ -459,11 +566,15 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     sy.load(i, y);
                     sz.load(i, z);
                     if (WARM && yo) gstore<T, NU>(yo + i * NU, y);
+                    T ck[2][NX];
+                    if constexpr (PERSYS) crow_issue<T, NX, SYSTM>(blk, tcol, SB::Krm, ck[0]);
 #pragma unroll
                     for (int r = 0; r < NU; ++r) {
-                        T c[NX];
-                        if constexpr (PERSYS) gload<T, NX>(blk + SB::Krm + r * NX, c);
-                        T kx = dot<T, O::Kx, NX, FAST>([&](int k) { if constexpr (PERSYS) return c[k]; else return P.K[r + k * NU]; },
+                        if constexpr (PERSYS) {
+                            crow_ready<T, NX, SYSTM>(ck[r & 1]);
+                            if (r + 1 < NU) crow_issue<T, NX, SYSTM>(blk, tcol, SB::Krm + (r + 1) * NX, ck[(r + 1) & 1]);
+                        }
+                        T kx = dot<T, O::Kx, NX, FAST>([&](int k) { if constexpr (PERSYS) return ck[r & 1][k]; else return P.K[r + k * NU]; },
                                                        [&](int k) { return x[k]; });
                         u[r] = N::sub(-kx, d[r]);                                                // :31
                         zn[r] = N::add(u[r], y[r]);                                              // :47
@@ -476,19 +587,26 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     sz.store(i, zn);
                     if (uo) gstore<T, NU>(uo + i * NU, u);
                     T xn[NX];
+                    T ca[2][NX], cb[2][NU];
+                    if constexpr (PERSYS) { crow_issue<T, NX, SYSTM>(blk, tcol, SB::Arm, ca[0]); crow_issue<T, NU, SYSTM>(blk, tcol, SB::Brm, cb[0]); }
 #pragma unroll
                     for (int r = 0; r < NX; ++r) {
-                        T ca[NX], cb[NU];
-                        if constexpr (PERSYS) { gload<T, NX>(blk + SB::Arm + r * NX, ca); gload<T, NU>(blk + SB::Brm + r * NU, cb); }
-                        T ax = dot<T, O::Ax, NX, FAST>([&](int k) { if constexpr (PERSYS) return ca[k]; else return P.A[r + k * NX]; },
+                        if constexpr (PERSYS) {
+                            if constexpr (SYSTM) crow_ready2<T, NX, NU, true>(ca[r & 1], cb[r & 1]);
+                            if (r + 1 < NX) {
+                                crow_issue<T, NX, SYSTM>(blk, tcol, SB::Arm + (r + 1) * NX, ca[(r + 1) & 1]);
+                                crow_issue<T, NU, SYSTM>(blk, tcol, SB::Brm + (r + 1) * NU, cb[(r + 1) & 1]);
+                            }
+                        }
+                        T ax = dot<T, O::Ax, NX, FAST>([&](int k) { if constexpr (PERSYS) return ca[r & 1][k]; else return P.A[r + k * NX]; },
                                                        [&](int k) { return x[k]; });
                         if constexpr (FAST) {
                             T acc = ax;
 #pragma unroll
-                            for (int k = 0; k < NU; ++k) acc = N::fma(PERSYS ? cb[k] : P.B[r + k * NX], u[k], acc);
+                            for (int k = 0; k < NU; ++k) acc = N::fma(PERSYS ? cb[r & 1][k] : P.B[r + k * NX], u[k], acc);
                             xn[r] = acc;
                         } else {
-                            T bu = dot<T, O::Bu, NU, FAST>([&](int k) { if constexpr (PERSYS) return cb[k]; else return P.B[r + k * NX]; },
+                            T bu = dot<T, O::Bu, NU, FAST>([&](int k) { if constexpr (PERSYS) return cb[r & 1][k]; else return P.B[r + k * NX]; },
                                                            [&](int k) { return u[k]; });
                             xn[r] = N::add(ax, bu);                                              // :35
                         }
@@ -579,31 +697,46 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     else q[j] = N::sub(cq, N::mul(rho_l, N::sub(v[j], g[j])));                   // :82
                 }
                 T s[NU], d[NU];
+                T cbt[2][NX];
+                if constexpr (PERSYS) crow_issue<T, NX, SYSTM>(blk, tcol, SB::B, cbt[0]);
 #pragma unroll
                 for (int r_ = 0; r_ < NU; ++r_) {
-                    T c[NX];
-                    if constexpr (PERSYS) gload<T, NX>(blk + SB::B + r_ * NX, c);
-                    T bp = dot<T, O::Btp, NX, FAST>([&](int k) { if constexpr (PERSYS) return c[k]; else return P.B[k + r_ * NX]; },
+                    if constexpr (PERSYS) {
+                        crow_ready<T, NX, SYSTM>(cbt[r_ & 1]);
+                        if (r_ + 1 < NU) crow_issue<T, NX, SYSTM>(blk, tcol, SB::B + (r_ + 1) * NX, cbt[(r_ + 1) & 1]);
+                    }
+                    T bp = dot<T, O::Btp, NX, FAST>([&](int k) { if constexpr (PERSYS) return cbt[r_ & 1][k]; else return P.B[k + r_ * NX]; },
                                                     [&](int k) { return p[k]; });
                     s[r_] = N::add(bp, r[r_]);
                 }
+                T cqi[2][NU];
+                if constexpr (PERSYS) crow_issue<T, NU, SYSTM>(blk, tcol, SB::Qirm, cqi[0]);
 #pragma unroll
                 for (int r_ = 0; r_ < NU; ++r_) {
-                    T c[NU];
-                    if constexpr (PERSYS) gload<T, NU>(blk + SB::Qirm + r_ * NU, c);
-                    d[r_] = dot<T, O::Qs, NU, FAST>([&](int k) { if constexpr (PERSYS) return c[k]; else return P.Qi[r_ + k * NU]; },
+                    if constexpr (PERSYS) {
+                        crow_ready<T, NU, SYSTM>(cqi[r_ & 1]);
+                        if (r_ + 1 < NU) crow_issue<T, NU, SYSTM>(blk, tcol, SB::Qirm + (r_ + 1) * NU, cqi[(r_ + 1) & 1]);
+                    }
+                    d[r_] = dot<T, O::Qs, NU, FAST>([&](int k) { if constexpr (PERSYS) return cqi[r_ & 1][k]; else return P.Qi[r_ + k * NU]; },
                                                     [&](int k) { return s[k]; });                // :19
                 }
                 sd.store(i, d, cont);
                 if (WARM && wdo) gstore<T, NU>(wdo + i * NU, d);
                 T pn[NX];
+                T cm[2][NX], ckt[2][NU];
+                if constexpr (PERSYS) { crow_issue<T, NX, SYSTM>(blk, tcol, SB::Mrm, cm[0]); crow_issue<T, NU, SYSTM>(blk, tcol, SB::K, ckt[0]); }
 #pragma unroll
                 for (int r_ = 0; r_ < NX; ++r_) {
-                    T cm[NX], ck[NU];
-                    if constexpr (PERSYS) { gload<T, NX>(blk + SB::Mrm + r_ * NX, cm); gload<T, NU>(blk + SB::K + r_ * NU, ck); }
-                    T mp = dot<T, O::Mp, NX, FAST>([&](int k) { if constexpr (PERSYS) return cm[k]; else return P.M[r_ + k * NX]; },
+                    if constexpr (PERSYS) {
+                        if constexpr (SYSTM) crow_ready2<T, NX, NU, true>(cm[r_ & 1], ckt[r_ & 1]);
+                        if (r_ + 1 < NX) {
+                            crow_issue<T, NX, SYSTM>(blk, tcol, SB::Mrm + (r_ + 1) * NX, cm[(r_ + 1) & 1]);
+                            crow_issue<T, NU, SYSTM>(blk, tcol, SB::K + (r_ + 1) * NU, ckt[(r_ + 1) & 1]);
+                        }
+                    }
+                    T mp = dot<T, O::Mp, NX, FAST>([&](int k) { if constexpr (PERSYS) return cm[r_ & 1][k]; else return P.M[r_ + k * NX]; },
                                                    [&](int k) { return p[k]; });
-                    T kr = dot<T, O::Ktr, NU, FAST>([&](int k) { if constexpr (PERSYS) return ck[k]; else return P.K[k + r_ * NU]; },
+                    T kr = dot<T, O::Ktr, NU, FAST>([&](int k) { if constexpr (PERSYS) return ckt[r_ & 1][k]; else return P.K[k + r_ * NU]; },
                                                     [&](int k) { return r[k]; });
                     pn[r_] = N::sub(N::add(q[r_], mp), kr);                                      // :20
                 }
@@ -636,6 +769,11 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             atomicAdd(a.stats + 2, n_trips);
             atomicAdd(a.stats + 3, n_inst);
         }
+    }
+    if constexpr (SYSTM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tcol) : "memory");
     }
 }
 

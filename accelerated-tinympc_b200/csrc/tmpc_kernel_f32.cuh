@@ -71,28 +71,7 @@ __device__ __forceinline__ float2 prode(float2 a, float2 b, float2 Z)
     else return f2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
 }
 
-// ---- TMEM scratch (per-thread columns) -------------------------------------------------------------
-__device__ __forceinline__ void tm_ld8(uint32_t a, float *r)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
-                 : "r"(a) : "memory");
-}
-__device__ __forceinline__ void tm_ld4(uint32_t a, float *r)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(a) : "memory");
-}
-__device__ __forceinline__ void tm_st8(uint32_t a, const float *r)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 :: "r"(a), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tm_st4(uint32_t a, const float *r)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
-                 :: "r"(a), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]) : "memory");
-}
+// ---- TMEM scratch (per-thread columns): tm_ld8 / tm_ld4 / tm_st8 / tm_st4 / tm_wait_st are in tmpc_kernel.cuh ----
 // The loaded registers are only valid after tcgen05.wait::ld; passing them through the wait as in/out operands
 // gives the compiler the data dependence (it must not schedule a use above the wait).
 template <int N> __device__ __forceinline__ void tm_wait_ld(float (&r)[N])
@@ -110,7 +89,6 @@ template <int N> __device__ __forceinline__ void tm_wait_ld(float (&r)[N])
                        "+f"(r[22]), "+f"(r[23]) :: "memory");
     }
 }
-__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // g and v for one thread: NX*NH columns each.  TM = tensor memory, else shared memory (same interface).
 template <int NX, int NH, int BLOCK, bool TM> struct XStore;

@@ -106,3 +106,29 @@ def test_per_instance_systems_solve_bit_exact(pkg, oracle, dtype):
     assert len(set(itn.tolist())) > 5
     stt = s.stats()
     assert stt["iterations"] == int(itn.sum()) and stt["pattern"] == 0
+
+
+def test_tmem_resident_and_global_block_kernels_agree(pkg, monkeypatch):
+    """fp32 systems solve: coefficients resident in tensor memory (default) vs re-read from the global block
+    (TMPC_KERNEL=sys_global) -- identical results, including ragged batch sizes and the refill of single lanes."""
+    import torch
+    S = 333   # not a multiple of the block size
+    base, A, Bm, Q, R, rho = _systems(pkg, S, np.float32)
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, S, mult=0.6)
+    dev = torch.device("cuda:0")
+    outs = []
+    for variant in (None, "sys_global"):
+        if variant:
+            monkeypatch.setenv("TMPC_KERNEL", variant)
+        s = pkg.capi.Solver(base, dtype=np.float32, policy="parity")
+        sy = pkg.capi.Systems(s, A, Bm, Q, R, rho)
+        x = torch.empty((S, 10, 12), device=dev); u = torch.empty((S, 9, 4), device=dev)
+        it = torch.empty(S, dtype=torch.int32, device=dev); st = torch.empty(S, dtype=torch.int32, device=dev)
+        sy.solve_raw(torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev), True, x, u, it, st, None)
+        torch.cuda.synchronize()
+        outs.append((it.cpu().numpy(), x.cpu().numpy(), u.cpu().numpy()))
+        if variant:
+            monkeypatch.delenv("TMPC_KERNEL")
+    for a, b, name in zip(outs[0], outs[1], ("iter", "x", "u")):
+        assert_same(a, b, name)
+    assert outs[0][0].min() < outs[0][0].max()

@@ -147,8 +147,8 @@ def main():
         q = s.stats()
         if best is None or q["kernel_ms"] < best["kernel_ms"]:
             best = q
-    emit("systems_solve_parity", "per-instance models (2.2 KB of coefficients per instance read through L1/L2 every stage)", B, best, "q",
-         680 + 2240, extra={"coefficient_bytes_per_iteration": 9 * 2 * 400 * 4})
+    emit("systems_solve_parity", "per-instance models: each lane's 496 loop coefficients resident in tensor memory (TMPC_KERNEL=sys_global: re-read "
+         "from its global block every stage)", B, best, "q", 680 + 4 * 960, extra={"kernel_variant": os.environ.get("TMPC_KERNEL", "sys_tmem")})
 
 
 if __name__ == "__main__":
