@@ -396,13 +396,11 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
     constexpr bool PERSYS = SYS != 0, SYSTM = SYS == 2;
     static_assert(!SYSTM || (BLOCK == 128 && sizeof(T) == 4 && SysBlock<NX, NU>::TMLEN <= 512 && SysBlock<NX, NU>::TMLEN % 8 == 0),
                   "TMEM-resident systems: 4 warps, one 512-column TMEM lane per thread, float");
-    // model source: the shared constant-bank image, or (PERSYS) this lane's own block in global memory, read through
-    // the read-only path every time it is used (the 2.2 KB of coefficients per instance do not fit registers)
+    // model source: the shared constant-bank image, or (PERSYS) this lane's own SysBlock: global memory read through the
+    // read-only path, or its prefix kept in tensor memory (the ~2 KB of coefficients per instance do not fit registers)
     using SB = SysBlock<NX, NU>;
     const T *blk = PERSYS ? a.sys : nullptr;   // idle lanes keep a valid block (instance 0)
     T rho_l = P.rho, nrho_l = P.nrho;
-    // coefficient vector of one dot product: K values the shared image holds at stride `st` from `off`, or (PERSYS) the
-    // contiguous run at blk + poff fetched with 16-byte loads
     auto mQd = [&](int i) -> T { if constexpr (PERSYS) return __ldg(blk + SB::Qd + i); else return P.Qd[i]; };
     using N = Num<T>;
     using O = Orders<T, NX, NU>;
