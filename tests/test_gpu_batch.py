@@ -110,3 +110,42 @@ def test_rollout_large_shape(pkg, oracle):
         assert_same(h["iter"][k], r.iter, "iter step %d" % k)
         x = oracle.plant_step(prob, x, r.u[:, 0], dtype=np.float32)
         assert_same(h["x0"][k + 1], x, "x0 step %d" % k)
+
+
+def test_argument_errors_are_reported(pkg):
+    """Error behaviour of the batch / systems entry points: negative codes + a message, no crash."""
+    import ctypes as C
+    capi = pkg.capi
+    prob = pkg.problems.quadrotor(20)
+    s = capi.Solver(prob, dtype=np.float32, policy="parity")
+    lib = s.lib
+    h = C.c_void_p()
+    assert lib.tmpc_batch_create(s._ctx, 0, C.byref(h)) == -1                       # batch < 1
+    b = capi.Batch(s, 16)
+    assert lib.tmpc_batch_set_x0(b._b, None, capi.TMPC_MEM_HOST) == -1              # NULL source
+    assert b"NULL" in lib.tmpc_batch_last_error(b._b)
+    short = np.zeros((5, 12), np.float32)
+    assert lib.tmpc_batch_set_xref_table(b._b, short.ctypes.data, 5, None, capi.TMPC_MEM_HOST) == -1   # fewer rows than N
+    assert lib.tmpc_batch_get(b._b, 99, short.ctypes.data, capi.TMPC_MEM_HOST) == -1                     # bad selector
+    assert lib.tmpc_batch_rollout(b._b, -1, 1, None, None, None, None, capi.TMPC_MEM_HOST) == -1
+    assert lib.tmpc_batch_rollout(b._b, 0, 1, None, None, None, None, capi.TMPC_MEM_HOST) == 0
+    # systems: batch mismatch, host buffers rejected, wrong shape unsupported
+    S = 8
+    sy = capi.Systems(s, np.repeat(prob.Adyn[None], S, 0), np.repeat(prob.Bdyn[None], S, 0), np.repeat(prob.Q[None], S, 0),
+                      np.repeat(prob.R[None], S, 0), np.full(S, prob.rho))
+    args = capi.TmpcSolveArgs()
+    args.batch = S + 1
+    args.mem = capi.TMPC_MEM_DEVICE
+    assert lib.tmpc_solve_systems(s._ctx, C.byref(args), sy._p) == -1
+    args.batch = S
+    args.mem = capi.TMPC_MEM_HOST
+    assert lib.tmpc_solve_systems(s._ctx, C.byref(args), sy._p) == -1
+    assert b"device buffers" in lib.tmpc_last_error(s._ctx)
+    big = capi.Solver(pkg.problems.random_system(), dtype=np.float32, policy="parity")
+    p = C.c_void_p()
+    z = np.zeros(32 * 32 * 2, np.float32)
+    assert lib.tmpc_systems_precompute(big._ctx, 2, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 0,
+                                       capi.TMPC_MEM_HOST, C.byref(p)) == -2       # 32/8 per-instance systems not compiled
+    # a singular R + B'PB is reported per instance, not as a crash
+    Sz = capi.Systems(s, np.zeros((2, 12, 12)), np.zeros((2, 12, 4)), np.zeros((2, 12)), np.zeros((2, 4)), np.zeros(2))
+    assert Sz.get("sweeps").tolist() == [-1, -1]
