@@ -1,0 +1,59 @@
+"""GPU, at BASELINE.json's FULL size (1,048,576 quadrotor instances, config 2): size-independent properties, plus the
+oracle on a 100,000-instance prefix.  Everything through the C ABI with device buffers (as bench.py does)."""
+import numpy as np
+import pytest
+
+from conftest import assert_same
+
+pytestmark = pytest.mark.gpu
+B = 1 << 20
+
+
+def _solve_device(pkg, solver, x0, xref, lo=0, hi=None):
+    import torch
+    hi = len(x0) if hi is None else hi
+    n = hi - lo
+    dev = torch.device("cuda:0")
+    x0d = torch.from_numpy(x0[lo:hi]).to(dev)
+    xrd = torch.from_numpy(xref).to(dev)
+    x = torch.empty((n, 10, 12), device=dev); u = torch.empty((n, 9, 4), device=dev)
+    it = torch.empty(n, dtype=torch.int32, device=dev); st = torch.empty(n, dtype=torch.int32, device=dev); rs = torch.empty((n, 4), device=dev)
+    solver.solve_raw(n, x0d, xrd, True, pkg.capi.TMPC_MEM_DEVICE, x, u, it, st, rs)
+    torch.cuda.synchronize()
+    return {"x": x, "u": u, "iter": it, "status": st, "resid": rs}
+
+
+def test_full_size_properties(pkg, oracle, monkeypatch):
+    import torch
+    prob = pkg.problems.quadrotor(20)
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
+    s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    a = _solve_device(pkg, s, x0, xref)
+    assert s.stats()["pattern"] == 1 and s.stats()["iterations"] == int(a["iter"].sum().item())
+    # 1. the oracle on a prefix (bit-exact), and the published statistics of the workload (mean 34.2, 7.4 % at max_iter)
+    n = 100_000
+    ref = oracle.solve_batch(prob, x0[:n], xref, dtype=np.float32, nthreads=16)
+    assert_same(a["iter"][:n].cpu().numpy(), ref.iter, "iter prefix")
+    assert_same(a["x"][:n].cpu().numpy(), ref.x, "x prefix")
+    assert_same(a["u"][:n].cpu().numpy(), ref.u, "u prefix")
+    it = a["iter"].cpu().numpy()
+    assert abs(it.mean() - 34.1) < 0.2 and abs((it == 100).mean() - 0.072) < 0.005
+    # 2. idempotence: the same call again gives the same bits (lane refill order is timing-dependent, results must not be)
+    b = _solve_device(pkg, s, x0, xref)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # 3. shard independence: two half batches == the full batch (what the multi-GPU path relies on)
+    lo = _solve_device(pkg, s, x0, xref, 0, B // 2)
+    hi = _solve_device(pkg, s, x0, xref, B // 2, B)
+    for k in a:
+        assert torch.equal(a[k], torch.cat([lo[k], hi[k]])), k
+    # 4. the dense kernel instance (no structure specialisation) gives the same values everywhere
+    monkeypatch.setenv("TMPC_DENSE", "1")
+    sd = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    d = _solve_device(pkg, sd, x0, xref)
+    assert sd.stats()["pattern"] == 0
+    for k in a:
+        assert bool((a[k] == d[k]).all()), k          # value equality (+0 == -0)
+    # 5. a checksum of checksums over the outputs, stable across runs / kernels (float64 accumulation on the device)
+    cs = lambda o: (float(o["x"].double().sum()), float(o["u"].double().sum()), int(o["iter"].sum()))
+    assert cs(a) == cs(b) == cs(d)
