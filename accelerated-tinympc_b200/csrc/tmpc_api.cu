@@ -70,8 +70,9 @@ struct tmpc_ctx_impl {
     size_t g_in_bytes = 0, g_out_bytes = 0;
     unsigned *g_done = nullptr;
     size_t g_done_n = 0;
-    cudaStream_t g_copy = nullptr;
-    cudaEvent_t g_h2d = nullptr;
+    cudaStream_t g_copy = nullptr, g_in_stream = nullptr;
+    cudaEvent_t g_h2d = nullptr, g_first = nullptr;
+    unsigned *g_gate = nullptr;   // [0] instances whose inputs have arrived, [1] gate timeout flag
     // stats of the last solve
     tmpc_stats stats{};
     bool stats_pending = false;
@@ -435,6 +436,7 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     unsigned *done;
     int done_shift;
     const void *sys;
+    unsigned *gate;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
@@ -500,6 +502,7 @@ int ensure_stage(tmpc_ctx_impl *c, int k, size_t in_bytes, size_t out_bytes)
 
 
 typedef int (*wait_value32_fn)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned, unsigned);
+typedef int (*write_value32_fn)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned, unsigned);
 
 // Cold solve from/to HOST memory: ONE persistent-kernel launch over the whole batch, outputs copied back while the
 // kernel is still running.  The kernel bumps done[inst >> shift] after the last store of each instance; the copy
@@ -514,6 +517,7 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     const size_t xrow = (size_t)nx * N, urow = (size_t)nu * (N - 1);
     const int64_t B = a->batch;
     static wait_value32_fn wait32 = nullptr;
+    static write_value32_fn write32 = nullptr;
     static bool wait32_probed = false;
     if (!wait32_probed) {
         void *fn = nullptr;
@@ -521,6 +525,12 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
             qr == cudaDriverEntryPointSuccess)
             wait32 = reinterpret_cast<wait_value32_fn>(fn);
+        else
+            cudaGetLastError();
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
+            qr == cudaDriverEntryPointSuccess)
+            write32 = reinterpret_cast<write_value32_fn>(fn);
         else
             cudaGetLastError();
         wait32_probed = true;
@@ -556,9 +566,31 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     cudaStream_t s = c->stream;
     char *din = (char *)c->g_in;
     char *d_x0 = din, *d_xref = din + (size_t)B * nx * es;
-    CUDA_TRY(c, cudaMemcpyAsync(d_x0, a->x0, (size_t)B * nx * es, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(d_xref, a->Xref, a->xref_shared ? xrow * es : (size_t)B * xrow * es, cudaMemcpyHostToDevice, s));
+    // Inputs: the H2D of x0 (and of per-instance Xref) is OVERLAPPED with the kernel.  It runs in 131,072-instance chunks on
+    // its own stream; after each chunk a stream memory operation advances an arrival counter; the kernel starts as soon
+    // as the first chunk is in and its lanes check the counter before touching an instance (gate_wait).  Everything is
+    // enqueued before the kernel launch, so even a staged (pageable) copy cannot wait on the kernel.
+    const bool overlap = write32 != nullptr && B < (int64_t)0xffffffffu && !getenv("TMPC_NO_H2D_OVERLAP");
+    if (!c->g_in_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->g_in_stream, cudaStreamNonBlocking));
+    if (!c->g_first) CUDA_TRY(c, cudaEventCreateWithFlags(&c->g_first, cudaEventDisableTiming));
+    if (!c->g_gate) CUDA_TRY(c, cudaMalloc((void **)&c->g_gate, 2 * sizeof(unsigned)));
+    cudaStream_t hs = c->g_in_stream;
+    CUDA_TRY(c, cudaMemsetAsync(c->g_gate, 0, 2 * sizeof(unsigned), hs));
+    if (a->xref_shared) CUDA_TRY(c, cudaMemcpyAsync(d_xref, a->Xref, xrow * es, cudaMemcpyHostToDevice, hs));
+    const int64_t ICH = overlap ? 131072 : B;
+    for (int64_t b0 = 0; b0 < B; b0 += ICH) {
+        const int64_t n = std::min<int64_t>(ICH, B - b0);
+        CUDA_TRY(c, cudaMemcpyAsync(d_x0 + b0 * nx * es, (const char *)a->x0 + b0 * nx * es, (size_t)n * nx * es, cudaMemcpyHostToDevice, hs));
+        if (!a->xref_shared)
+            CUDA_TRY(c, cudaMemcpyAsync(d_xref + b0 * xrow * es, (const char *)a->Xref + b0 * xrow * es, (size_t)n * xrow * es,
+                                        cudaMemcpyHostToDevice, hs));
+        if (overlap && write32(hs, (unsigned long long)(uintptr_t)c->g_gate, (unsigned)(b0 + n), 0u) != 0)
+            return fail(c, TMPC_ERR_CUDA, "cuStreamWriteValue32 failed");
+        if (b0 == 0) CUDA_TRY(c, cudaEventRecord(c->g_first, hs));
+    }
+    if (!overlap) CUDA_TRY(c, cudaEventRecord(c->g_first, hs));   // everything must be in before the kernel starts
     CUDA_TRY(c, cudaMemsetAsync(c->g_done, 0, sizeof(unsigned) * nch, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(s, c->g_first, 0));
     // the copy stream must not evaluate its waits against counters left by a previous solve
     CUDA_TRY(c, cudaEventRecord(c->g_h2d, s));
     CUDA_TRY(c, cudaStreamWaitEvent(c->g_copy, c->g_h2d, 0));
@@ -575,6 +607,7 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     da.x = d_x; da.u = d_u; da.iter = (int *)d_it; da.status = (int *)d_st; da.resid = d_rs;
     da.done = wait32 ? c->g_done : nullptr;
     da.done_shift = shift;
+    da.gate = overlap ? c->g_gate : nullptr;
     int rc = launch_device(c, da, false, s, true);
     if (rc != TMPC_OK) return rc;
     cudaStream_t cs = c->g_copy;
@@ -596,6 +629,12 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     }
     CUDA_TRY(c, cudaStreamSynchronize(cs));
     CUDA_TRY(c, cudaStreamSynchronize(s));
+    CUDA_TRY(c, cudaStreamSynchronize(hs));
+    if (overlap) {
+        unsigned g[2] = {0, 0};
+        CUDA_TRY(c, cudaMemcpy(g, c->g_gate, sizeof g, cudaMemcpyDeviceToHost));
+        if (g[1]) return fail(c, TMPC_ERR_CUDA, "input gate timed out: the overlapped H2D did not deliver an instance's inputs within 2 s");
+    }
     c->stats_pending = true;
     return TMPC_OK;
 }
@@ -694,7 +733,10 @@ int tmpc_destroy(tmpc_ctx *ctx)
     if (c->g_out) cudaFree(c->g_out);
     if (c->g_done) cudaFree(c->g_done);
     if (c->g_copy) cudaStreamDestroy(c->g_copy);
+    if (c->g_in_stream) cudaStreamDestroy(c->g_in_stream);
     if (c->g_h2d) cudaEventDestroy(c->g_h2d);
+    if (c->g_first) cudaEventDestroy(c->g_first);
+    if (c->g_gate) cudaFree(c->g_gate);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_model_w) cudaFree(c->d_model_w);
     if (c->ev0) cudaEventDestroy(c->ev0);

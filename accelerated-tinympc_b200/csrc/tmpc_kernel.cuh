@@ -192,7 +192,26 @@ template <class T> struct SolveArgs {
     unsigned *done;               // nullable: done[inst >> done_shift] += 1 when every output of inst is written
     int done_shift;
     const T *sys;                 // per-instance systems (PERSYS kernels): [instance][SysBlock::STRIDE], else null
+    unsigned *gate;               // nullable: gate[0] = number of leading instances whose inputs have arrived in device memory
+                                  // (advanced by stream memory operations between the chunks of an overlapped H2D), gate[1] = timeout flag
 };
+
+// Overlapped H2D: an instance may be claimed before its x0 / Xref chunk has landed.  Wait for the arrival counter (never in
+// practice: the kernel consumes ~5 GB/s of inputs, PCIe delivers 50); give up after ~2 s instead of hanging the device.
+template <class T> __device__ __forceinline__ bool gate_wait(const SolveArgs<T> &a, long long idx)
+{
+    if (!a.gate) return true;
+    volatile unsigned *g = a.gate;
+    if ((long long)g[0] <= idx) {
+        const long long t0 = clock64();
+        while ((long long)g[0] <= idx) {
+            __nanosleep(200);
+            if (clock64() - t0 > 4000000000LL) { g[1] = 1u; return false; }
+        }
+    }
+    __threadfence();   // the inputs were written before the counter advanced: order the reads after the observation
+    return true;
+}
 
 // Per-instance system block (PERSYS: every instance brings its own model + cache; the "systems" batching axis),
 // written by the batched precompute kernel.  Every matrix a mat-vec sweeps ROW-wise is stored row-major next to its
@@ -453,7 +472,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             base = __shfl_sync(FULLM, base, leader);
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.batch) {
+                if (idx < a.batch && gate_wait(a, idx)) {
                     inst = idx;
                     phase = PH_RUN;
                     it = 0;

@@ -57,3 +57,35 @@ def test_full_size_properties(pkg, oracle, monkeypatch):
     # 5. a checksum of checksums over the outputs, stable across runs / kernels (float64 accumulation on the device)
     cs = lambda o: (float(o["x"].double().sum()), float(o["u"].double().sum()), int(o["iter"].sum()))
     assert cs(a) == cs(b) == cs(d)
+
+
+def test_host_path_with_overlapped_input_copy(pkg, oracle):
+    """tmpc_solve(TMPC_MEM_HOST) overlaps the H2D of x0 / per-instance Xref with the kernel (arrival counter + in-kernel
+    gate) and the D2H with the kernel (completion counters): 400,000 tracking instances = 4 input chunks, 7 output chunks;
+    results must equal the device-buffer path and the oracle."""
+    import torch
+    prob = pkg.problems.quadrotor(20)
+    n = 400_000
+    x0, xref = pkg.workloads.quadrotor_tracking_batch(0, n)
+    s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    host = s.solve(x0, xref)                                   # pageable numpy buffers
+    dev = torch.device("cuda:0")
+    x = torch.empty((n, 10, 12), device=dev); u = torch.empty((n, 9, 4), device=dev)
+    it = torch.empty(n, dtype=torch.int32, device=dev); st = torch.empty(n, dtype=torch.int32, device=dev); rs = torch.empty((n, 4), device=dev)
+    s.solve_raw(n, torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev), False, pkg.capi.TMPC_MEM_DEVICE, x, u, it, st, rs)
+    torch.cuda.synchronize()
+    assert_same(host["iter"], it.cpu().numpy(), "iter host vs device")
+    assert_same(host["x"], x.cpu().numpy(), "x host vs device")
+    assert_same(host["u"], u.cpu().numpy(), "u host vs device")
+    assert_same(host["resid"], rs.cpu().numpy(), "resid host vs device")
+    m = 20_000
+    ref = oracle.solve_batch(prob, x0[-m:], xref[-m:], dtype=np.float32, nthreads=16)     # the LAST instances: last input chunk
+    assert_same(host["iter"][-m:], ref.iter, "iter tail vs oracle")
+    assert_same(host["u"][-m:], ref.u, "u tail vs oracle")
+    # pinned buffers through the same path
+    px0 = torch.from_numpy(x0).pin_memory(); pxr = torch.from_numpy(xref).pin_memory()
+    hx = torch.empty((n, 10, 12)).pin_memory(); hu = torch.empty((n, 9, 4)).pin_memory()
+    hit = torch.empty(n, dtype=torch.int32).pin_memory(); hst = torch.empty(n, dtype=torch.int32).pin_memory(); hrs = torch.empty((n, 4)).pin_memory()
+    s.solve_raw(n, px0, pxr, False, pkg.capi.TMPC_MEM_HOST, hx, hu, hit, hst, hrs)
+    assert_same(hit.numpy(), host["iter"], "iter pinned")
+    assert_same(hx.numpy(), host["x"], "x pinned")
