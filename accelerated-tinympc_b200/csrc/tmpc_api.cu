@@ -35,6 +35,7 @@ struct tmpc_ctx_impl {
     int nx = 0, nu = 0, N = 0, dtype = 0, policy = 0;
     bool has_model = false;
     float rollout_ms = 0.f;  // device time of the last tmpc_batch_rollout
+    bool const_bounds = false;  // bounds identical at every horizon stage (fp32 12/4/10 image)
     int pattern = 0;  // structural-sparsity specialisation the current model conforms to (0 = dense)
     bool warm_variant_ready = false;
     std::string err;
@@ -124,11 +125,11 @@ KernelInfo make_info_g()
     return k;
 }
 
-template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT>
+template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT, bool CB>
 KernelInfo make_info_f32()
 {
     KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM, PAT>;
+    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM, PAT, CB>;
     k.smem = tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES;
     k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::ModelF32<NX, NU, NH>);
@@ -159,13 +160,13 @@ bool pick_warp(int policy, bool warm, KernelInfo &out)
     return true;
 }
 
-template <int NX, int NU, int NH, int BLOCK, bool TM, class PAT = tmpc::PatDense<NX>>
+template <int NX, int NU, int NH, int BLOCK, bool TM, class PAT = tmpc::PatDense<NX>, bool CB = false>
 bool pick_f32(int policy, bool warm, KernelInfo &out)
 {
     if (policy == TMPC_ORDER_PARITY)
-        out = warm ? make_info_f32<NX, NU, NH, BLOCK, false, true, TM, PAT>() : make_info_f32<NX, NU, NH, BLOCK, false, false, TM, PAT>();
+        out = warm ? make_info_f32<NX, NU, NH, BLOCK, false, true, TM, PAT, CB>() : make_info_f32<NX, NU, NH, BLOCK, false, false, TM, PAT, CB>();
     else
-        out = warm ? make_info_f32<NX, NU, NH, BLOCK, true, true, TM, PAT>() : make_info_f32<NX, NU, NH, BLOCK, true, false, TM, PAT>();
+        out = warm ? make_info_f32<NX, NU, NH, BLOCK, true, true, TM, PAT, CB>() : make_info_f32<NX, NU, NH, BLOCK, true, false, TM, PAT, CB>();
     return true;
 }
 
@@ -194,15 +195,22 @@ bool pick(int policy, bool warm, KernelInfo &out)
 // Compiled shapes.  Thread-per-instance needs the per-instance state to fit shared memory:
 //   quadrotor 12/4/10: 360 scalars -> 128 threads (f32) / 64 threads (f64) per SM
 //   cartpole   4/1/10: 111 scalars -> 256 threads (f32) / 128 (f64)
-bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out, int pattern = 0)
+// pattern: bit 0..7 = structural-sparsity pattern id (0 dense), bit 8 = bounds constant over the horizon
+bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out, int pattern_bits = 0)
 {
+    const int pattern = pattern_bits & 0xff;
+    const bool cb = (pattern_bits & 0x100) != 0;
     if (nx == 12 && nu == 4 && N == 10) {
         if (dtype == TMPC_F32) {
             const int v = kernel_variant();
             // model-structure specialisation (tmpc_kernel_f32.cuh PatQuadrotor): chosen by build_model when the
             // actual matrices conform
-            if (v == 2 && pattern == tmpc::PatQuadrotor::id) return pick_f32<12, 4, 10, 256, true, tmpc::PatQuadrotor>(policy, warm, out);
-            if (v == 2) return pick_f32<12, 4, 10, 256, true>(policy, warm, out);   // g,v in TMEM: 256 instances / SM
+            if (v == 2 && pattern == tmpc::PatQuadrotor::id)
+                return cb ? pick_f32<12, 4, 10, 256, true, tmpc::PatQuadrotor, true>(policy, warm, out)
+                          : pick_f32<12, 4, 10, 256, true, tmpc::PatQuadrotor, false>(policy, warm, out);
+            if (v == 2)                                                              // g,v in TMEM: 256 instances / SM
+                return cb ? pick_f32<12, 4, 10, 256, true, tmpc::PatDense<12>, true>(policy, warm, out)
+                          : pick_f32<12, 4, 10, 256, true, tmpc::PatDense<12>, false>(policy, warm, out);
             if (v == 1) return pick_f32<12, 4, 10, 128, false>(policy, warm, out);  // all state in shared memory
             return pick<float, 12, 4, 10, 128, false>(policy, warm, out);
         }
@@ -329,6 +337,15 @@ template <int NX, int NU, int NH> void build_model_f32(tmpc_ctx_impl *c, std::ve
     m->dua_tol = (float)c->dua;
     m->max_iter = c->max_iter;
     m->check_term = c->check_term;
+    // bounds identical at every stage?  (then the CB kernel instance reads stage 0's rows with fixed addresses)
+    bool cb = !getenv("TMPC_NO_CONST_BOUNDS");
+    for (int i = 1; i < NH && cb; ++i)
+        for (int j = 0; j < NX && cb; ++j)
+            if (m->xmin[i * NX + j] != m->xmin[j] || m->xmax[i * NX + j] != m->xmax[j]) cb = false;
+    for (int i = 1; i < NH - 1 && cb; ++i)
+        for (int j = 0; j < NU && cb; ++j)
+            if (m->umin[i * NU + j] != m->umin[j] || m->umax[i * NU + j] != m->umax[j]) cb = false;
+    c->const_bounds = cb;
 }
 
 // lane-major coefficient image of the warp-per-instance kernel (layout: tmpc_kernel_warp.cuh ModelWarp)
@@ -471,7 +488,7 @@ int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cuda
 int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
 {
     KernelInfo ki;
-    if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern))
+    if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern | (c->const_bounds ? 0x100 : 0)))
         return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
     return launch_kernel_info(c, ki, da, s, time_it);
 }
@@ -946,7 +963,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
         cudaEventCreate(&kev[2 * k + 1]);
         {
             KernelInfo ki;
-            lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern);
+            lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern | (c->const_bounds ? 0x100 : 0));
             cudaFuncSetAttribute(ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem);
             // stats accumulate over chunks; only the work counter is reset per chunk
             cudaMemsetAsync(c->d_counter, 0, (k == 0 ? 5 : 1) * sizeof(unsigned long long), st.s);

@@ -106,3 +106,20 @@ def test_structure_specialisation_and_dense_fallback(pkg, oracle, monkeypatch):
     o1 = pkg.capi.Solver(prob, dtype=np.float32, policy="parity").solve(x0, xref, warm=warm)
     for k in warm:
         assert_same(o1["warm"][k], r1.state[k], "warm." + k)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_stage_varying_bounds(pkg, oracle, dtype):
+    """Bounds that differ from stage to stage (x_min/x_max are nx x N, u_min/u_max nu x (N-1) in the reference,
+    types.hpp:87-90): the constant-bounds kernel instance must not be chosen; results equal the oracle's."""
+    import copy
+    prob = copy.deepcopy(pkg.problems.quadrotor(20))
+    N, nx, nu = prob.N, prob.nx, prob.nu
+    k = np.arange(N)[:, None]
+    prob.x_max = 5.0 - 0.3 * k * np.ones((1, nx)); prob.x_min = -5.0 + 0.2 * k * np.ones((1, nx))
+    prob.u_max = 0.5 - 0.03 * k[:-1] * np.ones((1, nu)); prob.u_min = -0.5 + 0.01 * k[:-1] * np.ones((1, nu))
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, 3000, mult=0.5)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=dtype, nthreads=8)
+    out = pkg.capi.Solver(prob, dtype=dtype, policy="parity").solve(x0, xref)
+    _cmp_exact(out, ref)
+    assert len(set(ref.iter.tolist())) > 10
