@@ -5,6 +5,7 @@
 #include "tmpc_kernel.cuh"
 #include "tmpc_kernel_f32.cuh"
 #include "tmpc_kernel_warp.cuh"
+#include "tmpc_kernel_small.cuh"
 #include "tmpc_steps.cuh"
 
 #include <algorithm>
@@ -138,6 +139,27 @@ KernelInfo make_info_f32()
     return k;
 }
 
+template <int NX, int NH, int BLOCK, bool FAST, bool WARM>
+KernelInfo make_info_small()
+{
+    KernelInfo k;
+    k.fn = (const void *)&tmpc::admm_kernel_small<NX, NH, BLOCK, FAST, WARM>;
+    k.smem = 0;   // the whole per-instance state lives in registers
+    k.block = BLOCK;
+    k.model_bytes = sizeof(tmpc::Model<float, NX, 1, NH>);
+    k.model_kind = 0;
+    k.per_block = BLOCK;
+    return k;
+}
+
+template <int NX, int NH, int BLOCK>
+bool pick_small(int policy, bool warm, KernelInfo &out)
+{
+    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_small<NX, NH, BLOCK, false, true>() : make_info_small<NX, NH, BLOCK, false, false>();
+    else out = warm ? make_info_small<NX, NH, BLOCK, true, true>() : make_info_small<NX, NH, BLOCK, true, false>();
+    return true;
+}
+
 template <int NH, int WARPS, bool FAST, bool WARM, bool TM>
 KernelInfo make_info_warp()
 {
@@ -217,7 +239,16 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
         return pick<double, 12, 4, 10, 64, false>(policy, warm, out);
     }
     if (nx == 4 && nu == 1 && N == 10) {
-        if (dtype == TMPC_F32) return pick<float, 4, 1, 10, 512, false>(policy, warm, out);   // 444 B of state: 512 instances / SM
+        if (dtype == TMPC_F32) {
+            // register-resident single-input kernel (tmpc_kernel_small.cuh); TMPC_KERNEL=generic | generic_unroll:
+            // the shared-memory kernel (444 B of state: 512 instances / SM)
+            const char *e = getenv("TMPC_KERNEL");
+            if (e && !strcmp(e, "generic")) return pick<float, 4, 1, 10, 512, false>(policy, warm, out);
+            if (e && !strcmp(e, "generic_unroll")) return pick<float, 4, 1, 10, 512, true>(policy, warm, out);
+            if (e && !strcmp(e, "small256")) return pick_small<4, 10, 256>(policy, warm, out);
+            if (e && !strcmp(e, "small512")) return pick_small<4, 10, 512>(policy, warm, out);
+            return pick_small<4, 10, 384>(policy, warm, out);
+        }
         return pick<double, 4, 1, 10, 128, false>(policy, warm, out);
     }
     // large shape: one warp per instance.  g,v in tensor memory -> 16 instances / SM (TMPC_KERNEL=warp_smem: all state in

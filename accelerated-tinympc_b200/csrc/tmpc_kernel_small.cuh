@@ -1,0 +1,284 @@
+// fp32 kernel for SMALL single-input shapes (nu = 1, nx a multiple of 4; compiled: cartpole 4/1/10, config 4):
+// same algorithm and bit-exact results as tmpc_kernel.cuh, organised for a shape whose whole ADMM state is a
+// hundred scalars.
+//
+//  * the generic kernel keeps {d,y,z,g,v} in shared memory and walks the horizon with a run-time stage index; at
+//    4/1/10 an iteration is only ~1400 FP instructions, so the LDS/STS round trips, the address arithmetic and the
+//    bound look-ups are a third of everything it issues (ncu: issue slots 88 % busy, FMA pipe 55 %).  Here the state
+//    (111 scalars + the p_N seed) lives in REGISTERS for the life of the instance and both sweeps are fully unrolled
+//    over the horizon: every state access is a register, every coefficient and bound a fixed constant-bank operand;
+//  * element-wise work and the nx-row accumulations run on row pairs as FADD2 (products stay scalar FMUL, rounded
+//    individually: the evaluation order of the reference is kept, see Orders<> in tmpc_kernel.cuh);
+//  * termination is predicted one trip ahead as in the 12/4/10 kernel, so most instances need no emission trip.
+#pragma once
+#include "tmpc_kernel_f32.cuh"
+
+namespace tmpc {
+
+template <int NX, int NH, int BLOCK, bool FAST, bool WARM>
+__global__ void __launch_bounds__(BLOCK, 1)
+admm_kernel_small(const __grid_constant__ Model<float, NX, 1, NH> P, const __grid_constant__ SolveArgs<float> a)
+{
+    static_assert(NX % 4 == 0, "16-byte rows of x");
+    using O = Orders<float, NX, 1>;
+    static_assert(O::Ax == ORD_SEQ && O::Mp == ORD_SEQ && O::Bu == ORD_SEQ && O::Qs == ORD_SEQ, "row sweeps are sequential at nu = 1");
+    constexpr int H = NX / 2;
+    constexpr unsigned FULLM = 0xffffffffu;
+    constexpr int XROW = NX * NH, UROW = NH - 1;
+    const float2 Z = make_float2(-0.f, -0.f);   // only reaches prod2 when a TMPC_PROD2_* switch is on
+    const unsigned lane = threadIdx.x & 31;
+
+    // ---- per-instance state, registers
+    float2 g[NH][H], v[NH][H], pn[H];
+    float d[NH - 1], y[NH - 1], z[NH - 1];
+    float x0[NX];
+#pragma unroll
+    for (int i = 0; i < NH; ++i)
+#pragma unroll
+        for (int j = 0; j < H; ++j) g[i][j] = v[i][j] = f2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NH - 1; ++i) d[i] = y[i] = z[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < H; ++j) pn[j] = f2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x0[j] = 0.f;
+
+    long long inst = -1;
+    int it = 0;
+    int phase = PH_FREE;
+    bool exhausted = false;
+    bool spec = false;
+    float res[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned long long n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
+
+    for (;;) {
+        // ------------------------------------------------------------------ lane refill
+        const bool need = (phase == PH_FREE) && !exhausted;
+        const unsigned m = __ballot_sync(FULLM, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(m));
+            base = __shfl_sync(FULLM, base, leader);
+            if (need) {
+                const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
+                if (idx < a.batch && gate_wait(a, idx)) {
+                    inst = idx; phase = PH_RUN; it = 0;
+                    spec = (P.max_iter <= 1);
+                    res[0] = res[1] = res[2] = res[3] = 0.f;
+                    gload<float, NX>(a.x0 + inst * NX, x0);
+                    float xr[NX];
+                    gload<float, NX>(a.Xref + inst * a.xref_stride + (NH - 1) * NX, xr);
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) {   // p_N seed: -(Xref_{N-1}^T Pinf)  (admm.cpp:83)
+                        const float t = -dot<float, O::XtP, NX, FAST>([&](int k) { return P.Pf[k + j * NX]; }, [&](int k) { return xr[k]; });
+                        if (j & 1) pn[j / 2].y = t; else pn[j / 2].x = t;
+                    }
+                    if (WARM && a.wd) {
+#pragma unroll
+                        for (int i = 0; i < NH - 1; ++i) {
+                            d[i] = __ldg(a.wd + inst * UROW + i);
+                            y[i] = __ldg(a.wy + inst * UROW + i);
+                            z[i] = __ldg(a.wz + inst * UROW + i);
+                        }
+#pragma unroll
+                        for (int i = 0; i < NH; ++i) {
+                            float tg[NX], tv[NX];
+                            gload<float, NX>(a.wg + inst * XROW + i * NX, tg);
+                            gload<float, NX>(a.wv + inst * XROW + i * NX, tv);
+#pragma unroll
+                            for (int j = 0; j < H; ++j) { g[i][j] = f2(tg[2 * j], tg[2 * j + 1]); v[i][j] = f2(tv[2 * j], tv[2 * j + 1]); }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NH - 1; ++i) d[i] = y[i] = z[i] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < NH; ++i)
+#pragma unroll
+                            for (int j = 0; j < H; ++j) g[i][j] = v[i][j] = f2(0.f, 0.f);
+                    }
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (__all_sync(FULLM, phase == PH_FREE)) break;
+        ++n_trips;
+
+        const bool emit = (phase == PH_EMIT);
+        if (phase == PH_RUN) ++it;
+
+        // ------------------------------------------------------------------ forward sweep
+        // forward_pass (admm.cpp:27-37) + update_slack (:45-61) + update_dual (:67-71) + residual maxima (:95-98)
+        float pri_x = 0.f, dua_x = 0.f, pri_u = 0.f, dua_u = 0.f;
+        {
+            float x[NX];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) x[j] = x0[j];
+            const bool wr = emit || (spec && phase == PH_RUN);
+            float *xo = (wr && a.x) ? a.x + inst * XROW : nullptr;
+            float *uo = (wr && a.u) ? a.u + inst * UROW : nullptr;
+            float *go = (WARM && wr && a.wg) ? a.wg + inst * XROW : nullptr;
+            float *yo = (WARM && wr && a.wy) ? a.wy + inst * UROW : nullptr;
+
+#pragma unroll
+            for (int i = 0; i < NH; ++i) {
+                float2 xn[H];
+                if (i < NH - 1) {
+                    // u_i = -(Kinf x_i) - d_i                                                        :31
+                    const float kx = dot<float, O::Kx, NX, FAST>([&](int k) { return P.K[k]; }, [&](int k) { return x[k]; });
+                    const float u = __fsub_rn(-kx, d[i]);
+                    if (WARM && yo && emit) yo[i] = y[i];
+                    float zn = __fadd_rn(u, y[i]);                                                   // :47
+                    zn = fminf(P.umax[i], fmaxf(P.umin[i], zn));                                     // :53
+                    pri_u = fmaxf(pri_u, fabsf(__fsub_rn(u, zn)));                                   // :97
+                    dua_u = fmaxf(dua_u, fabsf(__fsub_rn(z[i], zn)));                                // :98
+                    y[i] = __fsub_rn(__fadd_rn(y[i], u), zn);                                        // :69
+                    z[i] = zn;
+                    if (WARM && yo && !emit) yo[i] = y[i];
+                    if (uo) uo[i] = u;
+                    // x_{i+1} = A x_i + B u_i                                                        :35
+                    float2 ax[H];
+                    matvec2<ORD_SEQ, NX, NX, NX, 0, FAST>(P.A, x, ax, Z);
+#pragma unroll
+                    for (int j = 0; j < H; ++j) {
+                        const float2 b2 = f2(P.B[2 * j], P.B[2 * j + 1]);
+                        if constexpr (FAST) xn[j] = __ffma2_rn(b2, f2(u, u), ax[j]);
+                        else xn[j] = add2(ax[j], f2(__fmul_rn(b2.x, u), __fmul_rn(b2.y, u)));
+                    }
+                }
+                // state slack / dual / residuals of stage i
+                if (WARM && go && emit) {
+                    float t[NX];
+#pragma unroll
+                    for (int j = 0; j < H; ++j) { t[2 * j] = g[i][j].x; t[2 * j + 1] = g[i][j].y; }
+                    gstore<float, NX>(go + i * NX, t);
+                }
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const float2 x2 = f2(x[2 * j], x[2 * j + 1]);
+                    float2 t = add2(x2, g[i][j]);                                                    // :48
+                    t.x = fminf(P.xmax[i * NX + 2 * j], fmaxf(P.xmin[i * NX + 2 * j], t.x));         // :59
+                    t.y = fminf(P.xmax[i * NX + 2 * j + 1], fmaxf(P.xmin[i * NX + 2 * j + 1], t.y));
+                    const float2 rp = sub2(x2, t), rd = sub2(v[i][j], t);
+                    pri_x = fmaxf(pri_x, fmaxf(fabsf(rp.x), fabsf(rp.y)));                           // :95
+                    dua_x = fmaxf(dua_x, fmaxf(fabsf(rd.x), fabsf(rd.y)));                           // :96
+                    g[i][j] = sub2(add2(g[i][j], x2), t);                                            // :70
+                    v[i][j] = t;
+                }
+                if (WARM && go && !emit) {
+                    float t[NX];
+#pragma unroll
+                    for (int j = 0; j < H; ++j) { t[2 * j] = g[i][j].x; t[2 * j + 1] = g[i][j].y; }
+                    gstore<float, NX>(go + i * NX, t);
+                }
+                if (xo) gstore<float, NX>(xo + i * NX, x);
+                if (i < NH - 1) {
+#pragma unroll
+                    for (int j = 0; j < H; ++j) { x[2 * j] = xn[j].x; x[2 * j + 1] = xn[j].y; }
+                }
+            }
+        }
+
+        // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
+        bool final_bwd = false;
+        bool finished = false;
+        if (phase == PH_RUN) {
+            const bool chk = (it % P.check_term) == 0;
+            if (chk) {
+                res[0] = pri_x; res[1] = __fmul_rn(dua_x, P.rho); res[2] = pri_u; res[3] = __fmul_rn(dua_u, P.rho);
+            }
+            const bool conv = chk && res[0] < P.pri_tol && res[2] < P.pri_tol && res[1] < P.dua_tol && res[3] < P.dua_tol;
+            if (conv || it >= P.max_iter) {
+                if (a.iter) a.iter[inst] = it;
+                if (a.status) a.status[inst] = conv ? 1 : 11;
+                if (a.resid) *reinterpret_cast<float4 *>(a.resid + inst * 4) = make_float4(res[0], res[1], res[2], res[3]);
+                n_iter += (unsigned)it; n_solved += conv ? 1u : 0u; ++n_inst;
+                final_bwd = !conv;
+                if (spec) { phase = PH_FREE; finished = true; }   // x,u of this very trip are already in the output
+                else phase = PH_EMIT;
+                spec = false;
+            } else {
+                constexpr float SF = TMPC_SPEC_FACTOR;
+                const bool next_chk = ((it + 1) % P.check_term) == 0;
+                spec = (it + 1 >= P.max_iter) ||
+                       (next_chk && res[0] < SF * P.pri_tol && res[2] < SF * P.pri_tol && res[1] < SF * P.dua_tol && res[3] < SF * P.dua_tol);
+            }
+        } else if (phase == PH_EMIT) {
+            phase = PH_FREE;
+            finished = true;
+        }
+
+        // ------------------------------------------------------------------ backward sweep
+        // update_linear_cost (admm.cpp:77-85) recomputed per stage + backward_pass_grad (:15-22)
+        const bool cont = (phase == PH_RUN);
+        const bool wout = WARM && (cont || final_bwd) && a.wd;
+        if (__any_sync(FULLM, cont || wout)) {
+            float p[NX];
+            const float *xr_base = a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
+            float *wdo = wout ? a.wd + inst * UROW : nullptr;
+            float *wvo = wout ? a.wv + inst * XROW : nullptr;
+            float *wzo = wout ? a.wz + inst * UROW : nullptr;
+            auto store_v = [&](int i) {
+                float t[NX];
+#pragma unroll
+                for (int j = 0; j < H; ++j) { t[2 * j] = v[i][j].x; t[2 * j + 1] = v[i][j].y; }
+                gstore<float, NX>(wvo + i * NX, t);
+            };
+            if (WARM && wvo) store_v(NH - 1);
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                const float2 dvg = sub2(v[NH - 1][j], g[NH - 1][j]);
+                float2 t;
+                if constexpr (FAST) t = __ffma2_rn(f2(P.nrho, P.nrho), dvg, pn[j]);
+                else t = sub2(pn[j], f2(__fmul_rn(P.rho, dvg.x), __fmul_rn(P.rho, dvg.y)));          // :84
+                p[2 * j] = t.x; p[2 * j + 1] = t.y;
+            }
+#pragma unroll
+            for (int i = NH - 2; i >= 0; --i) {
+                float xr[NX];
+                gload<float, NX>(xr_base + i * NX, xr);
+                if (WARM && wvo) { store_v(i); wzo[i] = z[i]; }
+                const float r = __fmul_rn(P.nrho, __fsub_rn(z[i], y[i]));                            // :80
+                // d_i = Quu_inv (B^T p_{i+1} + r_i)                                                  :19
+                const float bp = dot<float, O::Btp, NX, FAST>([&](int k) { return P.B[k]; }, [&](int k) { return p[k]; });
+                const float dn = __fmul_rn(P.Qi[0], __fadd_rn(bp, r));
+                if (cont) d[i] = dn;
+                if (WARM && wdo) wdo[i] = dn;
+                // p_i = q_i + AmBKt p_{i+1} - Kinf^T r_i                                             :20
+                float2 mp[H];
+                matvec2<ORD_SEQ, NX, NX, NX, 0, FAST>(P.M, p, mp, Z);
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const float2 cq = neg2(f2(__fmul_rn(xr[2 * j], P.Qd[2 * j]), __fmul_rn(xr[2 * j + 1], P.Qd[2 * j + 1])));   // :81
+                    const float2 dvg = sub2(v[i][j], g[i][j]);
+                    float2 q;
+                    if constexpr (FAST) q = __ffma2_rn(f2(P.nrho, P.nrho), dvg, cq);
+                    else q = sub2(cq, f2(__fmul_rn(P.rho, dvg.x), __fmul_rn(P.rho, dvg.y)));         // :82
+                    const float2 kr = f2(__fmul_rn(P.K[2 * j], r), __fmul_rn(P.K[2 * j + 1], r));
+                    const float2 t = sub2(add2(q, mp[j]), kr);
+                    p[2 * j] = t.x; p[2 * j + 1] = t.y;
+                }
+            }
+        }
+        if (finished && a.done) { __threadfence(); atomicAdd(a.done + (inst >> a.done_shift), 1u); }
+    }
+
+    if (a.stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_iter += __shfl_down_sync(FULLM, n_iter, o);
+            n_solved += __shfl_down_sync(FULLM, n_solved, o);
+            n_trips += __shfl_down_sync(FULLM, n_trips, o);
+            n_inst += __shfl_down_sync(FULLM, n_inst, o);
+        }
+        if (lane == 0) {
+            atomicAdd(a.stats + 0, n_iter);
+            atomicAdd(a.stats + 1, n_solved);
+            atomicAdd(a.stats + 2, n_trips);
+            atomicAdd(a.stats + 3, n_inst);
+        }
+    }
+}
+
+}  // namespace tmpc
