@@ -7,6 +7,8 @@
 #include "tmpc_kernel_warp.cuh"
 #include "tmpc_kernel_small.cuh"
 #include "tmpc_steps.cuh"
+#include "tmpc_kernel_rt.cuh"
+#include "tmpc_orders_rt.hpp"
 
 #include <algorithm>
 #include <cstdio>
@@ -28,6 +30,7 @@ struct KernelInfo {
     size_t model_bytes;
     int model_kind;  // 0: tmpc::Model<T,...> (generic kernel)   1: tmpc::ModelF32<...> (packed fp32 kernel)
                      // 2: tmpc::ModelWarp (warp-per-instance kernel; pointers into the ctx's device model image)
+                     // 3: tmpc::ModelRT<T> (run-time-shape kernel; pointers into the ctx's device model image + scratch)
     int per_block;   // instances resident per block (threads for the thread-per-instance kernels, warps for kind 2)
 };
 
@@ -49,6 +52,13 @@ struct tmpc_ctx_impl {
     tmpc::ModelWarp model_w{};             // warp-per-instance kernel: scalars + pointers into d_model_w
     float *d_model_w = nullptr;            // device image: fwd4 | bwd4 | Pt | Qd | xmin | xmax | umin | umax
     size_t d_model_w_floats = 0;
+    // run-time-shape kernel (tmpc_kernel_rt.cuh): ModelRT<T> image, its device arrays, per-lane scratch
+    std::vector<unsigned char> model_rt;
+    void *d_model_rt = nullptr;
+    size_t d_model_rt_bytes = 0;
+    void *d_rt_scratch = nullptr;
+    size_t d_rt_scratch_bytes = 0;
+    bool rt_ready = false;
     // settings
     double pri = 1e-3, dua = 1e-3;
     int max_iter = 100, check_term = 1, en_state = 1, en_input = 1;
@@ -218,10 +228,13 @@ bool pick(int policy, bool warm, KernelInfo &out)
 //   quadrotor 12/4/10: 360 scalars -> 128 threads (f32) / 64 threads (f64) per SM
 //   cartpole   4/1/10: 111 scalars -> 256 threads (f32) / 128 (f64)
 // pattern: bit 0..7 = structural-sparsity pattern id (0 dense), bit 8 = bounds constant over the horizon
+bool force_rt();
+bool lookup_kernel_rt(int nx, int nu, int N, int dtype, int policy, KernelInfo &out);
 bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out, int pattern_bits = 0)
 {
     const int pattern = pattern_bits & 0xff;
     const bool cb = (pattern_bits & 0x100) != 0;
+    if (force_rt()) return lookup_kernel_rt(nx, nu, N, dtype, policy, out);
     if (nx == 12 && nu == 4 && N == 10) {
         if (dtype == TMPC_F32) {
             const int v = kernel_variant();
@@ -258,13 +271,42 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
         if (e && !strcmp(e, "warp_smem")) return pick_warp<50, 12, false>(policy, warm, out);
         return pick_warp<50, 16, true>(policy, warm, out);
     }
-    return false;
+    return lookup_kernel_rt(nx, nu, N, dtype, policy, out);
 }
 
 bool shape_parity_pinned(int nx, int nu)
 {
-    // evaluation orders verified bit-for-bit against the compiled reference (oracle/, tests/)
-    return (nx == 12 && nu == 4) || (nx == 4 && nu == 1) || (nx == 32 && nu == 8);
+    // evaluation orders verified bit-for-bit against the compiled reference (oracle/, tests/): the three BASELINE shapes
+    // by the fixtures under tests/golden, every other shape up to 64 by the dispatch rule that oracle/pin_shapes.py
+    // checks against the compiled reference on 60+ shapes (tmpc_orders_rt.hpp)
+    return nx >= 1 && nu >= 1 && nx <= tmpc::RT_MAXD && nu <= tmpc::RT_MAXD;
+}
+
+bool rt_shape_ok(int nx, int nu, int N)
+{
+    return nx >= 1 && nu >= 1 && N >= 2 && nx <= tmpc::RT_MAXD && nu <= tmpc::RT_MAXD &&
+           (long long)nx * N < (1LL << 24) && (long long)nu * N < (1LL << 24);
+}
+
+bool force_rt()
+{
+    const char *e = getenv("TMPC_KERNEL");
+    return e && !strcmp(e, "rt");
+}
+
+// run-time-shape kernel: any other shape (TMPC_KERNEL=rt forces it for the compiled shapes too)
+bool lookup_kernel_rt(int nx, int nu, int N, int dtype, int policy, KernelInfo &out)
+{
+    if (!rt_shape_ok(nx, nu, N)) return false;
+    const bool fast = policy == TMPC_ORDER_FAST;
+    if (dtype == TMPC_F32) out.fn = fast ? (const void *)&tmpc::admm_kernel_rt<float, true> : (const void *)&tmpc::admm_kernel_rt<float, false>;
+    else out.fn = fast ? (const void *)&tmpc::admm_kernel_rt<double, true> : (const void *)&tmpc::admm_kernel_rt<double, false>;
+    out.smem = tmpc::rt_smem_bytes(nx, nu, dtype == TMPC_F32 ? 4 : 8);
+    out.block = tmpc::RT_BLOCK;
+    out.model_bytes = dtype == TMPC_F32 ? sizeof(tmpc::ModelRT<float>) : sizeof(tmpc::ModelRT<double>);
+    out.model_kind = 3;
+    out.per_block = tmpc::RT_BLOCK;
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -447,8 +489,81 @@ bool build_model_warp(tmpc_ctx_impl *c)
     return true;
 }
 
+// Run-time-shape kernel: device image = K | A | B | Qi | M | Pf | Qd | xmin | xmax | umin | umax (scalars of the ctx dtype)
+// followed by the reduction programs (uint16); ModelRT<T> holds pointers into it.
+template <class T> bool build_model_rt_t(tmpc_ctx_impl *c)
+{
+    const int nx = c->nx, nu = c->nu, N = c->N;
+    const tmpc_rt::Orders o = tmpc_rt::build_orders(nx, nu, N, (int)sizeof(T));
+    if (o.max_depth > tmpc::RT_STACK) return false;
+    const size_t n_x = (size_t)N * nx, n_u = (size_t)(N - 1) * nu;
+    const size_t cnt[11] = {(size_t)nu * nx, (size_t)nx * nx, (size_t)nx * nu, (size_t)nu * nu, (size_t)nx * nx, (size_t)nx * nx,
+                            (size_t)nx, n_x, n_x, n_u, n_u};
+    size_t off[12];
+    off[0] = 0;
+    for (int k = 0; k < 11; ++k) off[k + 1] = off[k] + ((cnt[k] + 3) & ~size_t(3));
+    const size_t prog_off = off[11] * sizeof(T);
+    const size_t bytes = prog_off + ((o.prog.size() * 2 + 15) & ~size_t(15));
+    std::vector<unsigned char> img(bytes, 0);
+    T *h = reinterpret_cast<T *>(img.data());
+    const std::vector<unsigned char> *src[7] = {&c->Kinf, &c->Adyn, &c->Bdyn, &c->Quu_inv, &c->AmBKt, &c->Pinf, &c->Q};
+    for (int k = 0; k < 7; ++k) std::memcpy(h + off[k], src[k]->data(), cnt[k] * sizeof(T));
+    const T inf = std::numeric_limits<T>::infinity();
+    const bool xs = c->en_state && c->has_xb, us = c->en_input && c->has_ub;
+    for (size_t k = 0; k < n_x; ++k) {
+        h[off[7] + k] = xs ? reinterpret_cast<const T *>(c->xmin.data())[k] : -inf;
+        h[off[8] + k] = xs ? reinterpret_cast<const T *>(c->xmax.data())[k] : inf;
+    }
+    for (size_t k = 0; k < n_u; ++k) {
+        h[off[9] + k] = us ? reinterpret_cast<const T *>(c->umin.data())[k] : -inf;
+        h[off[10] + k] = us ? reinterpret_cast<const T *>(c->umax.data())[k] : inf;
+    }
+    std::memcpy(img.data() + prog_off, o.prog.data(), o.prog.size() * 2);
+    if (cudaSetDevice(c->device) != cudaSuccess) return false;
+    if (c->d_model_rt_bytes < bytes) {
+        if (c->d_model_rt) cudaFree(c->d_model_rt);
+        c->d_model_rt = nullptr; c->d_model_rt_bytes = 0;
+        if (cudaMalloc(&c->d_model_rt, bytes) != cudaSuccess) return false;
+        c->d_model_rt_bytes = bytes;
+    }
+    // the previous image may still be in use by a kernel on the ctx stream
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+    if (cudaMemcpy(c->d_model_rt, img.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    c->model_rt.assign(sizeof(tmpc::ModelRT<T>), 0);
+    tmpc::ModelRT<T> &m = *reinterpret_cast<tmpc::ModelRT<T> *>(c->model_rt.data());
+    const T *d = reinterpret_cast<const T *>(c->d_model_rt);
+    m.nx = nx; m.nu = nu; m.N = N;
+    m.K = d + off[0]; m.A = d + off[1]; m.B = d + off[2]; m.Qi = d + off[3]; m.M = d + off[4]; m.Pf = d + off[5]; m.Qd = d + off[6];
+    m.xmin = d + off[7]; m.xmax = d + off[8]; m.umin = d + off[9]; m.umax = d + off[10];
+    m.prog = reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(c->d_model_rt) + prog_off);
+    auto pr = [](const tmpc_rt::Prod &p) { tmpc::ProdRT r; r.a = p.a; r.b = p.b; return r; };
+    m.Kx = pr(o.Kx); m.Ax = pr(o.Ax); m.Bu = pr(o.Bu); m.Btp = pr(o.Btp); m.Qs = pr(o.Qs); m.Mp = pr(o.Mp); m.Ktr = pr(o.Ktr); m.XtP = pr(o.XtP);
+    m.head_Kx = o.head_Kx; m.head_Ax = o.head_Ax; m.head_Qs = o.head_Qs; m.head_Mp = o.head_Mp;
+    m.rt_u = o.rt_u; m.rt_x = o.rt_x; m.rt_p = o.rt_p; m.off_u = o.off_u; m.off_x = o.off_x; m.off_p = o.off_p; m.pk = o.pk; m.sb = o.sb;
+    m.rho = (T)c->rho; m.nrho = -(T)c->rho; m.pri_tol = (T)c->pri; m.dua_tol = (T)c->dua;
+    m.max_iter = c->max_iter; m.check_term = c->check_term;
+    c->rt_ready = true;
+    return true;
+}
+
+bool build_model_rt(tmpc_ctx_impl *c)
+{
+    if (!rt_shape_ok(c->nx, c->nu, c->N)) return false;
+    return c->dtype == TMPC_F32 ? build_model_rt_t<float>(c) : build_model_rt_t<double>(c);
+}
+
 bool build_model(tmpc_ctx_impl *c)
 {
+    KernelInfo probe;
+    if (lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, false, probe) && probe.model_kind == 3) {
+        if (!build_model_rt(c)) return false;
+        // the stand-alone step kernels and the plant step exist for the compiled shapes only
+        const bool f32 = c->dtype == TMPC_F32;
+        if (c->nx == 12 && c->nu == 4 && c->N == 10) f32 ? build_model_t<float, 12, 4, 10>(c) : build_model_t<double, 12, 4, 10>(c);
+        if (c->nx == 4 && c->nu == 1 && c->N == 10) f32 ? build_model_t<float, 4, 1, 10>(c) : build_model_t<double, 4, 1, 10>(c);
+        if (c->nx == 32 && c->nu == 8 && c->N == 50 && f32) build_model_t<float, 32, 8, 50>(c);
+        return true;
+    }
     if (c->nx == 32 && c->nu == 8 && c->dtype == TMPC_F32) {
         if (cudaSetDevice(c->device) != cudaSuccess) return false;
         if (!build_model_warp(c)) return false;
@@ -492,7 +607,51 @@ static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
 void *model_param(tmpc_ctx_impl *c, const KernelInfo &ki)
 {
     if (ki.model_kind == 2) return (void *)&c->model_w;
+    if (ki.model_kind == 3) return (void *)c->model_rt.data();
     return ki.model_kind == 1 ? (void *)c->model_f32.data() : (void *)c->model.data();
+}
+
+// Grid of the persistent kernel for `da.batch` instances; for the run-time-shape kernel also its per-lane scratch and
+// the launch-dependent fields of its model image.
+int plan_launch(tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da, cudaStream_t s, long long &blocks)
+{
+    blocks = (da.batch + ki.per_block - 1) / ki.per_block;
+    long long max_blocks = c->sm_count;
+    if (ki.model_kind == 3) {
+        // persistent grid = every block the SMs can hold; the per-lane scratch (state of the resident instances) is
+        // capped at 16 GB of HBM
+        if (!c->rt_ready) return fail(c, TMPC_ERR_STATE, "run-time-shape model image not built");
+        int per_sm = 1;
+        CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ki.fn, ki.block, ki.smem));
+        if (per_sm < 1) per_sm = 1;
+        if (const char *e = getenv("TMPC_RT_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        max_blocks = (long long)c->sm_count * per_sm;
+        const long long per_block_bytes = tmpc::rt_scratch_elems(c->nx, c->nu, c->N) * ki.block * (long long)esize(c);
+        const long long cap = (16LL << 30) / per_block_bytes;
+        if (cap < 1) return fail(c, TMPC_ERR_UNSUPPORTED, "shape needs more than 16 GB of scratch for one block");
+        if (max_blocks > cap) max_blocks = cap;
+    }
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    if (ki.model_kind == 3) {
+        const size_t need = (size_t)tmpc::rt_scratch_elems(c->nx, c->nu, c->N) * (size_t)blocks * ki.block * esize(c);
+        if (c->d_rt_scratch_bytes < need) {
+            CUDA_TRY(c, cudaDeviceSynchronize());   // kernels of earlier calls / chunks may still use the old area
+            if (c->d_rt_scratch) cudaFree(c->d_rt_scratch);
+            c->d_rt_scratch = nullptr; c->d_rt_scratch_bytes = 0;
+            CUDA_TRY(c, cudaMalloc(&c->d_rt_scratch, need));
+            c->d_rt_scratch_bytes = need;
+        }
+        if (c->dtype == TMPC_F32) {
+            auto &m = *reinterpret_cast<tmpc::ModelRT<float> *>(c->model_rt.data());
+            m.scratch = (float *)c->d_rt_scratch; m.lanes = blocks * ki.block; m.warm = da.wd ? 1 : 0;
+        } else {
+            auto &m = *reinterpret_cast<tmpc::ModelRT<double> *>(c->model_rt.data());
+            m.scratch = (double *)c->d_rt_scratch; m.lanes = blocks * ki.block; m.warm = da.wd ? 1 : 0;
+        }
+    }
+    (void)s;
+    return TMPC_OK;
 }
 
 // Launch one persistent kernel (already chosen) for one device-resident batch on `s`.
@@ -502,9 +661,11 @@ int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cuda
     CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), s));
     da.counter = c->d_counter;
     da.stats = c->d_counter + 1;
-    long long blocks = (da.batch + ki.per_block - 1) / ki.per_block;
-    if (blocks > c->sm_count) blocks = c->sm_count;
-    if (blocks < 1) blocks = 1;
+    long long blocks = 1;
+    {
+        const int rc = plan_launch(c, ki, da, s, blocks);
+        if (rc != TMPC_OK) return rc;
+    }
     void *params[2] = {model_param(c, ki), &da};
     if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev0, s));
     CUDA_TRY(c, cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, s));
@@ -732,7 +893,7 @@ int tmpc_create(tmpc_ctx **out, int device, int nx, int nu, int N, int dtype, in
     KernelInfo ki;
     if (!lookup_kernel(nx, nu, N, dtype, order_policy, false, ki)) {
         char b[160];
-        snprintf(b, sizeof b, "shape nx=%d nu=%d N=%d has no compiled sm_100a kernel (have 12/4/10, 4/1/10 in f32/f64 and 32/8/50 in f32)", nx, nu, N);
+        snprintf(b, sizeof b, "shape nx=%d nu=%d N=%d is outside what the kernels cover (1 <= nx, nu <= 64, N >= 2)", nx, nu, N);
         return fail(nullptr, TMPC_ERR_UNSUPPORTED, b);
     }
     int ndev = 0;
@@ -789,6 +950,8 @@ int tmpc_destroy(tmpc_ctx *ctx)
     if (c->g_gate) cudaFree(c->g_gate);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_model_w) cudaFree(c->d_model_w);
+    if (c->d_model_rt) cudaFree(c->d_model_rt);
+    if (c->d_rt_scratch) cudaFree(c->d_rt_scratch);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1000,7 +1163,8 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
             cudaMemsetAsync(c->d_counter, 0, (k == 0 ? 5 : 1) * sizeof(unsigned long long), st.s);
             da.counter = c->d_counter;
             da.stats = c->d_counter + 1;
-            long long blocks = std::min<long long>((n + ki.per_block - 1) / ki.per_block, c->sm_count);
+            long long blocks = 1;
+            if ((rc_all = plan_launch(c, ki, da, st.s, blocks)) != TMPC_OK) break;
             void *params[2] = {model_param(c, ki), &da};
             cudaEventRecord(kev[2 * k], st.s);
             cudaError_t e = cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, st.s);

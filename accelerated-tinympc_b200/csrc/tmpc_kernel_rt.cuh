@@ -1,0 +1,348 @@
+// Run-time-shape ADMM kernel: any nx, nu <= 64 and any horizon, float or double.
+//
+// The reference fixes NSTATES / NINPUTS / NHORIZON at compile time (glob_opts.hpp:3-9) and its vendored Eigen picks the
+// floating-point EVALUATION ORDER of every product from those sizes at compile time.  The three BASELINE shapes have their
+// own kernels (tmpc_kernel_f32 / _small / _warp .cuh) with that order baked into templates; this kernel serves every other
+// shape with the order expressed as DATA: for each of the 8 products on the path the host (tmpc_orders_rt.hpp) emits a
+// small postfix "reduction program" -- (leaf index, number of adds that follow) per term -- that reproduces the reference
+// build's summation tree exactly, including the rows that Eigen's linear-vectorised assignment peels off by the run-time
+// address of the destination column.  PARITY results are therefore bit-identical to tiny_solve for any shape
+// (oracle/pin_shapes.py pins the dispatch rule against the compiled reference on 60+ shapes).
+//
+// Structure (same as tmpc_kernel.cuh, /root/reference/src/tinympc/admm.cpp:111-152): persistent grid, one thread owns one
+// instance at a time, per-lane early exit + refill from a global counter.  The per-instance state does not fit on chip
+// for arbitrary shapes, so it lives in a per-lane scratch area of HBM laid out [element][lane]: every access of a warp is
+// one coalesced 128-byte (float) line and the working set of the resident lanes stays in the 126 MB L2 for small shapes.
+// v/z are double-buffered (vnew/znew are written to the other buffer and the roles swap when the iteration continues),
+// which gives the reference's "v, z one iteration behind on an early exit" for the warm-start write-back without extra
+// traffic.  Scratch accesses bypass L1 (ld/st.global.cg): L1 is left to the shared model, bounds and programs, which are
+// read through the read-only path at warp-uniform addresses.  The vectors a mat-vec sweeps (x_i, u_i / p_{i+1}, r_i and
+// the product under construction) and the operand stack of the reduction programs are indexed at run time, so they live
+// in SHARED memory, [element][thread] (conflict-free), sized by the shape at launch: (3 max(nx,nu) + 8) scalars per thread.
+#pragma once
+#include "tmpc_kernel.cuh"
+
+namespace tmpc {
+
+constexpr int RT_MAXD = 64;    // nx, nu <= 64
+constexpr int RT_STACK = 8;    // operand stack of a reduction program (host checks the depth)
+constexpr int RT_BLOCK = 128;
+
+struct ProdRT {
+    int a, b;  // program offsets (entries of ModelRT::prog): a = packet-path rows, b = scalar-path rows
+};
+
+template <class T> struct ModelRT {
+    int nx, nu, N;
+    const T *K, *A, *B, *Qi, *M, *Pf, *Qd, *xmin, *xmax, *umin, *umax;  // device image, matrices column-major
+    const unsigned short *prog;                                         // entry = leaf | (adds << 8)
+    ProdRT Kx, Ax, Bu, Btp, Qs, Mp, Ktr, XtP;
+    // rows [lo, hi) of a destination column take program a, the others program b (tmpc_orders_rt.hpp):
+    //   head < 0: all rows a;  else unrolled assignment: [0, head);  rt_*: peeled by the address of the column
+    int head_Kx, head_Ax, head_Qs, head_Mp;
+    int rt_u, rt_x, rt_p, off_u, off_x, off_p, pk, sb;
+    T rho, nrho, pri_tol, dua_tol;
+    int max_iter, check_term;
+    T *scratch;       // [elements_per_lane][lanes]
+    long long lanes;  // gridDim.x * blockDim.x
+    int warm;
+};
+
+// dynamic shared memory of one block
+__host__ __device__ inline size_t rt_smem_bytes(int nx, int nu, size_t scalar)
+{
+    const int D = nx > nu ? nx : nu;
+    return (size_t)(3 * D + RT_STACK) * RT_BLOCK * scalar;
+}
+
+// elements of per-lane scratch
+__host__ __device__ inline long long rt_scratch_elems(int nx, int nu, int N)
+{
+    return 2LL * nx + 5LL * nu * (N - 1) + 4LL * nx * N;
+}
+
+// sum_k c(k) x(k): PARITY = the program's tree over individually rounded products; FAST = one FMA chain
+template <class T, bool FAST, class C, class X>
+__device__ __forceinline__ T dot_rt(const unsigned short *__restrict__ prog, int K, const C &c, const X &x, T *st /* [RT_STACK][RT_BLOCK] */)
+{
+    using N = Num<T>;
+    if constexpr (FAST) {
+        T acc = N::mul(c(0), x(0));
+        for (int k = 1; k < K; ++k) acc = N::fma(c(k), x(k), acc);
+        return acc;
+    } else {
+        int sp = 0;
+        T acc = T(0);
+        for (int k = 0; k < K; ++k) {
+            const unsigned w = __ldg(prog + k);
+            const int j = w & 0xff;
+            int nm = w >> 8;
+            const T e = N::mul(c(j), x(j));
+            if (nm == 0) {                 // push
+                if (k) st[(sp++ & (RT_STACK - 1)) * RT_BLOCK] = acc;
+                acc = e;
+            } else {                       // first add joins the top of the stack with the new term, the rest pop
+                acc = N::add(acc, e);
+                while (--nm) acc = N::add(st[(--sp & (RT_STACK - 1)) * RT_BLOCK], acc);
+            }
+        }
+        return acc;
+    }
+}
+
+template <class T> __device__ __forceinline__ void rt_head(const ModelRT<T> &P, int R, int head, int rt, int off, int col, int &lo, int &hi)
+{
+    if (head < 0) { lo = 0; hi = R; return; }
+    if (!rt) { lo = 0; hi = head; return; }
+    const int mask = P.pk - 1;
+    int first = (P.pk - (((off + col * R * P.sb) / P.sb) & mask)) & mask;
+    if (first > R) first = R;
+    lo = first;
+    hi = first + ((R - first) / P.pk) * P.pk;
+}
+
+template <class T, bool FAST>
+__global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant__ ModelRT<T> P, const __grid_constant__ SolveArgs<T> a)
+{
+    using N = Num<T>;
+    const int nx = P.nx, nu = P.nu, NH = P.N;
+    const int XROW = nx * NH, UROW = nu * (NH - 1);
+    const long long lanes = P.lanes;
+    const unsigned lane = threadIdx.x & 31;
+    constexpr unsigned FULLM = 0xffffffffu;
+    T *S = P.scratch + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    auto ld = [&](int e) -> T { return __ldcg(S + (long long)e * lanes); };
+    auto stg = [&](int e, T v) { __stcg(S + (long long)e * lanes, v); };
+    // run-time indexed vectors + operand stack in shared memory, [element][thread]
+    extern __shared__ __align__(16) unsigned char rt_smem[];
+    const int D = nx > nu ? nx : nu;
+    T *va = reinterpret_cast<T *>(rt_smem) + threadIdx.x;
+    T *vb = va + D * RT_BLOCK, *vc = vb + D * RT_BLOCK, *stk = vc + D * RT_BLOCK;
+    constexpr int VS = RT_BLOCK;   // stride between consecutive elements of a thread's vector
+    // scratch map
+    const int oX0 = 0, oPN = nx, oD = 2 * nx, oY = oD + UROW, oZ0 = oY + UROW, oZ1 = oZ0 + UROW, oU = oZ1 + UROW,
+              oG = oU + UROW, oV0 = oG + XROW, oV1 = oV0 + XROW, oXo = oV1 + XROW;
+
+    long long inst = -1;
+    int it = 0, cur = 0;
+    bool active = false, exhausted = false;
+    T res[4] = {T(0), T(0), T(0), T(0)};
+    unsigned long long n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
+
+    for (;;) {
+        // ------------------------------------------------------------------ lane refill
+        const bool need = !active && !exhausted;
+        const unsigned m = __ballot_sync(FULLM, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(m));
+            base = __shfl_sync(FULLM, base, leader);
+            if (need) {
+                const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
+                if (idx < a.batch && gate_wait(a, idx)) {
+                    inst = idx;
+                    active = true;
+                    it = 0;
+                    cur = 0;
+                    res[0] = res[1] = res[2] = res[3] = T(0);
+                    for (int j = 0; j < nx; ++j) stg(oX0 + j, __ldg(a.x0 + inst * nx + j));
+                    // p_N seed: -(Xref_{N-1}^T * Pinf)   (admm.cpp:83)
+                    const T *xr = a.Xref + inst * a.xref_stride + (long long)(NH - 1) * nx;
+                    for (int j = 0; j < nx; ++j) va[j * VS] = __ldg(xr + j);
+                    for (int j = 0; j < nx; ++j) {
+                        const T *col = P.Pf + (long long)j * nx;
+                        stg(oPN + j, -dot_rt<T, FAST>(P.prog + P.XtP.a, nx, [&](int k) { return __ldg(col + k); },
+                                                      [&](int k) { return va[k * VS]; }, stk));
+                    }
+                    if (P.warm && a.wd) {
+                        for (int e = 0; e < UROW; ++e) {
+                            stg(oD + e, a.wd[inst * UROW + e]);
+                            stg(oY + e, a.wy[inst * UROW + e]);
+                            stg(oZ0 + e, a.wz[inst * UROW + e]);
+                        }
+                        for (int e = 0; e < XROW; ++e) {
+                            stg(oG + e, a.wg[inst * XROW + e]);
+                            stg(oV0 + e, a.wv[inst * XROW + e]);
+                        }
+                    } else {
+                        for (int e = 0; e < UROW; ++e) { stg(oD + e, T(0)); stg(oY + e, T(0)); stg(oZ0 + e, T(0)); }
+                        for (int e = 0; e < XROW; ++e) { stg(oG + e, T(0)); stg(oV0 + e, T(0)); }
+                    }
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (__all_sync(FULLM, !active)) break;
+        ++n_trips;
+        if (!active) continue;
+        ++it;
+        const int oV = cur ? oV1 : oV0, oVn = cur ? oV0 : oV1, oZ = cur ? oZ1 : oZ0, oZn = cur ? oZ0 : oZ1;
+
+        // ------------------------------------------------------------------ forward sweep
+        // forward_pass (admm.cpp:27-37) + update_slack (:45-61) + update_dual (:67-71) + residual maxima (:95-98)
+        T pri_x = T(0), dua_x = T(0), pri_u = T(0), dua_u = T(0);
+        for (int j = 0; j < nx; ++j) va[j * VS] = ld(oX0 + j);
+        for (int i = 0; i < NH; ++i) {
+            for (int j = 0; j < nx; ++j) {
+                const int e = i * nx + j;
+                const T x = va[j * VS];
+                T g = ld(oG + e);
+                const T v = ld(oV + e);
+                T vn = N::add(x, g);                                                            // :48
+                vn = N::mn(__ldg(P.xmax + e), N::mx(__ldg(P.xmin + e), vn));                    // :59
+                pri_x = N::mx(pri_x, N::abs(N::sub(x, vn)));                                    // :95
+                dua_x = N::mx(dua_x, N::abs(N::sub(v, vn)));                                    // :96
+                g = N::sub(N::add(g, x), vn);                                                   // :70
+                stg(oG + e, g);
+                stg(oVn + e, vn);
+                stg(oXo + e, x);
+            }
+            if (i == NH - 1) break;
+            int lo, hi;
+            rt_head(P, nu, P.head_Kx, P.rt_u, P.off_u, i, lo, hi);
+            for (int r = 0; r < nu; ++r) {
+                const int e = i * nu + r;
+                const T *row = P.K + r;
+                const T kx = dot_rt<T, FAST>(P.prog + ((r >= lo && r < hi) ? P.Kx.a : P.Kx.b), nx,
+                                             [&](int k) { return __ldg(row + k * nu); }, [&](int k) { return va[k * VS]; }, stk);
+                const T u = N::sub(-kx, ld(oD + e));                                            // :31
+                T y = ld(oY + e);
+                const T z = ld(oZ + e);
+                T zn = N::add(u, y);                                                            // :47
+                zn = N::mn(__ldg(P.umax + e), N::mx(__ldg(P.umin + e), zn));                    // :53
+                pri_u = N::mx(pri_u, N::abs(N::sub(u, zn)));                                    // :97
+                dua_u = N::mx(dua_u, N::abs(N::sub(z, zn)));                                    // :98
+                y = N::sub(N::add(y, u), zn);                                                   // :69
+                stg(oY + e, y);
+                stg(oZn + e, zn);
+                stg(oU + e, u);
+                vb[r * VS] = u;
+            }
+            rt_head(P, nx, P.head_Ax, P.rt_x, P.off_x, i + 1, lo, hi);
+            for (int r = 0; r < nx; ++r) {
+                const bool pa = r >= lo && r < hi;
+                const T *ra = P.A + r, *rb = P.B + r;
+                const T ax = dot_rt<T, FAST>(P.prog + (pa ? P.Ax.a : P.Ax.b), nx, [&](int k) { return __ldg(ra + k * nx); },
+                                             [&](int k) { return va[k * VS]; }, stk);
+                if constexpr (FAST) {
+                    T acc = ax;
+                    for (int k = 0; k < nu; ++k) acc = N::fma(__ldg(rb + k * nx), vb[k * VS], acc);
+                    vc[r * VS] = acc;
+                } else {
+                    const T bu = dot_rt<T, FAST>(P.prog + (pa ? P.Bu.a : P.Bu.b), nu, [&](int k) { return __ldg(rb + k * nx); },
+                                                 [&](int k) { return vb[k * VS]; }, stk);
+                    vc[r * VS] = N::add(ax, bu);                                                // :35
+                }
+            }
+            for (int j = 0; j < nx; ++j) va[j * VS] = vc[j * VS];
+        }
+
+        // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
+        const bool chk = (it % P.check_term) == 0;
+        if (chk) {
+            res[0] = pri_x;
+            res[1] = N::mul(dua_x, P.rho);
+            res[2] = pri_u;
+            res[3] = N::mul(dua_u, P.rho);
+        }
+        const bool conv = chk && res[0] < P.pri_tol && res[2] < P.pri_tol && res[1] < P.dua_tol && res[3] < P.dua_tol;
+        const bool fin = conv || it >= P.max_iter;
+        const bool wback = P.warm && a.wd;
+        // a max_iter exit still does v = vnew, z = znew and the backward pass of its last iteration (admm.cpp:141-144)
+        if (!fin || (!conv && wback)) {
+            cur ^= 1;
+            const int oVc = cur ? oV1 : oV0, oZc = cur ? oZ1 : oZ0;
+            // -------------------------------------------------------------- backward sweep
+            // update_linear_cost (admm.cpp:77-85) recomputed per stage + backward_pass_grad (:15-22)
+            const T *xr_base = a.Xref + inst * a.xref_stride;
+            for (int j = 0; j < nx; ++j) {
+                const int e = (NH - 1) * nx + j;
+                const T dv = N::sub(ld(oVc + e), ld(oG + e));
+                if constexpr (FAST) va[j * VS] = N::fma(P.nrho, dv, ld(oPN + j));
+                else va[j * VS] = N::sub(ld(oPN + j), N::mul(P.rho, dv));                        // :84
+            }
+            for (int i = NH - 2; i >= 0; --i) {
+                for (int j = 0; j < nu; ++j) vb[j * VS] = N::mul(P.nrho, N::sub(ld(oZc + i * nu + j), ld(oY + i * nu + j)));   // :80
+                for (int r = 0; r < nu; ++r) {
+                    const T *col = P.B + (long long)r * nx;
+                    const T bp = dot_rt<T, FAST>(P.prog + P.Btp.a, nx, [&](int k) { return __ldg(col + k); },
+                                                 [&](int k) { return va[k * VS]; }, stk);
+                    vc[r * VS] = N::add(bp, vb[r * VS]);
+                }
+                int lo, hi;
+                rt_head(P, nu, P.head_Qs, 0, 0, i, lo, hi);
+                for (int r = 0; r < nu; ++r) {
+                    const T *row = P.Qi + r;
+                    stg(oD + i * nu + r, dot_rt<T, FAST>(P.prog + ((r >= lo && r < hi) ? P.Qs.a : P.Qs.b), nu,
+                                                         [&](int k) { return __ldg(row + k * nu); }, [&](int k) { return vc[k * VS]; }, stk));   // :19
+                }
+                rt_head(P, nx, P.head_Mp, P.rt_p, P.off_p, i, lo, hi);
+                for (int r = 0; r < nx; ++r) {   // p_i is built in vc (s is dead)
+                    const int e = i * nx + r;
+                    const T cq = -N::mul(__ldg(xr_base + e), __ldg(P.Qd + r));                  // :81
+                    const T dv = N::sub(ld(oVc + e), ld(oG + e));
+                    T q;
+                    if constexpr (FAST) q = N::fma(P.nrho, dv, cq);
+                    else q = N::sub(cq, N::mul(P.rho, dv));                                      // :82
+                    const T *rm = P.M + r, *ck = P.K + (long long)r * nu;
+                    const T mp = dot_rt<T, FAST>(P.prog + ((r >= lo && r < hi) ? P.Mp.a : P.Mp.b), nx,
+                                                 [&](int k) { return __ldg(rm + k * nx); }, [&](int k) { return va[k * VS]; }, stk);
+                    const T kr = dot_rt<T, FAST>(P.prog + P.Ktr.a, nu, [&](int k) { return __ldg(ck + k); },
+                                                 [&](int k) { return vb[k * VS]; }, stk);
+                    vc[r * VS] = N::sub(N::add(q, mp), kr);                                      // :20
+                }
+                for (int j = 0; j < nx; ++j) va[j * VS] = vc[j * VS];
+            }
+        }
+        if (fin) {
+            if (a.iter) a.iter[inst] = it;
+            if (a.status) a.status[inst] = conv ? 1 : 11;
+            if (a.resid) {
+                a.resid[inst * 4 + 0] = res[0];
+                a.resid[inst * 4 + 1] = res[1];
+                a.resid[inst * 4 + 2] = res[2];
+                a.resid[inst * 4 + 3] = res[3];
+            }
+            if (a.x) for (int e = 0; e < XROW; ++e) a.x[inst * XROW + e] = ld(oXo + e);
+            if (a.u) for (int e = 0; e < UROW; ++e) a.u[inst * UROW + e] = ld(oU + e);
+            if (wback) {
+                // converged: cur was not advanced -> v, z are those of the previous iteration (SURVEY 8a note W)
+                const int oVc = cur ? oV1 : oV0, oZc = cur ? oZ1 : oZ0;
+                for (int e = 0; e < UROW; ++e) {
+                    a.wd[inst * UROW + e] = ld(oD + e);
+                    a.wy[inst * UROW + e] = ld(oY + e);
+                    a.wz[inst * UROW + e] = ld(oZc + e);
+                }
+                for (int e = 0; e < XROW; ++e) {
+                    a.wg[inst * XROW + e] = ld(oG + e);
+                    a.wv[inst * XROW + e] = ld(oVc + e);
+                }
+            }
+            n_iter += (unsigned)it;
+            n_solved += conv ? 1u : 0u;
+            ++n_inst;
+            active = false;
+            if (a.done) { __threadfence(); atomicAdd(a.done + (inst >> a.done_shift), 1u); }
+        }
+    }
+
+    if (a.stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_iter += __shfl_down_sync(FULLM, n_iter, o);
+            n_solved += __shfl_down_sync(FULLM, n_solved, o);
+            n_trips += __shfl_down_sync(FULLM, n_trips, o);
+            n_inst += __shfl_down_sync(FULLM, n_inst, o);
+        }
+        if (lane == 0) {
+            atomicAdd(a.stats + 0, n_iter);
+            atomicAdd(a.stats + 1, n_solved);
+            atomicAdd(a.stats + 2, n_trips);
+            atomicAdd(a.stats + 3, n_inst);
+        }
+    }
+}
+
+}  // namespace tmpc

@@ -45,7 +45,10 @@ namespace {
 
 struct Inst {
     TinyCache cache;
-    TinyWorkspace work;
+    // 16-byte aligned like a global/static TinyWorkspace (how the reference's examples and generated code hold it:
+    // quadrotor_hovering.cpp:25-28, codegen.cpp:350-470).  Matters only for shapes whose nx or nu is not a multiple of
+    // the SSE packet: Eigen then peels rows by the run-time address of each column (see tinympc_oracle.c).
+    alignas(16) TinyWorkspace work;
     TinySettings settings;
     TinySolver solver;
 };

@@ -31,7 +31,32 @@ typedef struct {
     int Mp;  /* AmBKt * p_{i+1}            admm.cpp:20 */
     int Ktr; /* Kinf^T * r_i               admm.cpp:20 */
     int XtP; /* Xref_{N-1}^T * Pinf        admm.cpp:83 */
+    /* Mixed rows (output length not a multiple of the packet width): rows [0, head) take the order above, rows
+     * [head, R) take ORD_TREE / ORD_SEQ (the scalar coefficient path of the linear-vectorised assignment,
+     * AssignEvaluator.h dense_assignment_loop<LinearVectorizedTraversal, CompleteUnrolling>).  head < 0 = all rows. */
+    int head_Kx, head_Ax, head_Qs, head_Mp;
+    int tail_x, tail_u; /* order of the scalar tail rows for K = nx and K = nu products */
+    /* Assignments too costly for complete unrolling (AssignEvaluator.h copy_using_evaluator_traits:
+     * size * (1 + source coefficient cost) > EIGEN_UNROLLING_LIMIT * pk) run dense_assignment_loop<
+     * LinearVectorizedTraversal, NoUnrolling>, which peels rows up to the first 16-byte aligned ADDRESS of the
+     * destination column: rows [first, first + ((R-first)/pk)*pk) take the packet path, the others the scalar path.
+     * rt_* = that applies to destination u.col(i) / x.col(i+1) / p.col(i); off_* = byte offset of the member in a
+     * 16-byte aligned TinyWorkspace (types.hpp:52-97 member order; a member is 16-aligned iff its byte size is a
+     * multiple of 16, else scalar-aligned). */
+    int rt_u, rt_x, rt_p, off_u, off_x, off_p, pk, sb;
 } orders_t;
+
+/* rows [lo, hi) of an R-row destination column `col` take the packet order */
+static void head_range(const orders_t *o, int R, int unrolled_head, int rt, int off, int col, int *lo, int *hi)
+{
+    if (unrolled_head < 0) { *lo = 0; *hi = R; return; }
+    if (!rt) { *lo = 0; *hi = unrolled_head; return; }
+    int mask = o->pk - 1;
+    int first = (o->pk - (((off + col * R * o->sb) / o->sb) & mask)) & mask;
+    if (first > R) first = R;
+    *lo = first;
+    *hi = first + ((R - first) / o->pk) * o->pk;
+}
 
 typedef struct {
     int32_t nx, nu, N, scalar_bytes;
@@ -71,29 +96,58 @@ static orders_t select_orders(int nx, int nu, int N, int scalar_bytes)
 
 static orders_t select_orders_builtin(int nx, int nu, int N, int scalar_bytes)
 {
-    (void)N;
     orders_t o;
     const int pk = 16 / scalar_bytes;
     const int large = 8; /* EIGEN_CACHEFRIENDLY_PRODUCT_THRESHOLD, arch/Default/Settings.h:30-31 */
     /* lazyProduct(col-major lhs, column rhs) (admm.cpp:31,35): packet path over the rows when
      * rows % pk == 0 (ProductEvaluators.h:574-575) -> sequential over k.  A 1-row Kinf is stored row-major,
      * so its single coefficient is a vectorised redux over the contiguous row. */
-    o.Kx = (nu == 1) ? ORD_VECREDUX : (nu % pk == 0 ? ORD_SEQ : ORD_TREE);
-    o.Ax = (nx % pk == 0) ? ORD_SEQ : ORD_TREE;
-    o.Bu = (nx % pk == 0) ? ORD_SEQ : ORD_TREE;
+    /* Completely unrolled scalar redux = half-split tree; beyond Redux.h's unrolling limit (cost 4K-1 against
+     * EIGEN_UNROLLING_LIMIT * pk for the linear traversal, i.e. K <= 110 float / 55 double) it is a plain loop. */
+    const int unroll_k = (110 * pk + 1) / 4;
+    o.tail_x = nx <= unroll_k ? ORD_TREE : ORD_SEQ;
+    o.tail_u = nu <= unroll_k ? ORD_TREE : ORD_SEQ;
+    o.Kx = (nu == 1) ? (nx <= unroll_k ? ORD_VECREDUX : ORD_VECLOOP) : ORD_SEQ;
+    o.head_Kx = (nu == 1) ? -1 : (nu / pk) * pk;
+    o.Ax = ORD_SEQ;
+    o.Bu = ORD_SEQ;
+    o.head_Ax = (nx / pk) * pk;
     /* Bdyn^T * p (admm.cpp:19) is a regular product evaluated into a temporary: GeneralProduct.h
      * product_type_selector<rows=nu, 1, depth=nx>: both >= 8 -> row-major GEMV; otherwise coefficient /
      * inner product = completely unrolled vectorised redux. */
     o.Btp = (nu >= large && nx >= large) ? ORD_GEMV_ROW : ORD_VECREDUX;
     /* Quu_inv * s: nu >= 8 -> col-major GEMV (sequential); else packet path (sequential). */
-    o.Qs = (nu >= large || nu % pk == 0 || nu == 1) ? ORD_SEQ : ORD_TREE;
+    o.Qs = ORD_SEQ;
+    o.head_Qs = (nu >= large) ? -1 : (nu / pk) * pk;
     /* q + AmBKt.lazyProduct(p) - Kinf^T.lazyProduct(r) (admm.cpp:20): Kinf^T is a row-major nx x nu lhs, which
      * has no packet path against a single column, so the whole expression is evaluated per coefficient and
      * AmBKt's strided row gives a scalar tree; when nu == 1, Kinf^T is a contiguous column vector, the
      * expression is packet-evaluable and AmBKt*p takes the sequential packet path. */
-    o.Mp = (nu == 1 && nx % pk == 0) ? ORD_SEQ : ORD_TREE;
-    o.Ktr = ORD_VECREDUX;
-    o.XtP = ORD_VECREDUX; /* admm.cpp:83: row vector * matrix, coefficient = redux over a contiguous column */
+    o.Mp = (nu == 1) ? ORD_SEQ : o.tail_x;
+    o.head_Mp = (nu == 1) ? (nx / pk) * pk : -1;
+    o.Ktr = nu <= unroll_k ? ORD_VECREDUX : ORD_VECLOOP;
+    o.XtP = nx <= unroll_k ? ORD_VECREDUX : ORD_VECLOOP;
+    if (o.Btp == ORD_VECREDUX && nx > unroll_k) o.Btp = ORD_VECLOOP;
+    o.pk = pk; o.sb = scalar_bytes;
+    {
+        const int lim = 110 * pk;
+        /* u.col(i) = -Kinf.lazyProduct(x) - d: source cost (4nx-1) + 1 + 1 + 1 */
+        o.rt_u = (nu != 1 && nu % pk != 0 && nu * (1 + 4 * nx + 2) > lim);
+        /* x.col(i+1) = A.lazyProduct(x) + B.lazyProduct(u): (4nx-1) + (4nu-1) + 1 */
+        o.rt_x = (nx % pk != 0 && nx * (1 + 4 * nx + 4 * nu - 1) > lim);
+        /* p.col(i) = q + AmBKt.lazyProduct(p) - Kinf^T.lazyProduct(r), packet-evaluable only when nu == 1 */
+        o.rt_p = (nu == 1 && nx % pk != 0 && nx * (1 + 1 + (4 * nx - 1) + 1 + 3 + 1) > lim);
+        int off = 0, bx = nx * N * scalar_bytes, bu = nu * (N - 1) * scalar_bytes;
+        int sizes[6] = {bx, bu, bx, bu, bx, bu}; /* x u q r p d */
+        int offs[6];
+        for (int k = 0; k < 6; ++k) {
+            int al = (sizes[k] % 16 == 0) ? 16 : scalar_bytes;
+            off = (off + al - 1) / al * al;
+            offs[k] = off;
+            off += sizes[k];
+        }
+        o.off_x = offs[0]; o.off_u = offs[1]; o.off_p = offs[4];
+    } /* admm.cpp:83: row vector * matrix, coefficient = redux over a contiguous column */
     return o;
 }
 

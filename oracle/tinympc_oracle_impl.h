@@ -141,6 +141,16 @@ static T SFX(reduce)(const T *e, int K, int order)
 
 /* out[r] = sum_k M[r + k*ld_k ...] : generic strided mat-vec with a named order.
  * M(r,k) = m[r*rs + k*ks]; vec x[k]. */
+static void SFX(matvec2)(T *out, const T *m, int rs, int ks, const T *x, int R, int K, int order, int lo, int hi,
+                         int tail_order, T *e)
+{
+    if (order == ORD_GEMV_COL) order = ORD_SEQ;
+    for (int r = 0; r < R; ++r) {
+        for (int k = 0; k < K; ++k) e[k] = m[r * rs + k * ks] * x[k];
+        out[r] = SFX(reduce)(e, K, (r >= lo && r < hi) ? order : tail_order);
+    }
+}
+
 static void SFX(matvec)(T *out, const T *m, int rs, int ks, const T *x, int R, int K, int order, T *e)
 {
     if (order == ORD_GEMV_COL) {
@@ -163,10 +173,13 @@ static void SFX(forward_pass)(const SFX(prob) *P, SFX(work) *w)
     for (int i = 0; i < N - 1; ++i) {
         const T *xi = w->x + i * n;
         T *ui = w->u + i * m;
-        SFX(matvec)(Kx, P->Kinf, 1, m, xi, m, n, P->ord.Kx, w->e);           /* :31 */
+        int lo, hi;
+        head_range(&P->ord, m, P->ord.head_Kx, P->ord.rt_u, P->ord.off_u, i, &lo, &hi);
+        SFX(matvec2)(Kx, P->Kinf, 1, m, xi, m, n, P->ord.Kx, lo, hi, P->ord.tail_x, w->e); /* :31 */
         for (int r = 0; r < m; ++r) ui[r] = (-Kx[r]) - w->d[i * m + r];
-        SFX(matvec)(Ax, P->Adyn, 1, n, xi, n, n, P->ord.Ax, w->e);           /* :35 */
-        SFX(matvec)(Bu, P->Bdyn, 1, n, ui, n, m, P->ord.Bu, w->e);
+        head_range(&P->ord, n, P->ord.head_Ax, P->ord.rt_x, P->ord.off_x, i + 1, &lo, &hi);
+        SFX(matvec2)(Ax, P->Adyn, 1, n, xi, n, n, P->ord.Ax, lo, hi, P->ord.tail_x, w->e); /* :35 */
+        SFX(matvec2)(Bu, P->Bdyn, 1, n, ui, n, m, P->ord.Bu, lo, hi, P->ord.tail_u, w->e);
         for (int r = 0; r < n; ++r) w->x[(i + 1) * n + r] = Ax[r] + Bu[r];
     }
 }
@@ -253,9 +266,12 @@ static void SFX(backward_pass_grad)(const SFX(prob) *P, SFX(work) *w)
         /* :19  d_i = Quu_inv * (B^T p_{i+1} + r_i);  (B^T)(r,k) = B[k + r*n] */
         SFX(matvec)(s, P->Bdyn, n, 1, pn, m, n, P->ord.Btp, w->e);
         for (int r = 0; r < m; ++r) s[r] = s[r] + ri[r];
-        SFX(matvec)(w->d + i * m, P->Quu_inv, 1, m, s, m, m, P->ord.Qs, w->e);
+        int lo, hi;
+        head_range(&P->ord, m, P->ord.head_Qs, 0, 0, i, &lo, &hi);
+        SFX(matvec2)(w->d + i * m, P->Quu_inv, 1, m, s, m, m, P->ord.Qs, lo, hi, P->ord.tail_u, w->e);
         /* :20  p_i = q_i + AmBKt p_{i+1} - Kinf^T r_i;  (K^T)(r,k) = K[k + r*m] */
-        SFX(matvec)(Mp, P->AmBKt, 1, n, pn, n, n, P->ord.Mp, w->e);
+        head_range(&P->ord, n, P->ord.head_Mp, P->ord.rt_p, P->ord.off_p, i, &lo, &hi);
+        SFX(matvec2)(Mp, P->AmBKt, 1, n, pn, n, n, P->ord.Mp, lo, hi, P->ord.tail_x, w->e);
         SFX(matvec)(Ktr, P->Kinf, m, 1, ri, n, m, P->ord.Ktr, w->e);
         for (int r = 0; r < n; ++r) w->p[i * n + r] = (w->q[i * n + r] + Mp[r]) - Ktr[r];
     }
@@ -425,8 +441,8 @@ int SFX(oracle_plant_step)(const oracle_problem *in, int64_t B, const void *x0_,
     for (int64_t b = 0; b < B; ++b) {
         const T *x0 = (const T *)x0_ + b * n, *u0 = (const T *)u0_ + b * u_stride;
         T *x1 = (T *)x1_ + b * n;
-        SFX(matvec)(Ax, P.Adyn, 1, n, x0, n, n, P.ord.Ax, e);
-        SFX(matvec)(Bu, P.Bdyn, 1, n, u0, n, m, P.ord.Bu, e);
+        SFX(matvec2)(Ax, P.Adyn, 1, n, x0, n, n, P.ord.Ax, 0, P.ord.head_Ax, P.ord.tail_x, e);
+        SFX(matvec2)(Bu, P.Bdyn, 1, n, u0, n, m, P.ord.Bu, 0, P.ord.head_Ax, P.ord.tail_u, e);
         for (int r = 0; r < n; ++r) x1[r] = Ax[r] + Bu[r];
     }
     return 0;

@@ -1,0 +1,148 @@
+"""GPU parity of the run-time-shape kernel (csrc/tmpc_kernel_rt.cuh + tmpc_orders_rt.hpp) through the C ABI: any
+nx, nu <= 64 and any horizon, bit-exact (PARITY policy) against
+  * fixtures generated from the UNMODIFIED reference compiled for each shape (tests/golden/shapes_*.npz), cold and warm;
+  * the CPU oracle on larger seeded batches (ragged sizes, per-instance Xref, settings variants);
+  * the specialised kernels and the reference fixtures of the three BASELINE shapes (TMPC_KERNEL=rt forces this kernel).
+FAST policy (FMA chains): x/u within 1e-4 relative on instances whose iteration count agrees (tolerance of north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_same
+from test_golden_shapes import DT, fixture_problem, load_shapes
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp_exact(out, ref, what=""):
+    for name in ("iter", "status", "x", "u", "resid"):
+        assert_same(out[name], getattr(ref, name), what + name)
+
+
+@pytest.mark.parametrize("tag", list(DT))
+def test_generic_shapes_match_reference_fixture(pkg, tag):
+    z, shapes = load_shapes(tag)
+    for key in shapes:
+        prob = fixture_problem(pkg, z, key)
+        g = lambda k: z[key + "/" + k]
+        s = pkg.capi.Solver(prob, dtype=DT[tag], policy="parity")
+        nx, nu, N = prob.nx, prob.nu, prob.N
+        B = g("x0").shape[0]
+        warm = {k: np.zeros((B, N - 1, nu) if k in "dyz" else (B, N, nx), DT[tag]) for k in ("d", "y", "g", "v", "z")}
+        o1 = s.solve(g("x0"), g("xref"), warm=warm)
+        for name in ("iter", "status", "resid", "x", "u"):
+            assert_same(o1[name], g(name), "%s cold %s" % (key, name))
+        assert s.stats()["parity_pinned"] == 1
+        o2 = s.solve((g("x0") * np.float32(1.01)).astype(np.float32), g("xref"), warm=o1["warm"])
+        for name in ("iter", "status", "resid", "x", "u"):
+            assert_same(o2[name], g("w_" + name), "%s warm %s" % (key, name))
+        for k in ("d", "y", "g", "v", "z"):
+            assert_same(o2["warm"][k], g("w_state_" + k), "%s warm state %s" % (key, k))
+        s.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,B", [((6, 3, 20), 4099), ((9, 4, 7), 1000), ((13, 7, 6), 777), ((20, 8, 12), 513), ((5, 1, 6), 2049),
+                                     ((24, 6, 10), 300), ((2, 2, 3), 129), ((1, 1, 2), 33)])
+def test_generic_shape_vs_oracle_per_instance_xref(pkg, oracle, shape, B, dtype):
+    nx, nu, N = shape
+    prob = pkg.problems.random_system(nx, nu, N, seed=7 + nx)
+    rng = np.random.default_rng(nx * 100 + nu)
+    x0 = rng.uniform(-2, 2, (B, nx)).astype(np.float32)
+    x0[::2] *= np.float32(0.1)
+    xref = rng.uniform(-0.3, 0.3, (B, N, nx)).astype(np.float32)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=dtype, nthreads=8)
+    s = pkg.capi.Solver(prob, dtype=dtype, policy="parity")
+    out = s.solve(x0, xref)
+    _cmp_exact(out, ref, "%s " % (shape,))
+    st = s.stats()
+    assert st["instances"] == B and st["iterations"] == int(ref.iter.sum()) and st["solved"] == int((ref.status == 1).sum())
+    assert len(set(ref.iter.tolist())) > 1
+
+
+def test_generic_shape_settings_variants(pkg, oracle):
+    base = dict(nx=10, nu=3, N=9)
+    rng = np.random.default_rng(3)
+    x0 = rng.uniform(-1.5, 1.5, (600, 10)).astype(np.float32)
+    xref = np.zeros((9, 10), np.float32)
+    for kw in (dict(check_termination=3), dict(max_iter=7), dict(en_state_bound=0), dict(en_input_bound=0, en_state_bound=0),
+               dict(abs_pri_tol=1e-2, abs_dua_tol=1e-1)):
+        prob = pkg.problems.random_system(base["nx"], base["nu"], base["N"], seed=11)
+        for k, v in kw.items():
+            setattr(prob, k, v)
+        ref = oracle.solve_batch(prob, x0, xref, dtype=np.float32, nthreads=4)
+        out = pkg.capi.Solver(prob, dtype=np.float32, policy="parity").solve(x0, xref)
+        _cmp_exact(out, ref, "%r " % (kw,))
+
+
+@pytest.mark.parametrize("which", ["q", "c", "l"])
+def test_rt_kernel_reproduces_baseline_shapes(pkg, oracle, which, monkeypatch):
+    """TMPC_KERNEL=rt runs the run-time-shape kernel on the three BASELINE shapes: it must agree bit for bit with the
+    oracle (hence with the specialised kernels and the reference fixtures those are pinned to), cold and warm."""
+    if which == "q":
+        prob = pkg.problems.quadrotor(20)
+        x0, xref = pkg.workloads.quadrotor_hover_batch(0, 3000, mult=0.5)
+    elif which == "c":
+        prob = pkg.problems.cartpole()
+        x0, xref = pkg.workloads.cartpole_batch(0, 5000)
+    else:
+        prob = pkg.problems.random_system()
+        rng = np.random.default_rng(5)
+        x0, xref = rng.uniform(-1, 1, (96, 32)).astype(np.float32), np.zeros((50, 32), np.float32)
+    B = x0.shape[0]
+    spec = pkg.capi.Solver(prob, dtype=np.float32, policy="parity").solve(x0, xref)
+    monkeypatch.setenv("TMPC_KERNEL", "rt")
+    s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    warm = {k: np.zeros((B, prob.N - 1, prob.nu) if k in "dyz" else (B, prob.N, prob.nx), np.float32) for k in ("d", "y", "g", "v", "z")}
+    out = s.solve(x0, xref, warm=warm)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=np.float32, want_state=True, nthreads=8)
+    _cmp_exact(out, ref, which + " rt ")
+    for name in ("iter", "status", "x", "u", "resid"):
+        assert_same(out[name], spec[name], which + " rt vs specialised " + name)
+    for k in ("d", "y", "g", "v", "z"):
+        assert_same(out["warm"][k], ref.state[k], which + " warm state " + k)
+
+
+def test_generic_shape_fast_policy_tolerance(pkg, oracle):
+    prob = pkg.problems.random_system(10, 4, 12, seed=21)
+    rng = np.random.default_rng(9)
+    x0 = (rng.uniform(-1, 1, (4000, 10)) * 0.3).astype(np.float32)
+    xref = np.zeros((12, 10), np.float32)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=np.float32, nthreads=8)
+    out = pkg.capi.Solver(prob, dtype=np.float32, policy="fast").solve(x0, xref)
+    same = out["iter"] == ref.iter
+    assert same.mean() > 0.85, "iteration counts agree on %.3f" % same.mean()
+    scale = np.abs(ref.x[same]).max(axis=(1, 2), keepdims=True) + 1e-6
+    assert (np.abs(out["x"][same] - ref.x[same]) / scale).max() < 1e-4       # north_star: 1e-4 relative in fp32
+    scale_u = np.abs(ref.u[same]).max(axis=(1, 2), keepdims=True) + 1e-6
+    assert (np.abs(out["u"][same] - ref.u[same]) / scale_u).max() < 1e-4
+
+
+def test_generic_shape_device_memory_path(pkg, oracle):
+    import torch
+    prob = pkg.problems.random_system(7, 2, 11, seed=4)
+    B = 3001
+    rng = np.random.default_rng(1)
+    x0 = (rng.uniform(-1, 1, (B, 7)) * 0.5).astype(np.float32)
+    xref = np.zeros((11, 7), np.float32)
+    ref = oracle.solve_batch(prob, x0, xref, dtype=np.float32, nthreads=8)
+    s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    dev = torch.device("cuda:0")
+    tx0, txr = torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev)
+    x = torch.empty((B, 11, 7), device=dev); u = torch.empty((B, 10, 2), device=dev)
+    it = torch.empty(B, dtype=torch.int32, device=dev); stt = torch.empty(B, dtype=torch.int32, device=dev)
+    rs = torch.empty((B, 4), device=dev)
+    s.solve_raw(B, tx0, txr, True, pkg.capi.TMPC_MEM_DEVICE, x, u, it, stt, rs, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert_same(it.cpu().numpy(), ref.iter, "iter")
+    assert_same(x.cpu().numpy(), ref.x, "x")
+    assert_same(u.cpu().numpy(), ref.u, "u")
+    assert_same(rs.cpu().numpy(), ref.resid, "resid")
+
+
+def test_shape_limits_are_reported(pkg):
+    prob = pkg.problems.random_system(8, 2, 5, seed=2)
+    prob.nx = 65
+    with pytest.raises(pkg.capi.TmpcError):
+        pkg.capi.Solver(prob, dtype=np.float32)
