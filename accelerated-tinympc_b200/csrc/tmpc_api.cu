@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <string>
 #include <type_traits>
@@ -489,55 +490,88 @@ bool build_model_warp(tmpc_ctx_impl *c)
     return true;
 }
 
-// Run-time-shape kernel: device image = K | A | B | Qi | M | Pf | Qd | xmin | xmax | umin | umax (scalars of the ctx dtype)
-// followed by the reduction programs (uint16); ModelRT<T> holds pointers into it.
+// Run-time-shape kernel: device image = Qd | xmin | xmax | umin | umax | for each product and order variant a row-major
+// copy of its coefficient matrix with the columns in program order | the reduction programs (uint16).
+// ModelRT<T> holds pointers into it.
 template <class T> bool build_model_rt_t(tmpc_ctx_impl *c)
 {
     const int nx = c->nx, nu = c->nu, N = c->N;
-    const tmpc_rt::Orders o = tmpc_rt::build_orders(nx, nu, N, (int)sizeof(T));
+    const tmpc_rt::Orders o = tmpc_rt::build_orders(nx, nu, N, (int)sizeof(T), c->policy == TMPC_ORDER_FAST);
     if (o.max_depth > tmpc::RT_STACK) return false;
+    const T *Kinf = reinterpret_cast<const T *>(c->Kinf.data()), *A = reinterpret_cast<const T *>(c->Adyn.data()),
+            *Bm = reinterpret_cast<const T *>(c->Bdyn.data()), *Qi = reinterpret_cast<const T *>(c->Quu_inv.data()),
+            *M = reinterpret_cast<const T *>(c->AmBKt.data()), *Pf = reinterpret_cast<const T *>(c->Pinf.data());
+    std::vector<T> img;
+    auto al4 = [&]() { while (img.size() % 4) img.push_back(T(0)); };
     const size_t n_x = (size_t)N * nx, n_u = (size_t)(N - 1) * nu;
-    const size_t cnt[11] = {(size_t)nu * nx, (size_t)nx * nx, (size_t)nx * nu, (size_t)nu * nu, (size_t)nx * nx, (size_t)nx * nx,
-                            (size_t)nx, n_x, n_x, n_u, n_u};
-    size_t off[12];
-    off[0] = 0;
-    for (int k = 0; k < 11; ++k) off[k + 1] = off[k] + ((cnt[k] + 3) & ~size_t(3));
-    const size_t prog_off = off[11] * sizeof(T);
-    const size_t bytes = prog_off + ((o.prog.size() * 2 + 15) & ~size_t(15));
-    std::vector<unsigned char> img(bytes, 0);
-    T *h = reinterpret_cast<T *>(img.data());
-    const std::vector<unsigned char> *src[7] = {&c->Kinf, &c->Adyn, &c->Bdyn, &c->Quu_inv, &c->AmBKt, &c->Pinf, &c->Q};
-    for (int k = 0; k < 7; ++k) std::memcpy(h + off[k], src[k]->data(), cnt[k] * sizeof(T));
+    const size_t o_qd = img.size();
+    img.insert(img.end(), reinterpret_cast<const T *>(c->Q.data()), reinterpret_cast<const T *>(c->Q.data()) + nx);
+    al4();
     const T inf = std::numeric_limits<T>::infinity();
     const bool xs = c->en_state && c->has_xb, us = c->en_input && c->has_ub;
-    for (size_t k = 0; k < n_x; ++k) {
-        h[off[7] + k] = xs ? reinterpret_cast<const T *>(c->xmin.data())[k] : -inf;
-        h[off[8] + k] = xs ? reinterpret_cast<const T *>(c->xmax.data())[k] : inf;
+    size_t o_b[4];
+    for (int w = 0; w < 4; ++w) {
+        o_b[w] = img.size();
+        const bool isx = w < 2, en = isx ? xs : us;
+        const std::vector<unsigned char> &src = w == 0 ? c->xmin : w == 1 ? c->xmax : w == 2 ? c->umin : c->umax;
+        const size_t n = isx ? n_x : n_u;
+        for (size_t k = 0; k < n; ++k) img.push_back(en ? reinterpret_cast<const T *>(src.data())[k] : ((w & 1) ? inf : -inf));
+        al4();
     }
-    for (size_t k = 0; k < n_u; ++k) {
-        h[off[9] + k] = us ? reinterpret_cast<const T *>(c->umin.data())[k] : -inf;
-        h[off[10] + k] = us ? reinterpret_cast<const T *>(c->umax.data())[k] : inf;
-    }
-    std::memcpy(img.data() + prog_off, o.prog.data(), o.prog.size() * 2);
+    // coefficient copies: element (r, k) of each product as the ADMM sweeps use it
+    struct PD { const tmpc_rt::Prod *p; int R, K; std::function<T(int, int)> at; };
+    const PD pd[8] = {
+        {&o.Kx, nu, nx, [&](int r, int k) { return Kinf[r + k * nu]; }},   // Kinf x
+        {&o.Ax, nx, nx, [&](int r, int k) { return A[r + k * nx]; }},      // Adyn x
+        {&o.Bu, nx, nu, [&](int r, int k) { return Bm[r + k * nx]; }},     // Bdyn u
+        {&o.Btp, nu, nx, [&](int r, int k) { return Bm[k + r * nx]; }},    // Bdyn^T p
+        {&o.Qs, nu, nu, [&](int r, int k) { return Qi[r + k * nu]; }},     // Quu_inv s
+        {&o.Mp, nx, nx, [&](int r, int k) { return M[r + k * nx]; }},      // AmBKt p
+        {&o.Ktr, nx, nu, [&](int r, int k) { return Kinf[k + r * nu]; }},  // Kinf^T r
+        {&o.XtP, nx, nx, [&](int r, int k) { return Pf[k + r * nx]; }},    // Xref^T Pinf
+    };
+    size_t o_cf[8][2];
+    for (int q = 0; q < 8; ++q)
+        for (int v = 0; v < 2; ++v) {
+            const tmpc_rt::Variant &var = v ? pd[q].p->b : pd[q].p->a;
+            if (v == 1 && var.prog == pd[q].p->a.prog) { o_cf[q][1] = o_cf[q][0]; continue; }
+            o_cf[q][v] = img.size();
+            for (int r = 0; r < pd[q].R; ++r)
+                for (int k = 0; k < pd[q].K; ++k)
+                    img.push_back(pd[q].at(r, var.kind == tmpc_rt::K_FIXED ? k : (o.prog[var.prog + k] & 0xff)));
+            al4();
+        }
+    const size_t prog_off = img.size() * sizeof(T);
+    const size_t bytes = prog_off + ((o.prog.size() * 2 + 15) & ~size_t(15));
+    std::vector<unsigned char> raw(bytes, 0);
+    std::memcpy(raw.data(), img.data(), img.size() * sizeof(T));
+    std::memcpy(raw.data() + prog_off, o.prog.data(), o.prog.size() * 2);
     if (cudaSetDevice(c->device) != cudaSuccess) return false;
+    // the previous image may still be in use by a kernel
+    if (cudaDeviceSynchronize() != cudaSuccess) return false;
     if (c->d_model_rt_bytes < bytes) {
         if (c->d_model_rt) cudaFree(c->d_model_rt);
         c->d_model_rt = nullptr; c->d_model_rt_bytes = 0;
         if (cudaMalloc(&c->d_model_rt, bytes) != cudaSuccess) return false;
         c->d_model_rt_bytes = bytes;
     }
-    // the previous image may still be in use by a kernel on the ctx stream
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
-    if (cudaMemcpy(c->d_model_rt, img.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    if (cudaMemcpy(c->d_model_rt, raw.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
     c->model_rt.assign(sizeof(tmpc::ModelRT<T>), 0);
     tmpc::ModelRT<T> &m = *reinterpret_cast<tmpc::ModelRT<T> *>(c->model_rt.data());
     const T *d = reinterpret_cast<const T *>(c->d_model_rt);
+    const unsigned short *dprog = reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(c->d_model_rt) + prog_off);
     m.nx = nx; m.nu = nu; m.N = N;
-    m.K = d + off[0]; m.A = d + off[1]; m.B = d + off[2]; m.Qi = d + off[3]; m.M = d + off[4]; m.Pf = d + off[5]; m.Qd = d + off[6];
-    m.xmin = d + off[7]; m.xmax = d + off[8]; m.umin = d + off[9]; m.umax = d + off[10];
-    m.prog = reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(c->d_model_rt) + prog_off);
-    auto pr = [](const tmpc_rt::Prod &p) { tmpc::ProdRT r; r.a = p.a; r.b = p.b; return r; };
-    m.Kx = pr(o.Kx); m.Ax = pr(o.Ax); m.Bu = pr(o.Bu); m.Btp = pr(o.Btp); m.Qs = pr(o.Qs); m.Mp = pr(o.Mp); m.Ktr = pr(o.Ktr); m.XtP = pr(o.XtP);
+    m.Qd = d + o_qd; m.xmin = d + o_b[0]; m.xmax = d + o_b[1]; m.umin = d + o_b[2]; m.umax = d + o_b[3];
+    tmpc::ProdRT<T> *dst[8] = {&m.Kx, &m.Ax, &m.Bu, &m.Btp, &m.Qs, &m.Mp, &m.Ktr, &m.XtP};
+    for (int q = 0; q < 8; ++q)
+        for (int v = 0; v < 2; ++v) {
+            const tmpc_rt::Variant &var = v ? pd[q].p->b : pd[q].p->a;
+            tmpc::VarRT<T> &dv = v ? dst[q]->b : dst[q]->a;
+            dv.coef = d + o_cf[q][v];
+            dv.prog = dprog + var.prog;
+            dv.kind = var.kind;
+            dv.order = var.order;
+        }
     m.head_Kx = o.head_Kx; m.head_Ax = o.head_Ax; m.head_Qs = o.head_Qs; m.head_Mp = o.head_Mp;
     m.rt_u = o.rt_u; m.rt_x = o.rt_x; m.rt_p = o.rt_p; m.off_u = o.off_u; m.off_x = o.off_x; m.off_p = o.off_p; m.pk = o.pk; m.sb = o.sb;
     m.rho = (T)c->rho; m.nrho = -(T)c->rho; m.pri_tol = (T)c->pri; m.dua_tol = (T)c->dua;

@@ -27,17 +27,27 @@ namespace tmpc {
 constexpr int RT_MAXD = 64;    // nx, nu <= 64
 constexpr int RT_STACK = 8;    // operand stack of a reduction program (host checks the depth)
 constexpr int RT_BLOCK = 128;
+constexpr int RT_MLP = 8;      // scratch elements whose loads are issued together in the element-wise loops
+constexpr int RT_MLPU = 4;     // ... in the loops that run a dot product per element
 
-struct ProdRT {
-    int a, b;  // program offsets (entries of ModelRT::prog): a = packet-path rows, b = scalar-path rows
+// One evaluation-order variant of one product: its reduction program and a ROW-MAJOR copy of the coefficient matrix with
+// the columns of every row already in program order, so a dot product walks one contiguous run of K coefficients.
+template <class T> struct VarRT {
+    const T *coef;               // [rows][K]
+    const unsigned short *prog;  // [K]: leaf | (adds << 8)
+    int kind;                    // 0 sequential chain (no program read), 1 terms in natural order, 2 gather by leaf index,
+                                 // 3 compile-time-K code for `order` (coefficients in natural order, no program read)
+    int order;                   // ORD_* of tmpc_kernel.cuh (kind 3)
+};
+template <class T> struct ProdRT {
+    VarRT<T> a, b;               // a = packet-path rows, b = scalar-path rows
 };
 
 template <class T> struct ModelRT {
     int nx, nu, N;
-    const T *K, *A, *B, *Qi, *M, *Pf, *Qd, *xmin, *xmax, *umin, *umax;  // device image, matrices column-major
-    const unsigned short *prog;                                         // entry = leaf | (adds << 8)
-    ProdRT Kx, Ax, Bu, Btp, Qs, Mp, Ktr, XtP;
-    // rows [lo, hi) of a destination column take program a, the others program b (tmpc_orders_rt.hpp):
+    const T *Qd, *xmin, *xmax, *umin, *umax;   // device image
+    ProdRT<T> Kx, Ax, Bu, Btp, Qs, Mp, Ktr, XtP;
+    // rows [lo, hi) of a destination column take variant a, the others variant b (tmpc_orders_rt.hpp):
     //   head < 0: all rows a;  else unrolled assignment: [0, head);  rt_*: peeled by the address of the column
     int head_Kx, head_Ax, head_Qs, head_Mp;
     int rt_u, rt_x, rt_p, off_u, off_x, off_p, pk, sb;
@@ -52,7 +62,7 @@ template <class T> struct ModelRT {
 __host__ __device__ inline size_t rt_smem_bytes(int nx, int nu, size_t scalar)
 {
     const int D = nx > nu ? nx : nu;
-    return (size_t)(3 * D + RT_STACK) * RT_BLOCK * scalar;
+    return (size_t)(3 * D + RT_STACK + 3 * RT_MLPU) * RT_BLOCK * scalar;
 }
 
 // elements of per-lane scratch
@@ -61,23 +71,62 @@ __host__ __device__ inline long long rt_scratch_elems(int nx, int nu, int N)
     return 2LL * nx + 5LL * nu * (N - 1) + 4LL * nx * N;
 }
 
-// sum_k c(k) x(k): PARITY = the program's tree over individually rounded products; FAST = one FMA chain
-template <class T, bool FAST, class C, class X>
-__device__ __forceinline__ T dot_rt(const unsigned short *__restrict__ prog, int K, const C &c, const X &x, T *st /* [RT_STACK][RT_BLOCK] */)
+// Tree-shaped orders with K known at compile time: the reduction is the fully unrolled register code of tmpc_kernel.cuh
+// (dot<T, ORD, K>), one instance per K <= 64, reached through a warp-uniform switch.  Not inlined: one copy per scalar type.
+template <class T, int ORD, int K> __device__ __forceinline__ T dot_fixed_k(const T *__restrict__ c, const T *__restrict__ xs)
+{
+    if constexpr (ORD == ORD_GEMV_ROW && K < Num<T>::PK) {
+        return T(0);   // never selected by the host (tmpc_orders_rt.hpp)
+    } else {
+        return dot<T, ORD, K, false>([&](int k) { return __ldg(c + k); }, [&](int k) { return xs[k * RT_BLOCK]; });
+    }
+}
+#define TMPC_RT_CASES4(b) TMPC_RT_CASE(b) TMPC_RT_CASE(b + 1) TMPC_RT_CASE(b + 2) TMPC_RT_CASE(b + 3)
+#define TMPC_RT_CASES16(b) TMPC_RT_CASES4(b) TMPC_RT_CASES4(b + 4) TMPC_RT_CASES4(b + 8) TMPC_RT_CASES4(b + 12)
+template <class T, int ORD> __device__ __noinline__ T dot_fixed(int K, const T *__restrict__ c, const T *__restrict__ xs)
+{
+    switch (K) {
+#define TMPC_RT_CASE(k) case (k): return dot_fixed_k<T, ORD, (k)>(c, xs);
+        TMPC_RT_CASES16(1) TMPC_RT_CASES16(17) TMPC_RT_CASES16(33) TMPC_RT_CASES16(49)
+#undef TMPC_RT_CASE
+    }
+    return T(0);
+}
+
+// sum_k c[k] x(k): PARITY = the variant's tree over individually rounded products; FAST = one FMA chain (`acc0` continues
+// a chain when `chain` is set).  c = the row's K coefficients in program order; xs = the thread's vector in shared memory
+// (element stride RT_BLOCK); st = the thread's operand stack in shared memory.
+template <class T, bool FAST>
+__device__ __forceinline__ T dot_rt(const VarRT<T> &v, int row, int K, const T *__restrict__ xs, T *__restrict__ st, T acc0 = T(0),
+                                    bool chain = false)
 {
     using N = Num<T>;
+    const T *__restrict__ c = v.coef + row * K;
     if constexpr (FAST) {
-        T acc = N::mul(c(0), x(0));
-        for (int k = 1; k < K; ++k) acc = N::fma(c(k), x(k), acc);
+        T acc = chain ? N::fma(__ldg(c), xs[0], acc0) : N::mul(__ldg(c), xs[0]);
+#pragma unroll 4
+        for (int k = 1; k < K; ++k) acc = N::fma(__ldg(c + k), xs[k * RT_BLOCK], acc);
         return acc;
     } else {
+        if (v.kind == 0) {
+            T acc = N::mul(__ldg(c), xs[0]);
+#pragma unroll 4
+            for (int k = 1; k < K; ++k) acc = N::add(N::mul(__ldg(c + k), xs[k * RT_BLOCK]), acc);
+            return acc;
+        }
+        if (v.kind == 3) {
+            if (v.order == ORD_TREE) return dot_fixed<T, ORD_TREE>(K, c, xs);
+            if (v.order == ORD_VECREDUX) return dot_fixed<T, ORD_VECREDUX>(K, c, xs);
+            return dot_fixed<T, ORD_GEMV_ROW>(K, c, xs);
+        }
+        const unsigned short *__restrict__ pg = v.prog;
+        const bool gather = v.kind == 2;
         int sp = 0;
         T acc = T(0);
         for (int k = 0; k < K; ++k) {
-            const unsigned w = __ldg(prog + k);
-            const int j = w & 0xff;
+            const unsigned w = __ldg(pg + k);
             int nm = w >> 8;
-            const T e = N::mul(c(j), x(j));
+            const T e = N::mul(__ldg(c + k), xs[(gather ? (int)(w & 0xff) : k) * RT_BLOCK]);
             if (nm == 0) {                 // push
                 if (k) st[(sp++ & (RT_STACK - 1)) * RT_BLOCK] = acc;
                 acc = e;
@@ -111,13 +160,15 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
     const unsigned lane = threadIdx.x & 31;
     constexpr unsigned FULLM = 0xffffffffu;
     T *S = P.scratch + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    auto ld = [&](int e) -> T { return __ldcg(S + (long long)e * lanes); };
-    auto stg = [&](int e, T v) { __stcg(S + (long long)e * lanes, v); };
+    auto at = [&](int e) -> T * { return S + (long long)e * lanes; };   // hot loops walk these pointers by `lanes`
+    auto ld = [&](int e) -> T { return __ldcg(at(e)); };
+    auto stg = [&](int e, T v) { __stcg(at(e), v); };
     // run-time indexed vectors + operand stack in shared memory, [element][thread]
     extern __shared__ __align__(16) unsigned char rt_smem[];
     const int D = nx > nu ? nx : nu;
     T *va = reinterpret_cast<T *>(rt_smem) + threadIdx.x;
     T *vb = va + D * RT_BLOCK, *vc = vb + D * RT_BLOCK, *stk = vc + D * RT_BLOCK;
+    T *pf = stk + RT_STACK * RT_BLOCK;   // prefetched scratch values of RT_MLPU rows (3 per row)
     constexpr int VS = RT_BLOCK;   // stride between consecutive elements of a thread's vector
     // scratch map
     const int oX0 = 0, oPN = nx, oD = 2 * nx, oY = oD + UROW, oZ0 = oY + UROW, oZ1 = oZ0 + UROW, oU = oZ1 + UROW,
@@ -150,11 +201,7 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
                     // p_N seed: -(Xref_{N-1}^T * Pinf)   (admm.cpp:83)
                     const T *xr = a.Xref + inst * a.xref_stride + (long long)(NH - 1) * nx;
                     for (int j = 0; j < nx; ++j) va[j * VS] = __ldg(xr + j);
-                    for (int j = 0; j < nx; ++j) {
-                        const T *col = P.Pf + (long long)j * nx;
-                        stg(oPN + j, -dot_rt<T, FAST>(P.prog + P.XtP.a, nx, [&](int k) { return __ldg(col + k); },
-                                                      [&](int k) { return va[k * VS]; }, stk));
-                    }
+                    for (int j = 0; j < nx; ++j) stg(oPN + j, -dot_rt<T, FAST>(P.XtP.a, j, nx, va, stk));
                     if (P.warm && a.wd) {
                         for (int e = 0; e < UROW; ++e) {
                             stg(oD + e, a.wd[inst * UROW + e]);
@@ -184,55 +231,74 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
         // forward_pass (admm.cpp:27-37) + update_slack (:45-61) + update_dual (:67-71) + residual maxima (:95-98)
         T pri_x = T(0), dua_x = T(0), pri_u = T(0), dua_u = T(0);
         for (int j = 0; j < nx; ++j) va[j * VS] = ld(oX0 + j);
+        const T *bxl = P.xmin, *bxh = P.xmax, *bul = P.umin, *buh = P.umax;
         for (int i = 0; i < NH; ++i) {
-            for (int j = 0; j < nx; ++j) {
-                const int e = i * nx + j;
-                const T x = va[j * VS];
-                T g = ld(oG + e);
-                const T v = ld(oV + e);
-                T vn = N::add(x, g);                                                            // :48
-                vn = N::mn(__ldg(P.xmax + e), N::mx(__ldg(P.xmin + e), vn));                    // :59
-                pri_x = N::mx(pri_x, N::abs(N::sub(x, vn)));                                    // :95
-                dua_x = N::mx(dua_x, N::abs(N::sub(v, vn)));                                    // :96
-                g = N::sub(N::add(g, x), vn);                                                   // :70
-                stg(oG + e, g);
-                stg(oVn + e, vn);
-                stg(oXo + e, x);
+            T *pG = at(oG + i * nx), *pV = at(oV + i * nx), *pVn = at(oVn + i * nx), *pXo = at(oXo + i * nx);
+            T *pD = at(oD + i * nu), *pY = at(oY + i * nu), *pZ = at(oZ + i * nu), *pZn = at(oZn + i * nu), *pU = at(oU + i * nu);
+            // the scratch reads of RT_MLP elements are issued together (memory-level parallelism: the state streams from L2/HBM)
+            for (int j0 = 0; j0 < nx; j0 += RT_MLP) {
+                T gg[RT_MLP], vv[RT_MLP];
+#pragma unroll
+                for (int t = 0; t < RT_MLP; ++t)
+                    if (j0 + t < nx) { gg[t] = __ldcg(pG + t * lanes); vv[t] = __ldcg(pV + t * lanes); }
+#pragma unroll
+                for (int t = 0; t < RT_MLP; ++t)
+                    if (j0 + t < nx) {
+                        const int j = j0 + t;
+                        const T x = va[j * VS];
+                        T g = gg[t];
+                        T vn = N::add(x, g);                                                    // :48
+                        vn = N::mn(__ldg(bxh + j), N::mx(__ldg(bxl + j), vn));                  // :59
+                        pri_x = N::mx(pri_x, N::abs(N::sub(x, vn)));                            // :95
+                        dua_x = N::mx(dua_x, N::abs(N::sub(vv[t], vn)));                        // :96
+                        g = N::sub(N::add(g, x), vn);                                           // :70
+                        __stcg(pG + t * lanes, g);
+                        __stcg(pVn + t * lanes, vn);
+                        __stcg(pXo + t * lanes, x);
+                    }
+                pG += RT_MLP * lanes; pV += RT_MLP * lanes; pVn += RT_MLP * lanes; pXo += RT_MLP * lanes;
             }
+            bxl += nx; bxh += nx;
             if (i == NH - 1) break;
             int lo, hi;
             rt_head(P, nu, P.head_Kx, P.rt_u, P.off_u, i, lo, hi);
-            for (int r = 0; r < nu; ++r) {
-                const int e = i * nu + r;
-                const T *row = P.K + r;
-                const T kx = dot_rt<T, FAST>(P.prog + ((r >= lo && r < hi) ? P.Kx.a : P.Kx.b), nx,
-                                             [&](int k) { return __ldg(row + k * nu); }, [&](int k) { return va[k * VS]; }, stk);
-                const T u = N::sub(-kx, ld(oD + e));                                            // :31
-                T y = ld(oY + e);
-                const T z = ld(oZ + e);
-                T zn = N::add(u, y);                                                            // :47
-                zn = N::mn(__ldg(P.umax + e), N::mx(__ldg(P.umin + e), zn));                    // :53
-                pri_u = N::mx(pri_u, N::abs(N::sub(u, zn)));                                    // :97
-                dua_u = N::mx(dua_u, N::abs(N::sub(z, zn)));                                    // :98
-                y = N::sub(N::add(y, u), zn);                                                   // :69
-                stg(oY + e, y);
-                stg(oZn + e, zn);
-                stg(oU + e, u);
-                vb[r * VS] = u;
+            for (int r0 = 0; r0 < nu; r0 += RT_MLPU) {
+                {
+                    T dd[RT_MLPU], yy[RT_MLPU], zz[RT_MLPU];
+#pragma unroll
+                    for (int t = 0; t < RT_MLPU; ++t)
+                        if (r0 + t < nu) { dd[t] = __ldcg(pD + t * lanes); yy[t] = __ldcg(pY + t * lanes); zz[t] = __ldcg(pZ + t * lanes); }
+#pragma unroll
+                    for (int t = 0; t < RT_MLPU; ++t) { pf[(3 * t) * VS] = dd[t]; pf[(3 * t + 1) * VS] = yy[t]; pf[(3 * t + 2) * VS] = zz[t]; }
+                }
+#pragma unroll 1
+                for (int t = 0; t < RT_MLPU; ++t)
+                    if (r0 + t < nu) {
+                        const int r = r0 + t;
+                        const T kx = dot_rt<T, FAST>((r >= lo && r < hi) ? P.Kx.a : P.Kx.b, r, nx, va, stk);
+                        const T u = N::sub(-kx, pf[(3 * t) * VS]);                              // :31
+                        T y = pf[(3 * t + 1) * VS];
+                        T zn = N::add(u, y);                                                    // :47
+                        zn = N::mn(__ldg(buh + r), N::mx(__ldg(bul + r), zn));                  // :53
+                        pri_u = N::mx(pri_u, N::abs(N::sub(u, zn)));                            // :97
+                        dua_u = N::mx(dua_u, N::abs(N::sub(pf[(3 * t + 2) * VS], zn)));         // :98
+                        y = N::sub(N::add(y, u), zn);                                           // :69
+                        __stcg(pY + t * lanes, y);
+                        __stcg(pZn + t * lanes, zn);
+                        __stcg(pU + t * lanes, u);
+                        vb[r * VS] = u;
+                    }
+                pD += RT_MLPU * lanes; pY += RT_MLPU * lanes; pZ += RT_MLPU * lanes; pZn += RT_MLPU * lanes; pU += RT_MLPU * lanes;
             }
+            bul += nu; buh += nu;
             rt_head(P, nx, P.head_Ax, P.rt_x, P.off_x, i + 1, lo, hi);
             for (int r = 0; r < nx; ++r) {
                 const bool pa = r >= lo && r < hi;
-                const T *ra = P.A + r, *rb = P.B + r;
-                const T ax = dot_rt<T, FAST>(P.prog + (pa ? P.Ax.a : P.Ax.b), nx, [&](int k) { return __ldg(ra + k * nx); },
-                                             [&](int k) { return va[k * VS]; }, stk);
+                const T ax = dot_rt<T, FAST>(pa ? P.Ax.a : P.Ax.b, r, nx, va, stk);
                 if constexpr (FAST) {
-                    T acc = ax;
-                    for (int k = 0; k < nu; ++k) acc = N::fma(__ldg(rb + k * nx), vb[k * VS], acc);
-                    vc[r * VS] = acc;
+                    vc[r * VS] = dot_rt<T, FAST>(P.Bu.a, r, nu, vb, stk, ax, true);
                 } else {
-                    const T bu = dot_rt<T, FAST>(P.prog + (pa ? P.Bu.a : P.Bu.b), nu, [&](int k) { return __ldg(rb + k * nx); },
-                                                 [&](int k) { return vb[k * VS]; }, stk);
+                    const T bu = dot_rt<T, FAST>(pa ? P.Bu.a : P.Bu.b, r, nu, vb, stk);
                     vc[r * VS] = N::add(ax, bu);                                                // :35
                 }
             }
@@ -264,34 +330,58 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
                 else va[j * VS] = N::sub(ld(oPN + j), N::mul(P.rho, dv));                        // :84
             }
             for (int i = NH - 2; i >= 0; --i) {
-                for (int j = 0; j < nu; ++j) vb[j * VS] = N::mul(P.nrho, N::sub(ld(oZc + i * nu + j), ld(oY + i * nu + j)));   // :80
+                {
+                    const T *pZ = at(oZc + i * nu), *pY = at(oY + i * nu);
+                    for (int j0 = 0; j0 < nu; j0 += RT_MLP) {
+                        T zz[RT_MLP], yy[RT_MLP];
+#pragma unroll
+                        for (int t = 0; t < RT_MLP; ++t)
+                            if (j0 + t < nu) { zz[t] = __ldcg(pZ + t * lanes); yy[t] = __ldcg(pY + t * lanes); }
+#pragma unroll
+                        for (int t = 0; t < RT_MLP; ++t)
+                            if (j0 + t < nu) vb[(j0 + t) * VS] = N::mul(P.nrho, N::sub(zz[t], yy[t]));   // :80
+                        pZ += RT_MLP * lanes; pY += RT_MLP * lanes;
+                    }
+                }
                 for (int r = 0; r < nu; ++r) {
-                    const T *col = P.B + (long long)r * nx;
-                    const T bp = dot_rt<T, FAST>(P.prog + P.Btp.a, nx, [&](int k) { return __ldg(col + k); },
-                                                 [&](int k) { return va[k * VS]; }, stk);
+                    const T bp = dot_rt<T, FAST>(P.Btp.a, r, nx, va, stk);
                     vc[r * VS] = N::add(bp, vb[r * VS]);
                 }
                 int lo, hi;
                 rt_head(P, nu, P.head_Qs, 0, 0, i, lo, hi);
+                T *pD = at(oD + i * nu);
                 for (int r = 0; r < nu; ++r) {
-                    const T *row = P.Qi + r;
-                    stg(oD + i * nu + r, dot_rt<T, FAST>(P.prog + ((r >= lo && r < hi) ? P.Qs.a : P.Qs.b), nu,
-                                                         [&](int k) { return __ldg(row + k * nu); }, [&](int k) { return vc[k * VS]; }, stk));   // :19
+                    __stcg(pD, dot_rt<T, FAST>((r >= lo && r < hi) ? P.Qs.a : P.Qs.b, r, nu, vc, stk));   // :19
+                    pD += lanes;
                 }
                 rt_head(P, nx, P.head_Mp, P.rt_p, P.off_p, i, lo, hi);
-                for (int r = 0; r < nx; ++r) {   // p_i is built in vc (s is dead)
-                    const int e = i * nx + r;
-                    const T cq = -N::mul(__ldg(xr_base + e), __ldg(P.Qd + r));                  // :81
-                    const T dv = N::sub(ld(oVc + e), ld(oG + e));
-                    T q;
-                    if constexpr (FAST) q = N::fma(P.nrho, dv, cq);
-                    else q = N::sub(cq, N::mul(P.rho, dv));                                      // :82
-                    const T *rm = P.M + r, *ck = P.K + (long long)r * nu;
-                    const T mp = dot_rt<T, FAST>(P.prog + ((r >= lo && r < hi) ? P.Mp.a : P.Mp.b), nx,
-                                                 [&](int k) { return __ldg(rm + k * nx); }, [&](int k) { return va[k * VS]; }, stk);
-                    const T kr = dot_rt<T, FAST>(P.prog + P.Ktr.a, nu, [&](int k) { return __ldg(ck + k); },
-                                                 [&](int k) { return vb[k * VS]; }, stk);
-                    vc[r * VS] = N::sub(N::add(q, mp), kr);                                      // :20
+                const T *pV = at(oVc + i * nx), *pG = at(oG + i * nx);
+                for (int r0 = 0; r0 < nx; r0 += RT_MLPU) {   // p_i is built in vc (s is dead)
+                    {
+                        T vv[RT_MLPU], gg[RT_MLPU], xr[RT_MLPU];
+#pragma unroll
+                        for (int t = 0; t < RT_MLPU; ++t)
+                            if (r0 + t < nx) {
+                                vv[t] = __ldcg(pV + t * lanes); gg[t] = __ldcg(pG + t * lanes);
+                                xr[t] = __ldg(xr_base + i * nx + r0 + t);
+                            }
+#pragma unroll
+                        for (int t = 0; t < RT_MLPU; ++t) { pf[(3 * t) * VS] = vv[t]; pf[(3 * t + 1) * VS] = gg[t]; pf[(3 * t + 2) * VS] = xr[t]; }
+                    }
+#pragma unroll 1
+                    for (int t = 0; t < RT_MLPU; ++t)
+                        if (r0 + t < nx) {
+                            const int r = r0 + t;
+                            const T cq = -N::mul(pf[(3 * t + 2) * VS], __ldg(P.Qd + r));        // :81
+                            const T dv = N::sub(pf[(3 * t) * VS], pf[(3 * t + 1) * VS]);
+                            T q;
+                            if constexpr (FAST) q = N::fma(P.nrho, dv, cq);
+                            else q = N::sub(cq, N::mul(P.rho, dv));                              // :82
+                            const T mp = dot_rt<T, FAST>((r >= lo && r < hi) ? P.Mp.a : P.Mp.b, r, nx, va, stk);
+                            const T kr = dot_rt<T, FAST>(P.Ktr.a, r, nu, vb, stk);
+                            vc[r * VS] = N::sub(N::add(q, mp), kr);                              // :20
+                        }
+                    pV += RT_MLPU * lanes; pG += RT_MLPU * lanes;
                 }
                 for (int j = 0; j < nx; ++j) va[j * VS] = vc[j * VS];
             }

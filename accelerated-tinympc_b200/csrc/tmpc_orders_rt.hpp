@@ -112,25 +112,42 @@ inline int build(Expr &x, int order, int K, int pk)
     return -1;
 }
 
-// postfix program: one entry per term, leaf | (adds that follow << 8); deeper operand first (a + b == b + a bit for bit
-// on non-NaN data), so the operand stack never exceeds the tree's Sethi-Ullman number
-inline int emit(const Expr &x, int root, std::vector<uint16_t> &out)
+// postfix program: one entry per term, leaf | (adds that follow << 8).  SEQ / TREE are emitted left operand first, which
+// keeps their terms in natural order (the kernel then walks the vector instead of gathering); the vectorised orders visit
+// the terms out of order anyway and are emitted deeper operand first (a + b == b + a bit for bit on non-NaN data).
+// Returns the operand-stack depth the program needs.
+inline int emit(const Expr &x, int root, bool inorder, std::vector<uint16_t> &out)
 {
     const size_t start = out.size();
     std::function<void(int)> go = [&](int i) {
         const Expr::Node &nd = x.n[i];
         if (nd.leaf >= 0) { out.push_back((uint16_t)nd.leaf); return; }
-        const bool lfirst = x.n[nd.l].depth >= x.n[nd.r].depth;
+        const bool lfirst = inorder || x.n[nd.l].depth >= x.n[nd.r].depth;
         go(lfirst ? nd.l : nd.r);
         go(lfirst ? nd.r : nd.l);
         out.back() = (uint16_t)(out.back() + 0x100);
     };
     go(root);
-    (void)start;
-    return x.n[root].depth;
+    int sp = 0, mx = 0;
+    for (size_t k = start; k < out.size(); ++k) {
+        ++sp;
+        mx = std::max(mx, sp);
+        sp -= out[k] >> 8;
+    }
+    return mx;
 }
 
-struct Prod { int a, b; };
+// K_FIXED: TREE / VECREDUX / GEMV_ROW run through the kernel's compile-time-K code (one unrolled instance per K <= 64);
+// the program is then unused and the coefficient copy stays in natural order.  The interpreter (K_INORDER / K_GATHER)
+// remains for VECLOOP (K beyond Eigen's unrolling limit: double, K > 55).
+enum Kind { K_SEQ = 0, K_INORDER = 1, K_GATHER = 2, K_FIXED = 3 };
+
+struct Variant {
+    int prog;   // offset into Orders::prog (K entries)
+    int kind;   // K_SEQ: acc = e_k + acc, no program needed; K_INORDER: terms 0..K-1 in order; K_GATHER: by leaf index
+    int order;
+};
+struct Prod { Variant a, b; };
 
 struct Orders {
     Prod Kx, Ax, Bu, Btp, Qs, Mp, Ktr, XtP;
@@ -140,23 +157,36 @@ struct Orders {
     int max_depth = 0;
 };
 
-inline Orders build_orders(int nx, int nu, int N, int sb)
+// fast = FAST policy: every product is one sequential FMA chain, no order to reproduce
+inline Orders build_orders(int nx, int nu, int N, int sb, bool fast = false)
 {
     Orders o{};
     const int pk = 16 / sb, large = 8;
     const int unroll_k = (110 * pk + 1) / 4;   // Redux.h: cost 4K-1 <= EIGEN_UNROLLING_LIMIT * pk
     const int tail_x = nx <= unroll_k ? TREE : SEQ, tail_u = nu <= unroll_k ? TREE : SEQ;
     auto add_prog = [&](int order, int K) {
+        if (fast) order = SEQ;
         Expr x;
         const int root = build(x, order, K, pk);
-        const int off = (int)o.prog.size();
-        o.max_depth = std::max(o.max_depth, emit(x, root, o.prog));
-        return off;
+        Variant v;
+        v.prog = (int)o.prog.size();
+        v.order = order;
+        const bool inorder = order == SEQ || order == TREE;
+        o.max_depth = std::max(o.max_depth, emit(x, root, inorder, o.prog));
+        bool ident = true, seq = true;
+        for (int k = 0; k < K; ++k) {
+            const uint16_t w = o.prog[v.prog + k];
+            ident = ident && (w & 0xff) == k;
+            seq = seq && (w >> 8) == (k ? 1 : 0);
+        }
+        v.kind = (ident && seq) ? K_SEQ : ident ? K_INORDER : K_GATHER;
+        if (v.kind != K_SEQ && (order == TREE || order == VECREDUX || (order == GEMV_ROW && K >= pk))) v.kind = K_FIXED;
+        return v;
     };
     auto two = [&](int oa, int ob, int K) {
         Prod p;
         p.a = add_prog(oa, K);
-        p.b = (ob == oa) ? p.a : add_prog(ob, K);
+        p.b = (ob == oa || fast) ? p.a : add_prog(ob, K);
         return p;
     };
     const int vred_x = nx <= unroll_k ? VECREDUX : VECLOOP, vred_u = nu <= unroll_k ? VECREDUX : VECLOOP;

@@ -58,7 +58,7 @@ def generic(nx, nu, N, B, **kw):
 
 
 if __name__ == "__main__":
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 19
     q = pkg.problems.quadrotor(20)
     x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
     run("quadrotor_specialised", q, x0, xref)
@@ -71,5 +71,14 @@ if __name__ == "__main__":
     run("cartpole_rt", c, x0, xref)
     os.environ.pop("TMPC_KERNEL")
     for shape in ((6, 3, 20), (10, 5, 10), (16, 8, 25), (24, 6, 10), (40, 10, 6), (64, 16, 8)):
-        generic(*shape, B=max(B // 4, 4096))
-    generic(16, 8, 25, B=max(B // 4, 4096), dtype=np.float64)
+        generic(*shape, B=max(B // 2, 4096))
+    generic(16, 8, 25, B=max(B // 2, 4096), dtype=np.float64)
+    # resident blocks per SM (scratch working set vs latency hiding)
+    for per_sm in ("1", "2", "3"):
+        os.environ["TMPC_RT_BLOCKS_PER_SM"] = per_sm
+        os.environ["TMPC_KERNEL"] = "rt"
+        x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
+        run("quadrotor_rt_blocks_per_sm_" + per_sm, q, x0, xref)
+        os.environ.pop("TMPC_KERNEL")
+        generic(16, 8, 25, B=max(B // 2, 4096))
+    os.environ.pop("TMPC_RT_BLOCKS_PER_SM")
