@@ -1305,6 +1305,32 @@ int tmpc_step(tmpc_ctx *ctx, int which, int64_t batch, const tmpc_workspace *ws,
         else go(double(), std::integral_constant<int, 4>(), std::integral_constant<int, 1>(), std::integral_constant<int, 10>());
     } else if (c->nx == 32 && c->nu == 8 && c->N == 50 && f32) {
         go(float(), std::integral_constant<int, 32>(), std::integral_constant<int, 8>(), std::integral_constant<int, 50>());
+    } else if (c->rt_ready) {
+        // any other shape: the run-time-shape step kernel (tmpc_kernel_rt.cuh)
+        auto go_rt = [&](auto tag) {
+            using T = decltype(tag);
+            tmpc::StepArgs<T> sa;
+            sa.batch = batch;
+            T **dst[12] = {&sa.x, &sa.u, &sa.q, &sa.r, &sa.p, &sa.d, &sa.v, &sa.vnew, &sa.z, &sa.znew, &sa.g, &sa.y};
+            for (int k = 0; k < 12; ++k) *dst[k] = (T *)dev[k];
+            sa.Xref = (const T *)d_xref;
+            sa.xref_stride = ws->xref_shared ? 0 : (long long)xrow;
+            sa.resid = (T *)d_res;
+            sa.term = d_term;
+            sa.iter = iter;
+            const tmpc::ModelRT<T> &m = *reinterpret_cast<const tmpc::ModelRT<T> *>(c->model_rt.data());
+            const size_t smem = tmpc::rt_smem_bytes(c->nx, c->nu, sizeof(T));
+            const unsigned blocks = (unsigned)((batch + tmpc::RT_BLOCK - 1) / tmpc::RT_BLOCK);
+            if (c->policy == TMPC_ORDER_PARITY) {
+                cudaFuncSetAttribute(tmpc::step_kernel_rt<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                tmpc::step_kernel_rt<T, false><<<blocks, tmpc::RT_BLOCK, smem, s>>>(m, sa, which);
+            } else {
+                cudaFuncSetAttribute(tmpc::step_kernel_rt<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                tmpc::step_kernel_rt<T, true><<<blocks, tmpc::RT_BLOCK, smem, s>>>(m, sa, which);
+            }
+            e = cudaGetLastError();
+        };
+        if (f32) go_rt(float()); else go_rt(double());
     } else {
         return fail(c, TMPC_ERR_UNSUPPORTED, "no step kernels for this shape");
     }

@@ -111,6 +111,24 @@ cudaError_t launch_plant(tmpc_ctx_impl *c, tmpc_batch_impl *b, void *x_next_hist
     return cudaGetLastError();
 }
 
+template <class T>
+cudaError_t launch_plant_rt(tmpc_ctx_impl *c, tmpc_batch_impl *b, void *x_next_hist, void *u0_hist, int *iter_hist, int *status_hist, cudaStream_t s)
+{
+    const unsigned blocks = (unsigned)((b->B + tmpc::RT_BLOCK - 1) / tmpc::RT_BLOCK);
+    const tmpc::ModelRT<T> &m = *reinterpret_cast<const tmpc::ModelRT<T> *>(c->model_rt.data());
+    const size_t smem = tmpc::rt_smem_bytes(c->nx, c->nu, sizeof(T));
+    if (c->policy == TMPC_ORDER_PARITY) {
+        cudaFuncSetAttribute(tmpc::plant_kernel_rt<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tmpc::plant_kernel_rt<T, false><<<blocks, tmpc::RT_BLOCK, smem, s>>>(m, b->B, (T *)b->x0, (const T *)b->u, (T *)x_next_hist, (T *)u0_hist,
+                                                                              b->iter, b->status, iter_hist, status_hist);
+    } else {
+        cudaFuncSetAttribute(tmpc::plant_kernel_rt<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tmpc::plant_kernel_rt<T, true><<<blocks, tmpc::RT_BLOCK, smem, s>>>(m, b->B, (T *)b->x0, (const T *)b->u, (T *)x_next_hist, (T *)u0_hist,
+                                                                             b->iter, b->status, iter_hist, status_hist);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t dispatch_plant(tmpc_ctx_impl *c, tmpc_batch_impl *b, void *xh, void *uh, int *ih, int *sh, cudaStream_t s)
 {
     const bool f32 = c->dtype == TMPC_F32;
@@ -119,6 +137,7 @@ cudaError_t dispatch_plant(tmpc_ctx_impl *c, tmpc_batch_impl *b, void *xh, void 
     if (c->nx == 4 && c->nu == 1 && c->N == 10)
         return f32 ? launch_plant<float, 4, 1, 10>(c, b, xh, uh, ih, sh, s) : launch_plant<double, 4, 1, 10>(c, b, xh, uh, ih, sh, s);
     if (c->nx == 32 && c->nu == 8 && c->N == 50 && f32) return launch_plant<float, 32, 8, 50>(c, b, xh, uh, ih, sh, s);
+    if (c->rt_ready) return f32 ? launch_plant_rt<float>(c, b, xh, uh, ih, sh, s) : launch_plant_rt<double>(c, b, xh, uh, ih, sh, s);
     return cudaErrorInvalidValue;
 }
 

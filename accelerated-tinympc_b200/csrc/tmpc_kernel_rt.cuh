@@ -21,6 +21,7 @@
 // in SHARED memory, [element][thread] (conflict-free), sized by the shape at launch: (3 max(nx,nu) + 8) scalars per thread.
 #pragma once
 #include "tmpc_kernel.cuh"
+#include "tmpc_steps.cuh"
 
 namespace tmpc {
 
@@ -433,6 +434,138 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
             atomicAdd(a.stats + 3, n_inst);
         }
     }
+}
+
+// The six step functions of the reference (admm.hpp:13-18) for any shape, on full workspaces in global memory
+// ([instance][stage][dim]); same evaluation orders as the fused kernel.  Unit-test surface (see tmpc_steps.cuh).
+template <class T, bool FAST>
+__global__ void __launch_bounds__(RT_BLOCK) step_kernel_rt(const __grid_constant__ ModelRT<T> P, const __grid_constant__ StepArgs<T> a, int which)
+{
+    using N = Num<T>;
+    const int nx = P.nx, nu = P.nu, NH = P.N;
+    const int XROW = nx * NH, UROW = nu * (NH - 1);
+    extern __shared__ __align__(16) unsigned char rt_smem[];
+    const int D = nx > nu ? nx : nu;
+    T *va = reinterpret_cast<T *>(rt_smem) + threadIdx.x;
+    T *vb = va + D * RT_BLOCK, *vc = vb + D * RT_BLOCK, *stk = vc + D * RT_BLOCK;
+    constexpr int VS = RT_BLOCK;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    T *x = a.x + b * XROW, *u = a.u + b * UROW, *q = a.q + b * XROW, *r = a.r + b * UROW, *p = a.p + b * XROW;
+    T *d = a.d + b * UROW, *v = a.v + b * XROW, *vnew = a.vnew + b * XROW, *z = a.z + b * UROW, *znew = a.znew + b * UROW;
+    T *g = a.g + b * XROW, *y = a.y + b * UROW;
+    const T *xr = a.Xref + b * a.xref_stride;
+    int lo, hi;
+    if (which == STEP_FORWARD) {                                                      // admm.cpp:27-37
+        for (int j = 0; j < nx; ++j) va[j * VS] = x[j];
+        for (int i = 0; i < NH - 1; ++i) {
+            rt_head(P, nu, P.head_Kx, P.rt_u, P.off_u, i, lo, hi);
+            for (int rr = 0; rr < nu; ++rr) {
+                const T kx = dot_rt<T, FAST>((rr >= lo && rr < hi) ? P.Kx.a : P.Kx.b, rr, nx, va, stk);
+                const T ui = N::sub(-kx, d[i * nu + rr]);
+                u[i * nu + rr] = ui;
+                vb[rr * VS] = ui;
+            }
+            rt_head(P, nx, P.head_Ax, P.rt_x, P.off_x, i + 1, lo, hi);
+            for (int rr = 0; rr < nx; ++rr) {
+                const bool pa = rr >= lo && rr < hi;
+                const T ax = dot_rt<T, FAST>(pa ? P.Ax.a : P.Ax.b, rr, nx, va, stk);
+                const T bu = dot_rt<T, FAST>(pa ? P.Bu.a : P.Bu.b, rr, nu, vb, stk);
+                vc[rr * VS] = N::add(ax, bu);
+            }
+            for (int j = 0; j < nx; ++j) { va[j * VS] = vc[j * VS]; x[(i + 1) * nx + j] = vc[j * VS]; }
+        }
+    } else if (which == STEP_SLACK) {                                                 // :45-61 (bounds are +-inf when disabled)
+        for (int k = 0; k < UROW; ++k) znew[k] = N::mn(__ldg(P.umax + k), N::mx(__ldg(P.umin + k), N::add(u[k], y[k])));
+        for (int k = 0; k < XROW; ++k) vnew[k] = N::mn(__ldg(P.xmax + k), N::mx(__ldg(P.xmin + k), N::add(x[k], g[k])));
+    } else if (which == STEP_DUAL) {                                                  // :67-71
+        for (int k = 0; k < UROW; ++k) y[k] = N::sub(N::add(y[k], u[k]), znew[k]);
+        for (int k = 0; k < XROW; ++k) g[k] = N::sub(N::add(g[k], x[k]), vnew[k]);
+    } else if (which == STEP_LINCOST) {                                               // :77-85
+        for (int k = 0; k < UROW; ++k) r[k] = N::mul(P.nrho, N::sub(znew[k], y[k]));
+        for (int i = 0; i < NH; ++i)
+            for (int j = 0; j < nx; ++j) {
+                const int k = i * nx + j;
+                q[k] = N::sub(-N::mul(xr[k], __ldg(P.Qd + j)), N::mul(P.rho, N::sub(vnew[k], g[k])));
+            }
+        for (int j = 0; j < nx; ++j) va[j * VS] = xr[(NH - 1) * nx + j];
+        for (int j = 0; j < nx; ++j) {
+            const T pn = -dot_rt<T, FAST>(P.XtP.a, j, nx, va, stk);
+            const int k = (NH - 1) * nx + j;
+            p[k] = N::sub(pn, N::mul(P.rho, N::sub(vnew[k], g[k])));
+        }
+    } else if (which == STEP_TERM) {                                                  // :91-109
+        int ok = 0;
+        if (a.iter % P.check_term == 0) {
+            T px = T(0), dx = T(0), pu = T(0), du = T(0);
+            for (int k = 0; k < XROW; ++k) {
+                px = N::mx(px, N::abs(N::sub(x[k], vnew[k])));
+                dx = N::mx(dx, N::abs(N::sub(v[k], vnew[k])));
+            }
+            for (int k = 0; k < UROW; ++k) {
+                pu = N::mx(pu, N::abs(N::sub(u[k], znew[k])));
+                du = N::mx(du, N::abs(N::sub(z[k], znew[k])));
+            }
+            dx = N::mul(dx, P.rho);
+            du = N::mul(du, P.rho);
+            a.resid[b * 4 + 0] = px; a.resid[b * 4 + 1] = dx; a.resid[b * 4 + 2] = pu; a.resid[b * 4 + 3] = du;
+            ok = (px < P.pri_tol && pu < P.pri_tol && dx < P.dua_tol && du < P.dua_tol) ? 1 : 0;
+        }
+        if (a.term) a.term[b] = ok;
+    } else if (which == STEP_BACKWARD) {                                              // :15-22
+        for (int j = 0; j < nx; ++j) va[j * VS] = p[(NH - 1) * nx + j];
+        for (int i = NH - 2; i >= 0; --i) {
+            for (int j = 0; j < nu; ++j) vb[j * VS] = r[i * nu + j];
+            for (int rr = 0; rr < nu; ++rr) vc[rr * VS] = N::add(dot_rt<T, FAST>(P.Btp.a, rr, nx, va, stk), vb[rr * VS]);
+            rt_head(P, nu, P.head_Qs, 0, 0, i, lo, hi);
+            for (int rr = 0; rr < nu; ++rr) d[i * nu + rr] = dot_rt<T, FAST>((rr >= lo && rr < hi) ? P.Qs.a : P.Qs.b, rr, nu, vc, stk);
+            rt_head(P, nx, P.head_Mp, P.rt_p, P.off_p, i, lo, hi);
+            for (int rr = 0; rr < nx; ++rr) {
+                const T mp = dot_rt<T, FAST>((rr >= lo && rr < hi) ? P.Mp.a : P.Mp.b, rr, nx, va, stk);
+                const T kr = dot_rt<T, FAST>(P.Ktr.a, rr, nu, vb, stk);
+                vc[rr * VS] = N::sub(N::add(q[i * nx + rr], mp), kr);
+            }
+            for (int j = 0; j < nx; ++j) { va[j * VS] = vc[j * VS]; p[i * nx + j] = vc[j * VS]; }
+        }
+    }
+}
+
+// The examples' plant step x1 = Adyn * x0 + Bdyn * u.col(0) (quadrotor_hovering.cpp:108) for any shape (see plant_kernel in
+// tmpc_batch.cuh).  Both products are REGULAR Eigen products here: rows >= 8 && depth >= 8 go through the column-major GEMV
+// (sequential for every row); smaller ones stay coefficient-based inside the sum and follow the packet / scalar rows of
+// the assignment to a 16-byte aligned x1 (rows [0, nx/pk*pk) sequential, the rest the scalar tree) -- pinned against the
+// compiled reference by oracle/pin_shapes.py.
+template <class T, bool FAST>
+__global__ void __launch_bounds__(RT_BLOCK) plant_kernel_rt(const __grid_constant__ ModelRT<T> P, long long batch, T *x0, const T *u, T *x_next_hist,
+                                                            T *u0_hist, const int *iter, const int *status, int *iter_hist, int *status_hist)
+{
+    using N = Num<T>;
+    const int nx = P.nx, nu = P.nu;
+    extern __shared__ __align__(16) unsigned char rt_smem[];
+    const int D = nx > nu ? nx : nu;
+    T *va = reinterpret_cast<T *>(rt_smem) + threadIdx.x;
+    T *vb = va + D * RT_BLOCK, *vc = vb + D * RT_BLOCK, *stk = vc + D * RT_BLOCK;
+    constexpr int VS = RT_BLOCK;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    for (int j = 0; j < nx; ++j) va[j * VS] = x0[b * nx + j];
+    for (int j = 0; j < nu; ++j) vb[j * VS] = u[b * (long long)(nu * (P.N - 1)) + j];
+    const int head = (nx / P.pk) * P.pk;
+    const int head_a = nx >= 8 ? nx : head, head_b = (nx >= 8 && nu >= 8) ? nx : head;
+    for (int r = 0; r < nx; ++r) {
+        const T ax = dot_rt<T, FAST>(r < head_a ? P.Ax.a : P.Ax.b, r, nx, va, stk);
+        if constexpr (FAST) vc[r * VS] = dot_rt<T, FAST>(P.Bu.a, r, nu, vb, stk, ax, true);
+        else vc[r * VS] = N::add(ax, dot_rt<T, FAST>(r < head_b ? P.Bu.a : P.Bu.b, r, nu, vb, stk));
+    }
+    for (int r = 0; r < nx; ++r) {
+        const T v = vc[r * VS];
+        x0[b * nx + r] = v;
+        if (x_next_hist) x_next_hist[b * nx + r] = v;
+    }
+    if (u0_hist)
+        for (int j = 0; j < nu; ++j) u0_hist[b * nu + j] = vb[j * VS];
+    if (iter_hist) iter_hist[b] = iter[b];
+    if (status_hist) status_hist[b] = status[b];
 }
 
 }  // namespace tmpc

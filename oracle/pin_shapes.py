@@ -55,6 +55,12 @@ def check(pkg, ora, shape, sc):
             if rc_r != rc_o or not np.array_equal(out_r, out_o):
                 if STEP_NAMES[which] not in bad:
                     bad.append(STEP_NAMES[which])
+    # the examples' plant step x1 = Adyn * x0 + Bdyn * u.col(0) (quadrotor_hovering.cpp:108)
+    xp = rng.uniform(-2, 2, (16, nx)).astype(DT[sc])
+    up = rng.uniform(-1, 1, (16, N - 1, nu)).astype(DT[sc])
+    exp = np.stack([ref.plant_step(prob, xp[b], up[b]) for b in range(16)])
+    if not np.array_equal(ora.plant_step(prob, xp, up[:, 0], dtype=DT[sc]), exp):
+        bad.append("plant_step")
     x0 = rng.uniform(-3, 3, (200, nx)).astype(np.float32)
     xref = rng.uniform(-0.5, 0.5, (N, nx)).astype(np.float32)
     r = ref.solve_batch(prob, x0, xref, want_state=True, nthreads=2)

@@ -207,7 +207,10 @@ int ref_plant_step(const ref_problem *P, const void *x0_, const void *u_, void *
     std::unique_ptr<Inst> I(new Inst);
     load_problem(*I, P);
     TinyWorkspace &work = I->work;
-    tiny_VectorNx x0, x1;
+    // 16-byte aligned like the examples' locals when NSTATES * sizeof(tinytype) is a multiple of 16; for other sizes
+    // Eigen peels rows by the run-time address of x1, so the alignment is fixed here (tinympc_oracle.c, plant step)
+    alignas(16) tiny_VectorNx x0;
+    alignas(16) tiny_VectorNx x1;
     std::memcpy(x0.data(), x0_, sizeof(T) * NSTATES);
     get(work.u, u_, 0, NUN);
     x1 = work.Adyn * x0 + work.Bdyn * work.u.col(0);

@@ -441,8 +441,13 @@ int SFX(oracle_plant_step)(const oracle_problem *in, int64_t B, const void *x0_,
     for (int64_t b = 0; b < B; ++b) {
         const T *x0 = (const T *)x0_ + b * n, *u0 = (const T *)u0_ + b * u_stride;
         T *x1 = (T *)x1_ + b * n;
-        SFX(matvec2)(Ax, P.Adyn, 1, n, x0, n, n, P.ord.Ax, 0, P.ord.head_Ax, P.ord.tail_x, e);
-        SFX(matvec2)(Bu, P.Bdyn, 1, n, u0, n, m, P.ord.Bu, 0, P.ord.head_Ax, P.ord.tail_u, e);
+        /* work.Adyn * x0 and work.Bdyn * u are REGULAR products here (not lazyProduct): GeneralProduct.h
+         * product_type_selector sends rows >= 8 && depth >= 8 to the column-major GEMV (sequential, every row, into a
+         * temporary); smaller ones stay coefficient-based inside the sum and follow the packet / scalar rows of the
+         * assignment to a 16-byte aligned x1: rows [0, n/pk*pk) sequential, the rest the scalar tree. */
+        const int ax_all = n >= 8, bu_all = n >= 8 && m >= 8;
+        SFX(matvec2)(Ax, P.Adyn, 1, n, x0, n, n, P.ord.Ax, 0, ax_all ? n : P.ord.head_Ax, P.ord.tail_x, e);
+        SFX(matvec2)(Bu, P.Bdyn, 1, n, u0, n, m, P.ord.Bu, 0, bu_all ? n : P.ord.head_Ax, P.ord.tail_u, e);
         for (int r = 0; r < n; ++r) x1[r] = Ax[r] + Bu[r];
     }
     return 0;

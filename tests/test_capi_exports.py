@@ -27,8 +27,9 @@ def test_header_symbols_are_exported(pkg):
 def test_create_rejects_bad_arguments(pkg):
     lib = pkg.capi.load()
     ctx = ctypes.c_void_p()
-    assert lib.tmpc_create(ctypes.byref(ctx), 0, 7, 3, 5, 0, 0) == -2      # shape without a compiled kernel
-    assert b"no compiled" in lib.tmpc_last_error(None)
+    assert lib.tmpc_create(ctypes.byref(ctx), 0, 65, 3, 5, 0, 0) == -2     # shape outside what the kernels cover
+    assert b"outside" in lib.tmpc_last_error(None)
+    assert lib.tmpc_create(ctypes.byref(ctx), 0, 7, 3, 1, 0, 0) == -2      # horizon < 2
     assert lib.tmpc_create(ctypes.byref(ctx), 0, 12, 4, 10, 9, 0) == -1     # bad dtype
     assert lib.tmpc_create(None, 0, 12, 4, 10, 0, 0) == -1
 

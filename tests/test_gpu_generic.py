@@ -146,3 +146,57 @@ def test_shape_limits_are_reported(pkg):
     prob.nx = 65
     with pytest.raises(pkg.capi.TmpcError):
         pkg.capi.Solver(prob, dtype=np.float32)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(6, 3, 7), (9, 4, 7), (13, 7, 6), (16, 8, 5), (5, 1, 6), (24, 6, 4)])
+def test_generic_shape_step_functions_vs_oracle(pkg, oracle, shape, dtype):
+    """The six step functions (admm.hpp:13-18) through tmpc_step on random full workspaces, bit-exact vs the oracle's."""
+    nx, nu, N = shape
+    prob = pkg.problems.random_system(nx, nu, N, seed=31 + nx)
+    s = pkg.capi.Solver(prob, dtype=dtype, policy="parity")
+    rng = np.random.default_rng(17 * nx + nu)
+    B = 5
+    names = ["x", "u", "q", "r", "p", "d", "v", "vnew", "z", "znew", "g", "y"]
+    for which in range(6):
+        ws = {k: rng.uniform(-1, 1, (B, N, nx) if k in ("x", "q", "p", "v", "vnew", "g") else (B, N - 1, nu)).astype(dtype) for k in names}
+        ws["Xref"] = rng.uniform(-1, 1, (N, nx)).astype(dtype)
+        ws["resid"] = rng.uniform(0, 1, (B, 4)).astype(dtype)
+        exp, exp_rc = [], []
+        for b in range(B):   # oracle image: x u q r p d v vnew z znew g y Xref resid
+            img = np.concatenate([ws[k][b].reshape(-1) for k in names] + [ws["Xref"].reshape(-1), ws["resid"][b]])
+            rc, out = oracle.step(prob, which, img, it=1, dtype=dtype)
+            exp.append(out)
+            exp_rc.append(rc)
+        term = s.step(which, ws, it=1)
+        for b in range(B):
+            got = np.concatenate([ws[k][b].reshape(-1) for k in names] + [ws["Xref"].reshape(-1), ws["resid"][b]])
+            assert_same(got, exp[b], "%s step %d instance %d" % (shape, which, b))
+            assert int(term[b]) == exp_rc[b]
+
+
+@pytest.mark.parametrize("shape", [(6, 3, 8), (9, 2, 6), (16, 8, 6), (10, 12, 5)])
+def test_generic_shape_rollout_vs_oracle(pkg, oracle, shape):
+    """Closed loop on the device (window = fixed Xref, duals reset, warm solve, plant step) for shapes beyond BASELINE's."""
+    nx, nu, N = shape
+    prob = pkg.problems.random_system(nx, nu, N, seed=41 + nx)
+    B, steps = 200, 4
+    rng = np.random.default_rng(nx)
+    x0 = (rng.uniform(-1, 1, (B, nx)) * 0.4).astype(np.float32)
+    xref = np.zeros((N, nx), np.float32)
+    s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    b = pkg.capi.Batch(s, B)
+    b.set_x0(x0)
+    b.set_xref(xref)
+    h = b.rollout(steps, reset_duals=True)
+    warm = {k: np.zeros((B, N - 1, nu) if k in "dyz" else (B, N, nx), np.float32) for k in ("d", "y", "g", "v", "z")}
+    x = x0
+    for k in range(steps):
+        warm["y"][:] = 0
+        warm["g"][:] = 0
+        r = oracle.solve_batch(prob, x, xref, dtype=np.float32, warm=warm, want_state=True, nthreads=8)
+        warm = {kk: r.state[kk] for kk in warm}
+        assert_same(h["iter"][k], r.iter, "iter step %d" % k)
+        assert_same(h["u0"][k], r.u[:, 0], "u0 step %d" % k)
+        x = oracle.plant_step(prob, x, r.u[:, 0], dtype=np.float32)
+        assert_same(h["x0"][k + 1], x, "x0 step %d" % k)

@@ -100,3 +100,17 @@ def test_plant_step(pkg, oracle, shape, tag):
     exp = np.stack([ref.plant_step(prob, x0[b], u[b]) for b in range(B)])
     got = oracle.plant_step(prob, x0, u[:, 0], dtype=DT[tag])
     assert_same(got, exp, "plant step")
+
+
+@pytest.mark.parametrize("shape", [(5, 2, 6), (9, 4, 7), (13, 7, 6), (24, 6, 10), (12, 9, 5), (5, 1, 6)])
+def test_generic_shapes(pkg, oracle, shape):
+    """Shapes beyond the three BASELINE ones: the reference is compiled for the shape on the spot (oracle/Makefile
+    refshape) and the oracle's shape-generic evaluation-order dispatch must match it bit for bit -- full solves, every
+    step function and the examples' plant step, float and double (oracle/pin_shapes.py runs the same check on 60+ shapes)."""
+    import os
+    if not os.path.isdir("/root/reference/src/tinympc"):
+        pytest.skip("/root/reference not present (tests/test_golden_shapes.py covers the committed fixtures)")
+    from oracle import pin_shapes
+    for sc in ("f32", "f64"):
+        bad, mean_it, solved = pin_shapes.check(pkg, oracle, shape, sc)
+        assert not bad, "%s %s: %s" % (shape, sc, bad)
