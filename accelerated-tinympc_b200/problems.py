@@ -159,3 +159,18 @@ def random_system(nx: int = 32, nu: int = 8, N: int = 50, seed: int = 2024, rho:
                 Quu_inv=c["Quu_inv"], AmBKt=c["AmBKt"], name="random_%d_%d_%d" % (nx, nu, N),
                 extra={"riccati_iters": c["riccati_iters"]})
     return p.with_bounds(-10.0, 10.0, -1.0, 1.0)
+
+
+def codegen_random() -> Problem:
+    """The reference's examples/codegen_random.cpp:20-39 verbatim: nx = 2, nu = 2, N = 3, column-major A = {1,5,1,2},
+    B = {3,3,4,1}, Q = 1, R = 2, rho = 0.1 and its (inverted: min > max) box bounds; cache by the codegen recursion,
+    work.Q = Q + rho as tiny_codegen stores it (codegen.cpp:255,433)."""
+    A = np.array([1, 5, 1, 2], np.float64).reshape(2, 2, order="F")
+    Bm = np.array([3, 3, 4, 1], np.float64).reshape(2, 2, order="F")
+    Q = np.array([1.0, 1.0]); R = np.array([2.0, 2.0]); rho = 0.1
+    c = precompute_cache(A, Bm, Q, R, rho)
+    p = Problem(nx=2, nu=2, N=3, rho=rho, Adyn=A, Bdyn=Bm, Q=c["Q_rho"], R=R, Kinf=c["Kinf"], Pinf=c["Pinf"],
+                Quu_inv=c["Quu_inv"], AmBKt=c["AmBKt"], name="codegen_random", extra={"riccati_iters": c["riccati_iters"]})
+    p.x_min = np.tile(np.array([1.0, 2.0]), (3, 1)); p.x_max = np.tile(np.array([-1.0, -2.0]), (3, 1))
+    p.u_min = np.tile(np.array([2.0, 3.0]), (2, 1)); p.u_max = np.tile(np.array([-2.0, -3.0]), (2, 1))
+    return p

@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 from oracle.pyoracle import RefLib  # noqa: E402
 
-SHAPES = [(2, 1, 5), (3, 1, 8), (5, 2, 6), (6, 3, 20), (7, 3, 9), (8, 2, 15), (9, 4, 7), (10, 5, 10), (12, 6, 8), (13, 7, 6),
+SHAPES = [(2, 2, 3), (2, 1, 5), (3, 1, 8), (5, 2, 6), (6, 3, 20), (7, 3, 9), (8, 2, 15), (9, 4, 7), (10, 5, 10), (12, 6, 8), (13, 7, 6),
           (16, 8, 25), (17, 9, 5), (24, 6, 10), (31, 7, 6), (40, 10, 6), (5, 1, 6), (12, 9, 5), (60, 1, 4), (57, 3, 4), (64, 16, 3)]
 DT = {"f32": np.float32, "f64": np.float64}
 B = 32
@@ -29,6 +29,8 @@ MODEL_KEYS = ("Adyn", "Bdyn", "Q", "Kinf", "Pinf", "Quu_inv", "AmBKt", "x_min", 
 
 def problem(pkg, shape):
     nx, nu, N = shape
+    if shape == (2, 2, 3):
+        return pkg.problems.codegen_random()   # the reference's own examples/codegen_random.cpp data
     return pkg.problems.random_system(nx, nu, N, seed=100 + nx * 7 + nu)
 
 
