@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(RT_BLOCK) plant_kernel_rt(const __grid_constan
     if (b >= batch) return;
     for (int j = 0; j < nx; ++j) va[j * VS] = x0[b * nx + j];
     for (int j = 0; j < nu; ++j) vb[j * VS] = u[b * (long long)(nu * (P.N - 1)) + j];
-    const int head = (nx / P.pk) * P.pk;
+    const int head = P.head_Ax < 0 ? nx : (nx / P.pk) * P.pk;
     const int head_a = nx >= 8 ? nx : head, head_b = (nx >= 8 && nu >= 8) ? nx : head;
     for (int r = 0; r < nx; ++r) {
         const T ax = dot_rt<T, FAST>(r < head_a ? P.Ax.a : P.Ax.b, r, nx, va, stk);

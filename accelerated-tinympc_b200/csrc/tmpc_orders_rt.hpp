@@ -164,6 +164,7 @@ inline Orders build_orders(int nx, int nu, int N, int sb, bool fast = false)
     const int pk = 16 / sb, large = 8;
     const int unroll_k = (110 * pk + 1) / 4;   // Redux.h: cost 4K-1 <= EIGEN_UNROLLING_LIMIT * pk
     const int tail_x = nx <= unroll_k ? TREE : SEQ, tail_u = nu <= unroll_k ? TREE : SEQ;
+    const int vred_x = nx <= unroll_k ? VECREDUX : VECLOOP, vred_u = nu <= unroll_k ? VECREDUX : VECLOOP;
     auto add_prog = [&](int order, int K) {
         if (fast) order = SEQ;
         Expr x;
@@ -189,12 +190,12 @@ inline Orders build_orders(int nx, int nu, int N, int sb, bool fast = false)
         p.b = (ob == oa || fast) ? p.a : add_prog(ob, K);
         return p;
     };
-    const int vred_x = nx <= unroll_k ? VECREDUX : VECLOOP, vred_u = nu <= unroll_k ? VECREDUX : VECLOOP;
     o.Kx = two(nu == 1 ? vred_x : SEQ, tail_x, nx);
     o.head_Kx = nu == 1 ? -1 : (nu / pk) * pk;
     o.Ax = two(SEQ, tail_x, nx);
-    o.Bu = two(SEQ, tail_u, nu);
-    o.head_Ax = (nx / pk) * pk;
+    // a 1-row Bdyn is stored row-major (like a 1-row Kinf): its single coefficient is a vectorised redux over the row
+    o.Bu = nx == 1 ? two(vred_u, vred_u, nu) : two(SEQ, tail_u, nu);
+    o.head_Ax = nx == 1 ? -1 : (nx / pk) * pk;
     o.Btp = two((nu >= large && nx >= large) ? GEMV_ROW : vred_x, vred_x, nx);
     o.Qs = two(SEQ, tail_u, nu);
     o.head_Qs = nu >= large ? -1 : (nu / pk) * pk;

@@ -45,6 +45,8 @@ def main():
                 subprocess.check_call(["make", "-s", "-C", HERE, "refshape", "NX=%d" % nx, "NU=%d" % nu, "NH=%d" % N, "SC=" + tag],
                                       stdout=subprocess.DEVNULL)
             ref = RefLib(cfg)
+            from oracle.pin_shapes import cleanup
+            cleanup(cfg)   # scratch build; stays mapped in this process
             prob = problem(pkg, shape)
             rng = np.random.default_rng(nx * 1000 + nu * 10 + N)
             x0 = rng.uniform(-3, 3, (B, nx)).astype(np.float32)

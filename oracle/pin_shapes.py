@@ -39,10 +39,22 @@ def build(shape, sc):
     return cfg
 
 
-def check(pkg, ora, shape, sc):
+def cleanup(cfg):
+    """Generic-shape reference builds are scratch: they would otherwise travel to the GPU box with every snapshot."""
+    import shutil
+    try:
+        os.remove(os.path.join(HERE, "_ref", "libref_%s.so" % cfg))
+    except OSError:
+        pass
+    shutil.rmtree(os.path.join(HERE, "_ref", "stage", cfg), ignore_errors=True)
+
+
+def check(pkg, ora, shape, sc, keep=False):
     nx, nu, N = shape
     cfg = build(shape, sc)
     ref = RefLib(cfg)
+    if not keep:
+        cleanup(cfg)   # the library stays mapped in this process
     prob = pkg.problems.random_system(nx, nu, N, seed=100 + nx * 7 + nu)
     rng = np.random.default_rng(nx * 1000 + nu * 10 + N)
     bad = []

@@ -112,6 +112,12 @@ static orders_t select_orders_builtin(int nx, int nu, int N, int scalar_bytes)
     o.Ax = ORD_SEQ;
     o.Bu = ORD_SEQ;
     o.head_Ax = (nx / pk) * pk;
+    if (nx == 1) {
+        /* a 1-row Bdyn is stored row-major (like a 1-row Kinf): its single coefficient is a vectorised redux over the
+         * contiguous row */
+        o.Bu = nu <= unroll_k ? ORD_VECREDUX : ORD_VECLOOP;
+        o.head_Ax = -1;
+    }
     /* Bdyn^T * p (admm.cpp:19) is a regular product evaluated into a temporary: GeneralProduct.h
      * product_type_selector<rows=nu, 1, depth=nx>: both >= 8 -> row-major GEMV; otherwise coefficient /
      * inner product = completely unrolled vectorised redux. */

@@ -446,8 +446,9 @@ int SFX(oracle_plant_step)(const oracle_problem *in, int64_t B, const void *x0_,
          * temporary); smaller ones stay coefficient-based inside the sum and follow the packet / scalar rows of the
          * assignment to a 16-byte aligned x1: rows [0, n/pk*pk) sequential, the rest the scalar tree. */
         const int ax_all = n >= 8, bu_all = n >= 8 && m >= 8;
-        SFX(matvec2)(Ax, P.Adyn, 1, n, x0, n, n, P.ord.Ax, 0, ax_all ? n : P.ord.head_Ax, P.ord.tail_x, e);
-        SFX(matvec2)(Bu, P.Bdyn, 1, n, u0, n, m, P.ord.Bu, 0, bu_all ? n : P.ord.head_Ax, P.ord.tail_u, e);
+        const int head = P.ord.head_Ax < 0 ? n : P.ord.head_Ax;
+        SFX(matvec2)(Ax, P.Adyn, 1, n, x0, n, n, P.ord.Ax, 0, ax_all ? n : head, P.ord.tail_x, e);
+        SFX(matvec2)(Bu, P.Bdyn, 1, n, u0, n, m, P.ord.Bu, 0, bu_all ? n : head, P.ord.tail_u, e);
         for (int r = 0; r < n; ++r) x1[r] = Ax[r] + Bu[r];
     }
     return 0;

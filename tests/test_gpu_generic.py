@@ -200,3 +200,34 @@ def test_generic_shape_rollout_vs_oracle(pkg, oracle, shape):
         assert_same(h["u0"][k], r.u[:, 0], "u0 step %d" % k)
         x = oracle.plant_step(prob, x, r.u[:, 0], dtype=np.float32)
         assert_same(h["x0"][k + 1], x, "x0 step %d" % k)
+
+
+SWEEP = [(1, 5, 9), (2, 16, 7), (3, 31, 4), (4, 56, 5), (5, 8, 3), (7, 32, 5), (8, 8, 2), (9, 24, 2), (11, 56, 3), (15, 1, 11),
+         (18, 20, 3), (19, 13, 7), (22, 16, 11), (28, 32, 2), (32, 31, 6), (33, 12, 9), (45, 64, 4), (55, 2, 5), (56, 7, 2),
+         (63, 12, 7), (64, 15, 2), (64, 64, 4), (1, 64, 3), (1, 1, 4), (57, 57, 3)]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_random_shape_sweep_vs_oracle(pkg, oracle, dtype):
+    """Shapes drawn across the whole supported range (every one of them also pinned oracle-vs-reference by
+    oracle/pin_shapes.py in the build container): cold solve + warm-started re-solve with state write-back."""
+    for shape in SWEEP:
+        nx, nu, N = shape
+        prob = pkg.problems.random_system(nx, nu, N, seed=3 + nx + 64 * nu)
+        rng = np.random.default_rng(nx * 64 + nu)
+        B = 70
+        x0 = rng.uniform(-2, 2, (B, nx)).astype(np.float32)
+        x0[::2] *= np.float32(0.05)
+        xref = rng.uniform(-0.2, 0.2, (N, nx)).astype(np.float32)
+        s = pkg.capi.Solver(prob, dtype=dtype, policy="parity")
+        warm = {k: np.zeros((B, N - 1, nu) if k in "dyz" else (B, N, nx), dtype) for k in ("d", "y", "g", "v", "z")}
+        o1 = s.solve(x0, xref, warm=warm)
+        r1 = oracle.solve_batch(prob, x0, xref, dtype=dtype, want_state=True, nthreads=4)
+        _cmp_exact(o1, r1, "%s cold " % (shape,))
+        x1 = (x0 * np.float32(0.97)).astype(np.float32)
+        o2 = s.solve(x1, xref, warm=o1["warm"])
+        r2 = oracle.solve_batch(prob, x1, xref, dtype=dtype, warm={k: r1.state[k] for k in warm}, want_state=True, nthreads=4)
+        _cmp_exact(o2, r2, "%s warm " % (shape,))
+        for k in warm:
+            assert_same(o2["warm"][k], r2.state[k], "%s warm state %s" % (shape, k))
+        s.close()
