@@ -60,6 +60,12 @@ constexpr int WARP_FWD4 = 18, WARP_BWD4 = 14;
 #ifndef TMPC_WARP_PROD2
 #define TMPC_WARP_PROD2 0
 #endif
+#ifndef TMPC_WARP_TREE2
+#define TMPC_WARP_TREE2 0   // AmBKt p: the scalar tree's adds issued pairwise as FADD2 (bit-identical, 16 instead of 31
+                            // instructions).  Measured on B200 (32,768 instances, PARITY): cold 5.01e7 it/s with it, 5.22e7
+                            // without; warm 4.24e7 vs 4.48e7 -- like the packed products, FADD2 holds the FMA pipe for two
+                            // cycles and the register pairing costs moves.  Default: scalar tree.
+#endif
 template <int K> __device__ __forceinline__ void prod_pairs(const float (&c)[K], const float (&x)[K], float (&e)[K], const float2 Z)
 {
     static_assert(K % 2 == 0, "pairs");
@@ -73,6 +79,23 @@ template <int K> __device__ __forceinline__ void prod_pairs(const float (&c)[K],
         }
     }
 }
+// Half-split tree over 32 terms (Redux.h redux_novec_unroller) with the adds of each level issued in pairs: the two
+// operands of every add are the same as in the scalar tree, so the result is bit-identical; 16 instructions instead of 31.
+__device__ __forceinline__ float tree32_pairs(const float (&e)[32])
+{
+    float2 a[8];   // level 1: (e0+e1, e2+e3), (e4+e5, e6+e7), ...
+#pragma unroll
+    for (int m = 0; m < 8; ++m) a[m] = add2(f2(e[4 * m], e[4 * m + 2]), f2(e[4 * m + 1], e[4 * m + 3]));
+    float2 b[4];   // level 2: ((e0+e1)+(e2+e3), (e4+e5)+(e6+e7)), ...
+#pragma unroll
+    for (int m = 0; m < 4; ++m) b[m] = add2(f2(a[2 * m].x, a[2 * m + 1].x), f2(a[2 * m].y, a[2 * m + 1].y));
+    // level 3: sums of 8: (b0.x+b0.y, b1.x+b1.y), (b2.x+b2.y, b3.x+b3.y)
+    const float2 c0 = add2(f2(b[0].x, b[1].x), f2(b[0].y, b[1].y)), c1 = add2(f2(b[2].x, b[3].x), f2(b[2].y, b[3].y));
+    // level 4: sums of 16: (c0.x+c0.y, c1.x+c1.y)
+    const float2 d = add2(f2(c0.x, c1.x), f2(c0.y, c1.y));
+    return __fadd_rn(d.x, d.y);
+}
+
 template <int K> __device__ __forceinline__ float sum_seq(const float (&e)[K])
 {
     float acc = e[0];
@@ -399,7 +422,8 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                     else {
                         float em[WNX];
                         prod_pairs<WNX>(Mc, pv, em, Z);
-                        mp = red_tree<float, 0, WNX>([&](int k) { return em[k]; });
+                        if constexpr (TMPC_WARP_TREE2) mp = tree32_pairs(em);
+                        else mp = red_tree<float, 0, WNX>([&](int k) { return em[k]; });
                     }
                     const float4 r0 = ub4[0], r1 = ub4[1];
                     const float rs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
