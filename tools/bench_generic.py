@@ -57,7 +57,7 @@ def generic(nx, nu, N, B, **kw):
     run("random_%d_%d_%d" % (nx, nu, N), prob, x0, np.zeros((N, nx), np.float32), **kw)
 
 
-if __name__ == "__main__":
+def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 19
     q = pkg.problems.quadrotor(20)
     x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
@@ -82,3 +82,7 @@ if __name__ == "__main__":
         os.environ.pop("TMPC_KERNEL")
         generic(16, 8, 25, B=max(B // 2, 4096))
     os.environ.pop("TMPC_RT_BLOCKS_PER_SM")
+
+
+if __name__ == "__main__":
+    main()
