@@ -48,7 +48,7 @@ class TmpcWorkspace(C.Structure):
 class TmpcStats(C.Structure):
     _fields_ = [("instances", C.c_int64), ("iterations", C.c_int64), ("solved", C.c_int64), ("trips", C.c_int64),
                 ("launches", C.c_int32), ("lanes", C.c_int32), ("kernel_ms", C.c_float), ("parity_pinned", C.c_int32),
-                ("pattern", C.c_int32), ("reserved_", C.c_int32)]
+                ("pattern", C.c_int32), ("scheduled", C.c_int32)]
 
 
 _lib = None

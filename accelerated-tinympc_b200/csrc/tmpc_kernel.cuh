@@ -194,7 +194,15 @@ template <class T> struct SolveArgs {
     const T *sys;                 // per-instance systems (PERSYS kernels): [instance][SysBlock::STRIDE], else null
     unsigned *gate;               // nullable: gate[0] = number of leading instances whose inputs have arrived in device memory
                                   // (advanced by stream memory operations between the chunks of an overlapped H2D), gate[1] = timeout flag
+    const unsigned *order;        // nullable: the k-th claim of the work counter solves instance order[k] (longest-expected-first
+                                  // schedule built by the host pre-pass, tmpc_api.cu lpt_prepare); null = instance k
 };
+
+// instance solved by the idx-th claim of the work counter
+template <class T> __device__ __forceinline__ long long claimed_instance(const SolveArgs<T> &a, long long idx)
+{
+    return a.order ? (long long)__ldg(a.order + idx) : idx;
+}
 
 // Overlapped H2D: an instance may be claimed before its x0 / Xref chunk has landed.  Wait for the arrival counter (never in
 // practice: the kernel consumes ~5 GB/s of inputs, PCIe delivers 50); give up after ~2 s instead of hanging the device.
@@ -486,7 +494,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
                 if (idx < a.batch && gate_wait(a, idx)) {
-                    inst = idx;
+                    inst = claimed_instance(a, idx);
                     phase = PH_RUN;
                     it = 0;
                     hit_max = false;

@@ -425,7 +425,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
                 if (idx < a.batch && gate_wait(a, idx)) {
-                    inst = idx; phase = PH_RUN; it = 0; fill = true;
+                    inst = claimed_instance(a, idx); phase = PH_RUN; it = 0; fill = true;
                     spec = (P.max_iter <= 1);
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
                 if (idx < a.batch && gate_wait(a, idx)) {
-                    inst = idx;
+                    inst = claimed_instance(a, idx);
                     active = true;
                     it = 0;
                     cur = 0;

@@ -199,6 +199,7 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
             inst = (long long)__shfl_sync(FULLM, b, 0);
         }
         if (inst >= a.batch || !gate_wait(a, inst)) break;
+        inst = claimed_instance(a, inst);
         const float *xref = a.Xref + inst * a.xref_stride;
         const float x0 = __ldg(a.x0 + inst * WNX + lane);
         // p_N seed: -(Xref_{N-1}^T Pinf)   (admm.cpp:83)

@@ -269,6 +269,8 @@ def main():
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_fp32_max, "unit": "TFLOP/s",
                 "frac": achieved / peak_fp32_max, "traffic": traffic,
                 "structure_pattern": stats.get("pattern"), "executed_flop_per_iteration": exec_flop,
+                "schedule": ("longest-expected-first: per-instance key kernel + CUB radix sort ahead of the solver kernel, on the same "
+                             "stream, inside the timed region and inside kernel_ms_per_launch") if stats.get("scheduled") else "index order",
                 "executed_tflops": stats["iterations"] * exec_flop / (kernel_ms * 1e-3) / 1e12,
                 "executed_frac": stats["iterations"] * exec_flop / (kernel_ms * 1e-3) / 1e12 / peak_fp32_max,
                 "peak_source": "SMs x 128 FMA lanes x 2 x clocks.max.sm (%d SMs, %d MHz); at the median clock under load "

@@ -117,7 +117,9 @@ typedef struct {
     int32_t parity_pinned;    /* 1 if this shape's evaluation order is verified against the reference */
     int32_t pattern;          /* model-structure specialisation the kernel ran with: 0 dense, 1 quadrotor (exact zeros
                                  and ones of Adyn / AmBKt dropped; value-identical results) */
-    int32_t reserved_;
+    int32_t scheduled;        /* 1 if the last solve used the longest-expected-first schedule (device-resident batches of at
+                                 least twice the resident lanes: a key per instance + a radix sort ahead of the kernel, on the
+                                 same stream and inside kernel_ms; TMPC_LPT=0 disables it) */
 } tmpc_stats;
 
 /* Statistics of the last tmpc_solve on this ctx (synchronises the ctx's stream). */

@@ -123,3 +123,34 @@ def test_stage_varying_bounds(pkg, oracle, dtype):
     out = pkg.capi.Solver(prob, dtype=dtype, policy="parity").solve(x0, xref)
     _cmp_exact(out, ref)
     assert len(set(ref.iter.tolist())) > 10
+
+
+def test_longest_first_schedule_is_result_neutral(pkg, oracle, monkeypatch):
+    """Device-resident batches of at least twice the resident lanes run with the longest-expected-first schedule
+    (tmpc_stats.scheduled): outputs must be identical to the index-order run and to the oracle, instance by instance."""
+    import torch
+    prob = pkg.problems.quadrotor(20)
+    B = 90000
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
+    dev = torch.device("cuda:0")
+
+    def run():
+        s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+        tx0, txr = torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev)
+        x = torch.empty((B, 10, 12), device=dev); u = torch.empty((B, 9, 4), device=dev)
+        it = torch.empty(B, dtype=torch.int32, device=dev); st = torch.empty(B, dtype=torch.int32, device=dev)
+        rs = torch.empty((B, 4), device=dev)
+        s.solve_raw(B, tx0, txr, True, pkg.capi.TMPC_MEM_DEVICE, x, u, it, st, rs, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return s.stats(), {"x": x.cpu().numpy(), "u": u.cpu().numpy(), "iter": it.cpu().numpy(), "status": st.cpu().numpy(), "resid": rs.cpu().numpy()}
+
+    st1, o1 = run()
+    assert st1["scheduled"] == 1 and st1["launches"] == 2
+    monkeypatch.setenv("TMPC_LPT", "0")
+    st0, o0 = run()
+    assert st0["scheduled"] == 0 and st0["launches"] == 1
+    ref = oracle.solve_batch(prob, x0, xref, dtype=np.float32, nthreads=8)
+    for k in ("iter", "status", "x", "u", "resid"):
+        assert_same(o1[k], o0[k], "scheduled vs index order " + k)
+        assert_same(o1[k], getattr(ref, k), "scheduled vs oracle " + k)
+    assert st1["trips"] <= st0["trips"]
