@@ -734,12 +734,13 @@ int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cuda
 // instances (key kernel 23 us + sort 43 us); 1M hover instances 10.93 -> 10.40 ms, 4M cartpole 12.39 -> 11.49 ms, 32/8/50 warm
 // re-solve 19.7 -> 18.0 ms; a workload without a tail pays the pre-pass (hover at mult 0.1: 5.29 -> 5.41 ms).
 template <class T>
-__global__ void lpt_key_kernel(long long batch, int nx, int nu, const T *__restrict__ K, const T *__restrict__ x0, const T *__restrict__ Xref,
-                               long long xref_stride, unsigned *__restrict__ keys, unsigned *__restrict__ vals)
+__global__ void lpt_key_kernel(long long batch, int nx, int nu, const T *__restrict__ K0, long long k_stride, const T *__restrict__ x0,
+                               const T *__restrict__ Xref, long long xref_stride, unsigned *__restrict__ keys, unsigned *__restrict__ vals)
 {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= batch) return;
     const T *x = x0 + i * nx, *xr = Xref + i * xref_stride;
+    const T *K = K0 + i * k_stride;   // k_stride = 0: the shared Kinf; else the instance's own (per-instance systems)
     float m = 0.f;
     // 8 rows of Kinf at a time in registers, every x0 / Xref element read once per row block (16-byte loads when the rows
     // are 16-byte aligned, i.e. nx a multiple of the vector width: the API requires 16-byte aligned device buffers)
@@ -774,7 +775,7 @@ bool lpt_wanted(const tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da)
 {
     const char *e = getenv("TMPC_LPT");
     if (e && !strcmp(e, "0")) return false;
-    if (da.done || da.gate || da.sys || !c->d_kinf || da.batch >= (1LL << 31)) return false;
+    if (da.done || da.gate || !c->d_kinf || da.batch >= (1LL << 31)) return false;
     if (e && !strcmp(e, "1")) return true;
     // Per-instance reference trajectories (tracking): measured 3 % SLOWER with the schedule (7.02 -> 7.35 ms per 1M launch):
     // x0 = Xref_0 + noise there, so the key ranks nothing, and the permuted order scatters the per-iteration Xref reads.
@@ -787,8 +788,10 @@ bool lpt_wanted(const tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da)
     return da.batch >= 2 * lanes && da.batch >= 16384;
 }
 
-int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s)
+// K / k_stride: Kinf (column-major) of instance i at K + i * k_stride; default = the ctx's shared Kinf
+int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = nullptr, long long k_stride = 0)
 {
+    if (!K) { K = c->d_kinf; k_stride = 0; }
     const size_t B = (size_t)da.batch;
     if (c->lpt_cap < B) {
         CUDA_TRY(c, cudaDeviceSynchronize());
@@ -806,10 +809,10 @@ int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s)
     unsigned *keys_in = c->lpt_buf, *keys_out = keys_in + c->lpt_cap, *vals_in = keys_out + c->lpt_cap, *vals_out = vals_in + c->lpt_cap;
     const unsigned blocks = (unsigned)((B + 255) / 256);
     if (c->dtype == TMPC_F32)
-        lpt_key_kernel<float><<<blocks, 256, 0, s>>>(da.batch, c->nx, c->nu, (const float *)c->d_kinf, (const float *)da.x0, (const float *)da.Xref,
+        lpt_key_kernel<float><<<blocks, 256, 0, s>>>(da.batch, c->nx, c->nu, (const float *)K, k_stride, (const float *)da.x0, (const float *)da.Xref,
                                                      da.xref_stride, keys_in, vals_in);
     else
-        lpt_key_kernel<double><<<blocks, 256, 0, s>>>(da.batch, c->nx, c->nu, (const double *)c->d_kinf, (const double *)da.x0,
+        lpt_key_kernel<double><<<blocks, 256, 0, s>>>(da.batch, c->nx, c->nu, (const double *)K, k_stride, (const double *)da.x0,
                                                       (const double *)da.Xref, da.xref_stride, keys_in, vals_in);
     CUDA_TRY(c, cudaGetLastError());
     size_t tb = c->lpt_temp_bytes;
@@ -827,7 +830,7 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
         return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
     bool ev0_done = false;
     c->lpt_used = 0;
-    if (lpt_wanted(c, ki, da)) {
+    if (!da.sys && lpt_wanted(c, ki, da)) {
         // the pre-pass is part of the solve: it runs on the same stream inside the timed region
         if (time_it) { CUDA_TRY(c, cudaEventRecord(c->ev0, s)); ev0_done = true; }
         const int rc = lpt_prepare(c, da, s);

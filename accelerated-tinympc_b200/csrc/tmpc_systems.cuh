@@ -312,7 +312,19 @@ int tmpc_solve_systems(tmpc_ctx *ctx, const tmpc_solve_args *a, const tmpc_syste
     c->stats.instances = a->batch;
     c->stats.iterations = c->stats.solved = c->stats.trips = 0;
     c->stats.launches = 0;
-    int rc = launch_kernel_info(c, ki, da, s, true);
+    // longest-expected-first schedule with each instance's own Kinf (tmpc_api.cu lpt_prepare)
+    bool ev0_done = false;
+    c->lpt_used = 0;
+    if (c->nx == 12 && c->nu == 4 && lpt_wanted(c, ki, da)) {
+        using SB = tmpc::SysBlock<12, 4>;
+        CUDA_TRY(c, cudaEventRecord(c->ev0, s));
+        ev0_done = true;
+        const char *kb = (const char *)sy->blocks + (size_t)SB::K * esize(c);
+        int rc0 = lpt_prepare(c, da, s, kb, (long long)sy->stride);
+        if (rc0 != TMPC_OK) return rc0;
+        c->lpt_used = 1;
+    }
+    int rc = launch_kernel_info(c, ki, da, s, true, ev0_done);
     if (rc == TMPC_OK) { c->stats_pending = true; c->stats.pattern = 0; }
     return rc;
 }
