@@ -138,7 +138,8 @@ KernelInfo make_info_g()
 {
     KernelInfo k;
     k.fn = (const void *)&tmpc::admm_kernel<T, NX, NU, NH, BLOCK, FAST, WARM, false, SYS>;
-    k.smem = tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES + (SYS == 2 ? 16 : 0);   // + the TMEM base slot
+    k.smem = SYS == 3 ? tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES_NOGV + 16                 // g, v in TMEM
+                      : tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES + (SYS == 2 ? 16 : 0);   // + the TMEM base slot
     k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::Model<T, NX, NU, NH>);
     k.model_kind = 0;
@@ -259,7 +260,16 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
             if (v == 1) return pick_f32<12, 4, 10, 128, false>(policy, warm, out);  // all state in shared memory
             return pick<float, 12, 4, 10, 128, false>(policy, warm, out);
         }
-        return pick<double, 12, 4, 10, 64, false>(policy, warm, out);
+        // double: g, v in tensor memory -> 128 instances / SM (TMPC_KERNEL=generic: all state in shared memory, 64 / SM)
+        {
+            const char *e = getenv("TMPC_KERNEL");
+            if (e && !strcmp(e, "generic")) return pick<double, 12, 4, 10, 64, false>(policy, warm, out);
+        }
+        if (policy == TMPC_ORDER_PARITY)
+            out = warm ? make_info_g<double, 12, 4, 10, 128, false, true, 3>() : make_info_g<double, 12, 4, 10, 128, false, false, 3>();
+        else
+            out = warm ? make_info_g<double, 12, 4, 10, 128, true, true, 3>() : make_info_g<double, 12, 4, 10, 128, true, false, 3>();
+        return true;
     }
     if (nx == 4 && nu == 1 && N == 10) {
         if (dtype == TMPC_F32) {

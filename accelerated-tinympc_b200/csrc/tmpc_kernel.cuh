@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace tmpc {
 
@@ -360,6 +361,68 @@ template <class T, int D, int STAGES, int BLOCK> struct SVec {
     }
 };
 
+// ---- g / v of a DOUBLE-precision instance in tensor memory (SYS == 3): a double is two 32-bit TMEM cells, stage i of the
+// thread's vector sits at columns [base + 2 D i, + 2 D) of its TMEM lane.  tcgen05.ld/st are warp-collective: every lane of
+// the warp must call load/store together (the sweeps do; the refill path is written accordingly).
+__device__ __forceinline__ void tm_ld8u(uint32_t a, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tm_ld16u(uint32_t a, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tm_st8u(uint32_t a, const uint32_t *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tm_st16u(uint32_t a, const uint32_t *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tm_wait8u(uint32_t *r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
+}
+__device__ __forceinline__ void tm_wait24u(uint32_t *r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]) :: "memory");
+}
+template <int D, int STAGES> struct TVecD {
+    static_assert(D == 12 || D == 4, "TMEM rows of 24 or 8 cells");
+    static constexpr int COLS = 2 * D * STAGES;
+    uint32_t base = 0;
+    __device__ __forceinline__ void load(int i, double (&o)[D]) const
+    {
+        uint32_t r[2 * D];
+        const uint32_t a = base + (uint32_t)(i * 2 * D);
+        if constexpr (D == 12) { tm_ld16u(a, r); tm_ld8u(a + 16, r + 16); tm_wait24u(r); }
+        else { tm_ld8u(a, r); tm_wait8u(r); }
+#pragma unroll
+        for (int j = 0; j < D; ++j) o[j] = __hiloint2double((int)r[2 * j + 1], (int)r[2 * j]);
+    }
+    __device__ __forceinline__ void store(int i, const double (&o)[D]) const
+    {
+        uint32_t r[2 * D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) { r[2 * j] = (uint32_t)__double2loint(o[j]); r[2 * j + 1] = (uint32_t)__double2hiint(o[j]); }
+        const uint32_t a = base + (uint32_t)(i * 2 * D);
+        if constexpr (D == 12) { tm_st16u(a, r); tm_st8u(a + 16, r + 16); }
+        else tm_st8u(a, r);
+    }
+};
+
 // global [instance][stage][dim] rows; 16-byte vector access when D is a multiple of the vector width
 template <class T, int D> __device__ __forceinline__ void gload(const T *p, T (&o)[D])
 {
@@ -400,6 +463,7 @@ template <class T, int NX, int NU, int NH, int BLOCK> struct SmemLayout {
     using SX = SVec<T, NX, NH, BLOCK>;
     using SP = SVec<T, NX, 1, BLOCK>;
     static constexpr size_t BYTES = 3 * SU::BYTES + 2 * SX::BYTES + SP::BYTES;
+    static constexpr size_t BYTES_NOGV = 3 * SU::BYTES + SP::BYTES;   // g, v in tensor memory (SYS == 3)
 };
 
 enum { PH_FREE = 0, PH_RUN = 1, PH_EMIT = 2 };
@@ -426,14 +490,17 @@ template <class T, int K1, int K2, bool TM> __device__ __forceinline__ void crow
     if constexpr (TM) { static_assert(K1 == 12 && K2 == 4, "12 + 4"); tm_wait16(c1, c2); }
 }
 
-// SYS: 0 = one shared model (constant bank); 1 = per-instance systems, coefficients fetched from the lane's global block;
+// SYS: 3 = one shared model, DOUBLE precision, g and v in tensor memory (480 of the lane's 512 cells at 12/4/10): 128 instead of
+//          64 instances per SM -- at 64 threads two of the SM's four schedulers have no warp at all;
+//      0 = one shared model (constant bank); 1 = per-instance systems, coefficients fetched from the lane's global block;
 //      2 = per-instance systems, the lane's loop coefficients (SysBlock prefix, 496 floats at 12/4) resident in TENSOR
 //          MEMORY: 128 threads per SM, one TMEM lane (512 columns) each, rewritten warp-collectively when a lane refills
 template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool UNROLL, int SYS = 0>
 __global__ void __launch_bounds__(BLOCK, 1)
 admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constant__ SolveArgs<T> a)
 {
-    constexpr bool PERSYS = SYS != 0, SYSTM = SYS == 2;
+    constexpr bool PERSYS = SYS == 1 || SYS == 2, SYSTM = SYS == 2, TMGV = SYS == 3;
+    static_assert(!TMGV || (BLOCK == 128 && sizeof(T) == 8 && 2 * 2 * NX * NH <= 512), "g/v in TMEM: 4 warps, doubles, 4 NX NH cells per lane");
     static_assert(!SYSTM || (BLOCK == 128 && sizeof(T) == 4 && SysBlock<NX, NU>::TMLEN <= 512 && SysBlock<NX, NU>::TMLEN % 8 == 0),
                   "TMEM-resident systems: 4 warps, one 512-column TMEM lane per thread, float");
     // model source: the shared constant-bank image, or (PERSYS) this lane's own SysBlock: global memory read through the
@@ -455,12 +522,13 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
     typename L::SU sd(sp, tid); sp += L::SU::BYTES;
     typename L::SU sy(sp, tid); sp += L::SU::BYTES;
     typename L::SU sz(sp, tid); sp += L::SU::BYTES;
-    typename L::SX sg(sp, tid); sp += L::SX::BYTES;
-    typename L::SX sv(sp, tid); sp += L::SX::BYTES;
+    using GV = std::conditional_t<TMGV, TVecD<(TMGV ? NX : 12), NH>, typename L::SX>;
+    GV sg = [&] { if constexpr (TMGV) return GV{}; else { GV t(sp, tid); sp += L::SX::BYTES; return t; } }();
+    GV sv = [&] { if constexpr (TMGV) return GV{}; else { GV t(sp, tid); sp += L::SX::BYTES; return t; } }();
     typename L::SP spn(sp, tid);
-    uint32_t tcol = 0;   // SYSTM: TMEM address of this thread's lane, column 0
-    if constexpr (SYSTM) {
-        uint32_t *slot = reinterpret_cast<uint32_t *>(smem + L::BYTES);
+    uint32_t tcol = 0;   // SYSTM / TMGV: TMEM address of this thread's lane, column 0
+    if constexpr (SYSTM || TMGV) {
+        uint32_t *slot = reinterpret_cast<uint32_t *>(smem + (TMGV ? L::BYTES_NOGV : L::BYTES));
         if (tid < 32) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"((uint32_t)__cvta_generic_to_shared(slot)) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -469,6 +537,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tcol = *slot + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
+        if constexpr (TMGV) { sg.base = tcol; sv.base = tcol + (uint32_t)(2 * NX * NH); }
     }
 
     long long inst = -1;
@@ -526,11 +595,13 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                             gload<T, NU>(a.wy + inst * UROW + i * NU, t); sy.store(i, t);
                             gload<T, NU>(a.wz + inst * UROW + i * NU, t); sz.store(i, t);
                         }
+                        if constexpr (!TMGV) {
 #pragma unroll 1
-                        for (int i = 0; i < NH; ++i) {
-                            T t[NX];
-                            gload<T, NX>(a.wg + inst * XROW + i * NX, t); sg.store(i, t);
-                            gload<T, NX>(a.wv + inst * XROW + i * NX, t); sv.store(i, t);
+                            for (int i = 0; i < NH; ++i) {
+                                T t[NX];
+                                gload<T, NX>(a.wg + inst * XROW + i * NX, t); sg.store(i, t);
+                                gload<T, NX>(a.wv + inst * XROW + i * NX, t); sv.store(i, t);
+                            }
                         }
                     } else {
                         T zu[NU], zx[NX];
@@ -540,12 +611,36 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                         for (int j = 0; j < NX; ++j) zx[j] = T(0);
 #pragma unroll 1
                         for (int i = 0; i < NH - 1; ++i) { sd.store(i, zu); sy.store(i, zu); sz.store(i, zu); }
+                        if constexpr (!TMGV) {
 #pragma unroll 1
-                        for (int i = 0; i < NH; ++i) { sg.store(i, zx); sv.store(i, zx); }
+                            for (int i = 0; i < NH; ++i) { sg.store(i, zx); sv.store(i, zx); }
+                        }
                     }
                 } else {
                     exhausted = true;
                 }
+            }
+            if constexpr (TMGV) {
+                // tcgen05 is warp-collective: every lane of the warp rewrites its g / v cells, refilled lanes with zeros (cold) or
+                // the caller's warm state, the others with what they hold
+                const bool fill = need && !exhausted;
+                const bool wfill = fill && WARM && a.wd;
+#pragma unroll 1
+                for (int i = 0; i < NH; ++i) {
+                    T g[NX], v[NX];
+                    sg.load(i, g);
+                    sv.load(i, v);
+                    if (wfill) {
+                        gload<T, NX>(a.wg + inst * XROW + i * NX, g);
+                        gload<T, NX>(a.wv + inst * XROW + i * NX, v);
+                    } else if (fill) {
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) g[j] = v[j] = T(0);
+                    }
+                    sg.store(i, g);
+                    sv.store(i, v);
+                }
+                tm_wait_st();
             }
             if constexpr (SYSTM) {
                 // tcgen05 is warp-collective: every lane rewrites its columns, lanes that were not refilled with what they hold
@@ -661,6 +756,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                 for (int i = 0; i < NH - 1; ++i) stage(i, false);
             }
             stage(NH - 1, true);
+            if constexpr (TMGV) tm_wait_st();   // the backward sweep reads the cells this sweep wrote
         }
 
         // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
@@ -808,7 +904,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             atomicAdd(a.stats + 3, n_inst);
         }
     }
-    if constexpr (SYSTM) {
+    if constexpr (SYSTM || TMGV) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tcol) : "memory");
