@@ -98,3 +98,25 @@ def test_host_api_precompute_cartpole():
     assert abs(q - 0.8396930620) < 1e-6
     hist = dict((int(a), int(b)) for a, b in re.findall(r"(\d+):(\d+)", out.split("iteration histogram:")[1]))
     assert sum(hist.values()) == 300 and max(hist) <= 5 and hist.get(1, 0) + hist.get(2, 0) >= 285
+
+
+@pytest.mark.parametrize("tag,rel", [("f32", 2e-5), ("f64", 1e-7)])
+def test_host_api_codegen_random_example(tag, rel):
+    """The reference's examples/codegen_random.cpp problem (2/2/3, inverted bounds) through tiny_setup / tiny_precompute /
+    tiny_solve on the GPU (run-time-shape kernel).  Expected values: the unmodified reference compiled for 2/2/3 in this
+    build container on the same problem: iter 100, status 11, and u(:,0), x(:,N-1).  The cache comes from the host
+    tiny_precompute here and from numpy for the expected values (last-bit differences, amplified by the unstable A over 100
+    iterations), hence a tolerance instead of bit equality -- bit-exact parity for this problem is in tests/golden/shapes_*."""
+    exp = {"f32": ([-0.908024787902832, 0.5177114009857178], [-0.8582912087440491, -1.9397375583648682]),
+           "f64": ([-0.9080255099352041, 0.5177118162726391], [-0.8582902801259293, -1.9397381761156707])}[tag]
+    p = subprocess.run([os.path.join(BIN, "codegen_random_" + tag), "0.5", "-0.3"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    out = p.stdout
+    assert "riccati sweeps 5" in out
+    assert re.search(r"rc 1 iter 100 status 11", out), out
+    u0 = [float(t) for t in re.search(r"u0 (\S+) (\S+)", out).groups()]
+    xN = [float(t) for t in re.search(r"xN (\S+) (\S+)", out).groups()]
+    np.testing.assert_allclose(u0, exp[0], rtol=rel)
+    np.testing.assert_allclose(xN, exp[1], rtol=rel)
+    K = [float(t) for t in re.search(r"Kinf (\S+) (\S+) (\S+) (\S+)", out).groups()]
+    np.testing.assert_allclose(K, [1.3597774779741059, -0.6322783070376652, 0.53346352483974, -0.10662252458139154], rtol=1e-6 if tag == "f32" else 1e-10)
