@@ -412,6 +412,20 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
 #pragma unroll
     for (int j = 0; j < NX; ++j) x0[j] = 0.f;
 
+    // p_N seed: -(Xref_{N-1}^T Pinf)  (admm.cpp:83).  It depends on the reference trajectory only, so with one Xref shared by the
+    // batch it is computed once per lane here instead of at every refill: the refill section runs at warp level nearly every
+    // trip (32 lanes x 1/34 terminations per trip at the headline workload) and the seed was 60 % of its instructions.
+    auto seed_pn = [&](const float *xl) {
+        float xr[NX], pn[NX];
+        gload<float, NX>(xl, xr);
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+            pn[j] = -dot<float, O::XtP, NX, FAST>([&](int k) { return P.Pt[k * NX + j]; }, [&](int k) { return xr[k]; });
+        spn.store(0, pn);
+    };
+    const bool shared_xref = (a.xref_stride == 0);
+    if (shared_xref) seed_pn(a.Xref + (NH - 1) * NX);
+
     for (;;) {
         // ------------------------------------------------------------------ lane refill (warp-uniform branch)
         const bool need = (phase == PH_FREE) && !exhausted;
@@ -429,12 +443,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     spec = (P.max_iter <= 1);
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);
-                    float xr[NX], pn[NX];
-                    gload<float, NX>(a.Xref + inst * a.xref_stride + (NH - 1) * NX, xr);
-#pragma unroll
-                    for (int j = 0; j < NX; ++j)   // p_N seed: -(Xref_{N-1}^T Pinf)  (admm.cpp:83)
-                        pn[j] = -dot<float, O::XtP, NX, FAST>([&](int k) { return P.Pt[k * NX + j]; }, [&](int k) { return xr[k]; });
-                    spn.store(0, pn);
+                    if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
                     if (WARM && a.wd) {
 #pragma unroll 1
                         for (int i = 0; i < NH - 1; ++i) {
@@ -457,11 +466,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             // g, v: every lane of the warp takes part (tcgen05 is warp-collective); lanes that are not being
             // refilled write back what they hold
             const bool wfill = WARM && a.wd;
-#pragma unroll 1
-            for (int i = 0; i < NH; ++i) {
-                float gv[2 * NX];
-                xs.load_issue(i, gv);
-                xs.wait(gv);
+            // (two stages per round trip: the section is bound by the latency of the tensor-memory reads, not by instructions)
+            auto refill_stage = [&](int i, float (&gv)[2 * NX]) {
                 if (fill) {
                     if (wfill) {
                         gload<float, NX>(a.wg + inst * XROW + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
@@ -472,6 +478,22 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     }
                 }
                 xs.store(i, *reinterpret_cast<float(*)[NX]>(gv), *reinterpret_cast<float(*)[NX]>(gv + NX));
+            };
+#pragma unroll 1
+            for (int i = 0; i + 1 < NH; i += 2) {
+                float gv0[2 * NX], gv1[2 * NX];
+                xs.load_issue(i, gv0);
+                xs.load_issue(i + 1, gv1);
+                xs.wait(gv0);
+                xs.wait(gv1);
+                refill_stage(i, gv0);
+                refill_stage(i + 1, gv1);
+            }
+            if constexpr (NH % 2 == 1) {
+                float gv[2 * NX];
+                xs.load_issue(NH - 1, gv);
+                xs.wait(gv);
+                refill_stage(NH - 1, gv);
             }
             xs.fence_st();
         }
