@@ -540,6 +540,17 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
         if constexpr (TMGV) { sg.base = tcol; sv.base = tcol + (uint32_t)(2 * NX * NH); }
     }
 
+    // the p_N seed depends on Xref_{N-1} and Pinf only: with one model and one Xref for the whole batch every lane computes
+    // it once here instead of inside the refill section, which runs at warp level nearly every trip
+    const bool seed_shared = !PERSYS && a.xref_stride == 0;
+    if (seed_shared) {
+        T xr[NX], pn[NX];
+        gload<T, NX>(a.Xref + (NH - 1) * NX, xr);
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+            pn[j] = -dot<T, O::XtP, NX, FAST>([&](int k) { return P.Pf[k + j * NX]; }, [&](int k) { return xr[k]; });
+        spn.store(0, pn);
+    }
     long long inst = -1;
     int it = 0;
     int phase = PH_FREE;
@@ -574,8 +585,8 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                         rho_l = __ldg(blk + SB::RHO);
                         nrho_l = -rho_l;
                     }
-                    // p_N seed: -(Xref_{N-1}^T * Pinf)   (admm.cpp:83)
-                    {
+                    // p_N seed: -(Xref_{N-1}^T * Pinf)   (admm.cpp:83); with one shared model and Xref it was computed once, above
+                    if (!seed_shared) {
                         T xr[NX], pn[NX];
                         gload<T, NX>(a.Xref + inst * a.xref_stride + (NH - 1) * NX, xr);
 #pragma unroll
