@@ -15,6 +15,10 @@
 #pragma once
 #include "tmpc_kernel.cuh"
 
+#ifndef TMPC_REFILL_PAIRS
+#define TMPC_REFILL_PAIRS 1
+#endif
+
 namespace tmpc {
 
 template <int NX, int NU, int NH> struct alignas(16) ModelF32 {
@@ -404,6 +408,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
     int it = 0;
     int phase = PH_FREE;
     bool exhausted = false;
+    bool deferred = false;   // warp-uniform: the previous trip postponed a single-lane refill
     bool spec = false;   // speculative emission: this trip's x,u go straight to the output because the lane is
                          // expected to terminate in it (residuals within SPEC_FACTOR of tolerance, or last iteration)
     float x0[NX];
@@ -429,7 +434,14 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
     for (;;) {
         // ------------------------------------------------------------------ lane refill (warp-uniform branch)
         const bool need = (phase == PH_FREE) && !exhausted;
-        const unsigned m = __ballot_sync(FULLM, need);
+        unsigned m = __ballot_sync(FULLM, need);
+        if constexpr (TMPC_REFILL_PAIRS) {
+            // The refill section runs for the whole warp; with one free lane it is deferred by one trip so that it usually
+            // serves two (another lane frees up with probability ~0.9 per trip at the headline workload)
+            const bool others_busy = __ballot_sync(FULLM, phase != PH_FREE) != 0;
+            if (m && __popc(m) < 2 && !deferred && others_busy) { deferred = true; m = 0; }
+            else deferred = false;
+        }
         if (m) {
             const int leader = __ffs(m) - 1;
             unsigned long long base = 0;
