@@ -556,6 +556,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
     int phase = PH_FREE;
     bool exhausted = false;
     bool hit_max = false;  // terminated by max_iter without converging (backward of that iteration still runs)
+    bool deferred = false;  // warp-uniform: the previous trip postponed a single-lane refill
     T x0[NX];
     T res[4] = {T(0), T(0), T(0), T(0)};
     unsigned long long n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
@@ -565,7 +566,12 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
     for (;;) {
         // ------------------------------------------------------------------ lane refill
         const bool need = (phase == PH_FREE) && !exhausted;
-        const unsigned m = __ballot_sync(FULLM, need);
+        unsigned m = __ballot_sync(FULLM, need);
+        {   // a single free lane waits one trip for a second one: the refill section runs for the whole warp (tmpc_kernel_f32.cuh)
+            const bool others_busy = __ballot_sync(FULLM, phase != PH_FREE) != 0;
+            if (m && __popc(m) < 2 && !deferred && others_busy) { deferred = true; m = 0; }
+            else deferred = false;
+        }
         if (m) {
             const int leader = __ffs(m) - 1;
             unsigned long long base = 0;
