@@ -662,16 +662,28 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             if constexpr (SYSTM) {
                 // tcgen05 is warp-collective: every lane rewrites its columns, lanes that were not refilled with what they hold
                 const bool fill = need && !exhausted;
-#pragma unroll 1
-                for (int c8 = 0; c8 < SB::TMLEN; c8 += 8) {
-                    float t[8];
-                    tm_ld8(tcol + c8, t);
-                    tm_wait8(t);
+                // four 8-column groups per tensor-memory round trip: the section is bound by the latency of the reads
+                auto put8 = [&](int c8, float (&t)[8]) {
                     if (fill) {
                         const float4 lo = __ldg(reinterpret_cast<const float4 *>(blk + c8)), hi = __ldg(reinterpret_cast<const float4 *>(blk + c8 + 4));
                         t[0] = lo.x; t[1] = lo.y; t[2] = lo.z; t[3] = lo.w; t[4] = hi.x; t[5] = hi.y; t[6] = hi.z; t[7] = hi.w;
                     }
                     tm_st8(tcol + c8, t);
+                };
+                constexpr int G32 = (SB::TMLEN / 32) * 32;
+#pragma unroll 1
+                for (int c = 0; c < G32; c += 32) {
+                    float t0[8], t1[8], t2[8], t3[8];
+                    tm_ld8(tcol + c, t0); tm_ld8(tcol + c + 8, t1); tm_ld8(tcol + c + 16, t2); tm_ld8(tcol + c + 24, t3);
+                    tm_wait8(t0); tm_wait8(t1); tm_wait8(t2); tm_wait8(t3);
+                    put8(c, t0); put8(c + 8, t1); put8(c + 16, t2); put8(c + 24, t3);
+                }
+#pragma unroll 1
+                for (int c8 = G32; c8 < SB::TMLEN; c8 += 8) {
+                    float t[8];
+                    tm_ld8(tcol + c8, t);
+                    tm_wait8(t);
+                    put8(c8, t);
                 }
                 tm_wait_st();
             }
