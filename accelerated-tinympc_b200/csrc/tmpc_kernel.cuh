@@ -662,7 +662,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             if constexpr (SYSTM) {
                 // tcgen05 is warp-collective: every lane rewrites its columns, lanes that were not refilled with what they hold
                 const bool fill = need && !exhausted;
-                // four 8-column groups per tensor-memory round trip: the section is bound by the latency of the reads
+                // eight 8-column groups per tensor-memory round trip: the section is bound by the latency of the reads
                 auto put8 = [&](int c8, float (&t)[8]) {
                     if (fill) {
                         const float4 lo = __ldg(reinterpret_cast<const float4 *>(blk + c8)), hi = __ldg(reinterpret_cast<const float4 *>(blk + c8 + 4));
@@ -670,13 +670,16 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     }
                     tm_st8(tcol + c8, t);
                 };
-                constexpr int G32 = (SB::TMLEN / 32) * 32;
+                constexpr int G32 = (SB::TMLEN / 64) * 64;
 #pragma unroll 1
-                for (int c = 0; c < G32; c += 32) {
-                    float t0[8], t1[8], t2[8], t3[8];
-                    tm_ld8(tcol + c, t0); tm_ld8(tcol + c + 8, t1); tm_ld8(tcol + c + 16, t2); tm_ld8(tcol + c + 24, t3);
-                    tm_wait8(t0); tm_wait8(t1); tm_wait8(t2); tm_wait8(t3);
-                    put8(c, t0); put8(c + 8, t1); put8(c + 16, t2); put8(c + 24, t3);
+                for (int c = 0; c < G32; c += 64) {
+                    float t[8][8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) tm_ld8(tcol + c + 8 * q, t[q]);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) tm_wait8(t[q]);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) put8(c + 8 * q, t[q]);
                 }
 #pragma unroll 1
                 for (int c8 = G32; c8 < SB::TMLEN; c8 += 8) {
