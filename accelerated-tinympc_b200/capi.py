@@ -18,7 +18,7 @@ TMPC_F32, TMPC_F64 = 0, 1
 TMPC_ORDER_PARITY, TMPC_ORDER_FAST = 0, 1
 TMPC_MEM_HOST, TMPC_MEM_DEVICE = 0, 1
 
-EXPORTS = ["tmpc_create", "tmpc_destroy", "tmpc_set_model", "tmpc_set_settings", "tmpc_solve", "tmpc_get_stats", "tmpc_step",
+EXPORTS = ["tmpc_create", "tmpc_destroy", "tmpc_set_model", "tmpc_set_settings", "tmpc_set_instance_bounds", "tmpc_solve", "tmpc_get_stats", "tmpc_step",
            "tmpc_host_alloc", "tmpc_host_free", "tmpc_last_error", "tmpc_version",
            "tmpc_batch_create", "tmpc_batch_destroy", "tmpc_batch_set_x0", "tmpc_batch_set_xref", "tmpc_batch_set_xref_table",
            "tmpc_batch_reset_dual_variables", "tmpc_batch_reset", "tmpc_batch_solve", "tmpc_batch_get", "tmpc_batch_rollout",
@@ -70,6 +70,8 @@ def load():
     lib.tmpc_set_model.argtypes = [C.c_void_p] + [C.c_void_p] * 7 + [C.c_double] + [C.c_void_p] * 4
     lib.tmpc_set_settings.restype = C.c_int
     lib.tmpc_set_settings.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.tmpc_set_instance_bounds.restype = C.c_int
+    lib.tmpc_set_instance_bounds.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int32]
     lib.tmpc_solve.restype = C.c_int
     lib.tmpc_solve.argtypes = [C.c_void_p, C.POINTER(TmpcSolveArgs)]
     lib.tmpc_get_stats.restype = C.c_int
@@ -164,6 +166,22 @@ class Solver:
         self._check(self.lib.tmpc_set_settings(self._ctx, prob.abs_pri_tol, prob.abs_dua_tol, prob.max_iter,
                                                prob.check_termination, prob.en_state_bound, prob.en_input_bound),
                     "tmpc_set_settings")
+
+    def set_instance_bounds(self, x_min=None, x_max=None, u_min=None, u_max=None):
+        """Per-instance boxes (the wrapper's set_xmin ... set_umax, tiny_wrapper.cpp:43-129, with a batch dimension):
+        numpy arrays [B, N, nx] / [B, N-1, nu]; all None = back to the shared bounds of the model."""
+        if x_min is None and x_max is None and u_min is None and u_max is None:
+            self._check(self.lib.tmpc_set_instance_bounds(self._ctx, 0, None, None, None, None, TMPC_MEM_HOST),
+                        "tmpc_set_instance_bounds")
+            return
+        dt = self.dtype
+        B = np.asarray(x_min).shape[0]
+        a = [np.ascontiguousarray(v, dtype=dt) for v in (x_min, x_max, u_min, u_max)]
+        for v, n in zip(a, (self.N * self.nx, self.N * self.nx, (self.N - 1) * self.nu, (self.N - 1) * self.nu)):
+            if v.size != B * n:
+                raise ValueError("bounds must be [B,N,nx] / [B,N-1,nu]")
+        self._check(self.lib.tmpc_set_instance_bounds(self._ctx, B, _addr(a[0]), _addr(a[1]), _addr(a[2]), _addr(a[3]),
+                                                      TMPC_MEM_HOST), "tmpc_set_instance_bounds")
 
     def solve_raw(self, batch, x0, Xref, xref_shared, mem, x=None, u=None, it=None, status=None, resid=None,
                   warm=None, stream=None):

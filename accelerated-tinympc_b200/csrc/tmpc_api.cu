@@ -62,6 +62,9 @@ struct tmpc_ctx_impl {
     void *d_rt_scratch = nullptr;
     size_t d_rt_scratch_bytes = 0;
     bool rt_ready = false;
+    // per-instance box bounds (tmpc_set_instance_bounds): device copies xmin | xmax | umin | umax, 0 = not set
+    void *d_ib[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long ib_batch = 0;
     // longest-expected-first schedule (lpt_prepare): device copy of Kinf, sort buffers
     void *d_kinf = nullptr;
     unsigned *lpt_buf = nullptr;     // keys_in | keys_out | vals_in | vals_out, `lpt_cap` entries each
@@ -605,7 +608,18 @@ bool build_model_rt(tmpc_ctx_impl *c)
     return c->dtype == TMPC_F32 ? build_model_rt_t<float>(c) : build_model_rt_t<double>(c);
 }
 
+bool build_model_shape(tmpc_ctx_impl *c);
 bool build_model(tmpc_ctx_impl *c)
+{
+    if (!build_model_shape(c)) return false;
+    // per-instance bounds run on the run-time-shape kernel whatever the shape: keep its image current
+    KernelInfo probe;
+    if (c->ib_batch && !(lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, false, probe) && probe.model_kind == 3))
+        return build_model_rt(c);
+    return true;
+}
+
+bool build_model_shape(tmpc_ctx_impl *c)
 {
     KernelInfo probe;
     if (lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, false, probe) && probe.model_kind == 3) {
@@ -699,9 +713,15 @@ int plan_launch(tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da, cudaS
         if (c->dtype == TMPC_F32) {
             auto &m = *reinterpret_cast<tmpc::ModelRT<float> *>(c->model_rt.data());
             m.scratch = (float *)c->d_rt_scratch; m.lanes = blocks * ki.block; m.warm = da.wd ? 1 : 0;
+            const bool xs = c->ib_batch && c->en_state, us = c->ib_batch && c->en_input;
+            m.ixmin = xs ? (const float *)c->d_ib[0] : nullptr; m.ixmax = xs ? (const float *)c->d_ib[1] : nullptr;
+            m.iumin = us ? (const float *)c->d_ib[2] : nullptr; m.iumax = us ? (const float *)c->d_ib[3] : nullptr;
         } else {
             auto &m = *reinterpret_cast<tmpc::ModelRT<double> *>(c->model_rt.data());
             m.scratch = (double *)c->d_rt_scratch; m.lanes = blocks * ki.block; m.warm = da.wd ? 1 : 0;
+            const bool xs = c->ib_batch && c->en_state, us = c->ib_batch && c->en_input;
+            m.ixmin = xs ? (const double *)c->d_ib[0] : nullptr; m.ixmax = xs ? (const double *)c->d_ib[1] : nullptr;
+            m.iumin = us ? (const double *)c->d_ib[2] : nullptr; m.iumax = us ? (const double *)c->d_ib[3] : nullptr;
         }
     }
     (void)s;
@@ -836,11 +856,17 @@ int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = n
 int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
 {
     KernelInfo ki;
-    if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern | (c->const_bounds ? 0x100 : 0)))
+    if (c->ib_batch) {
+        // per-instance bounds: the run-time-shape kernel reads each instance's own rows (index order, no scheduling pre-pass)
+        if (da.sys) return fail(c, TMPC_ERR_UNSUPPORTED, "per-instance bounds with per-instance systems");
+        if (da.batch != c->ib_batch) return fail(c, TMPC_ERR_INVALID, "batch differs from the batch of tmpc_set_instance_bounds");
+        if (!c->rt_ready || !lookup_kernel_rt(c->nx, c->nu, c->N, c->dtype, c->policy, ki))
+            return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
+    } else if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern | (c->const_bounds ? 0x100 : 0)))
         return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
     bool ev0_done = false;
     c->lpt_used = 0;
-    if (!da.sys && lpt_wanted(c, ki, da)) {
+    if (!da.sys && !c->ib_batch && lpt_wanted(c, ki, da)) {
         // the pre-pass is part of the solve: it runs on the same stream inside the timed region
         if (time_it) { CUDA_TRY(c, cudaEventRecord(c->ev0, s)); ev0_done = true; }
         const int rc = lpt_prepare(c, da, s);
@@ -1117,6 +1143,7 @@ int tmpc_destroy(tmpc_ctx *ctx)
     if (c->d_model_w) cudaFree(c->d_model_w);
     if (c->d_model_rt) cudaFree(c->d_model_rt);
     if (c->d_rt_scratch) cudaFree(c->d_rt_scratch);
+    for (void *p : c->d_ib) if (p) cudaFree(p);
     if (c->d_kinf) cudaFree(c->d_kinf);
     if (c->lpt_buf) cudaFree(c->lpt_buf);
     if (c->lpt_temp) cudaFree(c->lpt_temp);
@@ -1173,6 +1200,37 @@ int tmpc_set_settings(tmpc_ctx *ctx, double abs_pri_tol, double abs_dua_tol, int
     return TMPC_OK;
 }
 
+int tmpc_set_instance_bounds(tmpc_ctx *ctx, int64_t batch, const void *x_min, const void *x_max, const void *u_min,
+                             const void *u_max, int32_t mem)
+{
+    if (!ctx) return TMPC_ERR_INVALID;
+    tmpc_ctx_impl *c = CTX(ctx);
+    if (batch < 0) return fail(c, TMPC_ERR_INVALID, "negative batch");
+    if (mem != TMPC_MEM_HOST && mem != TMPC_MEM_DEVICE) return fail(c, TMPC_ERR_INVALID, "bad mem kind");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaDeviceSynchronize());   // an earlier solve may still read the previous copies
+    for (void *&p : c->d_ib) { if (p) cudaFree(p); p = nullptr; }
+    c->ib_batch = 0;
+    if (batch == 0) return TMPC_OK;
+    if (!x_min || !x_max || !u_min || !u_max) return fail(c, TMPC_ERR_INVALID, "all four bound arrays must be given");
+    if (!rt_shape_ok(c->nx, c->nu, c->N)) return fail(c, TMPC_ERR_UNSUPPORTED, "shape outside the run-time-shape kernel's range");
+    const size_t es = esize(c);
+    const size_t nb[4] = {(size_t)c->nx * c->N, (size_t)c->nx * c->N, (size_t)c->nu * (c->N - 1), (size_t)c->nu * (c->N - 1)};
+    const void *src[4] = {x_min, x_max, u_min, u_max};
+    for (int w = 0; w < 4; ++w) {
+        const size_t bytes = (size_t)batch * nb[w] * es;
+        CUDA_TRY(c, cudaMalloc(&c->d_ib[w], bytes));
+        CUDA_TRY(c, cudaMemcpy(c->d_ib[w], src[w], bytes, mem == TMPC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    }
+    c->ib_batch = batch;
+    if (c->has_model && !build_model(c)) {
+        for (void *&p : c->d_ib) { if (p) cudaFree(p); p = nullptr; }
+        c->ib_batch = 0;
+        return fail(c, TMPC_ERR_UNSUPPORTED, "shape not compiled");
+    }
+    return TMPC_OK;
+}
+
 int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
 {
     if (!ctx || !a) return TMPC_ERR_INVALID;
@@ -1213,7 +1271,11 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
         return TMPC_OK;
     }
     if (a->mem != TMPC_MEM_HOST) return fail(c, TMPC_ERR_INVALID, "bad mem kind");
-    if (!warm && !getenv("TMPC_HOST_CHUNKED")) return solve_host_gated(c, a);
+    if (c->ib_batch && a->batch != c->ib_batch)
+        return fail(c, TMPC_ERR_INVALID, "batch differs from the batch of tmpc_set_instance_bounds");
+    if (!warm && (c->ib_batch || !getenv("TMPC_HOST_CHUNKED"))) return solve_host_gated(c, a);
+    if (c->ib_batch)   // the chunked pipeline launches per chunk with chunk-relative instance numbers
+        return fail(c, TMPC_ERR_UNSUPPORTED, "per-instance bounds with a warm start from host memory: use device buffers or tmpc_batch");
 
     // ---- host buffers: chunked 3-deep pipeline  H2D(k+1) | solve(k) | D2H(k-1) on three streams
     // input chunk image : x0 | [Xref per instance] | [warm d y z g v]

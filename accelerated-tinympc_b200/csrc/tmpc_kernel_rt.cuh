@@ -57,6 +57,8 @@ template <class T> struct ModelRT {
     T *scratch;       // [elements_per_lane][lanes]
     long long lanes;  // gridDim.x * blockDim.x
     int warm;
+    // per-instance box bounds (tmpc_set_instance_bounds): [instance][N][nx] / [instance][N-1][nu]; a null pair = the shared rows above
+    const T *ixmin, *ixmax, *iumin, *iumax;
 };
 
 // dynamic shared memory of one block
@@ -233,6 +235,8 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
         T pri_x = T(0), dua_x = T(0), pri_u = T(0), dua_u = T(0);
         for (int j = 0; j < nx; ++j) va[j * VS] = ld(oX0 + j);
         const T *bxl = P.xmin, *bxh = P.xmax, *bul = P.umin, *buh = P.umax;
+        if (P.ixmin) { bxl = P.ixmin + inst * XROW; bxh = P.ixmax + inst * XROW; }
+        if (P.iumin) { bul = P.iumin + inst * UROW; buh = P.iumax + inst * UROW; }
         for (int i = 0; i < NH; ++i) {
             T *pG = at(oG + i * nx), *pV = at(oV + i * nx), *pVn = at(oVn + i * nx), *pXo = at(oXo + i * nx);
             T *pD = at(oD + i * nu), *pY = at(oY + i * nu), *pZ = at(oZ + i * nu), *pZn = at(oZn + i * nu), *pU = at(oU + i * nu);

@@ -73,6 +73,17 @@ int tmpc_set_model(tmpc_ctx *ctx, const void *Kinf, const void *Pinf, const void
 int tmpc_set_settings(tmpc_ctx *ctx, double abs_pri_tol, double abs_dua_tol, int max_iter,
                       int check_termination, int en_state_bound, int en_input_bound);
 
+/* Per-instance box bounds: the wrapper's set_xmin / set_xmax / set_umin / set_umax (tiny_wrapper.cpp:43-129 fill
+ * work.x_min ... work.u_max of its ONE workspace) with a leading batch dimension.  Arrays of the ctx dtype,
+ *   x_min, x_max [batch][N][nx], u_min, u_max [batch][N-1][nu]  (host or device, `mem` = tmpc_mem); all four given.
+ * The library keeps its own device copy.  While set, tmpc_solve / tmpc_batch_solve must be called with exactly
+ * this batch; instance i is projected onto its own box (admm.cpp:53,59) -- en_state_bound / en_input_bound still
+ * switch each family off -- and the solve runs on the run-time-shape kernel in index order, for every shape.
+ * batch = 0 (pointers ignored) returns to the shared bounds of tmpc_set_model.  Not applied by tmpc_step and
+ * tmpc_solve_systems; a warm start from HOST memory is refused (use device buffers or a tmpc_batch). */
+int tmpc_set_instance_bounds(tmpc_ctx *ctx, int64_t batch, const void *x_min, const void *x_max, const void *u_min,
+                             const void *u_max, int32_t mem);
+
 /* State that is live across tiny_solve calls (read before written: admm.cpp:31,47-48,69-70,96,98), per
  * instance, IN PLACE: read at the start of the solve, left exactly as the reference leaves its workspace
  * (d from the last executed backward pass, v/z one iteration behind vnew/znew on an early exit).
@@ -148,7 +159,8 @@ int tmpc_step(tmpc_ctx *ctx, int which, int64_t batch, const tmpc_workspace *ws,
  * residuals.  Every solve is a warm start from whatever the workspace holds (exactly like tiny_solve); a new
  * batch is zero-filled like the examples' init block (quadrotor_hovering.cpp:49-71).
  * `mem` says where the caller's array lives (tmpc_mem).  Bounds and model are the ctx's (tmpc_set_model /
- * tmpc_set_settings: set_umin/set_umax/set_xmin/set_xmax of the wrapper apply to every instance of the ctx).
+ * tmpc_set_settings: set_umin/set_umax/set_xmin/set_xmax of the wrapper apply to every instance of the ctx;
+ * tmpc_set_instance_bounds gives every instance its own).
  * All work is queued on the ctx's stream; calls with host arrays return when the copy is complete. */
 typedef struct tmpc_batch tmpc_batch;
 int tmpc_batch_create(tmpc_ctx *ctx, int64_t batch, tmpc_batch **out);
