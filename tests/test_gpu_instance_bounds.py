@@ -120,3 +120,34 @@ def test_instance_bounds_device_warm(pkg, oracle):
             assert_same(warm[k].cpu().numpy(), ref["state"][k], "round %d state %s" % (rnd, k))
         state = ref["state"]
     s.close()
+
+
+def test_instance_bounds_wrapper_calls(pkg, oracle):
+    """The wrapper's sequence with a batch dimension (tiny_wrapper.cpp:5-176): set_x0 / set_xref / set_*min,max per instance /
+    call_tiny_solve / get_x / get_u, then reset_dual_variables and a second solve from the workspace the first one left."""
+    capi = pkg.capi
+    B, dt = 131, np.float32
+    prob = pkg.problems.quadrotor(20)
+    x0, xref = pkg.workloads.quadrotor_hover_batch(9, 9 + B, mult=0.5)
+    boxes = _boxes(prob, B, np.random.default_rng(4), dt)
+    s = capi.Solver(prob, dtype=dt, policy="parity")
+    s.set_instance_bounds(*boxes)
+    b = capi.Batch(s, B)
+    b.set_x0(x0)
+    b.set_xref(xref)
+    b.solve()
+    r1 = _oracle_each(oracle, prob, x0, xref, boxes, dt, want_state=True)
+    _cmp({k: b.get(k) for k in ("iter", "status", "x", "u", "resid")}, r1, "first solve")
+    for k in ("d", "y", "g", "v", "z"):
+        assert_same(b.get(k), r1["state"][k], "workspace." + k)
+    x1 = (x0 * np.float32(0.97)).astype(np.float32)
+    b.set_x0(x1)
+    b.reset_dual_variables()
+    b.solve()
+    warm = {k: r1["state"][k].copy() for k in ("d", "y", "g", "v", "z")}
+    warm["y"][:] = 0
+    warm["g"][:] = 0
+    r2 = _oracle_each(oracle, prob, x1, xref, boxes, dt, warm=warm, want_state=True)
+    _cmp({k: b.get(k) for k in ("iter", "status", "x", "u", "resid")}, r2, "second solve")
+    b.close()
+    s.close()
