@@ -32,6 +32,7 @@ def test_create_rejects_bad_arguments(pkg):
     assert lib.tmpc_create(ctypes.byref(ctx), 0, 7, 3, 1, 0, 0) == -2      # horizon < 2
     assert lib.tmpc_create(ctypes.byref(ctx), 0, 12, 4, 10, 9, 0) == -1     # bad dtype
     assert lib.tmpc_create(None, 0, 12, 4, 10, 0, 0) == -1
+    assert lib.tmpc_set_instance_bounds(None, 4, None, None, None, None, 0) == -1   # no ctx: refused before any device call
 
 
 @pytest.mark.skipif(has_cuda(), reason="only meaningful on a box without a GPU")
