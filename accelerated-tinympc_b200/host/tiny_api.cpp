@@ -300,6 +300,16 @@ int tiny_solve_batch(TinySolver *s, const TinyBatchIn *in, TinyBatchOut *out)
     return 0;
 }
 
+int tiny_set_instance_bounds(TinySolver *s, int64_t batch, const tinytype *x_min, const tinytype *x_max, const tinytype *u_min,
+                             const tinytype *u_max, int on_device)
+{
+    if (!s) return fail("tiny_set_instance_bounds: NULL argument");
+    if (sync_model(s) != 0) return -1;   // creates the ctx on first use
+    int rc = tmpc_set_instance_bounds(backend(s)->ctx, batch, x_min, x_max, u_min, u_max, on_device ? TMPC_MEM_DEVICE : TMPC_MEM_HOST);
+    if (rc != TMPC_OK) return fail(std::string("tmpc_set_instance_bounds: ") + tmpc_last_error(backend(s)->ctx));
+    return 0;
+}
+
 void forward_pass(TinySolver *s) { run_step(s, 0, nullptr); }
 void update_slack(TinySolver *s) { run_step(s, 1, nullptr); }
 void update_dual(TinySolver *s) { run_step(s, 2, nullptr); }

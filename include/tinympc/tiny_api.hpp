@@ -51,6 +51,14 @@ typedef struct {
  * (instances that stop at max_iter have status 11), negative = error. */
 int tiny_solve_batch(TinySolver *solver, const TinyBatchIn *in, TinyBatchOut *out);
 
+/* One box per instance for tiny_solve_batch: the wrapper's set_xmin / set_xmax / set_umin / set_umax
+ * (tiny_wrapper.cpp:43-129) with a leading batch dimension.  x_min, x_max [batch][N][nx], u_min, u_max [batch][N-1][nu]
+ * (host arrays, or device arrays when on_device != 0); copied.  While set, tiny_solve_batch must be called with exactly
+ * this batch (tiny_solve itself, one instance, is refused); batch = 0 returns to the bounds of solver->work.
+ * Forwards to tmpc_set_instance_bounds (include/tmpc.h). */
+int tiny_set_instance_bounds(TinySolver *solver, int64_t batch, const tinytype *x_min, const tinytype *x_max,
+                             const tinytype *u_min, const tinytype *u_max, int on_device);
+
 /* policy 0 = bit-exact order of the reference's -O3 SSE2 build (default), 1 = FMA-contracted */
 int tiny_set_order_policy(TinySolver *solver, int policy);
 

@@ -120,3 +120,13 @@ def test_host_api_codegen_random_example(tag, rel):
     np.testing.assert_allclose(xN, exp[1], rtol=rel)
     K = [float(t) for t in re.search(r"Kinf (\S+) (\S+) (\S+) (\S+)", out).groups()]
     np.testing.assert_allclose(K, [1.3597774779741059, -0.6322783070376652, 0.53346352483974, -0.10662252458139154], rtol=1e-6 if tag == "f32" else 1e-10)
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_host_api_instance_bounds_example(tag):
+    """tiny_set_instance_bounds in front of tiny_solve_batch (host/examples/instance_bounds.cpp, self-checking): same boxes ->
+    bit-identical to the shared-bounds solve, tighter boxes on odd instances change only those, another batch size is
+    refused, clearing restores the shared-bounds results."""
+    p = subprocess.run([os.path.join(BIN, "instance_bounds_" + tag)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "instance bounds ok" in p.stdout
