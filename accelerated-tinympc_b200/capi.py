@@ -23,7 +23,10 @@ EXPORTS = ["tmpc_create", "tmpc_destroy", "tmpc_set_model", "tmpc_set_settings",
            "tmpc_batch_create", "tmpc_batch_destroy", "tmpc_batch_set_x0", "tmpc_batch_set_xref", "tmpc_batch_set_xref_table",
            "tmpc_batch_reset_dual_variables", "tmpc_batch_reset", "tmpc_batch_solve", "tmpc_batch_get", "tmpc_batch_rollout",
            "tmpc_batch_last_rollout_ms", "tmpc_batch_last_error",
-           "tmpc_systems_precompute", "tmpc_systems_destroy", "tmpc_systems_get", "tmpc_solve_systems"]
+           "tmpc_systems_precompute", "tmpc_systems_destroy", "tmpc_systems_get", "tmpc_solve_systems",
+           "tmpc_multi_create", "tmpc_multi_destroy", "tmpc_multi_device_count", "tmpc_multi_ctx", "tmpc_multi_set_model",
+           "tmpc_multi_set_settings", "tmpc_multi_set_instance_bounds", "tmpc_multi_solve", "tmpc_multi_get_stats",
+           "tmpc_multi_last_error", "tmpc_device_count"]
 
 SYS = {"Kinf": 0, "Pinf": 1, "Quu_inv": 2, "AmBKt": 3, "Adyn": 4, "Bdyn": 5, "Q": 6, "rho": 7, "sweeps": 8}
 
@@ -37,7 +40,8 @@ class TmpcWarm(C.Structure):
 class TmpcSolveArgs(C.Structure):
     _fields_ = [("batch", C.c_int64), ("x0", C.c_void_p), ("Xref", C.c_void_p), ("xref_shared", C.c_int32),
                 ("mem", C.c_int32), ("warm", C.POINTER(TmpcWarm)), ("x", C.c_void_p), ("u", C.c_void_p),
-                ("iter", C.c_void_p), ("status", C.c_void_p), ("resid", C.c_void_p), ("stream", C.c_void_p)]
+                ("iter", C.c_void_p), ("status", C.c_void_p), ("resid", C.c_void_p), ("stream", C.c_void_p),
+                ("u0", C.c_void_p)]
 
 
 class TmpcWorkspace(C.Structure):
@@ -114,12 +118,71 @@ def load():
     lib.tmpc_systems_get.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.tmpc_solve_systems.restype = C.c_int
     lib.tmpc_solve_systems.argtypes = [C.c_void_p, C.POINTER(TmpcSolveArgs), C.c_void_p]
+    lib.tmpc_multi_create.restype = C.c_int
+    lib.tmpc_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.tmpc_multi_destroy.restype = C.c_int
+    lib.tmpc_multi_destroy.argtypes = [C.c_void_p]
+    lib.tmpc_multi_device_count.restype = C.c_int
+    lib.tmpc_multi_device_count.argtypes = [C.c_void_p]
+    lib.tmpc_multi_ctx.restype = C.c_void_p
+    lib.tmpc_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+    lib.tmpc_multi_set_model.restype = C.c_int
+    lib.tmpc_multi_set_model.argtypes = [C.c_void_p] + [C.c_void_p] * 7 + [C.c_double] + [C.c_void_p] * 4
+    lib.tmpc_multi_set_settings.restype = C.c_int
+    lib.tmpc_multi_set_settings.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.tmpc_multi_set_instance_bounds.restype = C.c_int
+    lib.tmpc_multi_set_instance_bounds.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4
+    lib.tmpc_multi_solve.restype = C.c_int
+    lib.tmpc_multi_solve.argtypes = [C.c_void_p, C.POINTER(TmpcSolveArgs)]
+    lib.tmpc_multi_get_stats.restype = C.c_int
+    lib.tmpc_multi_get_stats.argtypes = [C.c_void_p, C.POINTER(TmpcStats), C.c_void_p]
+    lib.tmpc_multi_last_error.restype = C.c_char_p
+    lib.tmpc_multi_last_error.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
 
 class TmpcError(RuntimeError):
     pass
+
+
+def make_solve_args(batch, x0, Xref, xref_shared, mem, x=None, u=None, it=None, status=None, resid=None, warm=None,
+                    stream=None, u0=None):
+    """tmpc_solve_args from address providers (numpy / torch / int / None).  Returns (args, keep-alive)."""
+    args = TmpcSolveArgs()
+    args.batch = batch
+    args.x0 = _addr(x0)
+    args.Xref = _addr(Xref)
+    args.xref_shared = 1 if xref_shared else 0
+    args.mem = mem
+    w = None
+    if warm is not None:
+        w = TmpcWarm()
+        for k in ("d", "y", "g", "v", "z"):
+            setattr(w, k, _addr(warm[k]))
+        args.warm = C.pointer(w)
+    args.x, args.u, args.iter, args.status, args.resid = _addr(x), _addr(u), _addr(it), _addr(status), _addr(resid)
+    args.u0 = _addr(u0)
+    args.stream = stream
+    return args, w
+
+
+def host_io(s, x0, Xref, warm, outputs):
+    """numpy inputs checked / cast for a solver-like object `s` (dtype, nx, nu, N) + empty output arrays for `outputs`."""
+    dt = s.dtype
+    x0 = np.ascontiguousarray(x0, dtype=dt).reshape(-1, s.nx)
+    B = x0.shape[0]
+    Xref = np.ascontiguousarray(Xref, dtype=dt)
+    shared = Xref.size == s.N * s.nx
+    if not shared and Xref.size != B * s.N * s.nx:
+        raise ValueError("Xref must be [N,nx] or [B,N,nx]")
+    shapes = {"x": ((B, s.N, s.nx), dt), "u": ((B, s.N - 1, s.nu), dt), "u0": ((B, s.nu), dt),
+              "iter": ((B,), np.int32), "status": ((B,), np.int32), "resid": ((B, 4), dt)}
+    out = {k: np.empty(*shapes[k]) for k in outputs}
+    if warm is not None:
+        warm = {k: np.ascontiguousarray(warm[k], dtype=dt) for k in ("d", "y", "g", "v", "z")}
+        out["warm"] = warm
+    return x0, Xref, shared, out, warm
 
 
 def _addr(a):
@@ -184,40 +247,17 @@ class Solver:
                                                       TMPC_MEM_HOST), "tmpc_set_instance_bounds")
 
     def solve_raw(self, batch, x0, Xref, xref_shared, mem, x=None, u=None, it=None, status=None, resid=None,
-                  warm=None, stream=None):
+                  warm=None, stream=None, u0=None):
         """Thin call: every array argument is an address provider (numpy / torch / int) or None."""
-        args = TmpcSolveArgs()
-        args.batch = batch
-        args.x0 = _addr(x0)
-        args.Xref = _addr(Xref)
-        args.xref_shared = 1 if xref_shared else 0
-        args.mem = mem
-        w = None
-        if warm is not None:
-            w = TmpcWarm()
-            for k in ("d", "y", "g", "v", "z"):
-                setattr(w, k, _addr(warm[k]))
-            args.warm = C.pointer(w)
-        args.x, args.u, args.iter, args.status, args.resid = _addr(x), _addr(u), _addr(it), _addr(status), _addr(resid)
-        args.stream = stream
+        args, keep = make_solve_args(batch, x0, Xref, xref_shared, mem, x, u, it, status, resid, warm, stream, u0)
         self._check(self.lib.tmpc_solve(self._ctx, C.byref(args)), "tmpc_solve")
 
-    def solve(self, x0, Xref, warm=None):
-        """Host-array convenience (numpy in, numpy out) through TMPC_MEM_HOST."""
-        dt = self.dtype
-        x0 = np.ascontiguousarray(x0, dtype=dt).reshape(-1, self.nx)
-        B = x0.shape[0]
-        Xref = np.ascontiguousarray(Xref, dtype=dt)
-        shared = Xref.size == self.N * self.nx
-        if not shared and Xref.size != B * self.N * self.nx:
-            raise ValueError("Xref must be [N,nx] or [B,N,nx]")
-        out = {"x": np.empty((B, self.N, self.nx), dt), "u": np.empty((B, self.N - 1, self.nu), dt),
-               "iter": np.empty(B, np.int32), "status": np.empty(B, np.int32), "resid": np.empty((B, 4), dt)}
-        if warm is not None:
-            warm = {k: np.ascontiguousarray(warm[k], dtype=dt) for k in ("d", "y", "g", "v", "z")}
-            out["warm"] = warm
-        self.solve_raw(B, x0, Xref, shared, TMPC_MEM_HOST, out["x"], out["u"], out["iter"], out["status"],
-                       out["resid"], warm=warm)
+    def solve(self, x0, Xref, warm=None, outputs=("x", "u", "iter", "status", "resid")):
+        """Host-array convenience (numpy in, numpy out) through TMPC_MEM_HOST.  `outputs` is the output mask: any of
+        x, u, u0 (= u(:,0) alone), iter, status, resid."""
+        x0, Xref, shared, out, warm = host_io(self, x0, Xref, warm, outputs)
+        self.solve_raw(x0.shape[0], x0, Xref, shared, TMPC_MEM_HOST, out.get("x"), out.get("u"), out.get("iter"),
+                       out.get("status"), out.get("resid"), warm=warm, u0=out.get("u0"))
         return out
 
     def step(self, which, ws, it=1):
@@ -245,6 +285,84 @@ class Solver:
         if self._ctx:
             self.lib.tmpc_destroy(self._ctx)
             self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Multi:
+    """tmpc_multi: one host batch over several devices from one process (one ctx + one host worker thread per device,
+    contiguous instance ranges, no inter-device traffic).  devices: None = every visible device, an int n = the first n,
+    or a list of device indices."""
+
+    def __init__(self, prob, dtype=np.float32, policy="parity", devices=None):
+        self.lib = load()
+        self.prob = prob
+        self.dtype = np.dtype(dtype)
+        self.nx, self.nu, self.N = prob.nx, prob.nu, prob.N
+        self._m = C.c_void_p()
+        pol = {"parity": TMPC_ORDER_PARITY, "fast": TMPC_ORDER_FAST}[policy]
+        if devices is None:
+            n, arr = 0, None
+        elif isinstance(devices, int):
+            n, arr = devices, None
+        else:
+            n, arr = len(devices), (C.c_int * len(devices))(*devices)
+        rc = self.lib.tmpc_multi_create(C.byref(self._m), n, arr, prob.nx, prob.nu, prob.N,
+                                        TMPC_F32 if self.dtype == np.float32 else TMPC_F64, pol)
+        if rc != 0:
+            raise TmpcError("tmpc_multi_create: %d %s" % (rc, self.lib.tmpc_multi_last_error(None).decode()))
+        a = prob.cast(self.dtype)
+        self._model_keep = a
+        p = lambda k: _addr(a[k])
+        self._check(self.lib.tmpc_multi_set_model(self._m, p("Kinf"), p("Pinf"), p("Quu_inv"), p("AmBKt"), p("Adyn"), p("Bdyn"),
+                                                  p("Q"), float(prob.rho), p("x_min"), p("x_max"), p("u_min"), p("u_max")),
+                    "tmpc_multi_set_model")
+        self._check(self.lib.tmpc_multi_set_settings(self._m, prob.abs_pri_tol, prob.abs_dua_tol, prob.max_iter,
+                                                     prob.check_termination, prob.en_state_bound, prob.en_input_bound),
+                    "tmpc_multi_set_settings")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise TmpcError("%s: %d %s" % (what, rc, self.lib.tmpc_multi_last_error(self._m).decode()))
+
+    @property
+    def device_count(self):
+        return int(self.lib.tmpc_multi_device_count(self._m))
+
+    def set_instance_bounds(self, x_min=None, x_max=None, u_min=None, u_max=None):
+        if x_min is None:
+            return self._check(self.lib.tmpc_multi_set_instance_bounds(self._m, 0, None, None, None, None), "tmpc_multi_set_instance_bounds")
+        a = [np.ascontiguousarray(v, dtype=self.dtype) for v in (x_min, x_max, u_min, u_max)]
+        self._ib_keep = a
+        self._check(self.lib.tmpc_multi_set_instance_bounds(self._m, a[0].shape[0], _addr(a[0]), _addr(a[1]), _addr(a[2]), _addr(a[3])),
+                    "tmpc_multi_set_instance_bounds")
+
+    def solve_raw(self, batch, x0, Xref, xref_shared, x=None, u=None, it=None, status=None, resid=None, warm=None, u0=None):
+        args, keep = make_solve_args(batch, x0, Xref, xref_shared, TMPC_MEM_HOST, x, u, it, status, resid, warm, None, u0)
+        self._check(self.lib.tmpc_multi_solve(self._m, C.byref(args)), "tmpc_multi_solve")
+
+    def solve(self, x0, Xref, warm=None, outputs=("x", "u", "iter", "status", "resid")):
+        x0, Xref, shared, out, warm = host_io(self, x0, Xref, warm, outputs)
+        self.solve_raw(x0.shape[0], x0, Xref, shared, out.get("x"), out.get("u"), out.get("iter"), out.get("status"),
+                       out.get("resid"), warm=warm, u0=out.get("u0"))
+        return out
+
+    def stats(self):
+        n = self.device_count
+        tot, per = TmpcStats(), (TmpcStats * n)()
+        self._check(self.lib.tmpc_multi_get_stats(self._m, C.byref(tot), per), "tmpc_multi_get_stats")
+        d = {f[0]: getattr(tot, f[0]) for f in TmpcStats._fields_}
+        d["per_device"] = [{f[0]: getattr(per[i], f[0]) for f in TmpcStats._fields_} for i in range(n)]
+        return d
+
+    def close(self):
+        if self._m:
+            self.lib.tmpc_multi_destroy(self._m)
+            self._m = C.c_void_p()
 
     def __del__(self):
         try:

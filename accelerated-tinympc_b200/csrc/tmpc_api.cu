@@ -48,6 +48,10 @@ struct tmpc_ctx_impl {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // Launches of one ctx share the work counter, the statistics slot, the scheduling buffers and the run-time-shape scratch:
+    // they are serialised on the device through this event, whatever stream each one is queued on (order_after_previous).
+    cudaEvent_t last_launch = nullptr;
+    bool launched = false;
     int sm_count = 0;
     // model image exactly as the kernel's Model<T,...> struct (built on the host, passed by value)
     std::vector<unsigned char> model;      // tmpc::Model<T,...> image
@@ -668,6 +672,7 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     const void *sys;
     unsigned *gate;
     const unsigned *order;
+    void *u0;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
@@ -677,6 +682,19 @@ void *model_param(tmpc_ctx_impl *c, const KernelInfo &ki)
     if (ki.model_kind == 2) return (void *)&c->model_w;
     if (ki.model_kind == 3) return (void *)c->model_rt.data();
     return ki.model_kind == 1 ? (void *)c->model_f32.data() : (void *)c->model.data();
+}
+
+// Everything a launch of this ctx does on `s` from here on runs after the previous launch of the ctx has finished.
+int order_after_previous(tmpc_ctx_impl *c, cudaStream_t s)
+{
+    if (c->launched) CUDA_TRY(c, cudaStreamWaitEvent(s, c->last_launch, 0));
+    return TMPC_OK;
+}
+int mark_launch(tmpc_ctx_impl *c, cudaStream_t s)
+{
+    CUDA_TRY(c, cudaEventRecord(c->last_launch, s));
+    c->launched = true;
+    return TMPC_OK;
 }
 
 // Grid of the persistent kernel for `da.batch` instances; for the run-time-shape kernel also its per-lane scratch and
@@ -731,6 +749,10 @@ int plan_launch(tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da, cudaS
 // Launch one persistent kernel (already chosen) for one device-resident batch on `s`.
 int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cudaStream_t s, bool time_it, bool ev0_done = false)
 {
+    {
+        const int rc = order_after_previous(c, s);   // (a no-op wait when the caller already ordered this stream)
+        if (rc != TMPC_OK) return rc;
+    }
     CUDA_TRY(c, cudaFuncSetAttribute(ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
     CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), s));
     da.counter = c->d_counter;
@@ -744,6 +766,10 @@ int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cuda
     if (time_it && !ev0_done) CUDA_TRY(c, cudaEventRecord(c->ev0, s));
     CUDA_TRY(c, cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, s));
     if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev1, s));
+    {
+        const int rc = mark_launch(c, s);
+        if (rc != TMPC_OK) return rc;
+    }
     c->stats.launches += 1;
     c->stats.lanes = (int32_t)(blocks * ki.per_block);
     c->stats.pattern = c->pattern;
@@ -818,8 +844,16 @@ bool lpt_wanted(const tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da)
     return da.batch >= 2 * lanes && da.batch >= 16384;
 }
 
-// K / k_stride: Kinf (column-major) of instance i at K + i * k_stride; default = the ctx's shared Kinf
-int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = nullptr, long long k_stride = 0)
+__global__ void iota_kernel(unsigned *__restrict__ out, long long n, unsigned offset)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = offset + (unsigned)i;
+}
+
+// K / k_stride: Kinf (column-major) of instance i at K + i * k_stride; default = the ctx's shared Kinf.
+// tail > 0 (host pipeline): only the LEADING `tail` instances are ranked; the claim order becomes
+// [tail, tail+1, ..., batch-1, the leading `tail` instances longest-expected-first].
+int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = nullptr, long long k_stride = 0, long long tail = 0)
 {
     if (!K) { K = c->d_kinf; k_stride = 0; }
     const size_t B = (size_t)da.batch;
@@ -837,17 +871,23 @@ int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = n
         c->lpt_cap = B;
     }
     unsigned *keys_in = c->lpt_buf, *keys_out = keys_in + c->lpt_cap, *vals_in = keys_out + c->lpt_cap, *vals_out = vals_in + c->lpt_cap;
-    const unsigned blocks = (unsigned)((B + 255) / 256);
+    const size_t n_rank = tail > 0 ? (size_t)tail : B;
+    unsigned *sorted_out = vals_out + (B - n_rank);
+    if (n_rank < B) {
+        iota_kernel<<<(unsigned)((B - n_rank + 255) / 256), 256, 0, s>>>(vals_out, (long long)(B - n_rank), (unsigned)n_rank);
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    const unsigned blocks = (unsigned)((n_rank + 255) / 256);
     if (c->dtype == TMPC_F32)
-        lpt_key_kernel<float><<<blocks, 256, 0, s>>>(da.batch, c->nx, c->nu, (const float *)K, k_stride, (const float *)da.x0, (const float *)da.Xref,
+        lpt_key_kernel<float><<<blocks, 256, 0, s>>>((long long)n_rank, c->nx, c->nu, (const float *)K, k_stride, (const float *)da.x0, (const float *)da.Xref,
                                                      da.xref_stride, keys_in, vals_in);
     else
-        lpt_key_kernel<double><<<blocks, 256, 0, s>>>(da.batch, c->nx, c->nu, (const double *)K, k_stride, (const double *)da.x0,
+        lpt_key_kernel<double><<<blocks, 256, 0, s>>>((long long)n_rank, c->nx, c->nu, (const double *)K, k_stride, (const double *)da.x0,
                                                       (const double *)da.Xref, da.xref_stride, keys_in, vals_in);
     CUDA_TRY(c, cudaGetLastError());
     size_t tb = c->lpt_temp_bytes;
-    CUDA_TRY(c, cub::DeviceRadixSort::SortPairsDescending(c->lpt_temp, tb, (const unsigned *)keys_in, keys_out, (const unsigned *)vals_in, vals_out,
-                                                           (int)B, 16, 32, s));
+    CUDA_TRY(c, cub::DeviceRadixSort::SortPairsDescending(c->lpt_temp, tb, (const unsigned *)keys_in, keys_out, (const unsigned *)vals_in, sorted_out,
+                                                           (int)n_rank, 16, 32, s));
     da.order = vals_out;
     c->stats.launches += 1;   // the key kernel (the sort's kernels are CUB's)
     return TMPC_OK;
@@ -865,8 +905,12 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
     } else if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern | (c->const_bounds ? 0x100 : 0)))
         return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
     bool ev0_done = false;
-    c->lpt_used = 0;
-    if (!da.sys && !c->ib_batch && lpt_wanted(c, ki, da)) {
+    c->lpt_used = da.order ? 2 : 0;   // 2: the caller (host pipeline) brought its own claim order
+    {
+        const int rc = order_after_previous(c, s);   // the scheduling buffers may still be read by the previous launch
+        if (rc != TMPC_OK) return rc;
+    }
+    if (!da.sys && !c->ib_batch && !da.order && lpt_wanted(c, ki, da)) {
         // the pre-pass is part of the solve: it runs on the same stream inside the timed region
         if (time_it) { CUDA_TRY(c, cudaEventRecord(c->ev0, s)); ev0_done = true; }
         const int rc = lpt_prepare(c, da, s);
@@ -935,6 +979,11 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
             cudaGetLastError();
         wait32_probed = true;
     }
+    // TMPC_NO_STREAM_MEMOPS=1: behave as on a driver without stream memory operations (plain copy after the kernel, inputs
+    // complete before the launch) -- the fallback is exercised by the tests through this switch
+    const bool memops = !getenv("TMPC_NO_STREAM_MEMOPS");
+    const wait_value32_fn waitf = memops ? wait32 : nullptr;
+    const write_value32_fn writef = memops ? write32 : nullptr;
     // 65,536 instances per D2H chunk.  The read-back is PCIe-bound from its first byte (the kernel produces 57 GB/s of outputs,
     // PCIe carries 56): smaller chunks (measured 16K: +5 %, 4K: +35 % time) or small leading chunks (+1 %) only add per-copy cost.
     int shift = 16;
@@ -942,9 +991,14 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     while (shift > 10 && (B >> shift) < 8) --shift;   // small batches: at least ~8 chunks, >= 1024 instances each
     const int64_t CH = (int64_t)1 << shift;
     const int nch = (int)((B + CH - 1) / CH);
-    // device image: in = x0 | [Xref];  out = x | u | iter | status | resid
+    // device image: in = x0 | [Xref];  out = whichever of x | u | u0 | iter | status | resid the caller asked for
     const size_t in_bytes = (size_t)B * nx * es + (a->xref_shared ? xrow * es : (size_t)B * xrow * es);
-    const size_t out_bytes = (size_t)B * ((xrow + urow + 4) * es + 8) + 64;
+    auto a16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+    size_t o = 0;
+    auto region = [&](const void *want, size_t per) -> size_t { const size_t at = o; if (want) o = a16(o + (size_t)B * per); return at; };
+    const size_t o_x = region(a->x, xrow * es), o_u = region(a->u, urow * es), o_u0 = region(a->u0, nu * es);
+    const size_t o_it = region(a->iter, 4), o_st = region(a->status, 4), o_rs = region(a->resid, 4 * es);
+    const size_t out_bytes = o + 64;
     if (c->g_in_bytes < in_bytes) {
         if (c->g_in) cudaFree(c->g_in);
         c->g_in = nullptr; c->g_in_bytes = 0;
@@ -968,66 +1022,111 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     cudaStream_t s = c->stream;
     char *din = (char *)c->g_in;
     char *d_x0 = din, *d_xref = din + (size_t)B * nx * es;
+    DevArgs da{};
+    da.batch = B; da.x0 = d_x0; da.Xref = d_xref; da.xref_stride = a->xref_shared ? 0 : (long long)xrow;
     // Inputs: the H2D of x0 (and of per-instance Xref) is OVERLAPPED with the kernel.  It runs in 131,072-instance chunks on
     // its own stream; after each chunk a stream memory operation advances an arrival counter; the kernel starts as soon
     // as the first chunk is in and its lanes check the counter before touching an instance (gate_wait).  Everything is
     // enqueued before the kernel launch, so even a staged (pageable) copy cannot wait on the kernel.
-    const bool overlap = write32 != nullptr && B < (int64_t)0xffffffffu && !getenv("TMPC_NO_H2D_OVERLAP");
+    const bool overlap = writef != nullptr && B < (int64_t)0xffffffffu && !getenv("TMPC_NO_H2D_OVERLAP");
     if (!c->g_in_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->g_in_stream, cudaStreamNonBlocking));
     if (!c->g_first) CUDA_TRY(c, cudaEventCreateWithFlags(&c->g_first, cudaEventDisableTiming));
     if (!c->g_gate) CUDA_TRY(c, cudaMalloc((void **)&c->g_gate, 2 * sizeof(unsigned)));
     cudaStream_t hs = c->g_in_stream;
+    {
+        // the previous launch of this ctx may still read the input image, the claim order or the gate
+        const int rc = order_after_previous(c, hs);
+        if (rc != TMPC_OK) return rc;
+    }
     CUDA_TRY(c, cudaMemsetAsync(c->g_gate, 0, 2 * sizeof(unsigned), hs));
     if (a->xref_shared) CUDA_TRY(c, cudaMemcpyAsync(d_xref, a->Xref, xrow * es, cudaMemcpyHostToDevice, hs));
+    // Tail-sorted schedule.  Claimed in index order, a launch ends with a tail in which a few lanes finish max_iter-long
+    // instances while the rest of the GPU idles (+7.5 % on the hover workload); the full longest-expected-first order of the
+    // device path needs every x0 before the first claim, i.e. no H2D overlap.  Middle way: the LEADING quarter of the batch
+    // goes over first, is ranked by the same key (lpt_prepare, on the input stream, before the kernel starts: the persistent
+    // kernel fills every SM, nothing could run beside it) and is claimed LAST, longest first; the other three quarters
+    // stream in behind the running kernel and are claimed in index order.  Simulated on the hover workload's real iteration
+    // counts: makespan 1.018 x the mean lane load (index order 1.075, fully sorted 1.013).
+    int64_t T0 = 0;
+    {
+        KernelInfo ki;
+        const char *e = getenv("TMPC_LPT");
+        const bool off = e && !strcmp(e, "0");
+        if (!off && overlap && a->xref_shared && !c->ib_batch && c->d_kinf && nch >= 8 &&
+            lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, false, ki, c->pattern | (c->const_bounds ? 0x100 : 0)) &&
+            B >= 2 * (int64_t)ki.per_block * c->sm_count && B >= 16384)
+            T0 = ((B / 4 + CH - 1) / CH) * CH;
+    }
     const int64_t ICH = overlap ? 131072 : B;
-    for (int64_t b0 = 0; b0 < B; b0 += ICH) {
-        const int64_t n = std::min<int64_t>(ICH, B - b0);
+    const bool gate_stall_test = getenv("TMPC_TEST_GATE_STALL") != nullptr;
+    auto h2d = [&](int64_t b0, int64_t n) -> int {
         CUDA_TRY(c, cudaMemcpyAsync(d_x0 + b0 * nx * es, (const char *)a->x0 + b0 * nx * es, (size_t)n * nx * es, cudaMemcpyHostToDevice, hs));
         if (!a->xref_shared)
             CUDA_TRY(c, cudaMemcpyAsync(d_xref + b0 * xrow * es, (const char *)a->Xref + b0 * xrow * es, (size_t)n * xrow * es,
                                         cudaMemcpyHostToDevice, hs));
-        if (overlap && write32(hs, (unsigned long long)(uintptr_t)c->g_gate, (unsigned)(b0 + n), 0u) != 0)
+        return TMPC_OK;
+    };
+    int64_t fed = 0;
+    if (T0 > 0) {
+        int rc = h2d(0, T0);
+        if (rc != TMPC_OK) return rc;
+        if ((rc = lpt_prepare(c, da, hs, nullptr, 0, T0)) != TMPC_OK) return rc;
+        if (writef(hs, (unsigned long long)(uintptr_t)c->g_gate, (unsigned)T0, 0u) != 0) return fail(c, TMPC_ERR_CUDA, "cuStreamWriteValue32 failed");
+        CUDA_TRY(c, cudaEventRecord(c->g_first, hs));
+        fed = T0;
+    }
+    for (int64_t b0 = fed; b0 < B; b0 += ICH) {
+        const int64_t n = std::min<int64_t>(ICH, B - b0);
+        const int rc = h2d(b0, n);
+        if (rc != TMPC_OK) return rc;
+        // TMPC_TEST_GATE_STALL=1 (tests): the last arrival is never announced, so the lanes that claim those instances give up
+        if (overlap && !(gate_stall_test && b0 + n >= B) &&
+            writef(hs, (unsigned long long)(uintptr_t)c->g_gate, (unsigned)(b0 + n), 0u) != 0)
             return fail(c, TMPC_ERR_CUDA, "cuStreamWriteValue32 failed");
         if (b0 == 0) CUDA_TRY(c, cudaEventRecord(c->g_first, hs));
     }
     if (!overlap) CUDA_TRY(c, cudaEventRecord(c->g_first, hs));   // everything must be in before the kernel starts
+    {
+        const int rc = order_after_previous(c, s);   // ... and the completion counters / output image
+        if (rc != TMPC_OK) return rc;
+    }
     CUDA_TRY(c, cudaMemsetAsync(c->g_done, 0, sizeof(unsigned) * nch, s));
     CUDA_TRY(c, cudaStreamWaitEvent(s, c->g_first, 0));
     // the copy stream must not evaluate its waits against counters left by a previous solve
     CUDA_TRY(c, cudaEventRecord(c->g_h2d, s));
     CUDA_TRY(c, cudaStreamWaitEvent(c->g_copy, c->g_h2d, 0));
     char *dout = (char *)c->g_out;
-    auto a16 = [](size_t v) { return (v + 15) & ~size_t(15); };
-    size_t o = 0;
-    char *d_x = dout + o; o = a16(o + (size_t)B * xrow * es);
-    char *d_u = dout + o; o = a16(o + (size_t)B * urow * es);
-    char *d_it = dout + o; o = a16(o + (size_t)B * 4);
-    char *d_st = dout + o; o = a16(o + (size_t)B * 4);
-    char *d_rs = dout + o;
-    DevArgs da{};
-    da.batch = B; da.x0 = d_x0; da.Xref = d_xref; da.xref_stride = a->xref_shared ? 0 : (long long)xrow;
-    da.x = d_x; da.u = d_u; da.iter = (int *)d_it; da.status = (int *)d_st; da.resid = d_rs;
-    da.done = wait32 ? c->g_done : nullptr;
+    char *d_x = dout + o_x, *d_u = dout + o_u, *d_u0 = dout + o_u0, *d_it = dout + o_it, *d_st = dout + o_st, *d_rs = dout + o_rs;
+    da.x = a->x ? d_x : nullptr; da.u = a->u ? d_u : nullptr; da.u0 = a->u0 ? d_u0 : nullptr;
+    da.iter = a->iter ? (int *)d_it : nullptr; da.status = a->status ? (int *)d_st : nullptr; da.resid = a->resid ? d_rs : nullptr;
+    da.done = waitf ? c->g_done : nullptr;
     da.done_shift = shift;
     da.gate = overlap ? c->g_gate : nullptr;
     int rc = launch_device(c, da, false, s, true);
     if (rc != TMPC_OK) return rc;
     cudaStream_t cs = c->g_copy;
-    if (!wait32) {                                      // no stream mem-ops available: plain copy after the kernel
+    if (waitf) {
+        // Whatever happened inside the kernel (a lane that gave up at the input gate never reports its instance), the copy
+        // stream must drain: once the kernel is over every completion counter is released.
+        CUDA_TRY(c, cudaMemsetAsync(c->g_done, 0xff, sizeof(unsigned) * nch, s));
+    } else {                                            // no stream mem-ops available: plain copy after the kernel
         CUDA_TRY(c, cudaEventRecord(c->g_h2d, s));
         CUDA_TRY(c, cudaStreamWaitEvent(cs, c->g_h2d, 0));
     }
-    for (int k = 0; k < nch; ++k) {
+    // chunks in the order they complete: the index-ordered part first, the tail-sorted leading part last
+    const int k_first = (int)(T0 / CH);
+    for (int kk = 0; kk < nch; ++kk) {
+        const int k = (kk + k_first) % nch;
         const int64_t b0 = (int64_t)k * CH, n = std::min<int64_t>(CH, B - b0);
-        if (wait32) {
-            int e = wait32(cs, (unsigned long long)(uintptr_t)(c->g_done + k), (unsigned)n, 0u /*CU_STREAM_WAIT_VALUE_GEQ*/);
+        if (waitf) {
+            int e = waitf(cs, (unsigned long long)(uintptr_t)(c->g_done + k), (unsigned)n, 0u /*CU_STREAM_WAIT_VALUE_GEQ*/);
             if (e != 0) return fail(c, TMPC_ERR_CUDA, "cuStreamWaitValue32 failed");
         }
         auto back = [&](void *dst, const char *src, size_t per) {
             if (dst) cudaMemcpyAsync((char *)dst + b0 * per, src + b0 * per, n * per, cudaMemcpyDeviceToHost, cs);
         };
-        back(a->x, d_x, xrow * es); back(a->u, d_u, urow * es); back(a->iter, d_it, 4); back(a->status, d_st, 4);
-        back(a->resid, d_rs, 4 * es);
+        back(a->x, d_x, xrow * es); back(a->u, d_u, urow * es); back(a->u0, d_u0, nu * es); back(a->iter, d_it, 4);
+        back(a->status, d_st, 4); back(a->resid, d_rs, 4 * es);
     }
     CUDA_TRY(c, cudaStreamSynchronize(cs));
     CUDA_TRY(c, cudaStreamSynchronize(s));
@@ -1035,7 +1134,7 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     if (overlap) {
         unsigned g[2] = {0, 0};
         CUDA_TRY(c, cudaMemcpy(g, c->g_gate, sizeof g, cudaMemcpyDeviceToHost));
-        if (g[1]) return fail(c, TMPC_ERR_CUDA, "input gate timed out: the overlapped H2D did not deliver an instance's inputs within 2 s");
+        if (g[1]) return fail(c, TMPC_ERR_CUDA, "input gate timed out: the overlapped H2D did not deliver an instance's inputs within 2 s; outputs are incomplete");
     }
     c->stats_pending = true;
     return TMPC_OK;
@@ -1067,7 +1166,14 @@ cudaError_t launch_step(tmpc_ctx_impl *c, const tmpc::StepArgs<T> &sa, int which
 
 extern "C" {
 
-const char *tmpc_version(void) { return "tmpc 0.1 (sm_100a)"; }
+const char *tmpc_version(void) { return "tmpc 0.2 (sm_100a)"; }
+
+int tmpc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 const char *tmpc_last_error(const tmpc_ctx *ctx)
 {
@@ -1097,6 +1203,11 @@ int tmpc_create(tmpc_ctx **out, int device, int nx, int nu, int N, int dtype, in
     c->device = device; c->nx = nx; c->nu = nu; c->N = N; c->dtype = dtype; c->policy = order_policy;
     auto bail = [&](const char *what, cudaError_t er) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(er);
+        if (c->d_counter) cudaFree(c->d_counter);
+        if (c->last_launch) cudaEventDestroy(c->last_launch);
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->stream) cudaStreamDestroy(c->stream);
         delete c;
         return fail(nullptr, TMPC_ERR_CUDA, msg);
     };
@@ -1111,6 +1222,7 @@ int tmpc_create(tmpc_ctx **out, int device, int nx, int nu, int N, int dtype, in
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("event", e);
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventCreateWithFlags(&c->last_launch, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     if ((e = cudaMalloc(&c->d_counter, 5 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
     c->stats.parity_pinned = shape_parity_pinned(nx, nu) && order_policy == TMPC_ORDER_PARITY;
     *out = reinterpret_cast<tmpc_ctx *>(c);
@@ -1149,6 +1261,7 @@ int tmpc_destroy(tmpc_ctx *ctx)
     if (c->lpt_temp) cudaFree(c->lpt_temp);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->last_launch) cudaEventDestroy(c->last_launch);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return TMPC_OK;
@@ -1256,14 +1369,14 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
 
     if (a->mem == TMPC_MEM_DEVICE) {
         auto mis = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
-        if (mis(a->x0) || mis(a->Xref) || mis(a->x) || mis(a->u) ||
+        if (mis(a->x0) || mis(a->Xref) || mis(a->x) || mis(a->u) || mis(a->u0) ||
             (warm && (mis(a->warm->d) || mis(a->warm->y) || mis(a->warm->g) || mis(a->warm->v) || mis(a->warm->z))))
             return fail(c, TMPC_ERR_INVALID, "device buffers must be 16-byte aligned");
         DevArgs da{};
         da.batch = a->batch; da.x0 = a->x0; da.Xref = a->Xref;
         da.xref_stride = a->xref_shared ? 0 : (long long)xrow;
         if (warm) { da.wd = a->warm->d; da.wy = a->warm->y; da.wg = a->warm->g; da.wv = a->warm->v; da.wz = a->warm->z; }
-        da.x = a->x; da.u = a->u; da.iter = a->iter; da.status = a->status; da.resid = a->resid;
+        da.x = a->x; da.u = a->u; da.iter = a->iter; da.status = a->status; da.resid = a->resid; da.u0 = a->u0;
         cudaStream_t s = a->stream ? (cudaStream_t)a->stream : c->stream;
         int rc = launch_device(c, da, warm, s, true);
         if (rc != TMPC_OK) return rc;
@@ -1281,7 +1394,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
     // input chunk image : x0 | [Xref per instance] | [warm d y z g v]
     // output chunk image: x | u | iter | status | resid | [warm d y z g v]
     const size_t in_per = nx * es + (a->xref_shared ? 0 : xrow * es) + (warm ? (3 * urow + 2 * xrow) * es : 0);
-    const size_t out_per = (xrow + urow) * es + 8 + 4 * es;
+    const size_t out_per = (xrow + urow + nu) * es + 8 + 4 * es;
     int64_t chunk = std::min<int64_t>(a->batch, 131072);
     if (a->batch > chunk) chunk = (int64_t)((a->batch + ((a->batch + chunk - 1) / chunk) - 1) / ((a->batch + chunk - 1) / chunk));
     chunk = (chunk + 3) & ~int64_t(3);  // keep every sub-array 16-byte aligned
@@ -1324,6 +1437,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
                 off += chunk * per;
             };
             take(a->x, xrow * es); take(a->u, urow * es); take(a->iter, 4); take(a->status, 4); take(a->resid, 4 * es);
+            take(a->u0, nu * es);
             if (warm) {
                 take(a->warm->d, urow * es); take(a->warm->y, urow * es); take(a->warm->z, urow * es);
                 take(a->warm->g, xrow * es); take(a->warm->v, xrow * es);
@@ -1357,6 +1471,8 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
         auto outp = [&](size_t per) { char *p = dout + oo; oo += chunk * per; return p; };
         da.x = outp(xrow * es); da.u = outp(urow * es);
         da.iter = (int *)outp(4); da.status = (int *)outp(4); da.resid = outp(4 * es);
+        da.u0 = outp(nu * es);
+        if (!a->u0) da.u0 = nullptr;
         char *w_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
         if (warm) {
             // warm state is in place on the device: stage it straight into the OUTPUT image, solve there
@@ -1387,6 +1503,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
         //      so each chunk gets its own counter slot: reuse the ctx counter but order launches on st.s
         //      after the previous chunk's kernel)
         if (k > 0) cudaStreamWaitEvent(st.s, kev[2 * (k - 1) + 1], 0);
+        else if ((rc_all = order_after_previous(c, st.s)) != TMPC_OK) break;
         cudaEventCreate(&kev[2 * k]);
         cudaEventCreate(&kev[2 * k + 1]);
         {
@@ -1404,6 +1521,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
             cudaError_t e = cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, st.s);
             cudaEventRecord(kev[2 * k + 1], st.s);
             if (e != cudaSuccess) { rc_all = fail(c, TMPC_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e)); break; }
+            if ((rc_all = mark_launch(c, st.s)) != TMPC_OK) break;
             c->stats.launches += 1;
             c->stats.lanes = (int32_t)(blocks * ki.per_block);
             c->stats.pattern = c->pattern;
@@ -1418,6 +1536,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
                 o2 += chunk * per;
             };
             get(a->x, xrow * es); get(a->u, urow * es); get(a->iter, 4); get(a->status, 4); get(a->resid, 4 * es);
+            get(a->u0, nu * es);
             if (warm) {
                 get(a->warm->d, urow * es); get(a->warm->y, urow * es); get(a->warm->z, urow * es);
                 get(a->warm->g, xrow * es); get(a->warm->v, xrow * es);
@@ -1569,7 +1688,7 @@ int tmpc_get_stats(tmpc_ctx *ctx, tmpc_stats *out)
 int tmpc_host_alloc(void **ptr, uint64_t bytes)
 {
     if (!ptr) return TMPC_ERR_INVALID;
-    return cudaMallocHost(ptr, bytes) == cudaSuccess ? TMPC_OK : TMPC_ERR_CUDA;
+    return cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) == cudaSuccess ? TMPC_OK : TMPC_ERR_CUDA;
 }
 int tmpc_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? TMPC_OK : TMPC_ERR_CUDA; }
 
@@ -1577,3 +1696,4 @@ int tmpc_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? TMPC_O
 
 #include "tmpc_batch.cuh"
 #include "tmpc_systems.cuh"
+#include "tmpc_multi.cuh"

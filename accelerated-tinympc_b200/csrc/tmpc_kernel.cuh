@@ -197,6 +197,7 @@ template <class T> struct SolveArgs {
                                   // (advanced by stream memory operations between the chunks of an overlapped H2D), gate[1] = timeout flag
     const unsigned *order;        // nullable: the k-th claim of the work counter solves instance order[k] (longest-expected-first
                                   // schedule built by the host pre-pass, tmpc_api.cu lpt_prepare); null = instance k
+    T *u0;                        // nullable: out [batch][nu] = u(:,0), the control an MPC caller applies (quadrotor_hovering.cpp:110)
 };
 
 // instance solved by the idx-th claim of the work counter
@@ -205,15 +206,16 @@ template <class T> __device__ __forceinline__ long long claimed_instance(const S
     return a.order ? (long long)__ldg(a.order + idx) : idx;
 }
 
-// Overlapped H2D: an instance may be claimed before its x0 / Xref chunk has landed.  Wait for the arrival counter (never in
-// practice: the kernel consumes ~5 GB/s of inputs, PCIe delivers 50); give up after ~2 s instead of hanging the device.
-template <class T> __device__ __forceinline__ bool gate_wait(const SolveArgs<T> &a, long long idx)
+// Overlapped H2D: an instance may be claimed before its x0 / Xref chunk has landed.  Inputs arrive in INSTANCE order; wait until
+// the arrival counter covers instance `inst` (rarely: the kernel consumes ~5 GB/s of inputs, PCIe delivers 50); give up after
+// ~2 s instead of hanging the device (the host then releases the completion counters and reports the timeout).
+template <class T> __device__ __forceinline__ bool gate_wait(const SolveArgs<T> &a, long long inst)
 {
     if (!a.gate) return true;
     volatile unsigned *g = a.gate;
-    if ((long long)g[0] <= idx) {
+    if ((long long)g[0] <= inst) {
         const long long t0 = clock64();
-        while ((long long)g[0] <= idx) {
+        while ((long long)g[0] <= inst) {
             __nanosleep(200);
             if (clock64() - t0 > 4000000000LL) { g[1] = 1u; return false; }
         }
@@ -579,7 +581,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             base = __shfl_sync(FULLM, base, leader);
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.batch && gate_wait(a, idx)) {
+                if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) {
                     inst = claimed_instance(a, idx);
                     phase = PH_RUN;
                     it = 0;
@@ -751,6 +753,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     sy.store(i, y);
                     sz.store(i, zn);
                     if (uo) gstore<T, NU>(uo + i * NU, u);
+                    if (emit && a.u0 && i == 0) gstore<T, NU>(a.u0 + inst * NU, u);
                     T xn[NX];
                     T ca[2][NX], cb[2][NU];
                     if constexpr (PERSYS) { crow_issue<T, NX, SYSTM>(blk, tcol, SB::Arm, ca[0]); crow_issue<T, NU, SYSTM>(blk, tcol, SB::Brm, cb[0]); }

@@ -429,6 +429,13 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
         spn.store(0, pn);
     };
     const bool shared_xref = (a.xref_stride == 0);
+    // Controls-only callers (x = u = NULL, u0 given: what an MPC loop applies, quadrotor_hovering.cpp:110): u(:,0) of the trip in
+    // which the lane terminates is kept in registers and written with iter / status, so neither an emission trip nor a
+    // speculative one is needed.  Warm starts still emit (their g / y write-back rides on the emission sweep).
+    const bool u0only = !a.x && !a.u && !(WARM && a.wd);
+    float u0r[NU];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) u0r[j] = 0.f;
     if (shared_xref) seed_pn(a.Xref + (NH - 1) * NX);
 
     for (;;) {
@@ -450,9 +457,9 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             bool fill = false;
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.batch && gate_wait(a, idx)) {
+                if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) {
                     inst = claimed_instance(a, idx); phase = PH_RUN; it = 0; fill = true;
-                    spec = (P.max_iter <= 1);
+                    spec = (P.max_iter <= 1) && !u0only;
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);
                     if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
@@ -601,6 +608,11 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 sz.store(i, zn);
                 if (WARM && yo && !emit) gstore<float, NU>(yo + i * NU, y);
                 if (uo) gstore<float, NU>(uo + i * NU, u);
+                if (i == 0) {
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) u0r[j] = u[j];
+                    if (wr && a.u0 && !u0only) gstore<float, NU>(a.u0 + inst * NU, u);
+                }
                 // x_{i+1} = A x_i + B u_i                                                            :35
                 float2 xn[NX / 2];
                 if constexpr (FAST) {
@@ -644,10 +656,13 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 if (a.resid) *reinterpret_cast<float4 *>(a.resid + inst * 4) = make_float4(res[0], res[1], res[2], res[3]);
                 n_iter += (unsigned)it; n_solved += conv ? 1u : 0u; ++n_inst;
                 final_bwd = !conv;
-                if (spec) { phase = PH_FREE; finished = true; }   // x,u of this very trip are already in the output
+                if (u0only) {
+                    if (a.u0) gstore<float, NU>(a.u0 + inst * NU, u0r);
+                    phase = PH_FREE; finished = true;
+                } else if (spec) { phase = PH_FREE; finished = true; }   // x,u of this very trip are already in the output
                 else phase = PH_EMIT;
                 spec = false;
-            } else {
+            } else if (!u0only) {
                 // predict termination in the next trip: last allowed iteration, or every residual within 25 % of its
                 // tolerance at a check (ADMM crawls across the threshold); a wrong guess only costs stores
                 constexpr float SF = TMPC_SPEC_FACTOR;

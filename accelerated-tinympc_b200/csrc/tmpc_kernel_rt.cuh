@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
             base = __shfl_sync(FULLM, base, leader);
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.batch && gate_wait(a, idx)) {
+                if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) {
                     inst = claimed_instance(a, idx);
                     active = true;
                     it = 0;
@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
             }
             if (a.x) for (int e = 0; e < XROW; ++e) a.x[inst * XROW + e] = ld(oXo + e);
             if (a.u) for (int e = 0; e < UROW; ++e) a.u[inst * UROW + e] = ld(oU + e);
+            if (a.u0) for (int e = 0; e < nu; ++e) a.u0[inst * nu + e] = ld(oU + e);
             if (wback) {
                 // converged: cur was not advanced -> v, z are those of the previous iteration (SURVEY 8a note W)
                 const int oVc = cur ? oV1 : oV0, oZc = cur ? oZ1 : oZ0;

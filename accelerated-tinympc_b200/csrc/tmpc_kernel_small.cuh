@@ -62,7 +62,7 @@ admm_kernel_small(const __grid_constant__ Model<float, NX, 1, NH> P, const __gri
             base = __shfl_sync(FULLM, base, leader);
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.batch && gate_wait(a, idx)) {
+                if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) {
                     inst = claimed_instance(a, idx); phase = PH_RUN; it = 0;
                     spec = (P.max_iter <= 1);
                     res[0] = res[1] = res[2] = res[3] = 0.f;
@@ -137,6 +137,7 @@ admm_kernel_small(const __grid_constant__ Model<float, NX, 1, NH> P, const __gri
                     z[i] = zn;
                     if (WARM && yo && !emit) yo[i] = y[i];
                     if (uo) uo[i] = u;
+                    if (i == 0 && wr && a.u0) a.u0[inst] = u;
                     // x_{i+1} = A x_i + B u_i                                                        :35
                     float2 ax[H];
                     matvec2<ORD_SEQ, NX, NX, NX, 0, FAST>(P.A, x, ax, Z);

@@ -198,8 +198,9 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
             if (lane == 0) b = atomicAdd(a.counter, 1ull);
             inst = (long long)__shfl_sync(FULLM, b, 0);
         }
-        if (inst >= a.batch || !gate_wait(a, inst)) break;
+        if (inst >= a.batch) break;
         inst = claimed_instance(a, inst);
+        if (!gate_wait(a, inst)) break;
         const float *xref = a.Xref + inst * a.xref_stride;
         const float x0 = __ldg(a.x0 + inst * WNX + lane);
         // p_N seed: -(Xref_{N-1}^T Pinf)   (admm.cpp:83)
@@ -296,6 +297,7 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
                         sz[i * WNU + ur] = t.y;
                         ub[ur] = u;
                         if (uo) uo[i * WNU + ur] = u;
+                        if (i == 0 && a.u0) a.u0[inst * WNU + ur] = u;
                     }
                     __syncwarp();
                     {   // operands of stage i+1 (the nu-rows of the last stage do not exist: re-read stage i's)

@@ -306,7 +306,7 @@ int tmpc_solve_systems(tmpc_ctx *ctx, const tmpc_solve_args *a, const tmpc_syste
     da.batch = a->batch; da.x0 = a->x0; da.Xref = a->Xref;
     da.xref_stride = a->xref_shared ? 0 : (long long)c->nx * c->N;
     if (warm) { da.wd = a->warm->d; da.wy = a->warm->y; da.wg = a->warm->g; da.wv = a->warm->v; da.wz = a->warm->z; }
-    da.x = a->x; da.u = a->u; da.iter = a->iter; da.status = a->status; da.resid = a->resid;
+    da.x = a->x; da.u = a->u; da.iter = a->iter; da.status = a->status; da.resid = a->resid; da.u0 = a->u0;
     da.sys = sy->blocks;
     cudaStream_t s = a->stream ? (cudaStream_t)a->stream : c->stream;
     c->stats.instances = a->batch;
@@ -315,6 +315,10 @@ int tmpc_solve_systems(tmpc_ctx *ctx, const tmpc_solve_args *a, const tmpc_syste
     // longest-expected-first schedule with each instance's own Kinf (tmpc_api.cu lpt_prepare)
     bool ev0_done = false;
     c->lpt_used = 0;
+    {
+        const int rc = order_after_previous(c, s);   // the scheduling buffers may still be read by the previous launch
+        if (rc != TMPC_OK) return rc;
+    }
     if (c->nx == 12 && c->nu == 4 && lpt_wanted(c, ki, da)) {
         using SB = tmpc::SysBlock<12, 4>;
         CUDA_TRY(c, cudaEventRecord(c->ev0, s));

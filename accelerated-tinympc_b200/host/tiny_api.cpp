@@ -4,6 +4,7 @@
 #include "tinympc/tiny_api.hpp"
 #include "tmpc.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -19,8 +20,19 @@ int fail(const std::string &m) { g_err = m; return -1; }
 constexpr int kDtype = sizeof(tinytype) == 4 ? TMPC_F32 : TMPC_F64;
 
 struct Backend {
-    tmpc_ctx *ctx = nullptr;
+    tmpc_ctx *ctx = nullptr;        // device 0: single instances, step functions, device-memory batches
+    tmpc_multi *multi = nullptr;    // every selected device: host-memory batches (created on first use)
     int policy = TMPC_ORDER_PARITY;
+    int devices = 0;                // tiny_set_devices: 0 = every visible device, n = the first n
+    // what was last pushed to the device contexts: tmpc_set_model / tmpc_set_settings run only when something changed
+    uint64_t pushed_ctx = 0, pushed_multi = 0;
+    // per-instance bounds (tiny_set_instance_bounds): host copies so that they survive a context re-creation and can be
+    // installed on whichever backend the next tiny_solve_batch uses
+    int64_t ib_batch = 0;
+    bool ib_on_device = false;
+    std::vector<tinytype> ib[4];
+    const tinytype *ib_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ib_ctx = false, ib_multi = false;   // installed on ctx / on multi
 };
 
 Backend *backend(TinySolver *s)
@@ -29,15 +41,40 @@ Backend *backend(TinySolver *s)
     return static_cast<Backend *>(s->backend);
 }
 
-// (re)create the device context if needed and push model + settings (cheap: a few KB; done on every call because
-// the reference lets callers edit cache/work/settings fields freely between solves)
+// FNV-1a over everything tmpc_set_model / tmpc_set_settings take: the reference lets callers edit cache / work / settings
+// fields freely between solves, so every call looks at them -- but the device copies are rebuilt (a stream sync, a blocking
+// copy and an image rebuild inside tmpc_set_model) only when the fingerprint moved.
+uint64_t fingerprint(const TinySolver *s)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    const TinyWorkspace &w = *s->work;
+    const TinyCache &c = *s->cache;
+    const TinySettings &t = *s->settings;
+    for (const tiny_Matrix *m : {&c.Kinf, &c.Pinf, &c.Quu_inv, &c.AmBKt, &w.Adyn, &w.Bdyn, &w.Q, &w.x_min, &w.x_max, &w.u_min, &w.u_max})
+        mix(m->data(), sizeof(tinytype) * (size_t)m->rows() * m->cols());
+    mix(&c.rho, sizeof c.rho);
+    mix(&t.abs_pri_tol, sizeof t.abs_pri_tol); mix(&t.abs_dua_tol, sizeof t.abs_dua_tol);
+    const int iv[4] = {t.max_iter, t.check_termination, t.en_state_bound, t.en_input_bound};
+    mix(iv, sizeof iv);
+    return h | 1ull;   // never 0 (= nothing pushed yet)
+}
+
+// (re)create the device context if needed and push model + settings when they changed since the last push
 int sync_model(TinySolver *s)
 {
     Backend *b = backend(s);
     if (!b->ctx) {
         int rc = tmpc_create(&b->ctx, 0, s->nx, s->nu, s->N, kDtype, b->policy);
         if (rc != TMPC_OK) return fail(std::string("tmpc_create: ") + tmpc_last_error(nullptr));
+        b->pushed_ctx = 0;
+        b->ib_ctx = false;
     }
+    const uint64_t fp = fingerprint(s);
+    if (fp == b->pushed_ctx) return 0;
     const TinyWorkspace &w = *s->work;
     const TinyCache &c = *s->cache;
     int rc = tmpc_set_model(b->ctx, c.Kinf.data(), c.Pinf.data(), c.Quu_inv.data(), c.AmBKt.data(), w.Adyn.data(),
@@ -48,7 +85,42 @@ int sync_model(TinySolver *s)
     rc = tmpc_set_settings(b->ctx, (double)t.abs_pri_tol, (double)t.abs_dua_tol, t.max_iter, t.check_termination,
                            t.en_state_bound, t.en_input_bound);
     if (rc != TMPC_OK) return fail(std::string("tmpc_set_settings: ") + tmpc_last_error(b->ctx));
+    b->pushed_ctx = fp;
     return 0;
+}
+
+// the same for the multi-device backend (host-memory batches); returns 1 when there is only one device to use
+int sync_multi(TinySolver *s)
+{
+    Backend *b = backend(s);
+    if (!b->multi) {
+        int rc = tmpc_multi_create(&b->multi, b->devices, nullptr, s->nx, s->nu, s->N, kDtype, b->policy);
+        if (rc != TMPC_OK) return fail(std::string("tmpc_multi_create: ") + tmpc_multi_last_error(nullptr));
+        b->pushed_multi = 0;
+        b->ib_multi = false;
+    }
+    const uint64_t fp = fingerprint(s);
+    if (fp == b->pushed_multi) return 0;
+    const TinyWorkspace &w = *s->work;
+    const TinyCache &c = *s->cache;
+    int rc = tmpc_multi_set_model(b->multi, c.Kinf.data(), c.Pinf.data(), c.Quu_inv.data(), c.AmBKt.data(), w.Adyn.data(),
+                                  w.Bdyn.data(), w.Q.data(), (double)c.rho, w.x_min.data(), w.x_max.data(), w.u_min.data(),
+                                  w.u_max.data());
+    if (rc != TMPC_OK) return fail(std::string("tmpc_multi_set_model: ") + tmpc_multi_last_error(b->multi));
+    const TinySettings &t = *s->settings;
+    rc = tmpc_multi_set_settings(b->multi, (double)t.abs_pri_tol, (double)t.abs_dua_tol, t.max_iter, t.check_termination,
+                                 t.en_state_bound, t.en_input_bound);
+    if (rc != TMPC_OK) return fail(std::string("tmpc_multi_set_settings: ") + tmpc_multi_last_error(b->multi));
+    b->pushed_multi = fp;
+    return 0;
+}
+
+void drop_contexts(Backend *b)
+{
+    if (b->ctx) { tmpc_destroy(b->ctx); b->ctx = nullptr; }
+    if (b->multi) { tmpc_multi_destroy(b->multi); b->multi = nullptr; }
+    b->pushed_ctx = b->pushed_multi = 0;
+    b->ib_ctx = b->ib_multi = false;
 }
 
 // ---- small dense helpers in double, row-major std::vector (cold path only)
@@ -250,8 +322,21 @@ int tiny_set_order_policy(TinySolver *s, int policy)
 {
     if (!s || (policy != TMPC_ORDER_PARITY && policy != TMPC_ORDER_FAST)) return fail("tiny_set_order_policy: bad argument");
     Backend *b = backend(s);
-    if (b->ctx && b->policy != policy) { tmpc_destroy(b->ctx); b->ctx = nullptr; }
+    // the policy is a property of the device contexts: they are re-created on the next call; per-instance bounds are kept
+    // in the Backend and re-installed then (install_instance_bounds)
+    if (b->policy != policy) drop_contexts(b);
     b->policy = policy;
+    return 0;
+}
+
+int tiny_set_devices(TinySolver *s, int n)
+{
+    if (!s || n < 0) return fail("tiny_set_devices: bad argument");
+    const int visible = tmpc_device_count();
+    if (n > visible) return fail("tiny_set_devices: more devices than are visible");
+    Backend *b = backend(s);
+    if (b->devices != n && b->multi) { tmpc_multi_destroy(b->multi); b->multi = nullptr; b->pushed_multi = 0; b->ib_multi = false; }
+    b->devices = n;
     return 0;
 }
 
@@ -282,10 +367,45 @@ int tiny_solve(TinySolver *s)
     return st == TMPC_STATUS_SOLVED ? 0 : 1;    // admm.cpp:137,151
 }
 
+// Host batches of at least 32,768 instances go over every selected device (tmpc_multi: one ctx + one worker thread per
+// device, contiguous instance ranges); everything else -- small batches, device-memory batches -- runs on device 0.
+static bool use_multi(TinySolver *s, const TinyBatchIn *in)
+{
+    Backend *b = backend(s);
+    if (in->on_device || in->batch < 32768 || b->ib_on_device) return false;
+    const int want = b->devices ? b->devices : tmpc_device_count();
+    return want > 1;
+}
+
+// per-instance bounds live in the Backend; put them on the context family that is about to solve (and take them off the other
+// one so that a later call with the shared box is not surprised)
+static int install_instance_bounds(TinySolver *s, bool multi)
+{
+    Backend *b = backend(s);
+    const int mem = b->ib_on_device ? TMPC_MEM_DEVICE : TMPC_MEM_HOST;
+    const tinytype *p[4];
+    for (int k = 0; k < 4; ++k) p[k] = b->ib_on_device ? b->ib_dev[k] : b->ib[k].data();
+    if (b->ib_batch == 0) return 0;   // nothing set: tiny_set_instance_bounds(0) cleared both families
+    if (multi) {
+        if (!b->ib_multi) {
+            int rc = tmpc_multi_set_instance_bounds(b->multi, b->ib_batch, p[0], p[1], p[2], p[3]);
+            if (rc != TMPC_OK) return fail(std::string("tmpc_multi_set_instance_bounds: ") + tmpc_multi_last_error(b->multi));
+            b->ib_multi = true;
+        }
+        return 0;
+    }
+    if (!b->ib_ctx) {
+        int rc = tmpc_set_instance_bounds(b->ctx, b->ib_batch, p[0], p[1], p[2], p[3], mem);
+        if (rc != TMPC_OK) return fail(std::string("tmpc_set_instance_bounds: ") + tmpc_last_error(b->ctx));
+        b->ib_ctx = true;
+    }
+    return 0;
+}
+
 int tiny_solve_batch(TinySolver *s, const TinyBatchIn *in, TinyBatchOut *out)
 {
     if (!s || !in || !out) return fail("tiny_solve_batch: NULL argument");
-    if (sync_model(s) != 0) return -1;
+    Backend *b = backend(s);
     tmpc_warm warm = {in->d, in->y, in->g, in->v, in->z};
     const bool any = in->d || in->y || in->g || in->v || in->z;
     tmpc_solve_args a;
@@ -293,10 +413,19 @@ int tiny_solve_batch(TinySolver *s, const TinyBatchIn *in, TinyBatchOut *out)
     a.batch = in->batch; a.x0 = in->x0; a.Xref = in->Xref; a.xref_shared = in->xref_shared;
     a.mem = in->on_device ? TMPC_MEM_DEVICE : TMPC_MEM_HOST;
     a.warm = any ? &warm : nullptr;
-    a.x = out->x; a.u = out->u; a.iter = out->iter; a.status = out->status; a.resid = out->resid;
+    a.x = out->x; a.u = out->u; a.u0 = out->u0; a.iter = out->iter; a.status = out->status; a.resid = out->resid;
     a.stream = in->stream;
-    int rc = tmpc_solve(backend(s)->ctx, &a);
-    if (rc != TMPC_OK) return fail(std::string("tmpc_solve: ") + tmpc_last_error(backend(s)->ctx));
+    if (use_multi(s, in)) {
+        if (sync_multi(s) != 0) return -1;
+        if (install_instance_bounds(s, true) != 0) return -1;
+        int rc = tmpc_multi_solve(b->multi, &a);
+        if (rc != TMPC_OK) return fail(std::string("tmpc_multi_solve: ") + tmpc_multi_last_error(b->multi));
+        return 0;
+    }
+    if (sync_model(s) != 0) return -1;
+    if (install_instance_bounds(s, false) != 0) return -1;
+    int rc = tmpc_solve(b->ctx, &a);
+    if (rc != TMPC_OK) return fail(std::string("tmpc_solve: ") + tmpc_last_error(b->ctx));
     return 0;
 }
 
@@ -304,10 +433,27 @@ int tiny_set_instance_bounds(TinySolver *s, int64_t batch, const tinytype *x_min
                              const tinytype *u_max, int on_device)
 {
     if (!s) return fail("tiny_set_instance_bounds: NULL argument");
-    if (sync_model(s) != 0) return -1;   // creates the ctx on first use
-    int rc = tmpc_set_instance_bounds(backend(s)->ctx, batch, x_min, x_max, u_min, u_max, on_device ? TMPC_MEM_DEVICE : TMPC_MEM_HOST);
-    if (rc != TMPC_OK) return fail(std::string("tmpc_set_instance_bounds: ") + tmpc_last_error(backend(s)->ctx));
-    return 0;
+    if (batch < 0) return fail("tiny_set_instance_bounds: negative batch");
+    if (batch > 0 && (!x_min || !x_max || !u_min || !u_max)) return fail("tiny_set_instance_bounds: all four bound arrays must be given");
+    Backend *b = backend(s);
+    // forget what is installed anywhere, keep the new boxes here (host arrays are copied; device arrays stay the caller's until
+    // the context has taken its copy, which happens below)
+    if (b->ib_ctx && b->ctx) tmpc_set_instance_bounds(b->ctx, 0, nullptr, nullptr, nullptr, nullptr, TMPC_MEM_HOST);
+    if (b->ib_multi && b->multi) tmpc_multi_set_instance_bounds(b->multi, 0, nullptr, nullptr, nullptr, nullptr);
+    b->ib_ctx = b->ib_multi = false;
+    b->ib_batch = batch;
+    b->ib_on_device = batch > 0 && on_device != 0;
+    const tinytype *src[4] = {x_min, x_max, u_min, u_max};
+    const size_t per[4] = {(size_t)s->nx * s->N, (size_t)s->nx * s->N, (size_t)s->nu * (s->N - 1), (size_t)s->nu * (s->N - 1)};
+    for (int k = 0; k < 4; ++k) {
+        b->ib[k].clear();
+        b->ib_dev[k] = nullptr;
+        if (batch > 0 && !on_device) b->ib[k].assign(src[k], src[k] + (size_t)batch * per[k]);
+        if (batch > 0 && on_device) b->ib_dev[k] = src[k];
+    }
+    if (batch == 0) return 0;
+    if (sync_model(s) != 0) return -1;   // creates the ctx on first use: argument errors surface here, as before
+    return install_instance_bounds(s, false);
 }
 
 void forward_pass(TinySolver *s) { run_step(s, 0, nullptr); }
@@ -327,7 +473,7 @@ void tiny_free(TinySolver *s)
     if (!s) return;
     if (s->backend) {
         Backend *b = static_cast<Backend *>(s->backend);
-        if (b->ctx) tmpc_destroy(b->ctx);
+        drop_contexts(b);
         delete b;
     }
     delete s->settings;

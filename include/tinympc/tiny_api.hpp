@@ -45,6 +45,8 @@ typedef struct {
     int32_t *iter;    /* [batch] */
     int32_t *status;  /* [batch] 1 solved / 11 max_iter */
     tinytype *resid;  /* [batch][4] primal_state, dual_state, primal_input, dual_input; nullable */
+    tinytype *u0;     /* [batch][nu] u(:,0) alone: what an MPC loop applies (quadrotor_hovering.cpp:110); nullable.  Every
+                         pointer of this struct may be NULL (= not wanted): a controls-only caller sets u0, iter, status */
 } TinyBatchOut;
 
 /* tiny_solve for `batch` instances sharing solver's model, cache, bounds and settings.  0 = the call worked
@@ -59,8 +61,14 @@ int tiny_solve_batch(TinySolver *solver, const TinyBatchIn *in, TinyBatchOut *ou
 int tiny_set_instance_bounds(TinySolver *solver, int64_t batch, const tinytype *x_min, const tinytype *x_max,
                              const tinytype *u_min, const tinytype *u_max, int on_device);
 
-/* policy 0 = bit-exact order of the reference's -O3 SSE2 build (default), 1 = FMA-contracted */
+/* policy 0 = bit-exact order of the reference's -O3 SSE2 build (default), 1 = FMA-contracted.  Per-instance bounds survive
+ * the change. */
 int tiny_set_order_policy(TinySolver *solver, int policy);
+
+/* Devices tiny_solve_batch spreads a HOST batch over: 0 = every visible device (default), n = the first n.  Batches of at
+ * least 32,768 instances are split into contiguous instance ranges, one per device, solved concurrently (tmpc_multi_solve);
+ * results are identical to a one-device solve.  Device-memory batches and tiny_solve run on device 0. */
+int tiny_set_devices(TinySolver *solver, int n);
 
 /* Codegen-compatible data files (the reference's tiny_codegen output, codegen.cpp:322-477 and :131-160).
  * export: write solver's settings, cache, model and bounds as a `tiny_data_workspace.cpp` / `glob_opts.hpp` that a

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define TMPC_VERSION_MAJOR 0
-#define TMPC_VERSION_MINOR 1
+#define TMPC_VERSION_MINOR 2
 
 typedef enum {
     TMPC_OK = 0,
@@ -109,12 +109,20 @@ typedef struct {
     int32_t *status;     /* out [batch] work->status (1 solved / 11 not); NULL = skip */
     void *resid;         /* out [batch][4]: primal_state, dual_state, primal_input, dual_input (admm.cpp:95-98) */
     void *stream;        /* cudaStream_t (TMPC_MEM_DEVICE); NULL = the ctx's own stream */
+    void *u0;            /* out [batch][nu]: u(:,0) alone -- the control an MPC loop applies (quadrotor_hovering.cpp:110
+                            `x1 = Adyn x0 + Bdyn u.col(0)`); NULL = skip.  Every output pointer is its own mask bit: a
+                            controls-only caller passes x = u = NULL and u0 (+ iter / status) and gets 24 instead of 648
+                            bytes per quadrotor solve back, and the kernel then needs no trajectory-emission pass */
 } tmpc_solve_args;
 
 /* Run tiny_solve for every instance of the batch.  With TMPC_MEM_DEVICE the call is asynchronous on
  * `stream`; with TMPC_MEM_HOST it stages through pinned buffers in chunks (H2D / solve / D2H overlapped)
  * and returns when the outputs are in host memory.  Returns TMPC_OK even if some instances stop at
- * max_iter (their status is 11, as in the reference). */
+ * max_iter (their status is 11, as in the reference).
+ * Ordering: a ctx owns one work counter, one statistics slot and its scratch areas, so the launches of one ctx
+ * are SERIALISED ON THE DEVICE whatever streams they are queued on (each launch waits for the previous launch
+ * of the same ctx through an event); independent solves that should overlap need one ctx each.  One host thread
+ * at a time may call into a ctx. */
 int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *args);
 
 typedef struct {
@@ -220,11 +228,41 @@ int tmpc_systems_get(tmpc_systems *s, int32_t what, void *dst_host);
 /* tmpc_solve for a batch whose instance i uses system i.  Device buffers only (args->mem = TMPC_MEM_DEVICE). */
 int tmpc_solve_systems(tmpc_ctx *ctx, const tmpc_solve_args *args, const tmpc_systems *systems);
 
-/* Pinned host allocation helpers for TMPC_MEM_HOST callers that want full PCIe speed. */
+/* ---------------------------------------------------------------------------------------------------------
+ * One batch over SEVERAL devices from one process: the multi-GPU form of tmpc_solve for HOST-memory callers (the reference's
+ * callers are plain C++ loops, quadrotor_hovering.cpp:104; there is nothing to shard in the reference).  A tmpc_multi owns one
+ * tmpc_ctx and one host worker thread per device; tmpc_multi_solve splits the batch into contiguous instance ranges
+ * [B*r/G, B*(r+1)/G) (instances never interact, admm.cpp:111-152: no inter-device traffic), every worker runs tmpc_solve
+ * (TMPC_MEM_HOST) on its range of the caller's arrays concurrently, and the call returns when all outputs are in host memory.
+ * Results are identical, instance by instance, to a single-device tmpc_solve.  Small batches use fewer devices (at least
+ * 16,384 instances per device).  Pinned caller memory (tmpc_host_alloc) is DMA'd directly by every device.
+ *   ndev = 0: every visible device; else devices[0..ndev) (NULL = 0..ndev-1). */
+typedef struct tmpc_multi tmpc_multi;
+int tmpc_multi_create(tmpc_multi **out, int ndev, const int *devices, int nx, int nu, int N, int dtype, int order_policy);
+int tmpc_multi_destroy(tmpc_multi *m);
+int tmpc_multi_device_count(const tmpc_multi *m);
+tmpc_ctx *tmpc_multi_ctx(tmpc_multi *m, int index);   /* the index-th device's ctx (device-memory calls, batches, steps) */
+int tmpc_multi_set_model(tmpc_multi *m, const void *Kinf, const void *Pinf, const void *Quu_inv, const void *AmBKt,
+                         const void *Adyn, const void *Bdyn, const void *Q, double rho, const void *x_min,
+                         const void *x_max, const void *u_min, const void *u_max);
+int tmpc_multi_set_settings(tmpc_multi *m, double abs_pri_tol, double abs_dua_tol, int max_iter, int check_termination,
+                            int en_state_bound, int en_input_bound);
+/* per-instance boxes for the whole batch (HOST arrays; each device keeps its own range); batch = 0 clears them */
+int tmpc_multi_set_instance_bounds(tmpc_multi *m, int64_t batch, const void *x_min, const void *x_max, const void *u_min,
+                                   const void *u_max);
+int tmpc_multi_solve(tmpc_multi *m, const tmpc_solve_args *args);   /* args->mem must be TMPC_MEM_HOST; args->stream ignored */
+/* totals over the devices of the last tmpc_multi_solve (kernel_ms = the slowest device's); per_device: NULL or an array of
+ * tmpc_multi_device_count() entries */
+int tmpc_multi_get_stats(tmpc_multi *m, tmpc_stats *total, tmpc_stats *per_device);
+const char *tmpc_multi_last_error(const tmpc_multi *m);
+
+/* Pinned host allocation helpers for TMPC_MEM_HOST callers that want full PCIe speed (portable: every device of the
+ * process can DMA from / to it). */
 int tmpc_host_alloc(void **ptr, uint64_t bytes);
 int tmpc_host_free(void *ptr);
 
 const char *tmpc_last_error(const tmpc_ctx *ctx); /* ctx may be NULL: last error of tmpc_create */
+int tmpc_device_count(void);                      /* visible sm_100-class CUDA devices (0 when there is none) */
 const char *tmpc_version(void);
 
 #ifdef __cplusplus

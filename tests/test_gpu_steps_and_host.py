@@ -122,7 +122,7 @@ def test_host_api_codegen_random_example(tag, rel):
     np.testing.assert_allclose(K, [1.3597774779741059, -0.6322783070376652, 0.53346352483974, -0.10662252458139154], rtol=1e-6 if tag == "f32" else 1e-10)
 
 
-@pytest.mark.parametrize("tag", ["f32"])   # the f64 binary is built too; its kernel path is covered by test_gpu_instance_bounds.py
+@pytest.mark.parametrize("tag", ["f32", "f64"])
 def test_host_api_instance_bounds_example(tag):
     """tiny_set_instance_bounds in front of tiny_solve_batch (host/examples/instance_bounds.cpp, self-checking): same boxes ->
     bit-identical to the shared-bounds solve, tighter boxes on odd instances change only those, another batch size is
@@ -130,3 +130,14 @@ def test_host_api_instance_bounds_example(tag):
     p = subprocess.run([os.path.join(BIN, "instance_bounds_" + tag)], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "instance bounds ok" in p.stdout
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_host_api_batch_over_devices_and_controls_only(tag):
+    """tiny_solve_batch on one device, on every visible device (tiny_set_devices; contiguous instance ranges, one worker
+    thread per device) and with the controls-only output mask (host/examples/batch_devices.cpp, self-checking): all three
+    agree instance by instance, bit for bit.  With one visible GPU the multi-device path degenerates to one range."""
+    p = subprocess.run([os.path.join(BIN, "batch_devices_" + tag), DATA, "100000" if tag == "f32" else "40000"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "batch_devices ok" in p.stdout
