@@ -2,6 +2,7 @@
 // Owns: device/model state per context, kernel dispatch by (shape, dtype, policy), the chunked
 // host<->device pipeline for TMPC_MEM_HOST callers, statistics.  No solver arithmetic runs on the host.
 #include "tmpc.h"
+#include "tmpc_dispatch.hpp"
 #include "tmpc_kernel.cuh"
 #include "tmpc_kernel_f32.cuh"
 #include "tmpc_kernel_warp.cuh"
@@ -26,16 +27,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct KernelInfo {
-    const void *fn;
-    size_t smem;
-    int block;
-    size_t model_bytes;
-    int model_kind;  // 0: tmpc::Model<T,...> (generic kernel)   1: tmpc::ModelF32<...> (packed fp32 kernel)
-                     // 2: tmpc::ModelWarp (warp-per-instance kernel; pointers into the ctx's device model image)
-                     // 3: tmpc::ModelRT<T> (run-time-shape kernel; pointers into the ctx's device model image + scratch)
-    int per_block;   // instances resident per block (threads for the thread-per-instance kernels, warps for kind 2)
-};
+using tmpc_dispatch::KernelInfo;
 
 struct tmpc_ctx_impl {
     int device = 0;
@@ -65,6 +57,9 @@ struct tmpc_ctx_impl {
     size_t d_model_rt_bytes = 0;
     void *d_rt_scratch = nullptr;
     size_t d_rt_scratch_bytes = 0;
+    // per-lane coalesced scratch of the fp32 12/4/10 kernel (SolveArgs::scratch)
+    void *d_lane_scratch = nullptr;
+    size_t d_lane_scratch_bytes = 0;
     bool rt_ready = false;
     // per-instance box bounds (tmpc_set_instance_bounds): device copies xmin | xmax | umin | umax, 0 = not set
     void *d_ib[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -125,101 +120,8 @@ int fail(tmpc_ctx_impl *c, int code, const std::string &msg)
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// kernel table
+// kernel table (the instantiations live in k_*.cu, one translation unit per kernel family: tmpc_dispatch.hpp)
 // ---------------------------------------------------------------------------------------------
-template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool UNROLL>
-KernelInfo make_info()
-{
-    KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel<T, NX, NU, NH, BLOCK, FAST, WARM, UNROLL>;
-    k.smem = tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES;
-    k.block = BLOCK;
-    k.model_bytes = sizeof(tmpc::Model<T, NX, NU, NH>);
-    k.model_kind = 0;
-    k.per_block = BLOCK;
-    return k;
-}
-
-template <class T, int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, int SYS>
-KernelInfo make_info_g()
-{
-    KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel<T, NX, NU, NH, BLOCK, FAST, WARM, false, SYS>;
-    k.smem = SYS == 3 ? tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES_NOGV + 16                 // g, v in TMEM
-                      : tmpc::SmemLayout<T, NX, NU, NH, BLOCK>::BYTES + (SYS == 2 ? 16 : 0);   // + the TMEM base slot
-    k.block = BLOCK;
-    k.model_bytes = sizeof(tmpc::Model<T, NX, NU, NH>);
-    k.model_kind = 0;
-    k.per_block = BLOCK;
-    return k;
-}
-
-template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT, bool CB>
-KernelInfo make_info_f32()
-{
-    KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM, PAT, CB>;
-    k.smem = tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES;
-    k.block = BLOCK;
-    k.model_bytes = sizeof(tmpc::ModelF32<NX, NU, NH>);
-    k.model_kind = 1;
-    k.per_block = BLOCK;
-    return k;
-}
-
-template <int NX, int NH, int BLOCK, bool FAST, bool WARM>
-KernelInfo make_info_small()
-{
-    KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_small<NX, NH, BLOCK, FAST, WARM>;
-    k.smem = 0;   // the whole per-instance state lives in registers
-    k.block = BLOCK;
-    k.model_bytes = sizeof(tmpc::Model<float, NX, 1, NH>);
-    k.model_kind = 0;
-    k.per_block = BLOCK;
-    return k;
-}
-
-template <int NX, int NH, int BLOCK>
-bool pick_small(int policy, bool warm, KernelInfo &out)
-{
-    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_small<NX, NH, BLOCK, false, true>() : make_info_small<NX, NH, BLOCK, false, false>();
-    else out = warm ? make_info_small<NX, NH, BLOCK, true, true>() : make_info_small<NX, NH, BLOCK, true, false>();
-    return true;
-}
-
-template <int NH, int WARPS, bool FAST, bool WARM, bool TM>
-KernelInfo make_info_warp()
-{
-    KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_warp<NH, WARPS, FAST, WARM, TM>;
-    k.smem = tmpc::WarpSmem<NH, TM>::total_bytes(WARPS);
-    k.block = WARPS * 32;
-    k.model_bytes = sizeof(tmpc::ModelWarp);
-    k.model_kind = 2;
-    k.per_block = WARPS;
-    return k;
-}
-
-template <int NH, int WARPS, bool TM>
-bool pick_warp(int policy, bool warm, KernelInfo &out)
-{
-    static_assert(tmpc::WarpSmem<NH, TM>::total_bytes(WARPS) <= 232448, "per-block shared memory limit of sm_100");
-    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_warp<NH, WARPS, false, true, TM>() : make_info_warp<NH, WARPS, false, false, TM>();
-    else out = warm ? make_info_warp<NH, WARPS, true, true, TM>() : make_info_warp<NH, WARPS, true, false, TM>();
-    return true;
-}
-
-template <int NX, int NU, int NH, int BLOCK, bool TM, class PAT = tmpc::PatDense<NX>, bool CB = false>
-bool pick_f32(int policy, bool warm, KernelInfo &out)
-{
-    if (policy == TMPC_ORDER_PARITY)
-        out = warm ? make_info_f32<NX, NU, NH, BLOCK, false, true, TM, PAT, CB>() : make_info_f32<NX, NU, NH, BLOCK, false, false, TM, PAT, CB>();
-    else
-        out = warm ? make_info_f32<NX, NU, NH, BLOCK, true, true, TM, PAT, CB>() : make_info_f32<NX, NU, NH, BLOCK, true, false, TM, PAT, CB>();
-    return true;
-}
-
 // development switch: TMPC_KERNEL=generic | f32_smem | f32_tmem (default) selects the fp32 12/4/10 kernel
 int kernel_variant()
 {
@@ -228,18 +130,6 @@ int kernel_variant()
     if (!strcmp(e, "generic")) return 0;
     if (!strcmp(e, "f32_smem")) return 1;
     return 2;
-}
-
-template <class T, int NX, int NU, int NH, int BLOCK, bool UNROLL>
-bool pick(int policy, bool warm, KernelInfo &out)
-{
-    if (policy == TMPC_ORDER_PARITY)
-        out = warm ? make_info<T, NX, NU, NH, BLOCK, false, true, UNROLL>()
-                   : make_info<T, NX, NU, NH, BLOCK, false, false, UNROLL>();
-    else
-        out = warm ? make_info<T, NX, NU, NH, BLOCK, true, true, UNROLL>()
-                   : make_info<T, NX, NU, NH, BLOCK, true, false, UNROLL>();
-    return true;
 }
 
 // Compiled shapes.  Thread-per-instance needs the per-instance state to fit shared memory:
@@ -253,51 +143,33 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
     const int pattern = pattern_bits & 0xff;
     const bool cb = (pattern_bits & 0x100) != 0;
     if (force_rt()) return lookup_kernel_rt(nx, nu, N, dtype, policy, out);
+    const char *e = getenv("TMPC_KERNEL");
+    const bool generic = e && !strcmp(e, "generic");
     if (nx == 12 && nu == 4 && N == 10) {
         if (dtype == TMPC_F32) {
             const int v = kernel_variant();
-            // model-structure specialisation (tmpc_kernel_f32.cuh PatQuadrotor): chosen by build_model when the
-            // actual matrices conform
-            if (v == 2 && pattern == tmpc::PatQuadrotor::id)
-                return cb ? pick_f32<12, 4, 10, 256, true, tmpc::PatQuadrotor, true>(policy, warm, out)
-                          : pick_f32<12, 4, 10, 256, true, tmpc::PatQuadrotor, false>(policy, warm, out);
-            if (v == 2)                                                              // g,v in TMEM: 256 instances / SM
-                return cb ? pick_f32<12, 4, 10, 256, true, tmpc::PatDense<12>, true>(policy, warm, out)
-                          : pick_f32<12, 4, 10, 256, true, tmpc::PatDense<12>, false>(policy, warm, out);
-            if (v == 1) return pick_f32<12, 4, 10, 128, false>(policy, warm, out);  // all state in shared memory
-            return pick<float, 12, 4, 10, 128, false>(policy, warm, out);
+            if (v == 0) return tmpc_dispatch::lookup_generic(nx, nu, N, dtype, policy, warm, 0, out);
+            return tmpc_dispatch::lookup_f32(policy, warm, pattern, cb, v, out);
         }
         // double: g, v in tensor memory -> 128 instances / SM (TMPC_KERNEL=generic: all state in shared memory, 64 / SM)
-        {
-            const char *e = getenv("TMPC_KERNEL");
-            if (e && !strcmp(e, "generic")) return pick<double, 12, 4, 10, 64, false>(policy, warm, out);
-        }
-        if (policy == TMPC_ORDER_PARITY)
-            out = warm ? make_info_g<double, 12, 4, 10, 128, false, true, 3>() : make_info_g<double, 12, 4, 10, 128, false, false, 3>();
-        else
-            out = warm ? make_info_g<double, 12, 4, 10, 128, true, true, 3>() : make_info_g<double, 12, 4, 10, 128, true, false, 3>();
-        return true;
+        return tmpc_dispatch::lookup_generic(nx, nu, N, dtype, policy, warm, generic ? 1 : 0, out);
     }
     if (nx == 4 && nu == 1 && N == 10) {
         if (dtype == TMPC_F32) {
             // register-resident single-input kernel (tmpc_kernel_small.cuh); TMPC_KERNEL=generic | generic_unroll:
             // the shared-memory kernel (444 B of state: 512 instances / SM)
-            const char *e = getenv("TMPC_KERNEL");
-            if (e && !strcmp(e, "generic")) return pick<float, 4, 1, 10, 512, false>(policy, warm, out);
-            if (e && !strcmp(e, "generic_unroll")) return pick<float, 4, 1, 10, 512, true>(policy, warm, out);
-            if (e && !strcmp(e, "small256")) return pick_small<4, 10, 256>(policy, warm, out);
-            if (e && !strcmp(e, "small512")) return pick_small<4, 10, 512>(policy, warm, out);
-            return pick_small<4, 10, 384>(policy, warm, out);
+            if (generic) return tmpc_dispatch::lookup_generic(nx, nu, N, dtype, policy, warm, 0, out);
+            if (e && !strcmp(e, "generic_unroll")) return tmpc_dispatch::lookup_generic(nx, nu, N, dtype, policy, warm, 2, out);
+            if (e && !strcmp(e, "small256")) return tmpc_dispatch::lookup_small(256, policy, warm, out);
+            if (e && !strcmp(e, "small512")) return tmpc_dispatch::lookup_small(512, policy, warm, out);
+            return tmpc_dispatch::lookup_small(384, policy, warm, out);
         }
-        return pick<double, 4, 1, 10, 128, false>(policy, warm, out);
+        return tmpc_dispatch::lookup_generic(nx, nu, N, dtype, policy, warm, 0, out);
     }
     // large shape: one warp per instance.  g,v in tensor memory -> 16 instances / SM (TMPC_KERNEL=warp_smem: all state in
     // shared memory, 17.8 KB each -> 12 instances / SM)
-    if (nx == 32 && nu == 8 && N == 50 && dtype == TMPC_F32) {
-        const char *e = getenv("TMPC_KERNEL");
-        if (e && !strcmp(e, "warp_smem")) return pick_warp<50, 12, false>(policy, warm, out);
-        return pick_warp<50, 16, true>(policy, warm, out);
-    }
+    if (nx == 32 && nu == 8 && N == 50 && dtype == TMPC_F32)
+        return tmpc_dispatch::lookup_warp(!(e && !strcmp(e, "warp_smem")), policy, warm, out);
     return lookup_kernel_rt(nx, nu, N, dtype, policy, out);
 }
 
@@ -613,12 +485,13 @@ bool build_model_rt(tmpc_ctx_impl *c)
 }
 
 bool build_model_shape(tmpc_ctx_impl *c);
+bool ib_on_f32_kernel(const tmpc_ctx_impl *c);
 bool build_model(tmpc_ctx_impl *c)
 {
     if (!build_model_shape(c)) return false;
     // per-instance bounds run on the run-time-shape kernel whatever the shape: keep its image current
     KernelInfo probe;
-    if (c->ib_batch && !(lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, false, probe) && probe.model_kind == 3))
+    if (c->ib_batch && !ib_on_f32_kernel(c) && !(lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, false, probe) && probe.model_kind == 3))
         return build_model_rt(c);
     return true;
 }
@@ -673,6 +546,9 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     unsigned *gate;
     const unsigned *order;
     void *u0;
+    void *scratch;
+    int sc_ib, sc_xr, sc_wm, sc_chunks;
+    const void *ixmin, *ixmax, *iumin, *iumax;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
@@ -746,6 +622,35 @@ int plan_launch(tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da, cudaS
     return TMPC_OK;
 }
 
+// fp32 12/4/10 kernel: which regions of the per-lane coalesced scratch this launch needs (tmpc_kernel_f32.cuh ScratchMap)
+int plan_lane_scratch(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, long long blocks, bool ib)
+{
+    da.scratch = nullptr; da.sc_ib = da.sc_xr = da.sc_wm = -1; da.sc_chunks = 0;
+    da.ixmin = da.ixmax = da.iumin = da.iumax = nullptr;
+    if (ki.model_kind != 1 || ki.block != 256) return TMPC_OK;
+    using SM = tmpc::ScratchMap<12, 4, 10>;
+    int chunks = 0;
+    if (ib) {
+        da.sc_ib = chunks; chunks += SM::IB_CHUNKS;
+        if (c->en_state) { da.ixmin = c->d_ib[0]; da.ixmax = c->d_ib[1]; }
+        if (c->en_input) { da.iumin = c->d_ib[2]; da.iumax = c->d_ib[3]; }
+    }
+    if (da.xref_stride != 0 && !getenv("TMPC_NO_XR_SCRATCH")) { da.sc_xr = chunks; chunks += SM::XR_CHUNKS; }
+    if (da.wd && !getenv("TMPC_NO_WM_SCRATCH")) { da.sc_wm = chunks; chunks += SM::WM_CHUNKS; }
+    da.sc_chunks = chunks;
+    if (!chunks) return TMPC_OK;
+    const size_t need = (size_t)blocks * ki.block * chunks * 16;
+    if (c->d_lane_scratch_bytes < need) {
+        CUDA_TRY(c, cudaDeviceSynchronize());   // an earlier launch may still use the old area
+        if (c->d_lane_scratch) cudaFree(c->d_lane_scratch);
+        c->d_lane_scratch = nullptr; c->d_lane_scratch_bytes = 0;
+        CUDA_TRY(c, cudaMalloc(&c->d_lane_scratch, need));
+        c->d_lane_scratch_bytes = need;
+    }
+    da.scratch = c->d_lane_scratch;
+    return TMPC_OK;
+}
+
 // Launch one persistent kernel (already chosen) for one device-resident batch on `s`.
 int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cudaStream_t s, bool time_it, bool ev0_done = false)
 {
@@ -759,7 +664,8 @@ int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cuda
     da.stats = c->d_counter + 1;
     long long blocks = 1;
     {
-        const int rc = plan_launch(c, ki, da, s, blocks);
+        int rc = plan_launch(c, ki, da, s, blocks);
+        if (rc == TMPC_OK) rc = plan_lane_scratch(c, ki, da, blocks, c->ib_batch != 0 && !da.sys);
         if (rc != TMPC_OK) return rc;
     }
     void *params[2] = {model_param(c, ki), &da};
@@ -893,11 +799,24 @@ int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = n
     return TMPC_OK;
 }
 
+// per-instance bounds run on the specialised kernel where one exists with the IB option (fp32 12/4/10, TMEM variant)
+bool ib_on_f32_kernel(const tmpc_ctx_impl *c)
+{
+    return c->nx == 12 && c->nu == 4 && c->N == 10 && c->dtype == TMPC_F32 && kernel_variant() == 2 && !force_rt() && !getenv("TMPC_IB_RT");
+}
+
 int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
 {
     KernelInfo ki;
-    if (c->ib_batch) {
-        // per-instance bounds: the run-time-shape kernel reads each instance's own rows (index order, no scheduling pre-pass)
+    const bool ib_f32 = c->ib_batch && ib_on_f32_kernel(c);
+    if (ib_f32) {
+        // per-instance bounds on the specialised fp32 12/4/10 kernel: each lane copies its instance's box into its coalesced
+        // scratch rows at refill and projects onto it (IB instances of the kernel)
+        if (da.sys) return fail(c, TMPC_ERR_UNSUPPORTED, "per-instance bounds with per-instance systems");
+        if (da.batch != c->ib_batch) return fail(c, TMPC_ERR_INVALID, "batch differs from the batch of tmpc_set_instance_bounds");
+        if (!tmpc_dispatch::lookup_f32(c->policy, warm, c->pattern, false, 2, ki, true)) return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
+    } else if (c->ib_batch) {
+        // other shapes: the run-time-shape kernel reads each instance's own rows (index order, no scheduling pre-pass)
         if (da.sys) return fail(c, TMPC_ERR_UNSUPPORTED, "per-instance bounds with per-instance systems");
         if (da.batch != c->ib_batch) return fail(c, TMPC_ERR_INVALID, "batch differs from the batch of tmpc_set_instance_bounds");
         if (!c->rt_ready || !lookup_kernel_rt(c->nx, c->nu, c->N, c->dtype, c->policy, ki))
@@ -910,7 +829,7 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
         const int rc = order_after_previous(c, s);   // the scheduling buffers may still be read by the previous launch
         if (rc != TMPC_OK) return rc;
     }
-    if (!da.sys && !c->ib_batch && !da.order && lpt_wanted(c, ki, da)) {
+    if (!da.sys && (!c->ib_batch || ib_f32) && !da.order && lpt_wanted(c, ki, da)) {
         // the pre-pass is part of the solve: it runs on the same stream inside the timed region
         if (time_it) { CUDA_TRY(c, cudaEventRecord(c->ev0, s)); ev0_done = true; }
         const int rc = lpt_prepare(c, da, s);
@@ -1108,7 +1027,8 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     if (waitf) {
         // Whatever happened inside the kernel (a lane that gave up at the input gate never reports its instance), the copy
         // stream must drain: once the kernel is over every completion counter is released.
-        CUDA_TRY(c, cudaMemsetAsync(c->g_done, 0xff, sizeof(unsigned) * nch, s));
+        // (0x7f7f7f7f: cuStreamWaitValue32 GEQ is the cyclic comparison (int32)(*addr - value) >= 0, so "all ones" would read as -1)
+        CUDA_TRY(c, cudaMemsetAsync(c->g_done, 0x7f, sizeof(unsigned) * nch, s));
     } else {                                            // no stream mem-ops available: plain copy after the kernel
         CUDA_TRY(c, cudaEventRecord(c->g_h2d, s));
         CUDA_TRY(c, cudaStreamWaitEvent(cs, c->g_h2d, 0));
@@ -1255,6 +1175,7 @@ int tmpc_destroy(tmpc_ctx *ctx)
     if (c->d_model_w) cudaFree(c->d_model_w);
     if (c->d_model_rt) cudaFree(c->d_model_rt);
     if (c->d_rt_scratch) cudaFree(c->d_rt_scratch);
+    if (c->d_lane_scratch) cudaFree(c->d_lane_scratch);
     for (void *p : c->d_ib) if (p) cudaFree(p);
     if (c->d_kinf) cudaFree(c->d_kinf);
     if (c->lpt_buf) cudaFree(c->lpt_buf);
@@ -1389,6 +1310,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
     if (!warm && (c->ib_batch || !getenv("TMPC_HOST_CHUNKED"))) return solve_host_gated(c, a);
     if (c->ib_batch)   // the chunked pipeline launches per chunk with chunk-relative instance numbers
         return fail(c, TMPC_ERR_UNSUPPORTED, "per-instance bounds with a warm start from host memory: use device buffers or tmpc_batch");
+    // (the chunk loop below launches through plan_launch directly; it never sees per-instance bounds)
 
     // ---- host buffers: chunked 3-deep pipeline  H2D(k+1) | solve(k) | D2H(k-1) on three streams
     // input chunk image : x0 | [Xref per instance] | [warm d y z g v]
@@ -1516,6 +1438,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
             da.stats = c->d_counter + 1;
             long long blocks = 1;
             if ((rc_all = plan_launch(c, ki, da, st.s, blocks)) != TMPC_OK) break;
+            if ((rc_all = plan_lane_scratch(c, ki, da, blocks, false)) != TMPC_OK) break;
             void *params[2] = {model_param(c, ki), &da};
             cudaEventRecord(kev[2 * k], st.s);
             cudaError_t e = cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, st.s);

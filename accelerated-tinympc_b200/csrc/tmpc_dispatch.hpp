@@ -1,0 +1,36 @@
+// Kernel tables of the library, one translation unit per kernel family (k_*.cu) so that the families compile in parallel
+// and a change to one kernel rebuilds one object.  tmpc_api.cu owns contexts, model images and launches; it gets function
+// pointers, launch shapes and shared-memory sizes from the look-ups below.
+#pragma once
+#include <cstddef>
+
+namespace tmpc_dispatch {
+
+struct KernelInfo {
+    const void *fn;
+    size_t smem;
+    int block;
+    size_t model_bytes;
+    int model_kind;  // 0: tmpc::Model<T,...> (generic kernel)   1: tmpc::ModelF32<...> (packed fp32 kernel)
+                     // 2: tmpc::ModelWarp (warp-per-instance kernel; pointers into the ctx's device model image)
+                     // 3: tmpc::ModelRT<T> (run-time-shape kernel; pointers into the ctx's device model image + scratch)
+    int per_block;   // instances resident per block (threads for the thread-per-instance kernels, warps for kind 2)
+};
+
+// fp32 12/4/10 production kernel (tmpc_kernel_f32.cuh).  variant 2: g, v in tensor memory, 256 instances / SM (default);
+// 1: all state in shared memory, 128 / SM.  pattern: 0 dense, 1 quadrotor structure.
+// per_instance_bounds: the IB instances (variant 2 only; boxes read from the lane's scratch rows)
+bool lookup_f32(int policy, bool warm, int pattern, bool const_bounds, int variant, KernelInfo &out, bool per_instance_bounds = false);
+
+// generic shared-memory kernel (tmpc_kernel.cuh): fp64 shapes and the development variants of the fp32 shapes.
+// variant 0: default for the shape / dtype; 1: all state in shared memory; 2: horizon loops unrolled (4/1/10 fp32 only)
+bool lookup_generic(int nx, int nu, int N, int dtype, int policy, bool warm, int variant, KernelInfo &out);
+// per-instance systems instances of the generic kernel; global_coeffs: re-read the coefficients from global memory
+bool lookup_sys(int nx, int nu, int N, int dtype, int policy, bool warm, bool global_coeffs, KernelInfo &out);
+
+// register-resident single-input kernel, fp32 4/1/10 (tmpc_kernel_small.cuh); block = 256, 384 or 512
+bool lookup_small(int block, int policy, bool warm, KernelInfo &out);
+// warp-per-instance kernel, fp32 32/8/50 (tmpc_kernel_warp.cuh); tm: g, v in tensor memory (16 instances / SM), else 12
+bool lookup_warp(bool tm, int policy, bool warm, KernelInfo &out);
+
+}  // namespace tmpc_dispatch

@@ -198,6 +198,17 @@ template <class T> struct SolveArgs {
     const unsigned *order;        // nullable: the k-th claim of the work counter solves instance order[k] (longest-expected-first
                                   // schedule built by the host pre-pass, tmpc_api.cu lpt_prepare); null = instance k
     T *u0;                        // nullable: out [batch][nu] = u(:,0), the control an MPC caller applies (quadrotor_hovering.cpp:110)
+    // Per-lane coalesced scratch of the fp32 12/4/10 kernel (tmpc_kernel_f32.cuh LaneScratch): 16-byte chunks laid out
+    // [warp of the grid][chunk][lane of the warp], so that a warp's access to one chunk is one contiguous 512-byte run.  It
+    // holds what is private to the lane's CURRENT instance, lives for many iterations and does not fit on chip:
+    //   sc_ib: the instance's own box (tmpc_set_instance_bounds), copied in at refill, read by every forward sweep;
+    //   sc_xr: -(Xref o Q) of a per-instance reference trajectory, computed at refill, read by every backward sweep;
+    //   sc_wm: mirror of d / v / z written by every backward sweep of a warm-started solve (the reference leaves them one
+    //          iteration behind on an early exit), copied to the caller's buffers once, at termination.
+    // Each sc_* is the first chunk of its region or -1.  L2-resident: <= 157 chunks x 37,888 lanes = 95 MB, usually a third.
+    void *scratch;
+    int sc_ib, sc_xr, sc_wm, sc_chunks;
+    const T *ixmin, *ixmax, *iumin, *iumax;   // per-instance boxes [instance][N][nx] / [instance][N-1][nu]; a null pair = unbounded
 };
 
 // instance solved by the idx-th claim of the work counter

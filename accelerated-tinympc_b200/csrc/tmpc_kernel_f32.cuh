@@ -353,6 +353,41 @@ template <class PAT> struct MaskM {
     __host__ __device__ static constexpr uint32_t one(int) { return 0u; }
 };
 
+// This lane's rows of the per-lane coalesced scratch (SolveArgs::scratch): chunk c of the lane is one float4; the 32 lanes of
+// a warp hold chunk c in 512 contiguous bytes, so every access below is a fully coalesced LDG.128 / STG.128 that stays in
+// L2 (ld/st.global.cg: the lines are private to the lane, L1 would only be thrashed).
+struct LaneScratch {
+    float4 *base;
+    __device__ __forceinline__ LaneScratch(void *scratch, int chunks, int block_threads)
+    {
+        const long long gwarp = (long long)blockIdx.x * (block_threads >> 5) + (threadIdx.x >> 5);
+        base = reinterpret_cast<float4 *>(scratch) + (gwarp * chunks) * 32 + (threadIdx.x & 31);
+    }
+    __device__ __forceinline__ float4 ld(int c) const { return __ldcg(base + c * 32); }
+    __device__ __forceinline__ void st(int c, float4 v) const { __stcg(base + c * 32, v); }
+    template <int D> __device__ __forceinline__ void ldv(int c, float (&o)[D]) const
+    {
+#pragma unroll
+        for (int k = 0; k < D / 4; ++k) {
+            const float4 t = ld(c + k);
+            o[4 * k] = t.x; o[4 * k + 1] = t.y; o[4 * k + 2] = t.z; o[4 * k + 3] = t.w;
+        }
+    }
+    template <int D> __device__ __forceinline__ void stv(int c, const float (&o)[D]) const
+    {
+#pragma unroll
+        for (int k = 0; k < D / 4; ++k) st(c + k, make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+    }
+};
+// chunk maps (NX = 12, NU = 4): per-instance box of stage i = 8 chunks [xmin(3) xmax(3) umin(1) umax(1)]; -(Xref o Q) of stage
+// i = 3 chunks; warm mirror of stage i = 5 chunks [v(3) z(1) d(1)] (last stage: v only)
+template <int NX, int NU, int NH> struct ScratchMap {
+    static constexpr int CX = NX / 4, CU = NU / 4;
+    static constexpr int IB_STAGE = 2 * CX + 2 * CU, IB_CHUNKS = IB_STAGE * NH;
+    static constexpr int XR_STAGE = CX, XR_CHUNKS = XR_STAGE * (NH - 1);
+    static constexpr int WM_STAGE = CX + 2 * CU, WM_CHUNKS = WM_STAGE * (NH - 1) + CX;
+};
+
 template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
     using SU = SVec<float, NU, NH - 1, BLOCK>;
     using SP = SVec<float, NX, 1, BLOCK>;
@@ -363,10 +398,17 @@ template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
 // CB: the bounds are the same at every horizon stage (the usual box constraints, e.g. every example of the reference):
 // the kernel reads stage 0's row with compile-time addresses (operands straight from the constant bank) instead of
 // indexing the per-stage table with the loop counter (LDC.64 with a register index: 2.7 % of the instructions).
-template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT = PatDense<NX>, bool CB = false>
+// IB: every instance has its own box (tmpc_set_instance_bounds): the bound operands of the projection come from the lane's
+// scratch rows (filled at refill from the ctx's [instance][stage][dim] copy) instead of the constant bank.
+template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT = PatDense<NX>, bool CB = false, bool IB = false>
 __global__ void __launch_bounds__(BLOCK, 1)
 admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_constant__ SolveArgs<float> a)
 {
+    static_assert(!(IB && CB), "per-instance bounds are never constant over the batch");
+    using SM = ScratchMap<NX, NU, NH>;
+    const LaneScratch sc(a.scratch, a.sc_chunks, BLOCK);
+    const bool xr_sc = a.sc_xr >= 0;        // per-instance Xref: -(Xref o Q) rows precomputed at refill (kernel-uniform)
+    const bool wm_sc = WARM && a.sc_wm >= 0;  // warm mirror through the scratch (kernel-uniform)
     static_assert(NX % 4 == 0 && NU % 4 == 0, "packed kernel: 16-byte vectors of x and u");
     using O = Orders<float, NX, NU>;
     using L = SmemLayoutF32<NX, NU, NH, BLOCK, TM>;
@@ -429,13 +471,10 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
         spn.store(0, pn);
     };
     const bool shared_xref = (a.xref_stride == 0);
-    // Controls-only callers (x = u = NULL, u0 given: what an MPC loop applies, quadrotor_hovering.cpp:110): u(:,0) of the trip in
-    // which the lane terminates is kept in registers and written with iter / status, so neither an emission trip nor a
-    // speculative one is needed.  Warm starts still emit (their g / y write-back rides on the emission sweep).
+    // Controls-only callers (x = u = NULL, u0 given: what an MPC loop applies, quadrotor_hovering.cpp:110): u(:,0) is stored by
+    // every trip's stage 0, so the trip in which the lane terminates has already delivered it and neither an emission trip
+    // nor a speculative one is needed.  Warm starts still emit (their g / y write-back rides on the emission sweep).
     const bool u0only = !a.x && !a.u && !(WARM && a.wd);
-    float u0r[NU];
-#pragma unroll
-    for (int j = 0; j < NU; ++j) u0r[j] = 0.f;
     if (shared_xref) seed_pn(a.Xref + (NH - 1) * NX);
 
     for (;;) {
@@ -463,6 +502,47 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);
                     if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
+                    if (xr_sc) {
+                        // q_i's constant part -(Xref_i o Q) (admm.cpp:81) depends on the instance only: computed once here (same
+                        // two operations, same bits) instead of in every backward sweep, and kept in the lane's scratch rows
+                        const float *xl = a.Xref + inst * a.xref_stride;
+#pragma unroll 1
+                        for (int i = 0; i < NH - 1; ++i) {
+                            float xr[NX], cq[NX];
+                            gload<float, NX>(xl + i * NX, xr);
+#pragma unroll
+                            for (int j = 0; j < NX; j += 2) {
+                                const float2 t = neg2(prode(f2(xr[j], xr[j + 1]), f2(P.Qd[j], P.Qd[j + 1]), Z));
+                                cq[j] = t.x; cq[j + 1] = t.y;
+                            }
+                            sc.stv<NX>(a.sc_xr + SM::XR_STAGE * i, cq);
+                        }
+                    }
+                    if constexpr (IB) {
+                        // the instance's own box -> the lane's scratch rows, stage by stage (a missing / disabled family = +-inf)
+                        const float inf = __int_as_float(0x7f800000);
+#pragma unroll 1
+                        for (int i = 0; i < NH; ++i) {
+                            float lo[NX], hi[NX];
+                            if (a.ixmin) { gload<float, NX>(a.ixmin + inst * XROW + i * NX, lo); gload<float, NX>(a.ixmax + inst * XROW + i * NX, hi); }
+                            else {
+#pragma unroll
+                                for (int j = 0; j < NX; ++j) { lo[j] = -inf; hi[j] = inf; }
+                            }
+                            sc.stv<NX>(a.sc_ib + SM::IB_STAGE * i, lo);
+                            sc.stv<NX>(a.sc_ib + SM::IB_STAGE * i + SM::CX, hi);
+                            if (i < NH - 1) {
+                                float ul[NU], uh[NU];
+                                if (a.iumin) { gload<float, NU>(a.iumin + inst * UROW + i * NU, ul); gload<float, NU>(a.iumax + inst * UROW + i * NU, uh); }
+                                else {
+#pragma unroll
+                                    for (int j = 0; j < NU; ++j) { ul[j] = -inf; uh[j] = inf; }
+                                }
+                                sc.stv<NU>(a.sc_ib + SM::IB_STAGE * i + 2 * SM::CX, ul);
+                                sc.stv<NU>(a.sc_ib + SM::IB_STAGE * i + 2 * SM::CX + SM::CU, uh);
+                            }
+                        }
+                    }
                     if (WARM && a.wd) {
 #pragma unroll 1
                         for (int i = 0; i < NH - 1; ++i) {
@@ -535,7 +615,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             float *go = (WARM && wr && a.wg) ? a.wg + inst * XROW : nullptr;
             float *yo = (WARM && wr && a.wy) ? a.wy + inst * UROW : nullptr;
 
-            auto xpart = [&](int i, float (&gv)[2 * NX]) {
+            auto xpart = [&](int i, float (&gv)[2 * NX], const float (&bxl)[NX], const float (&bxh)[NX]) {
                 // state slack / dual / residuals for stage i (uses x_i)
                 xs.wait(gv);
                 float g[NX], vn[NX];
@@ -544,9 +624,14 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 for (int j = 0; j < NX; j += 2) {
                     const float2 x2 = f2(x[j], x[j + 1]), g2 = f2(gv[j], gv[j + 1]), v2 = f2(gv[NX + j], gv[NX + j + 1]);
                     float2 t = add2(x2, g2);                                                         // :48
-                    const int bi = CB ? 0 : i * NX;
-                    t.x = fminf(P.xmax[bi + j], fmaxf(P.xmin[bi + j], t.x));                       // :59
-                    t.y = fminf(P.xmax[bi + j + 1], fmaxf(P.xmin[bi + j + 1], t.y));
+                    if constexpr (IB) {
+                        t.x = fminf(bxh[j], fmaxf(bxl[j], t.x));                                   // :59, the instance's own box
+                        t.y = fminf(bxh[j + 1], fmaxf(bxl[j + 1], t.y));
+                    } else {
+                        const int bi = CB ? 0 : i * NX;
+                        t.x = fminf(P.xmax[bi + j], fmaxf(P.xmin[bi + j], t.x));                   // :59
+                        t.y = fminf(P.xmax[bi + j + 1], fmaxf(P.xmin[bi + j + 1], t.y));
+                    }
                     const float2 rp = sub2(x2, t), rd = sub2(v2, t);
                     pri_x = fmaxf(pri_x, fmaxf(fabsf(rp.x), fabsf(rp.y)));                           // :95
                     dua_x = fmaxf(dua_x, fmaxf(fabsf(rd.x), fabsf(rd.y)));                           // :96
@@ -562,6 +647,15 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             for (int i = 0; i < NH - 1; ++i) {
                 float gv[2 * NX];
                 xs.load_issue(i, gv);
+                // the instance's own box for this stage: 8 coalesced 16-byte loads from the lane's scratch rows, in flight
+                // behind the mat-vecs below
+                float bxl[NX], bxh[NX], bul[NU], buh[NU];
+                if constexpr (IB) {
+                    sc.ldv<NU>(a.sc_ib + SM::IB_STAGE * i + 2 * SM::CX, bul);
+                    sc.ldv<NU>(a.sc_ib + SM::IB_STAGE * i + 2 * SM::CX + SM::CU, buh);
+                    sc.ldv<NX>(a.sc_ib + SM::IB_STAGE * i, bxl);
+                    sc.ldv<NX>(a.sc_ib + SM::IB_STAGE * i + SM::CX, bxh);
+                }
                 float d[NU], y[NU], z[NU];
                 sd.load(i, d); sy.load(i, y); sz.load(i, z);
                 // [K;A] x_i in one column sweep
@@ -595,9 +689,14 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     const float2 d2 = f2(d[r], d[r + 1]), y2 = f2(y[r], y[r + 1]), z2 = f2(z[r], z[r + 1]);
                     const float2 u2 = sub2(neg2(ka[r / 2]), d2);                                     // :31
                     float2 t = add2(u2, y2);                                                         // :47
-                    const int bu = CB ? 0 : i * NU;
-                    t.x = fminf(P.umax[bu + r], fmaxf(P.umin[bu + r], t.x));                       // :53
-                    t.y = fminf(P.umax[bu + r + 1], fmaxf(P.umin[bu + r + 1], t.y));
+                    if constexpr (IB) {
+                        t.x = fminf(buh[r], fmaxf(bul[r], t.x));                                   // :53, the instance's own box
+                        t.y = fminf(buh[r + 1], fmaxf(bul[r + 1], t.y));
+                    } else {
+                        const int bu = CB ? 0 : i * NU;
+                        t.x = fminf(P.umax[bu + r], fmaxf(P.umin[bu + r], t.x));                   // :53
+                        t.y = fminf(P.umax[bu + r + 1], fmaxf(P.umin[bu + r + 1], t.y));
+                    }
                     const float2 rp = sub2(u2, t), rd = sub2(z2, t);
                     pri_u = fmaxf(pri_u, fmaxf(fabsf(rp.x), fabsf(rp.y)));                           // :97
                     dua_u = fmaxf(dua_u, fmaxf(fabsf(rd.x), fabsf(rd.y)));                           // :98
@@ -608,11 +707,10 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 sz.store(i, zn);
                 if (WARM && yo && !emit) gstore<float, NU>(yo + i * NU, y);
                 if (uo) gstore<float, NU>(uo + i * NU, u);
-                if (i == 0) {
-#pragma unroll
-                    for (int j = 0; j < NU; ++j) u0r[j] = u[j];
-                    if (wr && a.u0 && !u0only) gstore<float, NU>(a.u0 + inst * NU, u);
-                }
+                // u(:,0): with the trajectory outputs it is written by the emitting trip; a controls-only solve stores it in EVERY
+                // trip (16 bytes per lane, the terminating trip's value is the last one written) -- cheaper than keeping it in
+                // four registers across the sweep (measured: 10.21 -> 10.10 ms per 1M-instance launch)
+                if (i == 0 && a.u0 && (u0only ? phase == PH_RUN : wr)) gstore<float, NU>(a.u0 + inst * NU, u);
                 // x_{i+1} = A x_i + B u_i                                                            :35
                 float2 xn[NX / 2];
                 if constexpr (FAST) {
@@ -629,20 +727,27 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
 #pragma unroll
                     for (int j = 0; j < NX / 2; ++j) xn[j] = add2(ka[NU / 2 + j], bu[j]);
                 }
-                xpart(i, gv);
+                xpart(i, gv, bxl, bxh);
 #pragma unroll
                 for (int j = 0; j < NX / 2; ++j) { x[2 * j] = xn[j].x; x[2 * j + 1] = xn[j].y; }
             }
             {
                 float gv[2 * NX];
                 xs.load_issue(NH - 1, gv);
-                xpart(NH - 1, gv);
+                float bxl[NX], bxh[NX];
+                if constexpr (IB) {
+                    sc.ldv<NX>(a.sc_ib + SM::IB_STAGE * (NH - 1), bxl);
+                    sc.ldv<NX>(a.sc_ib + SM::IB_STAGE * (NH - 1) + SM::CX, bxh);
+                }
+                xpart(NH - 1, gv, bxl, bxh);
             }
             xs.fence_st();
         }
 
         // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
         bool final_bwd = false;
+        bool wb = false;         // WARM, scratch mirror: converged in this trip after >= 2 iterations -> the d / v / z the reference
+                                 // leaves in its workspace (those of iteration it - 1) go from the lane's scratch rows to the caller's
         bool finished = false;   // every output of this lane's instance is (or will be, after this trip's backward) written
         if (phase == PH_RUN) {
             const bool chk = (it % P.check_term) == 0;
@@ -656,10 +761,9 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 if (a.resid) *reinterpret_cast<float4 *>(a.resid + inst * 4) = make_float4(res[0], res[1], res[2], res[3]);
                 n_iter += (unsigned)it; n_solved += conv ? 1u : 0u; ++n_inst;
                 final_bwd = !conv;
-                if (u0only) {
-                    if (a.u0) gstore<float, NU>(a.u0 + inst * NU, u0r);
-                    phase = PH_FREE; finished = true;
-                } else if (spec) { phase = PH_FREE; finished = true; }   // x,u of this very trip are already in the output
+                wb = wm_sc && conv && it > 1 && a.wd;
+                if (u0only) { phase = PH_FREE; finished = true; }   // u(:,0) of this very trip is already in the output
+                else if (spec) { phase = PH_FREE; finished = true; }   // x,u of this very trip are already in the output
                 else phase = PH_EMIT;
                 spec = false;
             } else if (!u0only) {
@@ -678,19 +782,34 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
         // ------------------------------------------------------------------ backward sweep
         // update_linear_cost (admm.cpp:77-85) recomputed per stage + backward_pass_grad (:15-22)
         const bool cont = (phase == PH_RUN);
+        // Warm start: the caller's d / v / z must end up as the reference leaves its workspace -- after a max_iter exit those of
+        // the last iteration (this trip's backward still runs: final_bwd), after an early exit those of the iteration BEFORE
+        // the one that met the tolerances (admm.cpp:135-144).  The forward sweep has already overwritten v and z on chip, so
+        // every backward sweep of a continuing lane mirrors d, v, z: into the lane's coalesced scratch rows (wm_sc; copied out
+        // once, by `wb`, when the instance converges) or, without a scratch, straight into the caller's buffers.
         const bool wout = WARM && (cont || final_bwd) && a.wd;
-        if (__any_sync(FULLM, cont || wout)) {
+        const bool wmir = wout && cont && wm_sc;          // mirror to the scratch
+        const bool wdir = wout && !wmir;                  // write the caller's buffers directly
+        if (__any_sync(FULLM, cont || wout || wb)) {
             float p[NX];
             const float *xr_base = a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
-            float *wdo = wout ? a.wd + inst * UROW : nullptr;
-            float *wvo = wout ? a.wv + inst * XROW : nullptr;
-            float *wzo = wout ? a.wz + inst * UROW : nullptr;
+            float *wdo = (wdir || wb) ? a.wd + inst * UROW : nullptr;
+            float *wvo = (wdir || wb) ? a.wv + inst * XROW : nullptr;
+            float *wzo = (wdir || wb) ? a.wz + inst * UROW : nullptr;
             {
                 float gv[2 * NX], pn[NX];
                 xs.load_issue(NH - 1, gv);
                 spn.load(0, pn);
                 xs.wait(gv);
-                if (WARM && wvo) gstore<float, NX>(wvo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                if constexpr (WARM) {
+                    if (wdir) gstore<float, NX>(wvo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                    else if (wmir) sc.stv<NX>(a.sc_wm + SM::WM_STAGE * (NH - 1), *reinterpret_cast<float(*)[NX]>(gv + NX));
+                    else if (wb) {
+                        float t[NX];
+                        sc.ldv<NX>(a.sc_wm + SM::WM_STAGE * (NH - 1), t);
+                        gstore<float, NX>(wvo + (NH - 1) * NX, t);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < NX; ++j) {
                     const float dvg = __fsub_rn(gv[NX + j], gv[j]);
@@ -705,7 +824,9 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 float z[NU], y[NU], r[NU], xr[NX];
                 sz.load(i, z);
                 sy.load(i, y);
-                gload<float, NX>(xr_base + i * NX, xr);
+                // xr: Xref_i (shared trajectory: a uniform load) or, per-instance, the precomputed -(Xref_i o Q) from the scratch rows
+                if (xr_sc) sc.ldv<NX>(a.sc_xr + SM::XR_STAGE * i, xr);
+                else gload<float, NX>(xr_base + i * NX, xr);
 #pragma unroll
                 for (int j = 0; j < NU; j += 2) {                                                    // :80
                     float2 t = sub2(f2(z[j], z[j + 1]), f2(y[j], y[j + 1]));
@@ -756,17 +877,32 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
 #pragma unroll
                 for (int j = 0; j < NU / 2; ++j) { d[2 * j] = d2[j].x; d[2 * j + 1] = d2[j].y; }
                 sd.store(i, d, cont);
-                if (WARM && wdo) gstore<float, NU>(wdo + i * NU, d);
+                if constexpr (WARM) {
+                    if (wdir) gstore<float, NU>(wdo + i * NU, d);
+                    else if (wmir) { sc.stv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX + SM::CU, d); sc.stv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX, z); }
+                }
                 float2 kr[NX / 2];
                 matvec2<O::Ktr, NX, NU, NX, 0, FAST>(P.Kr, r, kr, Z);
                 xs.wait(gv);
-                if (WARM && wvo) {
-                    gstore<float, NX>(wvo + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
-                    gstore<float, NU>(wzo + i * NU, z);
+                if constexpr (WARM) {
+                    if (wdir) {
+                        gstore<float, NX>(wvo + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                        gstore<float, NU>(wzo + i * NU, z);
+                    } else if (wmir) {
+                        sc.stv<NX>(a.sc_wm + SM::WM_STAGE * i, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                    } else if (wb) {
+                        float tv[NX], tz[NU], td[NU];
+                        sc.ldv<NX>(a.sc_wm + SM::WM_STAGE * i, tv);
+                        sc.ldv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX, tz);
+                        sc.ldv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX + SM::CU, td);
+                        gstore<float, NX>(wvo + i * NX, tv);
+                        gstore<float, NU>(wzo + i * NU, tz);
+                        gstore<float, NU>(wdo + i * NU, td);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < NX; j += 2) {
-                    const float2 cq = neg2(prode(f2(xr[j], xr[j + 1]), f2(P.Qd[j], P.Qd[j + 1]), Z));              // :81
+                    const float2 cq = xr_sc ? f2(xr[j], xr[j + 1]) : neg2(prode(f2(xr[j], xr[j + 1]), f2(P.Qd[j], P.Qd[j + 1]), Z));   // :81
                     const float2 dvg = sub2(f2(gv[NX + j], gv[NX + j + 1]), f2(gv[j], gv[j + 1]));
                     float2 q;
                     if constexpr (FAST) q = __ffma2_rn(f2(P.nrho, P.nrho), dvg, cq);

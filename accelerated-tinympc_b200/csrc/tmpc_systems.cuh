@@ -166,30 +166,10 @@ int sys_stride(int nx, int nu)
     return 0;
 }
 
-// per-instance-systems instances of the generic kernel (SYS = 1: coefficients from the global block; 2: TMEM-resident)
-template <class T, int NX, int NU, int NH, int BLOCK, int SYS>
-bool pick_sys(int policy, bool warm, KernelInfo &out)
-{
-    if (policy == TMPC_ORDER_PARITY)
-        out = warm ? make_info_g<T, NX, NU, NH, BLOCK, false, true, SYS>() : make_info_g<T, NX, NU, NH, BLOCK, false, false, SYS>();
-    else
-        out = warm ? make_info_g<T, NX, NU, NH, BLOCK, true, true, SYS>() : make_info_g<T, NX, NU, NH, BLOCK, true, false, SYS>();
-    return true;
-}
-
 bool lookup_kernel_sys(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out)
 {
-    if (nx == 12 && nu == 4 && N == 10) {
-        if (dtype == TMPC_F32) {
-            const char *e = getenv("TMPC_KERNEL");   // TMPC_KERNEL=sys_global: coefficients re-read from the global block
-            if (e && !strcmp(e, "sys_global")) return pick_sys<float, 12, 4, 10, 128, 1>(policy, warm, out);
-            return pick_sys<float, 12, 4, 10, 128, 2>(policy, warm, out);
-        }
-        return pick_sys<double, 12, 4, 10, 64, 1>(policy, warm, out);
-    }
-    if (nx == 4 && nu == 1 && N == 10)
-        return dtype == TMPC_F32 ? pick_sys<float, 4, 1, 10, 512, 1>(policy, warm, out) : pick_sys<double, 4, 1, 10, 128, 1>(policy, warm, out);
-    return false;
+    const char *e = getenv("TMPC_KERNEL");   // TMPC_KERNEL=sys_global: coefficients re-read from the global block
+    return tmpc_dispatch::lookup_sys(nx, nu, N, dtype, policy, warm, e && !strcmp(e, "sys_global"), out);
 }
 
 }  // namespace

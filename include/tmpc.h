@@ -78,7 +78,9 @@ int tmpc_set_settings(tmpc_ctx *ctx, double abs_pri_tol, double abs_dua_tol, int
  *   x_min, x_max [batch][N][nx], u_min, u_max [batch][N-1][nu]  (host or device, `mem` = tmpc_mem); all four given.
  * The library keeps its own device copy.  While set, tmpc_solve / tmpc_batch_solve must be called with exactly
  * this batch; instance i is projected onto its own box (admm.cpp:53,59) -- en_state_bound / en_input_bound still
- * switch each family off -- and the solve runs on the run-time-shape kernel in index order, for every shape.
+ * switch each family off.  fp32 12/4/10 keeps its specialised kernel (each lane copies its instance's box into its
+ * coalesced, L2-resident scratch rows when it claims the instance and reads the stage's 128 bytes from there in every
+ * forward sweep); every other shape runs on the run-time-shape kernel in index order.
  * batch = 0 (pointers ignored) returns to the shared bounds of tmpc_set_model.  Not applied by tmpc_step and
  * tmpc_solve_systems; a warm start from HOST memory is refused (use device buffers or a tmpc_batch). */
 int tmpc_set_instance_bounds(tmpc_ctx *ctx, int64_t batch, const void *x_min, const void *x_max, const void *u_min,

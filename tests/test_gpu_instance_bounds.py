@@ -151,3 +151,31 @@ def test_instance_bounds_wrapper_calls(pkg, oracle):
     _cmp({k: b.get(k) for k in ("iter", "status", "x", "u", "resid")}, r2, "second solve")
     b.close()
     s.close()
+
+
+def test_instance_bounds_large_batch_on_the_specialised_kernel(pkg, oracle):
+    """fp32 12/4/10: per-instance boxes run on the specialised kernel (each lane copies its instance's box into its coalesced
+    scratch rows at refill).  A batch large enough for several refills per lane and for the longest-expected-first schedule
+    must agree bit for bit with the run-time-shape kernel on the same boxes (TMPC_IB_RT=1), and a prefix with the oracle."""
+    import os
+    prob = pkg.problems.quadrotor(20)
+    B, dt = 90_000, np.float32
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
+    b = _boxes(prob, B, np.random.default_rng(5), dt)
+    s = pkg.capi.Solver(prob, dtype=dt, policy="parity")
+    s.set_instance_bounds(*b)
+    out = s.solve(x0, xref)
+    s.close()
+    os.environ["TMPC_IB_RT"] = "1"
+    try:
+        s2 = pkg.capi.Solver(prob, dtype=dt, policy="parity")
+        s2.set_instance_bounds(*b)
+        out_rt = s2.solve(x0, xref)
+        s2.close()
+    finally:
+        del os.environ["TMPC_IB_RT"]
+    for k in ("iter", "status", "x", "u", "resid"):
+        assert_same(out[k], out_rt[k], "f32 kernel vs run-time-shape kernel " + k)
+    n = 1500
+    ref = _oracle_each(oracle, prob, x0[:n], xref, tuple(a[:n] for a in b), dt)
+    _cmp({k: out[k][:n] for k in ("iter", "status", "x", "u", "resid")}, ref, "prefix")
