@@ -547,7 +547,8 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     const unsigned *order;
     void *u0;
     void *scratch;
-    int sc_ib, sc_xr, sc_wm, sc_chunks;
+    int sc_ib, sc_wm, sc_chunks;
+    int test_flags;
     const void *ixmin, *ixmax, *iumin, *iumax;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
@@ -625,9 +626,10 @@ int plan_launch(tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da, cudaS
 // fp32 12/4/10 kernel: which regions of the per-lane coalesced scratch this launch needs (tmpc_kernel_f32.cuh ScratchMap)
 int plan_lane_scratch(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, long long blocks, bool ib)
 {
-    da.scratch = nullptr; da.sc_ib = da.sc_xr = da.sc_wm = -1; da.sc_chunks = 0;
+    da.scratch = nullptr; da.sc_ib = da.sc_wm = -1; da.sc_chunks = 0; da.test_flags = 0;
     da.ixmin = da.ixmax = da.iumin = da.iumax = nullptr;
-    if (ki.model_kind != 1 || ki.block != 256) return TMPC_OK;
+    if (ki.model_kind != 1) return TMPC_OK;
+    if (const char *e = getenv("TMPC_TEST_MIRROR")) da.test_flags = atoi(e);
     using SM = tmpc::ScratchMap<12, 4, 10>;
     int chunks = 0;
     if (ib) {
@@ -635,8 +637,7 @@ int plan_lane_scratch(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, long 
         if (c->en_state) { da.ixmin = c->d_ib[0]; da.ixmax = c->d_ib[1]; }
         if (c->en_input) { da.iumin = c->d_ib[2]; da.iumax = c->d_ib[3]; }
     }
-    if (da.xref_stride != 0 && !getenv("TMPC_NO_XR_SCRATCH")) { da.sc_xr = chunks; chunks += SM::XR_CHUNKS; }
-    if (da.wd && !getenv("TMPC_NO_WM_SCRATCH")) { da.sc_wm = chunks; chunks += SM::WM_CHUNKS; }
+    if (da.wd) { da.sc_wm = chunks; chunks += SM::WM_CHUNKS; }
     da.sc_chunks = chunks;
     if (!chunks) return TMPC_OK;
     const size_t need = (size_t)blocks * ki.block * chunks * 16;

@@ -202,12 +202,16 @@ template <class T> struct SolveArgs {
     // [warp of the grid][chunk][lane of the warp], so that a warp's access to one chunk is one contiguous 512-byte run.  It
     // holds what is private to the lane's CURRENT instance, lives for many iterations and does not fit on chip:
     //   sc_ib: the instance's own box (tmpc_set_instance_bounds), copied in at refill, read by every forward sweep;
-    //   sc_xr: -(Xref o Q) of a per-instance reference trajectory, computed at refill, read by every backward sweep;
-    //   sc_wm: mirror of d / v / z written by every backward sweep of a warm-started solve (the reference leaves them one
-    //          iteration behind on an early exit), copied to the caller's buffers once, at termination.
-    // Each sc_* is the first chunk of its region or -1.  L2-resident: <= 157 chunks x 37,888 lanes = 95 MB, usually a third.
+    //   sc_wm: mirror of d / v / z of a warm-started solve, written by the backward sweeps after which the next iteration may
+    //          converge (the reference leaves d / v / z one iteration behind on an early exit), copied to the caller's
+    //          buffers once, at termination.
+    // Each sc_* is the first chunk of its region or -1.  L2-resident: <= 128 chunks x 37,888 lanes = 78 MB.
+    // (A third candidate, -(Xref o Q) of per-instance trajectories precomputed at refill, LOST to re-reading the 48-byte Xref
+    // rows in place through L1: 7.95 vs 7.25 ms per 1M tracking instances, profiles/r02_scratch_ab.log.)
     void *scratch;
-    int sc_ib, sc_xr, sc_wm, sc_chunks;
+    int sc_ib, sc_wm, sc_chunks;
+    int test_flags;                           // tests only: 1 = never predict the mirror (every early exit takes the re-solve
+                                              // fall-back), 2 = mirror in every backward sweep
     const T *ixmin, *ixmax, *iumin, *iumax;   // per-instance boxes [instance][N][nx] / [instance][N-1][nu]; a null pair = unbounded
 };
 

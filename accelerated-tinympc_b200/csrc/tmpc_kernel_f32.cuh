@@ -379,14 +379,17 @@ struct LaneScratch {
         for (int k = 0; k < D / 4; ++k) st(c + k, make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
     }
 };
-// chunk maps (NX = 12, NU = 4): per-instance box of stage i = 8 chunks [xmin(3) xmax(3) umin(1) umax(1)]; -(Xref o Q) of stage
-// i = 3 chunks; warm mirror of stage i = 5 chunks [v(3) z(1) d(1)] (last stage: v only)
+// chunk maps (NX = 12, NU = 4): per-instance box of stage i = 8 chunks [xmin(3) xmax(3) umin(1) umax(1)]; warm mirror of
+// stage i = 5 chunks [v(3) z(1) d(1)] (last stage: v only)
 template <int NX, int NU, int NH> struct ScratchMap {
     static constexpr int CX = NX / 4, CU = NU / 4;
     static constexpr int IB_STAGE = 2 * CX + 2 * CU, IB_CHUNKS = IB_STAGE * NH;
-    static constexpr int XR_STAGE = CX, XR_CHUNKS = XR_STAGE * (NH - 1);
     static constexpr int WM_STAGE = CX + 2 * CU, WM_CHUNKS = WM_STAGE * (NH - 1) + CX;
 };
+#ifndef TMPC_MIRROR_FACTOR
+#define TMPC_MIRROR_FACTOR 4.0f   // warm start: a backward sweep mirrors d / v / z when the next iteration may converge, i.e. every
+                                  // residual is within this factor of its tolerance (see the kernel's backward section)
+#endif
 
 template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
     using SU = SVec<float, NU, NH - 1, BLOCK>;
@@ -407,8 +410,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
     static_assert(!(IB && CB), "per-instance bounds are never constant over the batch");
     using SM = ScratchMap<NX, NU, NH>;
     const LaneScratch sc(a.scratch, a.sc_chunks, BLOCK);
-    const bool xr_sc = a.sc_xr >= 0;        // per-instance Xref: -(Xref o Q) rows precomputed at refill (kernel-uniform)
-    const bool wm_sc = WARM && a.sc_wm >= 0;  // warm mirror through the scratch (kernel-uniform)
+
     static_assert(NX % 4 == 0 && NU % 4 == 0, "packed kernel: 16-byte vectors of x and u");
     using O = Orders<float, NX, NU>;
     using L = SmemLayoutF32<NX, NU, NH, BLOCK, TM>;
@@ -451,6 +453,9 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
     int phase = PH_FREE;
     bool exhausted = false;
     bool deferred = false;   // warp-uniform: the previous trip postponed a single-lane refill
+    long long redo = -1;       // WARM: instance to solve AGAIN from its untouched warm input, mirror forced on (see the backward section)
+    bool force_mirror = false; // WARM: this run mirrors d / v / z in every backward sweep
+    bool mirrored = false;     // WARM: the previous iteration's backward sweep mirrored d / v / z into the lane's scratch rows
     bool spec = false;   // speculative emission: this trip's x,u go straight to the output because the lane is
                          // expected to terminate in it (residuals within SPEC_FACTOR of tolerance, or last iteration)
     float x0[NX];
@@ -489,35 +494,25 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             else deferred = false;
         }
         if (m) {
-            const int leader = __ffs(m) - 1;
+            const unsigned mc = __ballot_sync(FULLM, need && redo < 0);   // lanes that claim a NEW instance (the others run theirs again)
+            const int leader = mc ? __ffs(mc) - 1 : 0;
             unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(m));
+            if (mc && (int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(mc));
             base = __shfl_sync(FULLM, base, leader);
             bool fill = false;
             if (need) {
-                const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) {
-                    inst = claimed_instance(a, idx); phase = PH_RUN; it = 0; fill = true;
+                long long ni = redo;
+                if (redo < 0) {
+                    const long long idx = (long long)base + __popc(mc & ((1u << lane) - 1u));
+                    if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) ni = claimed_instance(a, idx);
+                }
+                if (ni >= 0) {
+                    inst = ni; phase = PH_RUN; it = 0; fill = true;
+                    force_mirror = (redo >= 0) || (a.test_flags & 2); redo = -1; mirrored = false;
                     spec = (P.max_iter <= 1) && !u0only;
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);
                     if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
-                    if (xr_sc) {
-                        // q_i's constant part -(Xref_i o Q) (admm.cpp:81) depends on the instance only: computed once here (same
-                        // two operations, same bits) instead of in every backward sweep, and kept in the lane's scratch rows
-                        const float *xl = a.Xref + inst * a.xref_stride;
-#pragma unroll 1
-                        for (int i = 0; i < NH - 1; ++i) {
-                            float xr[NX], cq[NX];
-                            gload<float, NX>(xl + i * NX, xr);
-#pragma unroll
-                            for (int j = 0; j < NX; j += 2) {
-                                const float2 t = neg2(prode(f2(xr[j], xr[j + 1]), f2(P.Qd[j], P.Qd[j + 1]), Z));
-                                cq[j] = t.x; cq[j + 1] = t.y;
-                            }
-                            sc.stv<NX>(a.sc_xr + SM::XR_STAGE * i, cq);
-                        }
-                    }
                     if constexpr (IB) {
                         // the instance's own box -> the lane's scratch rows, stage by stage (a missing / disabled family = +-inf)
                         const float inf = __int_as_float(0x7f800000);
@@ -612,14 +607,11 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             const bool wr = emit || (spec && phase == PH_RUN);
             float *xo = (wr && a.x) ? a.x + inst * XROW : nullptr;
             float *uo = (wr && a.u) ? a.u + inst * UROW : nullptr;
-            float *go = (WARM && wr && a.wg) ? a.wg + inst * XROW : nullptr;
-            float *yo = (WARM && wr && a.wy) ? a.wy + inst * UROW : nullptr;
 
             auto xpart = [&](int i, float (&gv)[2 * NX], const float (&bxl)[NX], const float (&bxh)[NX]) {
                 // state slack / dual / residuals for stage i (uses x_i)
                 xs.wait(gv);
                 float g[NX], vn[NX];
-                if (WARM && go && emit) gstore<float, NX>(go + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
 #pragma unroll
                 for (int j = 0; j < NX; j += 2) {
                     const float2 x2 = f2(x[j], x[j + 1]), g2 = f2(gv[j], gv[j + 1]), v2 = f2(gv[NX + j], gv[NX + j + 1]);
@@ -639,7 +631,6 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     g[j] = gn.x; g[j + 1] = gn.y; vn[j] = t.x; vn[j + 1] = t.y;
                 }
                 xs.store(i, g, vn);
-                if (WARM && go && !emit) gstore<float, NX>(go + i * NX, g);
                 if (xo) gstore<float, NX>(xo + i * NX, x);
             };
 
@@ -683,7 +674,6 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     for (int j = 0; j < NX / 2; ++j) ka[NU / 2 + j] = aa[j];
                 }
                 float u[NU], zn[NU];
-                if (WARM && yo && emit) gstore<float, NU>(yo + i * NU, y);
 #pragma unroll
                 for (int r = 0; r < NU; r += 2) {
                     const float2 d2 = f2(d[r], d[r + 1]), y2 = f2(y[r], y[r + 1]), z2 = f2(z[r], z[r + 1]);
@@ -705,7 +695,6 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 }
                 sy.store(i, y);
                 sz.store(i, zn);
-                if (WARM && yo && !emit) gstore<float, NU>(yo + i * NU, y);
                 if (uo) gstore<float, NU>(uo + i * NU, u);
                 // u(:,0): with the trajectory outputs it is written by the emitting trip; a controls-only solve stores it in EVERY
                 // trip (16 bytes per lane, the terminating trip's value is the last one written) -- cheaper than keeping it in
@@ -746,22 +735,28 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
 
         // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
         bool final_bwd = false;
-        bool wb = false;         // WARM, scratch mirror: converged in this trip after >= 2 iterations -> the d / v / z the reference
-                                 // leaves in its workspace (those of iteration it - 1) go from the lane's scratch rows to the caller's
+        bool wfin = false;       // WARM: converged in this trip -> this trip's backward section writes the warm state back (below)
+        bool chk_now = false;
         bool finished = false;   // every output of this lane's instance is (or will be, after this trip's backward) written
         if (phase == PH_RUN) {
             const bool chk = (it % P.check_term) == 0;
+            chk_now = chk;
             if (chk) {
                 res[0] = pri_x; res[1] = __fmul_rn(dua_x, P.rho); res[2] = pri_u; res[3] = __fmul_rn(dua_u, P.rho);
             }
             const bool conv = chk && res[0] < P.pri_tol && res[2] < P.pri_tol && res[1] < P.dua_tol && res[3] < P.dua_tol;
-            if (conv || it >= P.max_iter) {
+            if (WARM && a.wd && conv && it > 1 && !mirrored) {
+                // Converged, but the previous backward sweep did not mirror d / v / z (the predicate below did not see it coming:
+                // not observed in 150,000 hover / closed-loop solves at factor 4, but nothing guarantees it).  Nothing of this
+                // instance has touched the caller's warm buffers yet: solve it again from there with the mirror forced on.
+                redo = inst; phase = PH_FREE; spec = false;
+            } else if (conv || it >= P.max_iter) {
                 if (a.iter) a.iter[inst] = it;
                 if (a.status) a.status[inst] = conv ? 1 : 11;
                 if (a.resid) *reinterpret_cast<float4 *>(a.resid + inst * 4) = make_float4(res[0], res[1], res[2], res[3]);
                 n_iter += (unsigned)it; n_solved += conv ? 1u : 0u; ++n_inst;
                 final_bwd = !conv;
-                wb = wm_sc && conv && it > 1 && a.wd;
+                wfin = WARM && conv && a.wd;
                 if (u0only) { phase = PH_FREE; finished = true; }   // u(:,0) of this very trip is already in the output
                 else if (spec) { phase = PH_FREE; finished = true; }   // x,u of this very trip are already in the output
                 else phase = PH_EMIT;
@@ -782,29 +777,43 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
         // ------------------------------------------------------------------ backward sweep
         // update_linear_cost (admm.cpp:77-85) recomputed per stage + backward_pass_grad (:15-22)
         const bool cont = (phase == PH_RUN);
-        // Warm start: the caller's d / v / z must end up as the reference leaves its workspace -- after a max_iter exit those of
-        // the last iteration (this trip's backward still runs: final_bwd), after an early exit those of the iteration BEFORE
-        // the one that met the tolerances (admm.cpp:135-144).  The forward sweep has already overwritten v and z on chip, so
-        // every backward sweep of a continuing lane mirrors d, v, z: into the lane's coalesced scratch rows (wm_sc; copied out
-        // once, by `wb`, when the instance converges) or, without a scratch, straight into the caller's buffers.
-        const bool wout = WARM && (cont || final_bwd) && a.wd;
-        const bool wmir = wout && cont && wm_sc;          // mirror to the scratch
-        const bool wdir = wout && !wmir;                  // write the caller's buffers directly
-        if (__any_sync(FULLM, cont || wout || wb)) {
+        // Warm start: the caller's buffers must end up as the reference leaves its workspace (SURVEY 8a note W):
+        //   max_iter exit (wfbw): this trip's backward still runs (admm.cpp:141-144): d, v = vnew, z = znew, g, y of this iteration;
+        //   early exit    (wfin): g, y of this iteration, but d, v, z of the iteration BEFORE (admm.cpp:135-138) -- which the forward
+        //                         sweep has already overwritten on chip.  So a continuing lane MIRRORS d, v, z into its coalesced
+        //                         scratch rows (wmir) in the backward sweep of every iteration after which the next one may converge:
+        //                         all residuals within TMPC_MIRROR_FACTOR of their tolerance (at the reference's own tolerances the
+        //                         largest ratio seen one iteration before convergence is 3.0; a miss is caught above and the
+        //                         instance is solved again).  That is 3-5 mirrored sweeps per solve instead of 14-34, and the
+        //                         caller's buffers are written exactly once, here, when the instance ends.
+        const bool wfbw = WARM && final_bwd && a.wd;
+        bool wmir = false;
+        if constexpr (WARM) {
+            constexpr float MF = TMPC_MIRROR_FACTOR;
+            const bool next_chk = ((it + 1) % P.check_term) == 0;
+            const bool near = !chk_now || (res[0] < MF * P.pri_tol && res[2] < MF * P.pri_tol && res[1] < MF * P.dua_tol && res[3] < MF * P.dua_tol);
+            wmir = cont && a.wd && (force_mirror || (next_chk && near && !(a.test_flags & 1)));
+            if (cont) mirrored = wmir;
+        }
+        if (__any_sync(FULLM, cont || wfbw || wfin)) {
             float p[NX];
             const float *xr_base = a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
-            float *wdo = (wdir || wb) ? a.wd + inst * UROW : nullptr;
-            float *wvo = (wdir || wb) ? a.wv + inst * XROW : nullptr;
-            float *wzo = (wdir || wb) ? a.wz + inst * UROW : nullptr;
+            const bool wprev = wfin && it > 1;      // d, v, z of the previous iteration: scratch rows -> caller
+            float *wdo = (wfbw || wfin) ? a.wd + inst * UROW : nullptr;
+            float *wvo = (wfbw || wfin) ? a.wv + inst * XROW : nullptr;
+            float *wzo = (wfbw || wfin) ? a.wz + inst * UROW : nullptr;
+            float *wgo = (wfbw || wfin) ? a.wg + inst * XROW : nullptr;
+            float *wyo = (wfbw || wfin) ? a.wy + inst * UROW : nullptr;
             {
                 float gv[2 * NX], pn[NX];
                 xs.load_issue(NH - 1, gv);
                 spn.load(0, pn);
                 xs.wait(gv);
                 if constexpr (WARM) {
-                    if (wdir) gstore<float, NX>(wvo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                    if (wfbw || wfin) gstore<float, NX>(wgo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv));
+                    if (wfbw) gstore<float, NX>(wvo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
                     else if (wmir) sc.stv<NX>(a.sc_wm + SM::WM_STAGE * (NH - 1), *reinterpret_cast<float(*)[NX]>(gv + NX));
-                    else if (wb) {
+                    else if (wprev) {
                         float t[NX];
                         sc.ldv<NX>(a.sc_wm + SM::WM_STAGE * (NH - 1), t);
                         gstore<float, NX>(wvo + (NH - 1) * NX, t);
@@ -824,9 +833,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 float z[NU], y[NU], r[NU], xr[NX];
                 sz.load(i, z);
                 sy.load(i, y);
-                // xr: Xref_i (shared trajectory: a uniform load) or, per-instance, the precomputed -(Xref_i o Q) from the scratch rows
-                if (xr_sc) sc.ldv<NX>(a.sc_xr + SM::XR_STAGE * i, xr);
-                else gload<float, NX>(xr_base + i * NX, xr);
+                gload<float, NX>(xr_base + i * NX, xr);
 #pragma unroll
                 for (int j = 0; j < NU; j += 2) {                                                    // :80
                     float2 t = sub2(f2(z[j], z[j + 1]), f2(y[j], y[j + 1]));
@@ -878,19 +885,23 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 for (int j = 0; j < NU / 2; ++j) { d[2 * j] = d2[j].x; d[2 * j + 1] = d2[j].y; }
                 sd.store(i, d, cont);
                 if constexpr (WARM) {
-                    if (wdir) gstore<float, NU>(wdo + i * NU, d);
+                    if (wfbw) gstore<float, NU>(wdo + i * NU, d);
                     else if (wmir) { sc.stv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX + SM::CU, d); sc.stv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX, z); }
                 }
                 float2 kr[NX / 2];
                 matvec2<O::Ktr, NX, NU, NX, 0, FAST>(P.Kr, r, kr, Z);
                 xs.wait(gv);
                 if constexpr (WARM) {
-                    if (wdir) {
+                    if (wfbw || wfin) {
+                        gstore<float, NX>(wgo + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
+                        gstore<float, NU>(wyo + i * NU, y);
+                    }
+                    if (wfbw) {
                         gstore<float, NX>(wvo + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
                         gstore<float, NU>(wzo + i * NU, z);
                     } else if (wmir) {
                         sc.stv<NX>(a.sc_wm + SM::WM_STAGE * i, *reinterpret_cast<float(*)[NX]>(gv + NX));
-                    } else if (wb) {
+                    } else if (wprev) {
                         float tv[NX], tz[NU], td[NU];
                         sc.ldv<NX>(a.sc_wm + SM::WM_STAGE * i, tv);
                         sc.ldv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX, tz);
@@ -902,7 +913,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 }
 #pragma unroll
                 for (int j = 0; j < NX; j += 2) {
-                    const float2 cq = xr_sc ? f2(xr[j], xr[j + 1]) : neg2(prode(f2(xr[j], xr[j + 1]), f2(P.Qd[j], P.Qd[j + 1]), Z));   // :81
+                    const float2 cq = neg2(prode(f2(xr[j], xr[j + 1]), f2(P.Qd[j], P.Qd[j + 1]), Z));              // :81
                     const float2 dvg = sub2(f2(gv[NX + j], gv[NX + j + 1]), f2(gv[j], gv[j + 1]));
                     float2 q;
                     if constexpr (FAST) q = __ffma2_rn(f2(P.nrho, P.nrho), dvg, cq);
