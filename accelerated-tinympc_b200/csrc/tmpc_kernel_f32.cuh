@@ -456,6 +456,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
     long long redo = -1;       // WARM: instance to solve AGAIN from its untouched warm input, mirror forced on (see the backward section)
     bool force_mirror = false; // WARM: this run mirrors d / v / z in every backward sweep
     bool mirrored = false;     // WARM: the previous iteration's backward sweep mirrored d / v / z into the lane's scratch rows
+    int flush = 0;             // WARM: the instance `finst` converged in the previous trip and its warm state is still on chip / in
+    long long finst = -1;      // the scratch rows: 1 = write g, y back; 2 = also d, v, z of the iteration before (from the scratch)
     bool spec = false;   // speculative emission: this trip's x,u go straight to the output because the lane is
                          // expected to terminate in it (residuals within SPEC_FACTOR of tolerance, or last iteration)
     float x0[NX];
@@ -493,14 +495,45 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             if (m && __popc(m) < 2 && !deferred && others_busy) { deferred = true; m = 0; }
             else deferred = false;
         }
-        if (m) {
-            const unsigned mc = __ballot_sync(FULLM, need && redo < 0);   // lanes that claim a NEW instance (the others run theirs again)
+        // WARM: a lane that converged in the previous trip writes its warm state back HERE, before this trip's emission sweep or a
+        // refill touches g / y (the section is warp-level anyway: tcgen05.ld/st are collective)
+        unsigned mf = 0;
+        if constexpr (WARM) mf = __ballot_sync(FULLM, flush != 0);
+        if (m | mf) {
+            const bool refill_now = need && ((m >> lane) & 1u);   // (a deferred single lane waits for the next trip)
+            const unsigned mc = __ballot_sync(FULLM, refill_now && redo < 0);   // lanes that claim a NEW instance (the others run theirs again)
             const int leader = mc ? __ffs(mc) - 1 : 0;
             unsigned long long base = 0;
             if (mc && (int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(mc));
             base = __shfl_sync(FULLM, base, leader);
             bool fill = false;
-            if (need) {
+            if constexpr (WARM) {
+                if (flush) {
+                    // y of the terminating iteration (still in shared memory); d, v, z of the iteration before it from the scratch
+                    // rows, fetched in two batches so that their L2 latency is paid twice, not once per row
+                    float *wyo = a.wy + finst * UROW;
+#pragma unroll
+                    for (int i = 0; i < NH - 1; ++i) { float t[NU]; sy.load(i, t); gstore<float, NU>(wyo + i * NU, t); }
+                    if (flush == 2) {
+                        float *wvo = a.wv + finst * XROW, *wzo = a.wz + finst * UROW, *wdo = a.wd + finst * UROW;
+                        float4 tv[NH * SM::CX];
+#pragma unroll
+                        for (int i = 0; i < NH; ++i)
+#pragma unroll
+                            for (int c = 0; c < SM::CX; ++c) tv[i * SM::CX + c] = sc.ld(a.sc_wm + SM::WM_STAGE * i + c);
+#pragma unroll
+                        for (int i = 0; i < NH; ++i)
+#pragma unroll
+                            for (int c = 0; c < SM::CX; ++c) reinterpret_cast<float4 *>(wvo + i * NX)[c] = tv[i * SM::CX + c];
+                        float4 tz[NH - 1], td[NH - 1];
+#pragma unroll
+                        for (int i = 0; i < NH - 1; ++i) { tz[i] = sc.ld(a.sc_wm + SM::WM_STAGE * i + SM::CX); td[i] = sc.ld(a.sc_wm + SM::WM_STAGE * i + SM::CX + SM::CU); }
+#pragma unroll
+                        for (int i = 0; i < NH - 1; ++i) { reinterpret_cast<float4 *>(wzo)[i] = tz[i]; reinterpret_cast<float4 *>(wdo)[i] = td[i]; }
+                    }
+                }
+            }
+            if (refill_now) {
                 long long ni = redo;
                 if (redo < 0) {
                     const long long idx = (long long)base + __popc(mc & ((1u << lane) - 1u));
@@ -514,38 +547,67 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     gload<float, NX>(a.x0 + inst * NX, x0);
                     if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
                     if constexpr (IB) {
-                        // the instance's own box -> the lane's scratch rows, stage by stage (a missing / disabled family = +-inf)
+                        // the instance's own box -> the lane's scratch rows (a missing / disabled family = +-inf).  Loads are issued
+                        // half a horizon at a time, so the copy costs a handful of memory round trips instead of one per stage
                         const float inf = __int_as_float(0x7f800000);
-#pragma unroll 1
-                        for (int i = 0; i < NH; ++i) {
-                            float lo[NX], hi[NX];
-                            if (a.ixmin) { gload<float, NX>(a.ixmin + inst * XROW + i * NX, lo); gload<float, NX>(a.ixmax + inst * XROW + i * NX, hi); }
-                            else {
+                        constexpr int HB = (NH + 1) / 2;
 #pragma unroll
-                                for (int j = 0; j < NX; ++j) { lo[j] = -inf; hi[j] = inf; }
-                            }
-                            sc.stv<NX>(a.sc_ib + SM::IB_STAGE * i, lo);
-                            sc.stv<NX>(a.sc_ib + SM::IB_STAGE * i + SM::CX, hi);
-                            if (i < NH - 1) {
-                                float ul[NU], uh[NU];
-                                if (a.iumin) { gload<float, NU>(a.iumin + inst * UROW + i * NU, ul); gload<float, NU>(a.iumax + inst * UROW + i * NU, uh); }
-                                else {
+                        for (int h = 0; h < 2; ++h) {
+                            float4 lo[HB * SM::CX], hi[HB * SM::CX];
 #pragma unroll
-                                    for (int j = 0; j < NU; ++j) { ul[j] = -inf; uh[j] = inf; }
+                            for (int q = 0; q < HB; ++q) {
+                                const int i = h * HB + q;
+#pragma unroll
+                                for (int c = 0; c < SM::CX; ++c) {
+                                    if (i < NH && a.ixmin) {
+                                        lo[q * SM::CX + c] = __ldg(reinterpret_cast<const float4 *>(a.ixmin + inst * XROW + i * NX) + c);
+                                        hi[q * SM::CX + c] = __ldg(reinterpret_cast<const float4 *>(a.ixmax + inst * XROW + i * NX) + c);
+                                    } else {
+                                        lo[q * SM::CX + c] = make_float4(-inf, -inf, -inf, -inf);
+                                        hi[q * SM::CX + c] = make_float4(inf, inf, inf, inf);
+                                    }
                                 }
-                                sc.stv<NU>(a.sc_ib + SM::IB_STAGE * i + 2 * SM::CX, ul);
-                                sc.stv<NU>(a.sc_ib + SM::IB_STAGE * i + 2 * SM::CX + SM::CU, uh);
+                            }
+#pragma unroll
+                            for (int q = 0; q < HB; ++q) {
+                                const int i = h * HB + q;
+                                if (i < NH) {
+#pragma unroll
+                                    for (int c = 0; c < SM::CX; ++c) {
+                                        sc.st(a.sc_ib + SM::IB_STAGE * i + c, lo[q * SM::CX + c]);
+                                        sc.st(a.sc_ib + SM::IB_STAGE * i + SM::CX + c, hi[q * SM::CX + c]);
+                                    }
+                                }
+                            }
+                        }
+                        {
+                            static_assert(SM::CU == 1, "one 16-byte chunk per input-bound row");
+                            float4 ul[NH - 1], uh[NH - 1];
+#pragma unroll
+                            for (int i = 0; i < NH - 1; ++i) {
+                                if (a.iumin) {
+                                    ul[i] = __ldg(reinterpret_cast<const float4 *>(a.iumin + inst * UROW + i * NU));
+                                    uh[i] = __ldg(reinterpret_cast<const float4 *>(a.iumax + inst * UROW + i * NU));
+                                } else { ul[i] = make_float4(-inf, -inf, -inf, -inf); uh[i] = make_float4(inf, inf, inf, inf); }
+                            }
+#pragma unroll
+                            for (int i = 0; i < NH - 1; ++i) {
+                                sc.st(a.sc_ib + SM::IB_STAGE * i + 2 * SM::CX, ul[i]);
+                                sc.st(a.sc_ib + SM::IB_STAGE * i + 2 * SM::CX + SM::CU, uh[i]);
                             }
                         }
                     }
                     if (WARM && a.wd) {
-#pragma unroll 1
+                        // warm d, y, z: every load in flight before the first store (one memory round trip, not one per stage)
+                        float td[NH - 1][NU], ty[NH - 1][NU], tz[NH - 1][NU];
+#pragma unroll
                         for (int i = 0; i < NH - 1; ++i) {
-                            float t[NU];
-                            gload<float, NU>(a.wd + inst * UROW + i * NU, t); sd.store(i, t);
-                            gload<float, NU>(a.wy + inst * UROW + i * NU, t); sy.store(i, t);
-                            gload<float, NU>(a.wz + inst * UROW + i * NU, t); sz.store(i, t);
+                            gload<float, NU>(a.wd + inst * UROW + i * NU, td[i]);
+                            gload<float, NU>(a.wy + inst * UROW + i * NU, ty[i]);
+                            gload<float, NU>(a.wz + inst * UROW + i * NU, tz[i]);
                         }
+#pragma unroll
+                        for (int i = 0; i < NH - 1; ++i) { sd.store(i, td[i]); sy.store(i, ty[i]); sz.store(i, tz[i]); }
                     } else {
                         float zu[NU];
 #pragma unroll
@@ -557,39 +619,72 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                     exhausted = true;
                 }
             }
-            // g, v: every lane of the warp takes part (tcgen05 is warp-collective); lanes that are not being
-            // refilled write back what they hold
+            // g, v: every lane of the warp takes part (tcgen05 is warp-collective); lanes that are not being refilled write back
+            // what they hold.  RB stages per round trip: the section is bound by the latency of the tensor-memory reads and -- with a
+            // warm start -- of the global loads of the new instance's g / v rows, not by instructions.  A lane that is flushing a
+            // converged instance stores the g it reads before anything overwrites it.
             const bool wfill = WARM && a.wd;
-            // (two stages per round trip: the section is bound by the latency of the tensor-memory reads, not by instructions)
-            auto refill_stage = [&](int i, float (&gv)[2 * NX]) {
-                if (fill) {
-                    if (wfill) {
-                        gload<float, NX>(a.wg + inst * XROW + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
-                        gload<float, NX>(a.wv + inst * XROW + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
-                    } else {
+            constexpr int RB = WARM ? 5 : 2;
+            float *wgo = (WARM && flush) ? a.wg + finst * XROW : nullptr;
+            auto refill_batch = [&](int i0, auto nb_tag) {
+                constexpr int NB = decltype(nb_tag)::value;
+                float gv[NB][2 * NX];
 #pragma unroll
-                        for (int j = 0; j < 2 * NX; ++j) gv[j] = 0.f;
+                for (int q = 0; q < NB; ++q) xs.load_issue(i0 + q, gv[q]);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) xs.wait(gv[q]);
+                if constexpr (WARM) {
+                    if (wgo) {
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) gstore<float, NX>(wgo + (i0 + q) * NX, *reinterpret_cast<float(*)[NX]>(gv[q]));
                     }
                 }
-                xs.store(i, *reinterpret_cast<float(*)[NX]>(gv), *reinterpret_cast<float(*)[NX]>(gv + NX));
+                if (fill) {
+                    if (wfill) {
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {
+                            gload<float, NX>(a.wg + inst * XROW + (i0 + q) * NX, *reinterpret_cast<float(*)[NX]>(gv[q]));
+                            gload<float, NX>(a.wv + inst * XROW + (i0 + q) * NX, *reinterpret_cast<float(*)[NX]>(gv[q] + NX));
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NB; ++q)
+#pragma unroll
+                            for (int j = 0; j < 2 * NX; ++j) gv[q][j] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q) xs.store(i0 + q, *reinterpret_cast<float(*)[NX]>(gv[q]), *reinterpret_cast<float(*)[NX]>(gv[q] + NX));
             };
+            if (m) {   // (a flush alone rewrites nothing)
 #pragma unroll 1
-            for (int i = 0; i + 1 < NH; i += 2) {
-                float gv0[2 * NX], gv1[2 * NX];
-                xs.load_issue(i, gv0);
-                xs.load_issue(i + 1, gv1);
-                xs.wait(gv0);
-                xs.wait(gv1);
-                refill_stage(i, gv0);
-                refill_stage(i + 1, gv1);
+                for (int i = 0; i + RB <= NH; i += RB) refill_batch(i, std::integral_constant<int, RB>());
+#pragma unroll 1
+                for (int i = NH / RB * RB; i < NH; ++i) refill_batch(i, std::integral_constant<int, 1>());
+                xs.fence_st();
+            } else if (WARM && mf) {
+                // flush without a refill in this warp: g still has to be read out of tensor memory (collectively) and stored
+#pragma unroll 1
+                for (int i = 0; i + RB <= NH; i += RB) {
+                    float gv[RB][2 * NX];
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) xs.load_issue(i + q, gv[q]);
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) xs.wait(gv[q]);
+                    if (wgo) {
+#pragma unroll
+                        for (int q = 0; q < RB; ++q) gstore<float, NX>(wgo + (i + q) * NX, *reinterpret_cast<float(*)[NX]>(gv[q]));
+                    }
+                }
+#pragma unroll 1
+                for (int i = NH / RB * RB; i < NH; ++i) {
+                    float gv[2 * NX];
+                    xs.load_issue(i, gv);
+                    xs.wait(gv);
+                    if (wgo) gstore<float, NX>(wgo + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
+                }
             }
-            if constexpr (NH % 2 == 1) {
-                float gv[2 * NX];
-                xs.load_issue(NH - 1, gv);
-                xs.wait(gv);
-                refill_stage(NH - 1, gv);
-            }
-            xs.fence_st();
+            if constexpr (WARM) flush = 0;
         }
         if (__all_sync(FULLM, phase == PH_FREE)) break;
         ++n_trips;
@@ -735,7 +830,6 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
 
         // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
         bool final_bwd = false;
-        bool wfin = false;       // WARM: converged in this trip -> this trip's backward section writes the warm state back (below)
         bool chk_now = false;
         bool finished = false;   // every output of this lane's instance is (or will be, after this trip's backward) written
         if (phase == PH_RUN) {
@@ -756,7 +850,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 if (a.resid) *reinterpret_cast<float4 *>(a.resid + inst * 4) = make_float4(res[0], res[1], res[2], res[3]);
                 n_iter += (unsigned)it; n_solved += conv ? 1u : 0u; ++n_inst;
                 final_bwd = !conv;
-                wfin = WARM && conv && a.wd;
+                if (WARM && conv && a.wd) { flush = it > 1 ? 2 : 1; finst = inst; }   // written back at the top of the next trip
                 if (u0only) { phase = PH_FREE; finished = true; }   // u(:,0) of this very trip is already in the output
                 else if (spec) { phase = PH_FREE; finished = true; }   // x,u of this very trip are already in the output
                 else phase = PH_EMIT;
@@ -779,13 +873,13 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
         const bool cont = (phase == PH_RUN);
         // Warm start: the caller's buffers must end up as the reference leaves its workspace (SURVEY 8a note W):
         //   max_iter exit (wfbw): this trip's backward still runs (admm.cpp:141-144): d, v = vnew, z = znew, g, y of this iteration;
-        //   early exit    (wfin): g, y of this iteration, but d, v, z of the iteration BEFORE (admm.cpp:135-138) -- which the forward
-        //                         sweep has already overwritten on chip.  So a continuing lane MIRRORS d, v, z into its coalesced
-        //                         scratch rows (wmir) in the backward sweep of every iteration after which the next one may converge:
-        //                         all residuals within TMPC_MIRROR_FACTOR of their tolerance (at the reference's own tolerances the
-        //                         largest ratio seen one iteration before convergence is 3.0; a miss is caught above and the
-        //                         instance is solved again).  That is 3-5 mirrored sweeps per solve instead of 14-34, and the
-        //                         caller's buffers are written exactly once, here, when the instance ends.
+        //   early exit  (flush): g, y of this iteration, but d, v, z of the iteration BEFORE (admm.cpp:135-138) -- which the forward
+        //                        sweep has already overwritten on chip.  So a continuing lane MIRRORS d, v, z into its coalesced
+        //                        scratch rows (wmir) in the backward sweep of every iteration after which the next one may converge:
+        //                        all residuals within TMPC_MIRROR_FACTOR of their tolerance (at the reference's own tolerances the
+        //                        largest ratio seen one iteration before convergence is 3.0; a miss is caught above and the
+        //                        instance is solved again).  That is 3-5 mirrored sweeps per solve instead of 14-34, and the
+        //                        caller's buffers are written exactly once, at the top of the trip after the instance ends.
         const bool wfbw = WARM && final_bwd && a.wd;
         bool wmir = false;
         if constexpr (WARM) {
@@ -795,29 +889,24 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
             wmir = cont && a.wd && (force_mirror || (next_chk && near && !(a.test_flags & 1)));
             if (cont) mirrored = wmir;
         }
-        if (__any_sync(FULLM, cont || wfbw || wfin)) {
+        if (__any_sync(FULLM, cont || wfbw)) {
             float p[NX];
             const float *xr_base = a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
-            const bool wprev = wfin && it > 1;      // d, v, z of the previous iteration: scratch rows -> caller
-            float *wdo = (wfbw || wfin) ? a.wd + inst * UROW : nullptr;
-            float *wvo = (wfbw || wfin) ? a.wv + inst * XROW : nullptr;
-            float *wzo = (wfbw || wfin) ? a.wz + inst * UROW : nullptr;
-            float *wgo = (wfbw || wfin) ? a.wg + inst * XROW : nullptr;
-            float *wyo = (wfbw || wfin) ? a.wy + inst * UROW : nullptr;
+            float *wdo = wfbw ? a.wd + inst * UROW : nullptr;
+            float *wvo = wfbw ? a.wv + inst * XROW : nullptr;
+            float *wzo = wfbw ? a.wz + inst * UROW : nullptr;
+            float *wgo = wfbw ? a.wg + inst * XROW : nullptr;
+            float *wyo = wfbw ? a.wy + inst * UROW : nullptr;
             {
                 float gv[2 * NX], pn[NX];
                 xs.load_issue(NH - 1, gv);
                 spn.load(0, pn);
                 xs.wait(gv);
                 if constexpr (WARM) {
-                    if (wfbw || wfin) gstore<float, NX>(wgo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv));
-                    if (wfbw) gstore<float, NX>(wvo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
-                    else if (wmir) sc.stv<NX>(a.sc_wm + SM::WM_STAGE * (NH - 1), *reinterpret_cast<float(*)[NX]>(gv + NX));
-                    else if (wprev) {
-                        float t[NX];
-                        sc.ldv<NX>(a.sc_wm + SM::WM_STAGE * (NH - 1), t);
-                        gstore<float, NX>(wvo + (NH - 1) * NX, t);
-                    }
+                    if (wfbw) {
+                        gstore<float, NX>(wgo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv));
+                        gstore<float, NX>(wvo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                    } else if (wmir) sc.stv<NX>(a.sc_wm + SM::WM_STAGE * (NH - 1), *reinterpret_cast<float(*)[NX]>(gv + NX));
                 }
 #pragma unroll
                 for (int j = 0; j < NX; ++j) {
@@ -892,23 +981,13 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> P, const __grid_con
                 matvec2<O::Ktr, NX, NU, NX, 0, FAST>(P.Kr, r, kr, Z);
                 xs.wait(gv);
                 if constexpr (WARM) {
-                    if (wfbw || wfin) {
+                    if (wfbw) {
                         gstore<float, NX>(wgo + i * NX, *reinterpret_cast<float(*)[NX]>(gv));
                         gstore<float, NU>(wyo + i * NU, y);
-                    }
-                    if (wfbw) {
                         gstore<float, NX>(wvo + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
                         gstore<float, NU>(wzo + i * NU, z);
                     } else if (wmir) {
                         sc.stv<NX>(a.sc_wm + SM::WM_STAGE * i, *reinterpret_cast<float(*)[NX]>(gv + NX));
-                    } else if (wprev) {
-                        float tv[NX], tz[NU], td[NU];
-                        sc.ldv<NX>(a.sc_wm + SM::WM_STAGE * i, tv);
-                        sc.ldv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX, tz);
-                        sc.ldv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX + SM::CU, td);
-                        gstore<float, NX>(wvo + i * NX, tv);
-                        gstore<float, NU>(wzo + i * NU, tz);
-                        gstore<float, NU>(wdo + i * NU, td);
                     }
                 }
 #pragma unroll

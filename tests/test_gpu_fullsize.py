@@ -89,3 +89,90 @@ def test_host_path_with_overlapped_input_copy(pkg, oracle):
     s.solve_raw(n, px0, pxr, False, pkg.capi.TMPC_MEM_HOST, hx, hu, hit, hst, hrs)
     assert_same(hit.numpy(), host["iter"], "iter pinned")
     assert_same(hx.numpy(), host["x"], "x pinned")
+
+
+def _device_solve_any(pkg, prob, x0, xref, warm=None, solver=None):
+    import torch
+    dev = torch.device("cuda:0")
+    n = len(x0)
+    s = solver or pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    x = torch.empty((n, prob.N, prob.nx), device=dev); u = torch.empty((n, prob.N - 1, prob.nu), device=dev)
+    it = torch.empty(n, dtype=torch.int32, device=dev); st = torch.empty(n, dtype=torch.int32, device=dev); rs = torch.empty((n, 4), device=dev)
+    s.solve_raw(n, torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev), xref.ndim == 2, pkg.capi.TMPC_MEM_DEVICE, x, u, it, st, rs, warm=warm)
+    torch.cuda.synchronize()
+    return s, {"x": x, "u": u, "iter": it, "status": st, "resid": rs}
+
+
+def _check_prefix(out, ref, n, what):
+    for k in ("iter", "status", "x", "u", "resid"):
+        assert_same(out[k][:n].cpu().numpy(), getattr(ref, k), "%s %s" % (what, k))
+
+
+def test_config3_tracking_full_size(pkg, oracle):
+    """BASELINE configs[2] at its named size: 4,194,304 tracking instances with per-instance reference windows.  Oracle on a
+    20,000-instance prefix and on the last 10,000; window periodicity (instances b and b + 290 k share k_b but not x0, so only the
+    statistics repeat); idempotence."""
+    import torch
+    prob = pkg.problems.quadrotor(20)
+    B3 = 1 << 22
+    x0, xref = pkg.workloads.quadrotor_tracking_batch(0, B3)
+    s, a = _device_solve_any(pkg, prob, x0, xref)
+    assert s.stats()["instances"] == B3 and s.stats()["iterations"] == int(a["iter"].sum().item())
+    n = 20_000
+    _check_prefix(a, oracle.solve_batch(prob, x0[:n], xref[:n], dtype=np.float32, nthreads=16), n, "config 3 prefix")
+    m = 10_000
+    ref = oracle.solve_batch(prob, x0[-m:], xref[-m:], dtype=np.float32, nthreads=16)
+    assert_same(a["iter"][-m:].cpu().numpy(), ref.iter, "config 3 tail iter")
+    assert_same(a["u"][-m:].cpu().numpy(), ref.u, "config 3 tail u")
+    assert bool((a["status"] == 1).all())                       # every tracking instance converges (SURVEY G4: 10-15 iterations)
+    _, b = _device_solve_any(pkg, prob, x0, xref, solver=s)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_config4_cartpole_full_size(pkg, oracle):
+    """BASELINE configs[3] at its named size: 16,777,216 cartpole instances.  Oracle on a 50,000-instance prefix, shard
+    independence (four quarter batches == the full batch), statistics of the seeded workload."""
+    import torch
+    prob = pkg.problems.cartpole()
+    B4 = 1 << 24
+    x0, xref = pkg.workloads.cartpole_batch(0, B4)
+    s, a = _device_solve_any(pkg, prob, x0, xref)
+    assert s.stats()["instances"] == B4 and s.stats()["iterations"] == int(a["iter"].sum().item())
+    n = 50_000
+    _check_prefix(a, oracle.solve_batch(prob, x0[:n], xref, dtype=np.float32, nthreads=16), n, "config 4 prefix")
+    q = B4 // 4
+    for j in (1, 3):
+        _, part = _device_solve_any(pkg, prob, x0[j * q:(j + 1) * q], xref, solver=s)
+        for k in a:
+            assert torch.equal(a[k][j * q:(j + 1) * q], part[k]), (j, k)
+    it = a["iter"].cpu().numpy()
+    assert abs(it.mean() - 55.9) < 0.5
+
+
+def test_config5_large_warm_full_size(pkg, oracle):
+    """BASELINE configs[4] at its named size: 262,144 instances of the 32/8/50 system, cold solve, x0 perturbed by 1 %, re-solve
+    warm-started from the state left in HBM.  Oracle (cold and warm, state included) on a 2,000-instance prefix; the cold
+    solve's statistics."""
+    import torch
+    prob = pkg.problems.random_system()
+    B5 = 1 << 18
+    dev = torch.device("cuda:0")
+    x0, xref = pkg.workloads.random_system_batch(0, B5)
+    warm = {k: torch.zeros((B5, 49, 8) if k in "dyz" else (B5, 50, 32), device=dev) for k in ("d", "y", "g", "v", "z")}
+    s, a = _device_solve_any(pkg, prob, x0, xref, warm=warm)
+    n = 2_000
+    r1 = oracle.solve_batch(prob, x0[:n], xref, dtype=np.float32, want_state=True, nthreads=16)
+    _check_prefix(a, r1, n, "config 5 cold prefix")
+    for k in warm:
+        assert_same(warm[k][:n].cpu().numpy(), r1.state[k], "config 5 cold state " + k)
+    it = a["iter"].cpu().numpy()
+    assert abs(it.mean() - 71) < 2
+    x1 = pkg.workloads.perturb_x0(x0, 0)
+    _, b = _device_solve_any(pkg, prob, x1, xref, warm=warm, solver=s)
+    r2 = oracle.solve_batch(prob, x1[:n], xref, dtype=np.float32, warm={k: r1.state[k] for k in ("d", "y", "g", "v", "z")}, want_state=True,
+                            nthreads=16)
+    _check_prefix(b, r2, n, "config 5 warm prefix")
+    for k in warm:
+        assert_same(warm[k][:n].cpu().numpy(), r2.state[k], "config 5 warm state " + k)
+    assert b["iter"].float().mean().item() < 0.6 * it.mean()      # the warm start pays (mean 27 vs 71 iterations)
