@@ -6,12 +6,12 @@
 namespace tmpc_dispatch {
 namespace {
 
-template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT, bool CB, bool IB = false>
+template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT, bool CB, bool IB = false, bool CSM = false>
 KernelInfo make_info_f32()
 {
     KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM, PAT, CB, IB>;
-    k.smem = tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES;
+    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM, PAT, CB, IB, CSM>;
+    k.smem = CSM ? tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES_CSM : tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES;
     k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::ModelF32<NX, NU, NH>);
     k.model_kind = 1;
@@ -33,6 +33,13 @@ bool pick_f32(int policy, bool warm, KernelInfo &out)
 
 bool lookup_f32(int policy, bool warm, int pattern, bool cb, int variant, KernelInfo &out, bool ib)
 {
+    if (variant == 3 && !ib && !warm && policy == TMPC_ORDER_PARITY && cb) {
+        // model image staged into shared memory by TMA (the A/B of tmpc_kernel_f32.cuh CSM); cold PARITY solves with constant bounds
+        out = pattern == tmpc::PatQuadrotor::id ? make_info_f32<12, 4, 10, 256, false, false, true, tmpc::PatQuadrotor, true, false, true>()
+                                                : make_info_f32<12, 4, 10, 256, false, false, true, tmpc::PatDense<12>, true, false, true>();
+        return true;
+    }
+    if (variant == 3) variant = 2;
     if (ib) {
         if (variant != 2) return false;
         return pattern == tmpc::PatQuadrotor::id ? pick_f32<12, 4, 10, 256, true, tmpc::PatQuadrotor, false, true>(policy, warm, out)

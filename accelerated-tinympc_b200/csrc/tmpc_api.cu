@@ -60,6 +60,8 @@ struct tmpc_ctx_impl {
     // per-lane coalesced scratch of the fp32 12/4/10 kernel (SolveArgs::scratch)
     void *d_lane_scratch = nullptr;
     size_t d_lane_scratch_bytes = 0;
+    bool duals_zero_next = false;  // tmpc_batch rollout with reset duals: the next launch of the fp32 12/4/10 kernel zero-fills y, g itself
+    void *d_model_f32 = nullptr;   // device copy of model_f32 (TMPC_KERNEL=f32_tma_cache: the kernel stages it into shared memory by TMA)
     bool rt_ready = false;
     // per-instance box bounds (tmpc_set_instance_bounds): device copies xmin | xmax | umin | umax, 0 = not set
     void *d_ib[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -129,6 +131,7 @@ int kernel_variant()
     if (!e) return 2;
     if (!strcmp(e, "generic")) return 0;
     if (!strcmp(e, "f32_smem")) return 1;
+    if (!strcmp(e, "f32_tma_cache")) return 3;
     return 2;
 }
 
@@ -149,7 +152,7 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
         if (dtype == TMPC_F32) {
             const int v = kernel_variant();
             if (v == 0) return tmpc_dispatch::lookup_generic(nx, nu, N, dtype, policy, warm, 0, out);
-            return tmpc_dispatch::lookup_f32(policy, warm, pattern, cb, v, out);
+            return tmpc_dispatch::lookup_f32(policy, warm, pattern, cb, v, out);   // (v == 3 falls back to 2 where it has no instance)
         }
         // double: g, v in tensor memory -> 128 instances / SM (TMPC_KERNEL=generic: all state in shared memory, 64 / SM)
         return tmpc_dispatch::lookup_generic(nx, nu, N, dtype, policy, warm, generic ? 1 : 0, out);
@@ -550,6 +553,7 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     int sc_ib, sc_wm, sc_chunks;
     int test_flags;
     const void *ixmin, *ixmax, *iumin, *iumax;
+    const void *model_g;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
@@ -624,12 +628,21 @@ int plan_launch(tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da, cudaS
 }
 
 // fp32 12/4/10 kernel: which regions of the per-lane coalesced scratch this launch needs (tmpc_kernel_f32.cuh ScratchMap)
-int plan_lane_scratch(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, long long blocks, bool ib)
+int plan_lane_scratch(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, long long blocks, bool ib, cudaStream_t s)
 {
     da.scratch = nullptr; da.sc_ib = da.sc_wm = -1; da.sc_chunks = 0; da.test_flags = 0;
     da.ixmin = da.ixmax = da.iumin = da.iumax = nullptr;
+    da.model_g = nullptr;
     if (ki.model_kind != 1) return TMPC_OK;
-    if (const char *e = getenv("TMPC_TEST_MIRROR")) da.test_flags = atoi(e);
+    if (kernel_variant() == 3) {
+        // (re-uploaded per launch: 3.9 KB on the launch stream, ordered before the kernel; the A/B variant is not tuned for launch cost)
+        if (!c->d_model_f32) CUDA_TRY(c, cudaMalloc(&c->d_model_f32, c->model_f32.size()));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_model_f32, c->model_f32.data(), c->model_f32.size(), cudaMemcpyHostToDevice, s));
+        da.model_g = c->d_model_f32;
+    }
+    if (const char *e = getenv("TMPC_TEST_MIRROR")) da.test_flags = atoi(e) & 3;
+    if (c->duals_zero_next && da.wd) da.test_flags |= 4;
+    c->duals_zero_next = false;
     using SM = tmpc::ScratchMap<12, 4, 10>;
     int chunks = 0;
     if (ib) {
@@ -666,7 +679,7 @@ int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cuda
     long long blocks = 1;
     {
         int rc = plan_launch(c, ki, da, s, blocks);
-        if (rc == TMPC_OK) rc = plan_lane_scratch(c, ki, da, blocks, c->ib_batch != 0 && !da.sys);
+        if (rc == TMPC_OK) rc = plan_lane_scratch(c, ki, da, blocks, c->ib_batch != 0 && !da.sys, s);
         if (rc != TMPC_OK) return rc;
     }
     void *params[2] = {model_param(c, ki), &da};
@@ -772,7 +785,7 @@ int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = n
         CUDA_TRY(c, cudaMalloc((void **)&c->lpt_buf, 4 * B * sizeof(unsigned)));
         size_t tb = 0;
         CUDA_TRY(c, cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const unsigned *)nullptr, (unsigned *)nullptr,
-                                                               (const unsigned *)nullptr, (unsigned *)nullptr, (int)B, 16, 32, s));
+                                                               (const unsigned *)nullptr, (unsigned *)nullptr, (int)B, 0, 32, s));
         CUDA_TRY(c, cudaMalloc(&c->lpt_temp, tb));
         c->lpt_temp_bytes = tb;
         c->lpt_cap = B;
@@ -806,6 +819,34 @@ bool ib_on_f32_kernel(const tmpc_ctx_impl *c)
     return c->nx == 12 && c->nu == 4 && c->N == 10 && c->dtype == TMPC_F32 && kernel_variant() == 2 && !force_rt() && !getenv("TMPC_IB_RT");
 }
 
+// Claim order from a per-instance integer key the caller already has on the device (tmpc_batch: the iteration counts of the
+// previous closed-loop step predict this step's almost perfectly): instances sorted by key, largest first.
+int lpt_from_keys(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const unsigned *keys, int key_bits)
+{
+    const size_t B = (size_t)da.batch;
+    if (c->lpt_cap < B) {
+        CUDA_TRY(c, cudaDeviceSynchronize());
+        if (c->lpt_buf) cudaFree(c->lpt_buf);
+        if (c->lpt_temp) cudaFree(c->lpt_temp);
+        c->lpt_buf = nullptr; c->lpt_temp = nullptr; c->lpt_cap = 0; c->lpt_temp_bytes = 0;
+        CUDA_TRY(c, cudaMalloc((void **)&c->lpt_buf, 4 * B * sizeof(unsigned)));
+        size_t tb = 0;
+        CUDA_TRY(c, cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const unsigned *)nullptr, (unsigned *)nullptr,
+                                                               (const unsigned *)nullptr, (unsigned *)nullptr, (int)B, 0, 32, s));
+        CUDA_TRY(c, cudaMalloc(&c->lpt_temp, tb));
+        c->lpt_temp_bytes = tb;
+        c->lpt_cap = B;
+    }
+    unsigned *keys_out = c->lpt_buf + c->lpt_cap, *vals_in = keys_out + c->lpt_cap, *vals_out = vals_in + c->lpt_cap;
+    iota_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(vals_in, (long long)B, 0u);
+    CUDA_TRY(c, cudaGetLastError());
+    size_t tb = c->lpt_temp_bytes;
+    CUDA_TRY(c, cub::DeviceRadixSort::SortPairsDescending(c->lpt_temp, tb, keys, keys_out, (const unsigned *)vals_in, vals_out, (int)B, 0, key_bits, s));
+    da.order = vals_out;
+    c->stats.launches += 1;
+    return TMPC_OK;
+}
+
 int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
 {
     KernelInfo ki;
@@ -825,7 +866,7 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
     } else if (!lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki, c->pattern | (c->const_bounds ? 0x100 : 0)))
         return fail(c, TMPC_ERR_UNSUPPORTED, "no kernel for this shape");
     bool ev0_done = false;
-    c->lpt_used = da.order ? 2 : 0;   // 2: the caller (host pipeline) brought its own claim order
+    c->lpt_used = da.order ? 2 : 0;   // 2: the caller (host pipeline, closed-loop batch) brought its own claim order
     {
         const int rc = order_after_previous(c, s);   // the scheduling buffers may still be read by the previous launch
         if (rc != TMPC_OK) return rc;
@@ -1177,6 +1218,7 @@ int tmpc_destroy(tmpc_ctx *ctx)
     if (c->d_model_rt) cudaFree(c->d_model_rt);
     if (c->d_rt_scratch) cudaFree(c->d_rt_scratch);
     if (c->d_lane_scratch) cudaFree(c->d_lane_scratch);
+    if (c->d_model_f32) cudaFree(c->d_model_f32);
     for (void *p : c->d_ib) if (p) cudaFree(p);
     if (c->d_kinf) cudaFree(c->d_kinf);
     if (c->lpt_buf) cudaFree(c->lpt_buf);
@@ -1439,7 +1481,7 @@ int tmpc_solve(tmpc_ctx *ctx, const tmpc_solve_args *a)
             da.stats = c->d_counter + 1;
             long long blocks = 1;
             if ((rc_all = plan_launch(c, ki, da, st.s, blocks)) != TMPC_OK) break;
-            if ((rc_all = plan_lane_scratch(c, ki, da, blocks, false)) != TMPC_OK) break;
+            if ((rc_all = plan_lane_scratch(c, ki, da, blocks, false, st.s)) != TMPC_OK) break;
             void *params[2] = {model_param(c, ki), &da};
             cudaEventRecord(kev[2 * k], st.s);
             cudaError_t e = cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, st.s);

@@ -18,7 +18,8 @@ struct KernelInfo {
 };
 
 // fp32 12/4/10 production kernel (tmpc_kernel_f32.cuh).  variant 2: g, v in tensor memory, 256 instances / SM (default);
-// 1: all state in shared memory, 128 / SM.  pattern: 0 dense, 1 quadrotor structure.
+// 1: all state in shared memory, 128 / SM; 3: as 2 with the model image staged into shared memory by a TMA bulk copy instead
+// of living in the constant bank (cold PARITY solves; everything else falls back to 2).  pattern: 0 dense, 1 quadrotor.
 // per_instance_bounds: the IB instances (variant 2 only; boxes read from the lane's scratch rows)
 bool lookup_f32(int policy, bool warm, int pattern, bool const_bounds, int variant, KernelInfo &out, bool per_instance_bounds = false);
 

@@ -210,9 +210,12 @@ template <class T> struct SolveArgs {
     // rows in place through L1: 7.95 vs 7.25 ms per 1M tracking instances, profiles/r02_scratch_ab.log.)
     void *scratch;
     int sc_ib, sc_wm, sc_chunks;
-    int test_flags;                           // tests only: 1 = never predict the mirror (every early exit takes the re-solve
-                                              // fall-back), 2 = mirror in every backward sweep
+    int test_flags;                           // 1, 2: tests only (1 = never predict the mirror: every early exit takes the re-solve
+                                              // fall-back; 2 = mirror in every backward sweep); 4 = the warm duals y, g are ZERO
+                                              // (closed loop with reset duals, quadrotor_hovering.cpp:100-101): not read at all
     const T *ixmin, *ixmax, *iumin, *iumax;   // per-instance boxes [instance][N][nx] / [instance][N-1][nu]; a null pair = unbounded
+    const void *model_g;                      // device copy of the kernel's model image (CSM instances of the fp32 kernel: staged
+                                              // into shared memory by one TMA bulk copy per CTA), else null
 };
 
 // instance solved by the idx-th claim of the work counter

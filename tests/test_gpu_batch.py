@@ -149,3 +149,32 @@ def test_argument_errors_are_reported(pkg):
     # a singular R + B'PB is reported per instance, not as a crash
     Sz = capi.Systems(s, np.zeros((2, 12, 12)), np.zeros((2, 12, 4)), np.zeros((2, 12)), np.zeros((2, 4)), np.zeros(2))
     assert Sz.get("sweeps").tolist() == [-1, -1]
+
+
+def test_large_rollout_uses_iteration_history_schedule(pkg, oracle):
+    """A closed loop large enough for the iteration-history schedule (claim order = previous step's iteration counts, largest
+    first) and for the in-kernel dual reset (fp32 12/4/10: y, g zero-filled on chip instead of memset + read): 160,000 hover
+    instances, 4 MPC steps; the first 2,000 instances against the oracle's closed loop (its own plant step), every step."""
+    prob = pkg.problems.quadrotor(20)
+    B, steps, n = 160_000, 4, 2_000
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
+    s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    b = pkg.capi.Batch(s, B)
+    b.set_x0(x0)
+    b.set_xref(xref)
+    h = b.rollout(steps, reset_duals=True)
+    assert s.stats()["scheduled"] == 2
+    xc, warm = x0[:n].copy(), None
+    for k in range(steps):
+        r = oracle.solve_batch(prob, xc, xref, dtype=np.float32, warm=warm, want_state=True, nthreads=8)
+        assert_same(h["iter"][k, :n], r.iter, "step %d iter" % k)
+        assert_same(h["status"][k, :n], r.status, "step %d status" % k)
+        assert_same(h["u0"][k, :n], r.u[:, 0, :], "step %d u0" % k)
+        xc = oracle.plant_step(prob, xc, r.u[:, 0, :], dtype=np.float32)
+        assert_same(h["x0"][k + 1, :n], xc, "step %d plant state" % k)
+        warm = {q: r.state[q].copy() for q in ("d", "y", "g", "v", "z")}
+        warm["y"][:] = 0
+        warm["g"][:] = 0
+    # the workspace the loop leaves behind (what a following wrapper-style call would start from)
+    for q in ("d", "v", "z", "y", "g"):
+        assert_same(b.get(q)[:n], r.state[q], "final workspace " + q)
