@@ -4,6 +4,7 @@
 #include "tmpc_dispatch.hpp"
 #include "tmpc_kernel_small.cuh"
 #include "tmpc_kernel_warp.cuh"
+#include "tmpc_kernel_warp4.cuh"
 
 namespace tmpc_dispatch {
 namespace {
@@ -60,9 +61,27 @@ bool lookup_small(int block, int policy, bool warm, KernelInfo &out)
     return pick_small<4, 10, 384>(policy, warm, out);
 }
 
-bool lookup_warp(bool tm, int policy, bool warm, KernelInfo &out)
+template <int NH, bool FAST, bool WARM>
+KernelInfo make_info_warp4()
 {
-    return tm ? pick_warp<50, 16, true>(policy, warm, out) : pick_warp<50, 12, false>(policy, warm, out);
+    static_assert(tmpc::Warp4Smem<NH>::total_bytes(4) <= 232448, "per-block shared memory limit of sm_100");
+    KernelInfo k;
+    k.fn = (const void *)&tmpc::admm_kernel_warp4<NH, FAST, WARM>;
+    k.smem = tmpc::Warp4Smem<NH>::total_bytes(4);
+    k.block = 128;
+    k.model_bytes = sizeof(tmpc::ModelWarp);
+    k.model_kind = 2;
+    k.per_block = 16;   // 4 warps x 4 slots
+    return k;
+}
+
+bool lookup_warp(int variant, int policy, bool warm, KernelInfo &out)
+{
+    if (variant == 1) return pick_warp<50, 16, true>(policy, warm, out);
+    if (variant == 2) return pick_warp<50, 12, false>(policy, warm, out);
+    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_warp4<50, false, true>() : make_info_warp4<50, false, false>();
+    else out = warm ? make_info_warp4<50, true, true>() : make_info_warp4<50, true, false>();
+    return true;
 }
 
 }  // namespace tmpc_dispatch

@@ -118,3 +118,34 @@ def test_large_step_functions(pkg, oracle):
                 off += n
             if which == 4:
                 assert term[b] == rc
+
+
+@pytest.mark.parametrize("variant", ["", "warp1", "warp_smem"])
+def test_large_kernel_variants_and_slot_refill(pkg, oracle, monkeypatch, variant):
+    """Default = four instances per warp (tmpc_kernel_warp4.cuh); TMPC_KERNEL=warp1 / warp_smem = the one-instance-per-warp
+    kernels.  1,100 instances on a 3-block grid cap would be too few to refill slots, so the batch is several times the resident
+    slots of the test GPU only in the sense that every slot is refilled many times in index order (148 SMs x 16 = 2,368 resident:
+    use a ragged 5,003 with a short max_iter so that the oracle stays cheap), cold and warm, state included."""
+    if variant:
+        monkeypatch.setenv("TMPC_KERNEL", variant)
+    prob = copy.deepcopy(pkg.problems.random_system())
+    prob.max_iter = 12
+    B = 5003
+    x0, xref = pkg.workloads.random_system_batch(0, B, amp=0.3)
+    r1 = oracle.solve_batch(prob, x0, xref, dtype=np.float32, want_state=True, nthreads=8)
+    assert (r1.status == 1).any() and (r1.status == 11).any()
+    s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    cold = s.solve(x0, xref)
+    for k in ("iter", "status", "resid", "x", "u"):
+        assert_same(cold[k], getattr(r1, k), "%s cold %s" % (variant, k))
+    o1 = s.solve(x0, xref, warm=_zeros_warm(prob, B))
+    for k in WARM_KEYS:
+        assert_same(o1["warm"][k], r1.state[k], "%s warm.%s" % (variant, k))
+    x1 = pkg.workloads.perturb_x0(x0, 0)
+    r2 = oracle.solve_batch(prob, x1, xref, dtype=np.float32, warm={k: r1.state[k] for k in WARM_KEYS}, want_state=True, nthreads=8)
+    o2 = s.solve(x1, xref, warm=o1["warm"], outputs=("x", "u", "u0", "iter", "status", "resid"))
+    for k in ("iter", "status", "resid", "x", "u"):
+        assert_same(o2[k], getattr(r2, k), "%s re-solve %s" % (variant, k))
+    assert_same(o2["u0"], r2.u[:, 0, :], "%s re-solve u0" % variant)
+    for k in WARM_KEYS:
+        assert_same(o2["warm"][k], r2.state[k], "%s warm2.%s" % (variant, k))
