@@ -172,7 +172,7 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
     // large shape: one warp per instance.  g,v in tensor memory -> 16 instances / SM (TMPC_KERNEL=warp_smem: all state in
     // shared memory, 17.8 KB each -> 12 instances / SM)
     if (nx == 32 && nu == 8 && N == 50 && dtype == TMPC_F32)
-        return tmpc_dispatch::lookup_warp(e && !strcmp(e, "warp_smem") ? 2 : e && !strcmp(e, "warp1") ? 1 : 0, policy, warm, out);
+        return tmpc_dispatch::lookup_warp(e && !strcmp(e, "warp_smem") ? 2 : e && !strcmp(e, "warp4") ? 0 : 1, policy, warm, out);
     return lookup_kernel_rt(nx, nu, N, dtype, policy, out);
 }
 

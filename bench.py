@@ -469,6 +469,21 @@ def main():
     del run, x, u, rs
     torch.cuda.empty_cache()
 
+    # ---- the same end-to-end step from ONE process over all N GPUs (tmpc_multi: what a C++ caller of tiny_solve_batch gets):
+    #      rank 0 drives every device, the other ranks wait on the rendezvous store (a CPU wait: no NCCL kernel on their GPUs)
+    if e2e is not None and world > 1:
+        store = dist.distributed_c10d._get_default_store()
+        barrier()
+        if rank == 0:
+            try:
+                e2e["one_process"] = multi_measure(torch, pkg, args, prob, world)
+            except Exception as ex:   # additional evidence only
+                e2e["one_process"] = {"error": repr(ex)}
+            store.set("tmpc_one_process_done", "1")
+        else:
+            store.wait(["tmpc_one_process_done"])
+        barrier()
+
     # ---- the other BASELINE configs + closed loop + dense instance, device-timed, same one JSON line
     configs = None
     if not args.no_configs:
@@ -646,10 +661,18 @@ def run_configs(torch, dist, pkg, args, dev, local, rank, world, barrier, allmax
 
 
 def multi_arm(torch, pkg, args, prob, config):
-    """ONE process, every visible GPU through tmpc_multi (one ctx + one worker thread per device): the product API's
-    multi-GPU path for host callers.  Hand-run (the driver's arm is one rank per GPU); prints one JSON line."""
+    """--impl multi (hand-run): ONE process, every visible GPU through tmpc_multi; prints one JSON line."""
+    out = multi_measure(torch, pkg, args, prob, args.gpus if args.gpus > 1 else None)
+    out["config"] = config
+    emit(json.dumps(out))
+    return 0
+
+
+def multi_measure(torch, pkg, args, prob, devices):
+    """ONE process, `devices` GPUs through tmpc_multi (one ctx + one worker thread per device): the product API's
+    multi-GPU path for host callers (tiny_solve_batch / tmpc_multi_solve)."""
     capi = pkg.capi
-    m = capi.Multi(prob, dtype=np.float32, policy=args.policy, devices=args.gpus if args.gpus > 1 else None)
+    m = capi.Multi(prob, dtype=np.float32, policy=args.policy, devices=devices)
     G = m.device_count
     B = args.batch * G
     x0_np, xref_np = pkg.workloads.quadrotor_hover_batch(0, B, mult=args.mult)
@@ -676,15 +699,15 @@ def multi_arm(torch, pkg, args, prob, config):
     u0_s, us = timed(lambda: m.solve_raw(B, hx0, hxr, True, None, None, hit, hst, None, u0=hu0))
     ok = iters_full == int(hit.sum()) and torch.equal(hu0, hu[:, 0, :])
     out = {"impl": "multi", "metric": "batched MPC solves/sec (quadrotor nx12 nu4 N10)", "n_gpus": G, "processes": 1, "unit": "solves/s",
-           "instances": B, "steps": K, "config": config,
+           "instances": B, "steps": K,
            "e2e": {"value": B / full_s, "ms_per_step": 1e3 * full_s, "d2h_bytes_per_step": int(B * 648), "h2d_bytes_per_step": int(B * 48 + 480),
                    "slowest_kernel_ms": fs["kernel_ms"],
                    "u0_only": {"value": B / u0_s, "ms_per_step": 1e3 * u0_s, "d2h_bytes_per_step": int(B * 24), "slowest_kernel_ms": us["kernel_ms"]}},
            "u0_equals_u_col0": bool(ok), "iterations": iters_full,
            "how": "tmpc_multi_solve(TMPC_MEM_HOST) on pinned host arrays: contiguous instance ranges, one ctx + one host worker thread per device"}
-    emit(json.dumps(out))
     m.close()
-    return 0
+    del hx, hu, hrs, hx0
+    return out
 
 
 if __name__ == "__main__":
