@@ -170,26 +170,31 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
 #pragma unroll
         for (int e = 0; e < NS; ++e) pri_x[e] = dua_x[e] = 0.f;
         {
-            float Ac[WNX], Kc[WNX], Bc[WNU];
-#pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                const float4 t = fwd4[g4 * 32 + lane], s = fwd4[(8 + g4) * 32 + lane];
-                Ac[4 * g4] = t.x; Ac[4 * g4 + 1] = t.y; Ac[4 * g4 + 2] = t.z; Ac[4 * g4 + 3] = t.w;
-                Kc[4 * g4] = s.x; Kc[4 * g4 + 1] = s.y; Kc[4 * g4 + 2] = s.z; Kc[4 * g4 + 3] = s.w;
-            }
+            // Coefficient rows are NOT held in registers across the sweep (72 registers: with four slots of state on top ptxas was
+            // re-materialising addresses with S2R inside the stage loop): each 16-byte chunk of Adyn(lane,:) / Kinf(ur,:) is read from
+            // the CTA's shared-memory image next to the x chunks it multiplies, one chunk ahead of its use.
+            float Bc[WNU];
 #pragma unroll
             for (int g4 = 0; g4 < 2; ++g4) {
                 const float4 t = fwd4[(16 + g4) * 32 + lane];
                 Bc[4 * g4] = t.x; Bc[4 * g4 + 1] = t.y; Bc[4 * g4 + 2] = t.z; Bc[4 * g4 + 3] = t.w;
             }
+            const float4 *xb4 = reinterpret_cast<const float4 *>(xb);
+            const float4 *cA4 = fwd4 + lane, *cK4 = fwd4 + 8 * 32 + lane;
+            struct Chunk { float4 cA, cK, v0, v1, v2, v3, vk; };
+            auto ld_chunk = [&](int g4, Chunk &c) {
+                c.cA = cA4[g4 * 32]; c.cK = cK4[g4 * 32];
+                c.v0 = xb4[g4]; c.v1 = xb4[8 + g4]; c.v2 = xb4[16 + g4]; c.v3 = xb4[24 + g4]; c.vk = xb4[sl * 8 + g4];
+            };
             float x[NS], g[NS], v[NS];
 #pragma unroll
             for (int e = 0; e < NS; ++e) { x[e] = x0[e]; tm_ld1(gcol(e, 0), g[e]); tm_ld1(vcol(e, 0), v[e]); }
             float xmn = bxmin[lane], xmx = bxmax[lane], umn = bumin[ur], umx = bumax[ur];
             float d = myd[ur], y = myy[ur], z = myz[ur];
-            float *xo[NS], *uo = (urun && a.u) ? a.u + uinst * UROW : nullptr;
+            float *uo = (urun && a.u) ? a.u + uinst * UROW + ur : nullptr;
+            float *xo[NS];     // always a valid row address (a.x may be null: then never stored through)
 #pragma unroll
-            for (int e = 0; e < NS; ++e) xo[e] = xw[e] ? a.x + inst[e] * XROW : nullptr;
+            for (int e = 0; e < NS; ++e) xo[e] = a.x + inst[e] * XROW + lane;
 #pragma unroll 1
             for (int i = 0; i < NH - 1; ++i) {
 #pragma unroll
@@ -197,35 +202,47 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                 __syncwarp();
                 asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(g[0]), "+f"(g[1]), "+f"(g[2]), "+f"(g[3]), "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory");
 #pragma unroll
-                for (int e = 0; e < NS; ++e) if (xo[e]) xo[e][i * WNX + lane] = x[e];
+                for (int e = 0; e < NS; ++e) if (xw[e]) xo[e][i * WNX] = x[e];
                 // Adyn(lane,:) x_i of every slot (pairs of slots advance as one FADD2 chain) and Kinf(ur,:) x_i of slot sl
                 float2 a01, a23;
                 float ka;
-#pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4) {
-                    const float4 v0 = reinterpret_cast<const float4 *>(xb)[g4], v1 = reinterpret_cast<const float4 *>(xb + WNX)[g4],
-                                 v2 = reinterpret_cast<const float4 *>(xb + 2 * WNX)[g4], v3 = reinterpret_cast<const float4 *>(xb + 3 * WNX)[g4];
-                    const float4 vk = reinterpret_cast<const float4 *>(xb + sl * WNX)[g4];
-                    const float s0[4] = {v0.x, v0.y, v0.z, v0.w}, s1[4] = {v1.x, v1.y, v1.z, v1.w}, s2[4] = {v2.x, v2.y, v2.z, v2.w},
-                                s3[4] = {v3.x, v3.y, v3.z, v3.w}, sk[4] = {vk.x, vk.y, vk.z, vk.w};
+                // four sequential-chain steps (one 16-byte chunk of the row) for the five chains this lane advances
+                auto do_chunk = [&](const Chunk &c, auto first_tag) {
+                    constexpr bool FIRST = decltype(first_tag)::value;
+                    const float A4[4] = {c.cA.x, c.cA.y, c.cA.z, c.cA.w}, K4[4] = {c.cK.x, c.cK.y, c.cK.z, c.cK.w};
+                    const float s0[4] = {c.v0.x, c.v0.y, c.v0.z, c.v0.w}, s1[4] = {c.v1.x, c.v1.y, c.v1.z, c.v1.w}, s2[4] = {c.v2.x, c.v2.y, c.v2.z, c.v2.w},
+                                s3[4] = {c.v3.x, c.v3.y, c.v3.z, c.v3.w}, sk[4] = {c.vk.x, c.vk.y, c.vk.z, c.vk.w};
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        const int k = 4 * g4 + t;
                         if constexpr (FAST) {
-                            if (k == 0) {
-                                a01 = __fmul2_rn(f2(Ac[0], Ac[0]), f2(s0[0], s1[0])); a23 = __fmul2_rn(f2(Ac[0], Ac[0]), f2(s2[0], s3[0]));
-                                ka = __fmul_rn(Kc[0], sk[0]);
+                            if (FIRST && t == 0) {
+                                a01 = __fmul2_rn(f2(A4[0], A4[0]), f2(s0[0], s1[0])); a23 = __fmul2_rn(f2(A4[0], A4[0]), f2(s2[0], s3[0]));
+                                ka = __fmul_rn(K4[0], sk[0]);
                             } else {
-                                a01 = __ffma2_rn(f2(Ac[k], Ac[k]), f2(s0[t], s1[t]), a01); a23 = __ffma2_rn(f2(Ac[k], Ac[k]), f2(s2[t], s3[t]), a23);
-                                ka = __fmaf_rn(Kc[k], sk[t], ka);
+                                a01 = __ffma2_rn(f2(A4[t], A4[t]), f2(s0[t], s1[t]), a01); a23 = __ffma2_rn(f2(A4[t], A4[t]), f2(s2[t], s3[t]), a23);
+                                ka = __fmaf_rn(K4[t], sk[t], ka);
                             }
                         } else {
-                            const float2 e01 = f2(__fmul_rn(Ac[k], s0[t]), __fmul_rn(Ac[k], s1[t])), e23 = f2(__fmul_rn(Ac[k], s2[t]), __fmul_rn(Ac[k], s3[t]));
-                            const float ek = __fmul_rn(Kc[k], sk[t]);
-                            if (k == 0) { a01 = e01; a23 = e23; ka = ek; }
+                            const float2 e01 = f2(__fmul_rn(A4[t], s0[t]), __fmul_rn(A4[t], s1[t])), e23 = f2(__fmul_rn(A4[t], s2[t]), __fmul_rn(A4[t], s3[t]));
+                            const float ek = __fmul_rn(K4[t], sk[t]);
+                            if (FIRST && t == 0) { a01 = e01; a23 = e23; ka = ek; }
                             else { a01 = add2(e01, a01); a23 = add2(e23, a23); ka = __fadd_rn(ek, ka); }
                         }
                     }
+                };
+                {
+                    Chunk ca, cb;
+                    ld_chunk(0, ca);
+                    ld_chunk(1, cb);
+                    do_chunk(ca, std::true_type());
+#pragma unroll 1
+                    for (int j = 0; j < 3; ++j) {      // chunks 1..6 in pairs, each loaded one chunk ahead of its use
+                        ld_chunk(2 * j + 2, ca);
+                        do_chunk(cb, std::false_type());
+                        ld_chunk(2 * j + 3, cb);
+                        do_chunk(ca, std::false_type());
+                    }
+                    do_chunk(cb, std::false_type());
                 }
                 const float ax[NS] = {a01.x, a01.y, a23.x, a23.y};
                 const float u = __fsub_rn(-ka, d);                                                     // :31  (slot sl, row ur)
@@ -238,7 +255,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                     myy[i * WNU + ur] = yn;
                     myz[i * WNU + ur] = t;
                     ub[sl * WNU + ur] = u;
-                    if (uo) uo[i * WNU + ur] = u;
+                    if (uo) uo[i * WNU] = u;
                     if (i == 0 && urun && a.u0) a.u0[uinst * WNU + ur] = u;
                 }
                 // state slack / dual / residuals of row `lane` of every slot, two slots per packed instruction
@@ -295,7 +312,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                 asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(g[0]), "+f"(g[1]), "+f"(g[2]), "+f"(g[3]), "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory");
 #pragma unroll
                 for (int e = 0; e < NS; ++e) {
-                    if (xo[e]) xo[e][i * WNX + lane] = x[e];
+                    if (xw[e]) xo[e][i * WNX] = x[e];
                     float t = __fadd_rn(x[e], g[e]);
                     t = fminf(xmx, fmaxf(xmn, t));
                     pri_x[e] = fmaxf(pri_x[e], fabsf(__fsub_rn(x[e], t)));
@@ -342,12 +359,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
         // update_linear_cost (admm.cpp:77-85) recomputed per stage + backward_pass_grad (:15-22)
         __syncwarp();   // the forward sweep's last reads of ub precede this sweep's writes
         {
-            float Mc[WNX], BTc[WNU], Qic[WNU], KTc[WNU];
-#pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                const float4 t = bwd4[g4 * 32 + lane];
-                Mc[4 * g4] = t.x; Mc[4 * g4 + 1] = t.y; Mc[4 * g4 + 2] = t.z; Mc[4 * g4 + 3] = t.w;
-            }
+            float BTc[WNU], Qic[WNU], KTc[WNU];     // (the AmBKt row is read chunk by chunk next to the p chunks it multiplies)
 #pragma unroll
             for (int g4 = 0; g4 < 2; ++g4) {
                 const float4 t = bwd4[(8 + g4) * 32 + lane], s = bwd4[(10 + g4) * 32 + lane], w = bwd4[(12 + g4) * 32 + lane];
@@ -359,10 +371,10 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
             const bool mir[NS] = {warm && (cont[0] || fbw[0]), warm && (cont[1] || fbw[1]), warm && (cont[2] || fbw[2]), warm && (cont[3] || fbw[3])};
             const bool umir = (sl == 0 ? mir[0] : sl == 1 ? mir[1] : sl == 2 ? mir[2] : mir[3]);
             const bool ucont = (sl == 0 ? cont[0] : sl == 1 ? cont[1] : sl == 2 ? cont[2] : cont[3]);
-            float *wvo[NS];
+            float *wvo[NS];     // row addresses (only stored through when mir[e])
 #pragma unroll
-            for (int e = 0; e < NS; ++e) wvo[e] = mir[e] ? a.wv + inst[e] * XROW : nullptr;
-            float *wdo = umir ? a.wd + uinst * UROW : nullptr, *wzo = umir ? a.wz + uinst * UROW : nullptr;
+            for (int e = 0; e < NS; ++e) wvo[e] = a.wv + inst[e] * XROW + lane;
+            float *wdo = umir ? a.wd + uinst * UROW + ur : nullptr, *wzo = umir ? a.wz + uinst * UROW + ur : nullptr;
             const float *xrf[NS];
 #pragma unroll
             for (int e = 0; e < NS; ++e) xrf[e] = a.Xref + inst[e] * a.xref_stride;
@@ -375,7 +387,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
 #pragma unroll
                 for (int e = 0; e < NS; ++e) {
                     const float pn = ws[e * S::SLOT + S::PN + lane];
-                    if (wvo[e]) wvo[e][(NH - 1) * WNX + lane] = v[e];
+                    if (mir[e]) wvo[e][(NH - 1) * WNX] = v[e];
                     const float dvg = __fsub_rn(v[e], g[e]);
                     if constexpr (FAST) p[e] = __fmaf_rn(P.nrho, dvg, pn);
                     else p[e] = __fsub_rn(pn, __fmul_rn(P.rho, dvg));                                  // :84
@@ -394,10 +406,10 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                 for (int e = 0; e < NS; ++e) {
                     xb[e * WNX + lane] = p[e];
                     xt[e * WNX + sl * 8 + ur] = p[e];       // p(4 j + sl) with j = ur = lane >> 2: packet j of SIMD lane sl
-                    if (wvo[e]) wvo[e][i * WNX + lane] = v[e];
+                    if (mir[e]) wvo[e][i * WNX] = v[e];
                 }
                 ub[sl * WNU + ur] = r;
-                if (wzo) wzo[i * WNU + ur] = z;
+                if (wzo) wzo[i * WNU] = z;
                 __syncwarp();
                 // Bdyn^T p_{i+1}: row ur, SIMD lane sl accumulates packets j = 0..7 of e(4j + sl) sequentially, every slot
                 float bp[NS];
@@ -442,20 +454,21 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                                      v2 = reinterpret_cast<const float4 *>(xb + 2 * WNX)[g4], v3 = reinterpret_cast<const float4 *>(xb + 3 * WNX)[g4];
                         const float s0[4] = {v0.x, v0.y, v0.z, v0.w}, s1[4] = {v1.x, v1.y, v1.z, v1.w}, s2[4] = {v2.x, v2.y, v2.z, v2.w},
                                     s3[4] = {v3.x, v3.y, v3.z, v3.w};
+                        const float4 mc = bwd4[g4 * 32 + lane];
+                        const float Mc[4] = {mc.x, mc.y, mc.z, mc.w};
                         if constexpr (FAST) {   // one FMA chain per slot
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
                                 const int k = 4 * g4 + t;
                                 if (k == 0) { m01 = __fmul2_rn(f2(Mc[0], Mc[0]), f2(s0[0], s1[0])); m23 = __fmul2_rn(f2(Mc[0], Mc[0]), f2(s2[0], s3[0])); }
-                                else { m01 = __ffma2_rn(f2(Mc[k], Mc[k]), f2(s0[t], s1[t]), m01); m23 = __ffma2_rn(f2(Mc[k], Mc[k]), f2(s2[t], s3[t]), m23); }
+                                else { m01 = __ffma2_rn(f2(Mc[t], Mc[t]), f2(s0[t], s1[t]), m01); m23 = __ffma2_rn(f2(Mc[t], Mc[t]), f2(s2[t], s3[t]), m23); }
                             }
                         } else {
                             float2 e01[4], e23[4];
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
-                                const int k = 4 * g4 + t;
-                                e01[t] = f2(__fmul_rn(Mc[k], s0[t]), __fmul_rn(Mc[k], s1[t]));
-                                e23[t] = f2(__fmul_rn(Mc[k], s2[t]), __fmul_rn(Mc[k], s3[t]));
+                                e01[t] = f2(__fmul_rn(Mc[t], s0[t]), __fmul_rn(Mc[t], s1[t]));
+                                e23[t] = f2(__fmul_rn(Mc[t], s2[t]), __fmul_rn(Mc[t], s3[t]));
                             }
                             q01[g4] = add2(add2(e01[0], e01[1]), add2(e01[2], e01[3]));
                             q23[g4] = add2(add2(e23[0], e23[1]), add2(e23[2], e23[3]));
@@ -520,7 +533,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                         d = sum_seq<WNU>(ed);
                     }
                     if (ucont) myd[i * WNU + ur] = d;
-                    if (wdo) wdo[i * WNU + ur] = d;
+                    if (wdo) wdo[i * WNU] = d;
                 }
                 {   // p_i = (q_i + AmBKt p_{i+1}) - Kinf^T r_i                                          :20
                     const float2 n01 = sub2(add2(f2(q[0], q[1]), m01), k01), n23 = sub2(add2(f2(q[2], q[3]), m23), k23);
