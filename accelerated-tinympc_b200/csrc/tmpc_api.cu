@@ -60,6 +60,7 @@ struct tmpc_ctx_impl {
     // per-lane coalesced scratch of the fp32 12/4/10 kernel (SolveArgs::scratch)
     void *d_lane_scratch = nullptr;
     size_t d_lane_scratch_bytes = 0;
+    int reserve_sms_next = 0;      // host pipeline: the next launch leaves this many SMs to the ranking kernels that run beside it
     bool duals_zero_next = false;  // tmpc_batch rollout with reset duals: the next launch of the fp32 12/4/10 kernel zero-fills y, g itself
     void *d_model_f32 = nullptr;   // device copy of model_f32 (TMPC_KERNEL=f32_tma_cache: the kernel stages it into shared memory by TMA)
     bool rt_ready = false;
@@ -554,6 +555,7 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     int test_flags;
     const void *ixmin, *ixmax, *iumin, *iumax;
     const void *model_g;
+    long long gate_split;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
@@ -583,7 +585,8 @@ int mark_launch(tmpc_ctx_impl *c, cudaStream_t s)
 int plan_launch(tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da, cudaStream_t s, long long &blocks)
 {
     blocks = (da.batch + ki.per_block - 1) / ki.per_block;
-    long long max_blocks = c->sm_count;
+    long long max_blocks = std::max(1, c->sm_count - c->reserve_sms_next);
+    c->reserve_sms_next = 0;
     if (ki.model_kind == 3) {
         // persistent grid = every block the SMs can hold; the per-lane scratch (state of the resident instances) is
         // capped at 16 GB of HBM
@@ -773,7 +776,8 @@ __global__ void iota_kernel(unsigned *__restrict__ out, long long n, unsigned of
 // K / k_stride: Kinf (column-major) of instance i at K + i * k_stride; default = the ctx's shared Kinf.
 // tail > 0 (host pipeline): only the LEADING `tail` instances are ranked; the claim order becomes
 // [tail, tail+1, ..., batch-1, the leading `tail` instances longest-expected-first].
-int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = nullptr, long long k_stride = 0, long long tail = 0)
+// part: 0 = everything; 1 = buffers + the index-ordered head of the order only (before the kernel starts); 2 = rank the tail only
+int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = nullptr, long long k_stride = 0, long long tail = 0, int part = 0)
 {
     if (!K) { K = c->d_kinf; k_stride = 0; }
     const size_t B = (size_t)da.batch;
@@ -793,10 +797,12 @@ int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = n
     unsigned *keys_in = c->lpt_buf, *keys_out = keys_in + c->lpt_cap, *vals_in = keys_out + c->lpt_cap, *vals_out = vals_in + c->lpt_cap;
     const size_t n_rank = tail > 0 ? (size_t)tail : B;
     unsigned *sorted_out = vals_out + (B - n_rank);
-    if (n_rank < B) {
+    if (n_rank < B && part != 2) {
         iota_kernel<<<(unsigned)((B - n_rank + 255) / 256), 256, 0, s>>>(vals_out, (long long)(B - n_rank), (unsigned)n_rank);
         CUDA_TRY(c, cudaGetLastError());
     }
+    da.order = vals_out;
+    if (part == 1) return TMPC_OK;
     const unsigned blocks = (unsigned)((n_rank + 255) / 256);
     if (c->dtype == TMPC_F32)
         lpt_key_kernel<float><<<blocks, 256, 0, s>>>((long long)n_rank, c->nx, c->nu, (const float *)K, k_stride, (const float *)da.x0, (const float *)da.Xref,
@@ -808,7 +814,6 @@ int lpt_prepare(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const void *K = n
     size_t tb = c->lpt_temp_bytes;
     CUDA_TRY(c, cub::DeviceRadixSort::SortPairsDescending(c->lpt_temp, tb, (const unsigned *)keys_in, keys_out, (const unsigned *)vals_in, sorted_out,
                                                            (int)n_rank, 16, 32, s));
-    da.order = vals_out;
     c->stats.launches += 1;   // the key kernel (the sort's kernels are CUB's)
     return TMPC_OK;
 }
@@ -992,23 +997,28 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     const bool overlap = writef != nullptr && B < (int64_t)0xffffffffu && !getenv("TMPC_NO_H2D_OVERLAP");
     if (!c->g_in_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->g_in_stream, cudaStreamNonBlocking));
     if (!c->g_first) CUDA_TRY(c, cudaEventCreateWithFlags(&c->g_first, cudaEventDisableTiming));
-    if (!c->g_gate) CUDA_TRY(c, cudaMalloc((void **)&c->g_gate, 2 * sizeof(unsigned)));
+    if (!c->g_gate) CUDA_TRY(c, cudaMalloc((void **)&c->g_gate, 4 * sizeof(unsigned)));
     cudaStream_t hs = c->g_in_stream;
     {
         // the previous launch of this ctx may still read the input image, the claim order or the gate
         const int rc = order_after_previous(c, hs);
         if (rc != TMPC_OK) return rc;
     }
-    CUDA_TRY(c, cudaMemsetAsync(c->g_gate, 0, 2 * sizeof(unsigned), hs));
+    CUDA_TRY(c, cudaMemsetAsync(c->g_gate, 0, 4 * sizeof(unsigned), hs));
     if (a->xref_shared) CUDA_TRY(c, cudaMemcpyAsync(d_xref, a->Xref, xrow * es, cudaMemcpyHostToDevice, hs));
     // Tail-sorted schedule.  Claimed in index order, a launch ends with a tail in which a few lanes finish max_iter-long
     // instances while the rest of the GPU idles (+7.5 % on the hover workload); the full longest-expected-first order of the
-    // device path needs every x0 before the first claim, i.e. no H2D overlap.  Middle way: the LEADING quarter of the batch
-    // goes over first, is ranked by the same key (lpt_prepare, on the input stream, before the kernel starts: the persistent
-    // kernel fills every SM, nothing could run beside it) and is claimed LAST, longest first; the other three quarters
-    // stream in behind the running kernel and are claimed in index order.  Simulated on the hover workload's real iteration
-    // counts: makespan 1.018 x the mean lane load (index order 1.075, fully sorted 1.013).
+    // device path needs every x0 before the first claim, i.e. no H2D overlap.  Middle way: a LEADING segment of the batch is
+    // ranked by the same key (lpt_prepare) and claimed LAST, longest first; the rest streams in behind the running kernel
+    // and is claimed in index order.  Simulated on the hover workload's real iteration counts: makespan 1.018 x the mean
+    // lane load with a quarter of the batch ranked, 1.013 with half (index order 1.075, fully sorted 1.013).
+    //   late (default): the persistent kernel is launched on all SMs BUT TWO as soon as a first small chunk of the
+    //     index-ordered part is in; the ranked segment (half the batch) goes over LAST and its key kernel + radix sort run
+    //     beside the solver on the two free SMs (a full grid leaves them no register file); the lanes reach those claims
+    //     milliseconds after the ranking is done (gate[2]).  Nothing but 32,768 instances of H2D precedes the launch.
+    //   TMPC_TAIL_FIRST=1: the ranked segment (a quarter) goes over FIRST and is ranked before the launch, full grid.
     int64_t T0 = 0;
+    const bool late = !getenv("TMPC_TAIL_FIRST");
     {
         KernelInfo ki;
         const char *e = getenv("TMPC_LPT");
@@ -1016,7 +1026,7 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
         if (!off && overlap && a->xref_shared && !c->ib_batch && c->d_kinf && nch >= 8 &&
             lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, false, ki, c->pattern | (c->const_bounds ? 0x100 : 0)) &&
             B >= 2 * (int64_t)ki.per_block * c->sm_count && B >= 16384)
-            T0 = ((B / 4 + CH - 1) / CH) * CH;
+            T0 = ((B / (late ? 2 : 4) + CH - 1) / CH) * CH;
     }
     const int64_t ICH = overlap ? 131072 : B;
     const bool gate_stall_test = getenv("TMPC_TEST_GATE_STALL") != nullptr;
@@ -1028,7 +1038,7 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
         return TMPC_OK;
     };
     int64_t fed = 0;
-    if (T0 > 0) {
+    if (T0 > 0 && !late) {
         int rc = h2d(0, T0);
         if (rc != TMPC_OK) return rc;
         if ((rc = lpt_prepare(c, da, hs, nullptr, 0, T0)) != TMPC_OK) return rc;
@@ -1036,15 +1046,36 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
         CUDA_TRY(c, cudaEventRecord(c->g_first, hs));
         fed = T0;
     }
-    for (int64_t b0 = fed; b0 < B; b0 += ICH) {
-        const int64_t n = std::min<int64_t>(ICH, B - b0);
+    if (T0 > 0 && late) {
+        const int rc = lpt_prepare(c, da, hs, nullptr, 0, T0, 1);   // the index-ordered head of the claim order, before the launch
+        if (rc != TMPC_OK) return rc;
+        da.gate_split = T0;
+        fed = T0;
+    }
+    bool first_chunk = true;
+    for (int64_t b0 = fed; b0 < B;) {
+        // (late: a small first chunk, so that the kernel starts at once; PCIe then delivers ~6e8 instances/s to a kernel that
+        //  consumes 1e8)
+        const int64_t n = std::min<int64_t>((late && T0 > 0 && first_chunk) ? 32768 : ICH, B - b0);
         const int rc = h2d(b0, n);
         if (rc != TMPC_OK) return rc;
         // TMPC_TEST_GATE_STALL=1 (tests): the last arrival is never announced, so the lanes that claim those instances give up
         if (overlap && !(gate_stall_test && b0 + n >= B) &&
             writef(hs, (unsigned long long)(uintptr_t)c->g_gate, (unsigned)(b0 + n), 0u) != 0)
             return fail(c, TMPC_ERR_CUDA, "cuStreamWriteValue32 failed");
-        if (b0 == 0) CUDA_TRY(c, cudaEventRecord(c->g_first, hs));
+        if (b0 == 0 || (late && T0 > 0 && first_chunk)) CUDA_TRY(c, cudaEventRecord(c->g_first, hs));
+        first_chunk = false;
+        b0 += n;
+    }
+    if (T0 > 0 && late) {
+        // the ranked segment: over the bus last, ranked on the SMs the solver leaves free, announced through gate[2]
+        int rc = h2d(0, T0);
+        if (rc == TMPC_OK) rc = lpt_prepare(c, da, hs, nullptr, 0, T0, 2);
+        if (rc != TMPC_OK) return rc;
+        if (!gate_stall_test && writef(hs, (unsigned long long)(uintptr_t)(c->g_gate + 2), 1u, 0u) != 0)
+            return fail(c, TMPC_ERR_CUDA, "cuStreamWriteValue32 failed");
+        c->reserve_sms_next = 2;
+        if (const char *e = getenv("TMPC_SORT_SMS")) c->reserve_sms_next = std::max(1, std::min(16, atoi(e)));
     }
     if (!overlap) CUDA_TRY(c, cudaEventRecord(c->g_first, hs));   // everything must be in before the kernel starts
     {

@@ -216,6 +216,9 @@ template <class T> struct SolveArgs {
     const T *ixmin, *ixmax, *iumin, *iumax;   // per-instance boxes [instance][N][nx] / [instance][N-1][nu]; a null pair = unbounded
     const void *model_g;                      // device copy of the kernel's model image (CSM instances of the fp32 kernel: staged
                                               // into shared memory by one TMA bulk copy per CTA), else null
+    long long gate_split;                     // host pipeline, 0 or T: instances [0, T) are the tail segment -- transferred LAST, ranked on
+                                              // the SMs the launch leaves free, claimed last (claims batch-T .. batch-1); gate[2] != 0 once
+                                              // they have arrived and order[] holds their ranking.  gate[0] then covers [T, batch) only.
 };
 
 // instance solved by the idx-th claim of the work counter
@@ -224,22 +227,31 @@ template <class T> __device__ __forceinline__ long long claimed_instance(const S
     return a.order ? (long long)__ldg(a.order + idx) : idx;
 }
 
-// Overlapped H2D: an instance may be claimed before its x0 / Xref chunk has landed.  Inputs arrive in INSTANCE order; wait until
-// the arrival counter covers instance `inst` (rarely: the kernel consumes ~5 GB/s of inputs, PCIe delivers 50); give up after
-// ~2 s instead of hanging the device (the host then releases the completion counters and reports the timeout).
-template <class T> __device__ __forceinline__ bool gate_wait(const SolveArgs<T> &a, long long inst)
+// Overlapped H2D: an instance may be claimed before its x0 / Xref chunk has landed.  Wait until gate[slot] exceeds `v` (rarely:
+// the kernel consumes ~5 GB/s of inputs, PCIe delivers 30-55); give up after ~2 s instead of hanging the device (the host then
+// releases the completion counters and reports the timeout).
+template <class T> __device__ __forceinline__ bool gate_spin(const SolveArgs<T> &a, int slot, long long v)
 {
-    if (!a.gate) return true;
     volatile unsigned *g = a.gate;
-    if ((long long)g[0] <= inst) {
+    if ((long long)g[slot] <= v) {
         const long long t0 = clock64();
-        while ((long long)g[0] <= inst) {
+        while ((long long)g[slot] <= v) {
             __nanosleep(200);
             if (clock64() - t0 > 4000000000LL) { g[1] = 1u; return false; }
         }
     }
     __threadfence();   // the inputs were written before the counter advanced: order the reads after the observation
     return true;
+}
+// The instance solved by the idx-th claim, once its inputs are in device memory; -1 if they never arrived.
+// gate[0] = end of the index-ordered part that has arrived, gate[2] = the tail segment (see gate_split) is in and ranked.
+template <class T> __device__ __forceinline__ long long claim_instance(const SolveArgs<T> &a, long long idx)
+{
+    if (!a.gate) return claimed_instance(a, idx);
+    if (a.gate_split > 0 && idx >= a.batch - a.gate_split && !gate_spin(a, 2, 0)) return -1;   // before order[idx] is read
+    const long long inst = claimed_instance(a, idx);
+    if (inst >= a.gate_split && !gate_spin(a, 0, inst)) return -1;
+    return inst;
 }
 
 // Per-instance system block (PERSYS: every instance brings its own model + cache; the "systems" batching axis),
@@ -599,8 +611,9 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
             base = __shfl_sync(FULLM, base, leader);
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) {
-                    inst = claimed_instance(a, idx);
+                const long long ci = idx < a.batch ? claim_instance(a, idx) : -1;
+                if (ci >= 0) {
+                    inst = ci;
                     phase = PH_RUN;
                     it = 0;
                     hit_max = false;

@@ -572,7 +572,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 long long ni = redo;
                 if (redo < 0) {
                     const long long idx = (long long)base + __popc(mc & ((1u << lane) - 1u));
-                    if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) ni = claimed_instance(a, idx);
+                    if (idx < a.batch) ni = claim_instance(a, idx);
                 }
                 if (ni >= 0) {
                     inst = ni; phase = PH_RUN; it = 0; fill = true;

@@ -194,8 +194,9 @@ __global__ void __launch_bounds__(RT_BLOCK) admm_kernel_rt(const __grid_constant
             base = __shfl_sync(FULLM, base, leader);
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) {
-                    inst = claimed_instance(a, idx);
+                const long long ci = idx < a.batch ? claim_instance(a, idx) : -1;
+                if (ci >= 0) {
+                    inst = ci;
                     active = true;
                     it = 0;
                     cur = 0;

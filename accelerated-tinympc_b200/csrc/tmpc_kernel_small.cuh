@@ -62,8 +62,9 @@ admm_kernel_small(const __grid_constant__ Model<float, NX, 1, NH> P, const __gri
             base = __shfl_sync(FULLM, base, leader);
             if (need) {
                 const long long idx = (long long)base + __popc(m & ((1u << lane) - 1u));
-                if (idx < a.batch && gate_wait(a, claimed_instance(a, idx))) {
-                    inst = claimed_instance(a, idx); phase = PH_RUN; it = 0;
+                const long long ci = idx < a.batch ? claim_instance(a, idx) : -1;
+                if (ci >= 0) {
+                    inst = ci; phase = PH_RUN; it = 0;
                     spec = (P.max_iter <= 1);
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);

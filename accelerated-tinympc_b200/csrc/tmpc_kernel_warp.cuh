@@ -199,8 +199,8 @@ admm_kernel_warp(const __grid_constant__ ModelWarp P, const __grid_constant__ So
             inst = (long long)__shfl_sync(FULLM, b, 0);
         }
         if (inst >= a.batch) break;
-        inst = claimed_instance(a, inst);
-        if (!gate_wait(a, inst)) break;
+        inst = claim_instance(a, inst);
+        if (inst < 0) break;
         const float *xref = a.Xref + inst * a.xref_stride;
         const float x0 = __ldg(a.x0 + inst * WNX + lane);
         // p_N seed: -(Xref_{N-1}^T Pinf)   (admm.cpp:83)

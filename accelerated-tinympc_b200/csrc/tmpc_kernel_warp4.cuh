@@ -56,6 +56,10 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
     const float Qd = __ldg(P.Qd + lane);
     const float2 Z = P.nz2;
     (void)Z;
+    // rho / -rho in registers for good: as constant-bank operands ptxas re-loads them (LDCU) at the top of every backward stage
+    // and the one warp of the scheduler waits out the load
+    float rho = P.rho, nrho = P.nrho;
+    asm volatile("" : "+f"(rho), "+f"(nrho));
     const bool warm = WARM && a.wd;
     unsigned long long n_iter = 0, n_solved = 0, n_inst = 0, n_trips = 0;
 
@@ -131,8 +135,8 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                 idx = (long long)__shfl_sync(FULLM, b, 0);
             }
             if (idx >= a.batch) { exhausted = true; continue; }
-            const long long ni = claimed_instance(a, idx);
-            if (!gate_wait(a, ni)) { exhausted = true; continue; }
+            const long long ni = claim_instance(a, idx);
+            if (ni < 0) { exhausted = true; continue; }
             inst[e] = ni; it[e] = 0; run[e] = true;
             res[e][0] = res[e][1] = res[e][2] = res[e][3] = 0.f;
             float *se = ws + e * S::SLOT;
@@ -231,18 +235,21 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                     }
                 };
                 {
-                    Chunk ca, cb;
-                    ld_chunk(0, ca);
-                    ld_chunk(1, cb);
-                    do_chunk(ca, std::true_type());
-#pragma unroll 1
-                    for (int j = 0; j < 3; ++j) {      // chunks 1..6 in pairs, each loaded one chunk ahead of its use
-                        ld_chunk(2 * j + 2, ca);
-                        do_chunk(cb, std::false_type());
-                        ld_chunk(2 * j + 3, cb);
-                        do_chunk(ca, std::false_type());
-                    }
+                    // straight-line, three chunk buffers, every chunk loaded TWO chunks (~80 issue slots) ahead of its use; the empty
+                    // asm statements pin the loads where they are written (ptxas otherwise sinks them next to their first use and the
+                    // single warp of the scheduler eats the whole shared-memory latency: 20 % of the stall samples of the first version)
+#define TMPC_PIN() asm volatile("" ::: "memory")
+                    Chunk ca, cb, cc;
+                    ld_chunk(0, ca); ld_chunk(1, cb); ld_chunk(2, cc); TMPC_PIN();
+                    do_chunk(ca, std::true_type());  ld_chunk(3, ca); TMPC_PIN();
+                    do_chunk(cb, std::false_type()); ld_chunk(4, cb); TMPC_PIN();
+                    do_chunk(cc, std::false_type()); ld_chunk(5, cc); TMPC_PIN();
+                    do_chunk(ca, std::false_type()); ld_chunk(6, ca); TMPC_PIN();
+                    do_chunk(cb, std::false_type()); ld_chunk(7, cb); TMPC_PIN();
+                    do_chunk(cc, std::false_type()); TMPC_PIN();
+                    do_chunk(ca, std::false_type()); TMPC_PIN();
                     do_chunk(cb, std::false_type());
+#undef TMPC_PIN
                 }
                 const float ax[NS] = {a01.x, a01.y, a23.x, a23.y};
                 const float u = __fsub_rn(-ka, d);                                                     // :31  (slot sl, row ur)
@@ -389,8 +396,8 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                     const float pn = ws[e * S::SLOT + S::PN + lane];
                     if (mir[e]) wvo[e][(NH - 1) * WNX] = v[e];
                     const float dvg = __fsub_rn(v[e], g[e]);
-                    if constexpr (FAST) p[e] = __fmaf_rn(P.nrho, dvg, pn);
-                    else p[e] = __fsub_rn(pn, __fmul_rn(P.rho, dvg));                                  // :84
+                    if constexpr (FAST) p[e] = __fmaf_rn(nrho, dvg, pn);
+                    else p[e] = __fsub_rn(pn, __fmul_rn(rho, dvg));                                  // :84
                 }
             }
             // stage operands one stage ahead
@@ -400,7 +407,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
             for (int e = 0; e < NS; ++e) { tm_ld1(gcol(e, NH - 2), g[e]); tm_ld1(vcol(e, NH - 2), v[e]); xr[e] = __ldg(xrf[e] + (NH - 2) * WNX + lane); }
 #pragma unroll 1
             for (int i = NH - 2; i >= 0; --i) {
-                const float r = __fmul_rn(P.nrho, __fsub_rn(z, y));                                    // :80  (slot sl, row ur)
+                const float r = __fmul_rn(nrho, __fsub_rn(z, y));                                    // :80  (slot sl, row ur)
                 asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(g[0]), "+f"(g[1]), "+f"(g[2]), "+f"(g[3]), "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory");
 #pragma unroll
                 for (int e = 0; e < NS; ++e) {
@@ -511,8 +518,8 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                 for (int e = 0; e < NS; ++e) {
                     const float cq = -__fmul_rn(xr[e], Qd);                                            // :81
                     const float dvg = __fsub_rn(v[e], g[e]);
-                    if constexpr (FAST) q[e] = __fmaf_rn(P.nrho, dvg, cq);
-                    else q[e] = __fsub_rn(cq, __fmul_rn(P.rho, dvg));                                  // :82
+                    if constexpr (FAST) q[e] = __fmaf_rn(nrho, dvg, cq);
+                    else q[e] = __fsub_rn(cq, __fmul_rn(rho, dvg));                                  // :82
                 }
                 __syncwarp();
                 {   // operands of stage i-1
