@@ -1016,9 +1016,15 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     //     index-ordered part is in; the ranked segment (half the batch) goes over LAST and its key kernel + radix sort run
     //     beside the solver on the two free SMs (a full grid leaves them no register file); the lanes reach those claims
     //     milliseconds after the ranking is done (gate[2]).  Nothing but 32,768 instances of H2D precedes the launch.
-    //   TMPC_TAIL_FIRST=1: the ranked segment (a quarter) goes over FIRST and is ranked before the launch, full grid.
+    //     Used when the caller wants neither x nor u back (controls-only: u0 / iter / status): measured 10.77 ms per 1M-instance
+    //     step against 10.84 ms tail-first on one GPU, and the gap grows when eight ranks share the host's H2D path.
+    //   first: the ranked segment (a quarter) goes over FIRST and is ranked before the launch, full grid.  Used for
+    //     trajectory outputs: those calls are bound by the D2H of 648 B per instance, and the ranked segment's outputs only
+    //     complete at the very end of the kernel -- with half the batch ranked that read-back (340 MB) would trail the
+    //     kernel instead of hiding behind it (measured 16.9 vs 14.3 ms per step).
+    //   TMPC_TAIL_FIRST=1 / TMPC_TAIL_LATE=1 force one or the other.
     int64_t T0 = 0;
-    const bool late = !getenv("TMPC_TAIL_FIRST");
+    const bool late = getenv("TMPC_TAIL_LATE") ? true : getenv("TMPC_TAIL_FIRST") ? false : (!a->x && !a->u);
     {
         KernelInfo ki;
         const char *e = getenv("TMPC_LPT");
