@@ -184,15 +184,15 @@ def log(*a):
 # device-resident measurement of one workload (used by the headline and by every entry of `configs`)
 # ------------------------------------------------------------------------------------------------------------------
 class DeviceRun:
-    def __init__(self, torch, pkg, prob, dev, local, policy, x0_np, xref_np, warm=False):
+    def __init__(self, torch, pkg, prob, dev, local, policy, x0_np, xref_np, warm=False, dtype=np.float32):
         self.torch, self.capi, self.prob, self.dev = torch, pkg.capi, prob, dev
         self.B = x0_np.shape[0]
         self.shared = xref_np.ndim == 2
-        self.solver = pkg.capi.Solver(prob, dtype=np.float32, policy=policy, device=local)
+        self.solver = pkg.capi.Solver(prob, dtype=dtype, policy=policy, device=local)
         B = self.B
-        self.x0 = torch.from_numpy(x0_np).to(dev)
-        self.xref = torch.from_numpy(xref_np).to(dev)
-        f32, i32 = torch.float32, torch.int32
+        self.x0 = torch.from_numpy(x0_np.astype(dtype)).to(dev)
+        self.xref = torch.from_numpy(xref_np.astype(dtype)).to(dev)
+        f32, i32 = (torch.float32 if np.dtype(dtype) == np.float32 else torch.float64), torch.int32
         self.x = torch.empty((B, prob.N, prob.nx), dtype=f32, device=dev)
         self.u = torch.empty((B, prob.N - 1, prob.nu), dtype=f32, device=dev)
         self.it = torch.empty(B, dtype=i32, device=dev)
@@ -242,14 +242,14 @@ class DeviceRun:
         self.solver.close()
 
 
-def oracle_check(prob, x0, xref, out, n, warm_in=None, what=("iter", "status", "x", "u")):
+def oracle_check(prob, x0, xref, out, n, warm_in=None, what=("iter", "status", "x", "u"), dtype=np.float32):
     """Bit-for-bit comparison of the first n instances with the CPU oracle (checker only; never inside a timed region)."""
     from oracle.pyoracle import OracleLib
     n = min(n, x0.shape[0])
     xr = xref if xref.ndim == 2 else xref[:n]
     w = None if warm_in is None else {k: v[:n] for k, v in warm_in.items()}
     t = time.perf_counter()
-    ref = OracleLib().solve_batch(prob, x0[:n], xr, dtype=np.float32, warm=w, nthreads=os.cpu_count() or 1)
+    ref = OracleLib().solve_batch(prob, x0[:n], xr, dtype=dtype, warm=w, nthreads=os.cpu_count() or 1)
     bad = {k: int((np.asarray(out[k][:n]) != getattr(ref, k)).sum()) for k in what}
     return {"instances": n, "bit_exact": all(v == 0 for v in bad.values()), "mismatching_elements": bad, "compared": list(what),
             "oracle_seconds": time.perf_counter() - t}
@@ -581,6 +581,30 @@ def run_configs(torch, dist, pkg, args, dev, local, rank, world, barrier, allmax
     entry("headline_dense_instance", "the headline workload (configs[1], %d instances per GPU, weak) on the DENSE kernel instance: no "
           "model-structure specialisation (TMPC_DENSE=1), every one of the 11,918 FLOP per iteration executed" % Bd, "q", run, Bd * world, ms, st,
           BYTES_PER_SOLVE["q"], chk, {"executed_flop_per_iteration": exec_flop_of(st.get("pattern"))})
+    run.close(); del run; torch.cuda.empty_cache()
+
+    # ---- the reference's SHIPPED scalar type (glob_opts.hpp:3 `typedef double tinytype`): the headline workload in fp64, an eighth
+    #      of the batch per GPU (fp64 runs at half the lane count and half the instances per SM)
+    Bf = max(args.batch // 8 // sc, 1024)
+    b0, b1 = pkg.sharding.shard_range(rank, world, per_rank=Bf)
+    x0, xref = W.quadrotor_hover_batch(b0, b1, mult=args.mult)
+    run = DeviceRun(torch, pkg, quad, dev, local, args.policy, x0, xref, dtype=np.float64)
+    ms, st = run.timed(K, WU, barrier)
+    ms = allmax(ms)
+    chk = oracle_check(quad, x0, xref, outputs_np(run), CHECK_PREFIX, dtype=np.float64) if rank == 0 else None
+    prop = torch.cuda.get_device_properties(local)
+    peak64 = prop.multi_processor_count * 64 * 2 * 1965e6 / 1e12
+    tf64 = st["iterations"] * FLOP_PER_ITER["q"] / (st["kernel_ms"] * 1e-3) / 1e12
+    out["headline_fp64"] = {
+        "workload": "the headline workload in double precision (the reference's shipped tinytype), %d instances per GPU, PARITY" % Bf,
+        "instances_total": Bf * world, "instances_per_gpu": Bf, "value": Bf * world * K / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms / K,
+        "kernel_ms_per_launch": allmax(st["kernel_ms"]), "iters_per_s": allsum(st["iterations"]) * K / (ms * 1e-3),
+        "mean_iters_per_solve": allsum(st["iterations"]) / (Bf * world), "dtype": "f64",
+        "roofline": {"bound": "fp64", "achieved": tf64, "peak": peak64, "unit": "TFLOP/s", "frac": tf64 / peak64,
+                     "peak_source": "SMs x 64 FP64 lanes x 2 x 1965 MHz (nominal; MEASURED_PEAKS.json has no FP64 entry)",
+                     "algorithmic_flop_per_iteration": FLOP_PER_ITER["q"], "traffic": None},
+        "oracle_check": chk}
+    log("configs.headline_fp64: %.3e solves/s, frac %.3f of FP64" % (out["headline_fp64"]["value"], tf64 / peak64))
     run.close(); del run; torch.cuda.empty_cache()
 
     # ---- config 4: cartpole 4/1/10, 16,777,216 instances in total, cold start

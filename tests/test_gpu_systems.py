@@ -132,3 +132,50 @@ def test_tmem_resident_and_global_block_kernels_agree(pkg, monkeypatch):
     for a, b, name in zip(outs[0], outs[1], ("iter", "x", "u")):
         assert_same(a, b, name)
     assert outs[0][0].min() < outs[0][0].max()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_per_instance_systems_solve_cartpole_shape(pkg, oracle, dtype):
+    """Per-instance systems at 4/1/10 (the cartpole of examples/codegen_cartpole.cpp with perturbed dynamics, input gain and rho):
+    batched precompute on the device, solve with instance i on system i, against the oracle system by system (caches as the device
+    computed them; work.Q = Q + rho as tiny_codegen stores it)."""
+    import copy
+    import torch
+    sc, m = pkg.problems.cartpole_model()
+    base = pkg.problems.cartpole()
+    S, per = 16, 40
+    rng = np.random.default_rng(7)
+    A = np.repeat(m["Adyn"][None], S, 0).copy()
+    off = ~np.eye(4, dtype=bool)
+    A[:, off] *= (1.0 + 0.1 * rng.uniform(-1, 1, (S, 1)))
+    Bm = m["Bdyn"][None] * (1.0 + 0.2 * rng.uniform(-1, 1, (S, 1, 1)))
+    Q = np.repeat(m["Q"].reshape(1, -1), S, 0)
+    R = np.repeat(m["R"].reshape(1, -1), S, 0)
+    rho = float(sc["rho"]) * (1.0 + 0.3 * rng.uniform(-1, 1, S))
+    cast = lambda a: a.astype(dtype).astype(np.float64)          # what the device sees
+    A, Bm, Q, R, rho = cast(A), cast(Bm), cast(Q), cast(R), cast(rho)
+    B = S * per
+    idx = np.repeat(np.arange(S), per)
+    s = pkg.capi.Solver(base, dtype=dtype, policy="parity")
+    sy = pkg.capi.Systems(s, A[idx], Bm[idx], Q[idx], R[idx], rho[idx], q_plus_rho=True)
+    x0, xref = pkg.workloads.cartpole_batch(0, B)
+    dev = torch.device("cuda:0")
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    f = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(dtype))).to(dev)
+    x = torch.empty((B, 10, 4), dtype=tdt, device=dev); u = torch.empty((B, 9, 1), dtype=tdt, device=dev)
+    it = torch.empty(B, dtype=torch.int32, device=dev); st = torch.empty(B, dtype=torch.int32, device=dev)
+    sy.solve_raw(f(x0), f(xref), True, x, u, it, st, None)
+    torch.cuda.synchronize()
+    K, P, Qi, M, Qd = sy.get("Kinf"), sy.get("Pinf"), sy.get("Quu_inv"), sy.get("AmBKt"), sy.get("Q")
+    itn, xn, un = it.cpu().numpy(), x.cpu().numpy(), u.cpu().numpy()
+    for sidx in range(S):
+        j = sidx * per
+        p = copy.deepcopy(base)
+        p.Adyn, p.Bdyn, p.rho = A[sidx], Bm[sidx], float(rho[sidx])
+        p.Q = Qd[j].astype(np.float64)
+        p.Kinf, p.Pinf, p.Quu_inv, p.AmBKt = (K[j].astype(np.float64), P[j].astype(np.float64), Qi[j].astype(np.float64), M[j].astype(np.float64))
+        ref = oracle.solve_batch(p, x0[j:j + per], xref, dtype=dtype, nthreads=4)
+        assert_same(itn[j:j + per], ref.iter, "iter sys %d" % sidx)
+        assert_same(xn[j:j + per], ref.x, "x sys %d" % sidx)
+        assert_same(un[j:j + per], ref.u, "u sys %d" % sidx)
+    assert len(set(itn.tolist())) > 3
