@@ -30,7 +30,7 @@ __global__ void xref_window_kernel(long long batch, int nx, int N, const T *tabl
 // forward_pass (admm.cpp:35): both products in their own order, one add per row -- pinned against the compiled
 // reference by tests/test_oracle_vs_ref.py::test_plant_step.  Also records the step's u0 / iter / status histories.
 template <class T, int NX, int NU, int NH, bool FAST>
-__global__ void plant_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, long long batch, T *x0, const T *u, T *x_next_hist,
+__global__ void plant_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, long long batch, T *x0, const T *u, long long u_stride, T *x_next_hist,
                              T *u0_hist, const int *iter, const int *status, int *iter_hist, int *status_hist)
 {
     using N = Num<T>;
@@ -41,7 +41,7 @@ __global__ void plant_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, lon
 #pragma unroll
     for (int j = 0; j < NX; ++j) x[j] = x0[b * NX + j];
 #pragma unroll
-    for (int j = 0; j < NU; ++j) u0[j] = u[b * (long long)(NU * (NH - 1)) + j];
+    for (int j = 0; j < NU; ++j) u0[j] = u[b * u_stride + j];   // u_stride: nu (N-1) = row 0 of the trajectory, nu = the u0-only buffer
 #pragma unroll
     for (int r = 0; r < NX; ++r) {
         T v;
@@ -80,6 +80,9 @@ struct tmpc_batch_impl {
     int *start = nullptr;          // [B] or null
     int64_t steps_done = 0;        // window offset of the next rollout step
     bool iter_valid = false;       // `iter` holds the iteration counts of a previous solve of these instances (schedule key)
+    void *u0 = nullptr;            // [B][nu]: u(:,0) of a controls-only rollout step (allocated by the first rollout)
+    const void *plant_u = nullptr; // what the plant step reads: `u` (row stride nu (N-1)) or `u0` (row stride nu)
+    long long plant_u_stride = 0;
     std::string err;
 };
 #define BAT(b) reinterpret_cast<tmpc_batch_impl *>(b)
@@ -104,10 +107,10 @@ cudaError_t launch_plant(tmpc_ctx_impl *c, tmpc_batch_impl *b, void *x_next_hist
     const unsigned blocks = (unsigned)((b->B + threads - 1) / threads);
     const tmpc::Model<T, NX, NU, NH> *m = reinterpret_cast<const tmpc::Model<T, NX, NU, NH> *>(c->model.data());
     if (c->policy == TMPC_ORDER_PARITY)
-        tmpc::plant_kernel<T, NX, NU, NH, false><<<blocks, threads, 0, s>>>(*m, b->B, (T *)b->x0, (const T *)b->u, (T *)x_next_hist,
+        tmpc::plant_kernel<T, NX, NU, NH, false><<<blocks, threads, 0, s>>>(*m, b->B, (T *)b->x0, (const T *)b->plant_u, b->plant_u_stride, (T *)x_next_hist,
                                                                                (T *)u0_hist, b->iter, b->status, iter_hist, status_hist);
     else
-        tmpc::plant_kernel<T, NX, NU, NH, true><<<blocks, threads, 0, s>>>(*m, b->B, (T *)b->x0, (const T *)b->u, (T *)x_next_hist,
+        tmpc::plant_kernel<T, NX, NU, NH, true><<<blocks, threads, 0, s>>>(*m, b->B, (T *)b->x0, (const T *)b->plant_u, b->plant_u_stride, (T *)x_next_hist,
                                                                               (T *)u0_hist, b->iter, b->status, iter_hist, status_hist);
     return cudaGetLastError();
 }
@@ -120,11 +123,11 @@ cudaError_t launch_plant_rt(tmpc_ctx_impl *c, tmpc_batch_impl *b, void *x_next_h
     const size_t smem = tmpc::rt_smem_bytes(c->nx, c->nu, sizeof(T));
     if (c->policy == TMPC_ORDER_PARITY) {
         cudaFuncSetAttribute(tmpc::plant_kernel_rt<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tmpc::plant_kernel_rt<T, false><<<blocks, tmpc::RT_BLOCK, smem, s>>>(m, b->B, (T *)b->x0, (const T *)b->u, (T *)x_next_hist, (T *)u0_hist,
+        tmpc::plant_kernel_rt<T, false><<<blocks, tmpc::RT_BLOCK, smem, s>>>(m, b->B, (T *)b->x0, (const T *)b->plant_u, b->plant_u_stride, (T *)x_next_hist, (T *)u0_hist,
                                                                               b->iter, b->status, iter_hist, status_hist);
     } else {
         cudaFuncSetAttribute(tmpc::plant_kernel_rt<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tmpc::plant_kernel_rt<T, true><<<blocks, tmpc::RT_BLOCK, smem, s>>>(m, b->B, (T *)b->x0, (const T *)b->u, (T *)x_next_hist, (T *)u0_hist,
+        tmpc::plant_kernel_rt<T, true><<<blocks, tmpc::RT_BLOCK, smem, s>>>(m, b->B, (T *)b->x0, (const T *)b->plant_u, b->plant_u_stride, (T *)x_next_hist, (T *)u0_hist,
                                                                              b->iter, b->status, iter_hist, status_hist);
     }
     return cudaGetLastError();
@@ -162,7 +165,9 @@ int batch_copy_out(tmpc_batch_impl *b, void *dst, const void *src, size_t bytes,
 // Longest-first schedule of a closed loop: consecutive MPC steps of one instance need almost the same number of iterations, so the
 // previous solve's `iter` ranks this one's load (sorted on the stream ahead of the kernel: 1M instances in ~40 us).  Only
 // for batches that keep the GPU busy for several rounds of lanes; TMPC_LPT=0 turns it off.
-int batch_solve_async(tmpc_batch_impl *b)
+// controls_only: neither x nor u is written (nothing can read them before the next solve overwrites them: the steps of a rollout
+// but the last); u(:,0) goes to b->u0, which is all the plant step needs -- and all the kernels then skip their emission work
+int batch_solve_async(tmpc_batch_impl *b, bool controls_only = false)
 {
     tmpc_ctx_impl *c = b->c;
     DevArgs da{};
@@ -170,6 +175,11 @@ int batch_solve_async(tmpc_batch_impl *b)
     da.xref_stride = b->xref_shared ? 0 : (long long)c->nx * c->N;
     da.wd = b->d; da.wy = b->y; da.wg = b->g; da.wv = b->v; da.wz = b->z;
     da.x = b->x; da.u = b->u; da.iter = b->iter; da.status = b->status; da.resid = b->resid;
+    b->plant_u = b->u; b->plant_u_stride = (long long)c->nu * (c->N - 1);
+    if (controls_only && b->u0) {
+        da.x = nullptr; da.u = nullptr; da.u0 = b->u0;
+        b->plant_u = b->u0; b->plant_u_stride = c->nu;
+    }
     c->stats.instances = b->B;
     c->stats.launches = 0;
     const char *e = getenv("TMPC_LPT");
@@ -224,6 +234,7 @@ int tmpc_batch_destroy(tmpc_batch *bt)
     cudaSetDevice(b->c->device);
     cudaStreamSynchronize(b->c->stream);
     if (b->base) cudaFree(b->base);
+    if (b->u0) cudaFree(b->u0);
     if (b->table) cudaFree(b->table);
     if (b->start) cudaFree(b->start);
     delete b;
@@ -368,6 +379,7 @@ int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void 
         return bfail(b, TMPC_ERR_CUDA, std::string("tmpc_batch_rollout: history allocation: ") + cudaGetErrorString(e));
     }
     if (dx) BCUDA_TRY(b, cudaMemcpyAsync(dx, b->x0, nxb, cudaMemcpyDeviceToDevice, s));
+    if (!b->u0 && steps > 1) BCUDA_TRY(b, cudaMalloc(&b->u0, (size_t)B * c->nu * es));
     cudaEvent_t r0, r1;
     BCUDA_TRY(b, cudaEventCreate(&r0));
     BCUDA_TRY(b, cudaEventCreate(&r1));
@@ -394,7 +406,8 @@ int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void 
                 cudaMemsetAsync(b->g, 0, (size_t)B * c->nx * c->N * es, s);
             }
         }
-        rc = batch_solve_async(b);   // 4. tiny_solve
+        // 4. tiny_solve.  Only the LAST step's trajectories can ever be read (tmpc_batch_get): the others are controls-only solves
+        rc = batch_solve_async(b, k + 1 < steps && !getenv("TMPC_ROLLOUT_FULL_OUTPUTS"));
         if (rc != TMPC_OK) break;
         // 5. plant step + histories
         e = dispatch_plant(c, b, dx ? dx + nxb * (k + 1) : nullptr, du ? du + nub * k : nullptr, di ? di + (size_t)B * k : nullptr,

@@ -514,8 +514,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
     const bool shared_xref = (a.xref_stride == 0);
     // Controls-only callers (x = u = NULL, u0 given: what an MPC loop applies, quadrotor_hovering.cpp:110): u(:,0) is stored by
     // every trip's stage 0, so the trip in which the lane terminates has already delivered it and neither an emission trip
-    // nor a speculative one is needed.  Warm starts still emit (their g / y write-back rides on the emission sweep).
-    const bool u0only = !a.x && !a.u && !(WARM && a.wd);
+    // nor a speculative one is needed -- warm starts included (their state is written back by the flush at the next trip).
+    const bool u0only = !a.x && !a.u;
     const bool duals_zero = WARM && (a.test_flags & 4);   // the caller reset y and g: zero-fill instead of reading them
     if (shared_xref) seed_pn(a.Xref + (NH - 1) * NX);
 

@@ -542,8 +542,8 @@ __global__ void __launch_bounds__(RT_BLOCK) step_kernel_rt(const __grid_constant
 // the assignment to a 16-byte aligned x1 (rows [0, nx/pk*pk) sequential, the rest the scalar tree) -- pinned against the
 // compiled reference by oracle/pin_shapes.py.
 template <class T, bool FAST>
-__global__ void __launch_bounds__(RT_BLOCK) plant_kernel_rt(const __grid_constant__ ModelRT<T> P, long long batch, T *x0, const T *u, T *x_next_hist,
-                                                            T *u0_hist, const int *iter, const int *status, int *iter_hist, int *status_hist)
+__global__ void __launch_bounds__(RT_BLOCK) plant_kernel_rt(const __grid_constant__ ModelRT<T> P, long long batch, T *x0, const T *u, long long u_stride,
+                                                            T *x_next_hist, T *u0_hist, const int *iter, const int *status, int *iter_hist, int *status_hist)
 {
     using N = Num<T>;
     const int nx = P.nx, nu = P.nu;
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(RT_BLOCK) plant_kernel_rt(const __grid_constan
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (b >= batch) return;
     for (int j = 0; j < nx; ++j) va[j * VS] = x0[b * nx + j];
-    for (int j = 0; j < nu; ++j) vb[j * VS] = u[b * (long long)(nu * (P.N - 1)) + j];
+    for (int j = 0; j < nu; ++j) vb[j * VS] = u[b * u_stride + j];
     const int head = P.head_Ax < 0 ? nx : (nx / P.pk) * P.pk;
     const int head_a = nx >= 8 ? nx : head, head_b = (nx >= 8 && nu >= 8) ? nx : head;
     for (int r = 0; r < nx; ++r) {
