@@ -519,36 +519,6 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
     const bool duals_zero = WARM && (a.test_flags & 4);   // the caller reset y and g: zero-fill instead of reading them
     if (shared_xref) seed_pn(a.Xref + (NH - 1) * NX);
 
-    // Claim-ahead.  A lane always holds ONE claimed instance it has not started (`nxt`): the moment it is claimed its input rows
-    // are prefetched into L2 (x0; with a warm start d, y, z, g, v; per-instance Xref; per-instance boxes), a whole solve before
-    // the refill section reads them.  That section runs for the whole warp (tcgen05 is collective) and used to wait out the DRAM
-    // latency of the refilled lanes' rows -- 3 round trips of ~1400 cycles on a warm start.
-    auto prefetch_rows = [&](const float *p, int floats) {
-        const char *q = reinterpret_cast<const char *>(p);
-        for (int off = 0; off < floats * 4 + 127; off += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(q + off));
-    };
-    auto prefetch_instance = [&](long long ni) {
-        prefetch_rows(a.x0 + ni * NX, NX);
-        if (!shared_xref) prefetch_rows(a.Xref + ni * a.xref_stride, XROW);
-        if (WARM && a.wd) {
-            prefetch_rows(a.wd + ni * UROW, UROW); prefetch_rows(a.wz + ni * UROW, UROW); prefetch_rows(a.wv + ni * XROW, XROW);
-            if (!duals_zero) { prefetch_rows(a.wy + ni * UROW, UROW); prefetch_rows(a.wg + ni * XROW, XROW); }
-        }
-        if constexpr (IB) {
-            if (a.ixmin) { prefetch_rows(a.ixmin + ni * XROW, XROW); prefetch_rows(a.ixmax + ni * XROW, XROW); }
-            if (a.iumin) { prefetch_rows(a.iumin + ni * UROW, UROW); prefetch_rows(a.iumax + ni * UROW, UROW); }
-        }
-    };
-    long long nxt = -1;      // claimed, not started; -1 = the work counter is exhausted
-    {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.counter, 32ull);
-        base = __shfl_sync(FULLM, base, 0);
-        const long long idx = (long long)base + lane;
-        if (idx < a.batch) nxt = claim_instance(a, idx);
-        if (nxt >= 0) prefetch_instance(nxt);
-    }
-
     for (;;) {
         // ------------------------------------------------------------------ lane refill (warp-uniform branch)
         const bool need = (phase == PH_FREE) && !exhausted;
@@ -601,11 +571,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
             if (refill_now) {
                 long long ni = redo;
                 if (redo < 0) {
-                    ni = nxt;                  // start the instance claimed (and prefetched) one refill ago, claim the one after it
-                    nxt = -1;
                     const long long idx = (long long)base + __popc(mc & ((1u << lane) - 1u));
-                    if (ni >= 0 && idx < a.batch) nxt = claim_instance(a, idx);
-                    if (nxt >= 0) prefetch_instance(nxt);
+                    if (idx < a.batch) ni = claim_instance(a, idx);
                 }
                 if (ni >= 0) {
                     inst = ni; phase = PH_RUN; it = 0; fill = true;
