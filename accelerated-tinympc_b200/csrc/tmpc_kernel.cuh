@@ -108,19 +108,13 @@ template <class T, int K, int L, class E> __device__ __forceinline__ T red_lane_
     return acc;
 }
 
-// sum_k c(k)*x(k) in the named order (PARITY) or as one FMA chain (FAST)
-template <class T, int ORD, int K, bool FAST, class C, class X>
-__device__ __forceinline__ T dot(const C &c, const X &x)
+// sum of the K individually rounded products e(0..K-1) in the named order of the reference build
+template <class T, int ORD, int K, class E>
+__device__ __forceinline__ T reduce_products(const E &e)
 {
     using N = Num<T>;
     constexpr int PK = N::PK;
-    if constexpr (FAST) {
-        T acc = N::mul(c(0), x(0));
-#pragma unroll
-        for (int k = 1; k < K; ++k) acc = N::fma(c(k), x(k), acc);
-        return acc;
-    } else {
-        auto e = [&](int k) -> T { return N::mul(c(k), x(k)); };
+    {
         if constexpr (ORD == ORD_SEQ) {
             T acc = e(0);
 #pragma unroll
@@ -158,6 +152,54 @@ __device__ __forceinline__ T dot(const C &c, const X &x)
 #pragma unroll
             for (int j = FULL; j < K; ++j) r = N::add(r, e(j));
             return r;
+        }
+    }
+}
+
+// sum_k c(k)*x(k) in the named order (PARITY) or as one FMA chain (FAST)
+template <class T, int ORD, int K, bool FAST, class C, class X>
+__device__ __forceinline__ T dot(const C &c, const X &x)
+{
+    using N = Num<T>;
+    if constexpr (FAST) {
+        T acc = N::mul(c(0), x(0));
+#pragma unroll
+        for (int k = 1; k < K; ++k) acc = N::fma(c(k), x(k), acc);
+        return acc;
+    } else {
+        return reduce_products<T, ORD, K>([&](int k) -> T { return N::mul(c(k), x(k)); });
+    }
+}
+
+// out[r] = sum_k c(r, k) x(k), r = 0..R-1, every row in the named order -- written so that the R independent chains ADVANCE
+// TOGETHER: sequential orders as a column sweep (term k of every row before term k+1 of any), tree orders four rows at a
+// time with their products formed k-major.  The one-warp-per-scheduler instances of the generic kernel (fp64: 128 threads per
+// SM) have nothing but this instruction-level parallelism to cover the FP64 pipe's latency; row-after-row dot products left
+// the scheduler waiting on each row's own chain (ncu, profiles/r02_ncu_fp64.md: issue slots 25 % busy).
+template <class T, int ORD, int R, int K, bool FAST, class C, class X>
+__device__ __forceinline__ void matvec_rows(const C &c, const X &x, T (&out)[R])
+{
+    using N = Num<T>;
+    if constexpr (FAST || ORD == ORD_SEQ) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r] = N::mul(c(r, 0), x(0));
+#pragma unroll
+        for (int k = 1; k < K; ++k)
+#pragma unroll
+            for (int r = 0; r < R; ++r) out[r] = FAST ? N::fma(c(r, k), x(k), out[r]) : N::add(N::mul(c(r, k), x(k)), out[r]);
+    } else {
+        constexpr int G = sizeof(T) == 8 ? 2 : 4;   // (a double product is two registers: larger groups spill)
+#pragma unroll
+        for (int r0 = 0; r0 < R; r0 += G) {
+            T e[G][K];
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (r0 + j < R) e[j][k] = N::mul(c(r0 + j, k), x(k));
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (r0 + j < R) out[r0 + j] = reduce_products<T, ORD, K>([&](int k) -> T { return e[j][k]; });
         }
     }
 }
@@ -765,15 +807,19 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     sz.load(i, z);
                     if (WARM && yo) gstore<T, NU>(yo + i * NU, y);
                     T ck[2][NX];
+                    T kxv[NU];
                     if constexpr (PERSYS) crow_issue<T, NX, SYSTM>(blk, tcol, SB::Krm, ck[0]);
+                    else matvec_rows<T, O::Kx, NU, NX, FAST>([&](int r, int k) { return P.K[r + k * NU]; }, [&](int k) { return x[k]; }, kxv);
 #pragma unroll
                     for (int r = 0; r < NU; ++r) {
+                        T kx;
                         if constexpr (PERSYS) {
                             crow_ready<T, NX, SYSTM>(ck[r & 1]);
                             if (r + 1 < NU) crow_issue<T, NX, SYSTM>(blk, tcol, SB::Krm + (r + 1) * NX, ck[(r + 1) & 1]);
+                            kx = dot<T, O::Kx, NX, FAST>([&](int k) { return ck[r & 1][k]; }, [&](int k) { return x[k]; });
+                        } else {
+                            kx = kxv[r];
                         }
-                        T kx = dot<T, O::Kx, NX, FAST>([&](int k) { if constexpr (PERSYS) return ck[r & 1][k]; else return P.K[r + k * NU]; },
-                                                       [&](int k) { return x[k]; });
                         u[r] = N::sub(-kx, d[r]);                                                // :31
                         zn[r] = N::add(u[r], y[r]);                                              // :47
                         zn[r] = N::mn(P.umax[i * NU + r], N::mx(P.umin[i * NU + r], zn[r]));     // :53
@@ -788,8 +834,23 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                     T xn[NX];
                     T ca[2][NX], cb[2][NU];
                     if constexpr (PERSYS) { crow_issue<T, NX, SYSTM>(blk, tcol, SB::Arm, ca[0]); crow_issue<T, NU, SYSTM>(blk, tcol, SB::Brm, cb[0]); }
+                    if constexpr (!PERSYS) {
+                        // shared model: all rows of Adyn x (and of Bdyn u) advance together (matvec_rows)
+                        matvec_rows<T, O::Ax, NX, NX, FAST>([&](int r, int k) { return P.A[r + k * NX]; }, [&](int k) { return x[k]; }, xn);
+                        if constexpr (FAST) {
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) {
+                            for (int k = 0; k < NU; ++k)
+#pragma unroll
+                                for (int r = 0; r < NX; ++r) xn[r] = N::fma(P.B[r + k * NX], u[k], xn[r]);
+                        } else {
+                            T bu[NX];
+                            matvec_rows<T, O::Bu, NX, NU, false>([&](int r, int k) { return P.B[r + k * NX]; }, [&](int k) { return u[k]; }, bu);
+#pragma unroll
+                            for (int r = 0; r < NX; ++r) xn[r] = N::add(xn[r], bu[r]);                  // :35
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < (PERSYS ? NX : 0); ++r) {
                         if constexpr (PERSYS) {
                             if constexpr (SYSTM) crow_ready2<T, NX, NU, true>(ca[r & 1], cb[r & 1]);
                             if (r + 1 < NX) {
@@ -899,8 +960,15 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                 T s[NU], d[NU];
                 T cbt[2][NX];
                 if constexpr (PERSYS) crow_issue<T, NX, SYSTM>(blk, tcol, SB::B, cbt[0]);
+                if constexpr (!PERSYS) {
+                    T bp[NU];
+                    matvec_rows<T, O::Btp, NU, NX, FAST>([&](int rr, int k) { return P.B[k + rr * NX]; }, [&](int k) { return p[k]; }, bp);
 #pragma unroll
-                for (int r_ = 0; r_ < NU; ++r_) {
+                    for (int j = 0; j < NU; ++j) s[j] = N::add(bp[j], r[j]);
+                    matvec_rows<T, O::Qs, NU, NU, FAST>([&](int rr, int k) { return P.Qi[rr + k * NU]; }, [&](int k) { return s[k]; }, d);   // :19
+                }
+#pragma unroll
+                for (int r_ = 0; r_ < (PERSYS ? NU : 0); ++r_) {
                     if constexpr (PERSYS) {
                         crow_ready<T, NX, SYSTM>(cbt[r_ & 1]);
                         if (r_ + 1 < NU) crow_issue<T, NX, SYSTM>(blk, tcol, SB::B + (r_ + 1) * NX, cbt[(r_ + 1) & 1]);
@@ -912,7 +980,7 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                 T cqi[2][NU];
                 if constexpr (PERSYS) crow_issue<T, NU, SYSTM>(blk, tcol, SB::Qirm, cqi[0]);
 #pragma unroll
-                for (int r_ = 0; r_ < NU; ++r_) {
+                for (int r_ = 0; r_ < (PERSYS ? NU : 0); ++r_) {
                     if constexpr (PERSYS) {
                         crow_ready<T, NU, SYSTM>(cqi[r_ & 1]);
                         if (r_ + 1 < NU) crow_issue<T, NU, SYSTM>(blk, tcol, SB::Qirm + (r_ + 1) * NU, cqi[(r_ + 1) & 1]);
@@ -925,8 +993,15 @@ admm_kernel(const __grid_constant__ Model<T, NX, NU, NH> P, const __grid_constan
                 T pn[NX];
                 T cm[2][NX], ckt[2][NU];
                 if constexpr (PERSYS) { crow_issue<T, NX, SYSTM>(blk, tcol, SB::Mrm, cm[0]); crow_issue<T, NU, SYSTM>(blk, tcol, SB::K, ckt[0]); }
+                if constexpr (!PERSYS) {
+                    T mp[NX], kr[NX];
+                    matvec_rows<T, O::Mp, NX, NX, FAST>([&](int rr, int k) { return P.M[rr + k * NX]; }, [&](int k) { return p[k]; }, mp);
+                    matvec_rows<T, O::Ktr, NX, NU, FAST>([&](int rr, int k) { return P.K[k + rr * NU]; }, [&](int k) { return r[k]; }, kr);
 #pragma unroll
-                for (int r_ = 0; r_ < NX; ++r_) {
+                    for (int j = 0; j < NX; ++j) pn[j] = N::sub(N::add(q[j], mp[j]), kr[j]);            // :20
+                }
+#pragma unroll
+                for (int r_ = 0; r_ < (PERSYS ? NX : 0); ++r_) {
                     if constexpr (PERSYS) {
                         if constexpr (SYSTM) crow_ready2<T, NX, NU, true>(cm[r_ & 1], ckt[r_ & 1]);
                         if (r_ + 1 < NX) {
