@@ -487,7 +487,6 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
     int phase = PH_FREE;
     bool exhausted = false;
     bool deferred = false;   // warp-uniform: the previous trip postponed a single-lane refill
-    long long pend = -1;       // claimed for this lane, not started yet (see claim_free_lanes)
     long long redo = -1;       // WARM: instance to solve AGAIN from its untouched warm input, mirror forced on (see the backward section)
     bool force_mirror = false; // WARM: this run mirrors d / v / z in every backward sweep
     bool mirrored = false;     // WARM: the previous iteration's backward sweep mirrored d / v / z into the lane's scratch rows
@@ -520,28 +519,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
     const bool duals_zero = WARM && (a.test_flags & 4);   // the caller reset y and g: zero-fill instead of reading them
     if (shared_xref) seed_pn(a.Xref + (NH - 1) * NX);
 
-    // Work claims are made as soon as a lane KNOWS it will need an instance -- right after the termination test, half a trip before
-    // the refill section runs -- so that the atomic on the work counter, the look-up of the claim order and the load of the new x0
-    // (three dependent memory round trips, ~1500 cycles) overlap the backward sweep of the warp's other lanes instead of heading
-    // the refill section, which the whole warp executes.
-    auto claim_free_lanes = [&]() {
-        const bool want = (phase == PH_FREE) && !exhausted && pend < 0 && redo < 0;
-        const unsigned mc = __ballot_sync(FULLM, want);
-        if (!mc) return;
-        const int leader = __ffs(mc) - 1;
-        unsigned long long base = 0;
-        if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(mc));
-        base = __shfl_sync(FULLM, base, leader);
-        if (want) {
-            const long long idx = (long long)base + __popc(mc & ((1u << lane) - 1u));
-            pend = idx < a.batch ? claim_instance(a, idx) : -1;
-            if (pend < 0) exhausted = true;
-            else gload<float, NX>(a.x0 + pend * NX, x0);     // (a free lane's x0 registers are dead)
-        }
-    };
-
     for (;;) {
-        claim_free_lanes();      // kernel start, and lanes whose refill was deferred past their claim (no-op otherwise)
         // ------------------------------------------------------------------ lane refill (warp-uniform branch)
         const bool need = (phase == PH_FREE) && !exhausted;
         unsigned m = __ballot_sync(FULLM, need);
@@ -558,6 +536,11 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
         if constexpr (WARM) mf = __ballot_sync(FULLM, flush != 0);
         if (m | mf) {
             const bool refill_now = need && ((m >> lane) & 1u);   // (a deferred single lane waits for the next trip)
+            const unsigned mc = __ballot_sync(FULLM, refill_now && redo < 0);   // lanes that claim a NEW instance (the others run theirs again)
+            const int leader = mc ? __ffs(mc) - 1 : 0;
+            unsigned long long base = 0;
+            if (mc && (int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(mc));
+            base = __shfl_sync(FULLM, base, leader);
             bool fill = false;
             if constexpr (WARM) {
                 if (flush) {
@@ -587,13 +570,16 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
             }
             if (refill_now) {
                 long long ni = redo;
-                if (redo < 0) { ni = pend; pend = -1; }      // claimed (and its x0 loaded) by claim_free_lanes
+                if (redo < 0) {
+                    const long long idx = (long long)base + __popc(mc & ((1u << lane) - 1u));
+                    if (idx < a.batch) ni = claim_instance(a, idx);
+                }
                 if (ni >= 0) {
-                    if (redo >= 0) gload<float, NX>(a.x0 + ni * NX, x0);
                     inst = ni; phase = PH_RUN; it = 0; fill = true;
                     force_mirror = (redo >= 0) || (a.test_flags & 2); redo = -1; mirrored = false;
                     spec = (P.max_iter <= 1) && !u0only;
                     res[0] = res[1] = res[2] = res[3] = 0.f;
+                    gload<float, NX>(a.x0 + inst * NX, x0);
                     if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
                     if constexpr (IB) {
                         // the instance's own box -> the lane's scratch rows (a missing / disabled family = +-inf).  Loads are issued
@@ -922,7 +908,6 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
             phase = PH_FREE;
             finished = true;
         }
-        claim_free_lanes();      // lanes that have just ended their instance: claim the next one now (see above)
 
         // ------------------------------------------------------------------ backward sweep
         // update_linear_cost (admm.cpp:77-85) recomputed per stage + backward_pass_grad (:15-22)
