@@ -59,9 +59,13 @@ def test_fast_policy_statistical_parity(pkg, oracle):
     out = pkg.capi.Solver(prob, dtype=np.float32, policy="fast").solve(x0, xref)
     same = out["iter"] == ref.iter
     # FAST is not the parity path: FMA contraction + sequential accumulation perturb every product by <= 1 ulp, and
-    # ADMM crawls across the 1e-3 threshold (the reference disagrees with itself on ~2.3 % of counts
-    # between its SSE2 and FMA builds).  Accept <= 10 % count mismatches; solutions must still agree to 1e-4.
-    assert (~same).mean() <= 0.10, "iteration mismatch rate %.4f" % (~same).mean()
+    # ADMM crawls across the 1e-3 threshold (the reference disagrees with itself on ~2.3 % of counts, by up to 11
+    # iterations, between its SSE2 and FMA builds).  Measured on B200 (profiles/r02_fast_policy_stats.log, 100,000 instances):
+    # 6.8 % of the counts move at mult 0.25 -- every one of them by exactly 1 iteration but a single instance (4) -- and 2.4 %
+    # at mult 1.0 (max 8).  SURVEY 8c P2 asked for <= 2.5 % and |delta| <= 11: FAST meets the |delta| half everywhere and the
+    # rate at mult 1.0 only, so it carries no parity claim.  Bounds here: rate <= 8 %, |delta iter| <= 11, x / u within 1e-4.
+    assert (~same).mean() <= 0.08, "iteration mismatch rate %.4f" % (~same).mean()
+    assert np.abs(out["iter"].astype(np.int64) - ref.iter).max() <= 11
     assert (out["status"] != ref.status).mean() <= 0.01
     scale = np.maximum(np.abs(ref.x[same]).max(), 1.0)
     assert np.abs(out["x"][same] - ref.x[same]).max() / scale <= 1e-4
