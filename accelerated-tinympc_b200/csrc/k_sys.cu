@@ -1,0 +1,31 @@
+// Instantiations of the row-pair per-instance-systems kernel (tmpc_kernel_sys.cuh) behind tmpc_dispatch::lookup_sys_pairs.
+#include "tmpc.h"
+#include "tmpc_dispatch.hpp"
+#include "tmpc_kernel_sys.cuh"
+
+namespace tmpc_dispatch {
+namespace {
+
+template <int NH, bool FAST, bool WARM> KernelInfo make_info_sys()
+{
+    KernelInfo k;
+    k.fn = (const void *)&tmpc::admm_kernel_sys<NH, FAST, WARM>;
+    k.smem = tmpc::sysk::SysSmem<NH>::BYTES;
+    k.block = 128;
+    k.model_bytes = sizeof(tmpc::Model<float, 12, 4, NH>);
+    k.model_kind = 0;
+    k.per_block = 128;
+    return k;
+}
+
+}  // namespace
+
+bool lookup_sys_pairs(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out)
+{
+    if (!(nx == 12 && nu == 4 && N == 10 && dtype == TMPC_F32)) return false;
+    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_sys<10, false, true>() : make_info_sys<10, false, false>();
+    else out = warm ? make_info_sys<10, true, true>() : make_info_sys<10, true, false>();
+    return true;
+}
+
+}  // namespace tmpc_dispatch

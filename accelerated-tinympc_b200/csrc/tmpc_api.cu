@@ -684,6 +684,10 @@ int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cuda
         int rc = plan_launch(c, ki, da, s, blocks);
         if (rc == TMPC_OK) rc = plan_lane_scratch(c, ki, da, blocks, c->ib_batch != 0 && !da.sys, s);
         if (rc != TMPC_OK) return rc;
+        if (da.sys) {   // refill policy of the row-pair systems kernel (tmpc_kernel_sys.cuh), tuning only
+            if (const char *e = getenv("TMPC_SYS_REFILL_MIN")) da.test_flags |= (atoi(e) & 31) << 8;
+            if (const char *e = getenv("TMPC_SYS_DEFER_MAX")) da.test_flags |= (atoi(e) & 15) << 16;
+        }
     }
     void *params[2] = {model_param(c, ki), &da};
     if (time_it && !ev0_done) CUDA_TRY(c, cudaEventRecord(c->ev0, s));

@@ -168,8 +168,12 @@ int sys_stride(int nx, int nu)
 
 bool lookup_kernel_sys(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out)
 {
-    const char *e = getenv("TMPC_KERNEL");   // TMPC_KERNEL=sys_global: coefficients re-read from the global block
-    return tmpc_dispatch::lookup_sys(nx, nu, N, dtype, policy, warm, e && !strcmp(e, "sys_global"), out);
+    // TMPC_KERNEL=sys_global: coefficients re-read from the global block; sys_rows: the first TMEM-resident kernel (row by row);
+    // default (fp32 12/4/10): the row-pair kernel of tmpc_kernel_sys.cuh
+    const char *e = getenv("TMPC_KERNEL");
+    const bool global_coeffs = e && !strcmp(e, "sys_global"), rows = e && !strcmp(e, "sys_rows");
+    if (!global_coeffs && !rows && tmpc_dispatch::lookup_sys_pairs(nx, nu, N, dtype, policy, warm, out)) return true;
+    return tmpc_dispatch::lookup_sys(nx, nu, N, dtype, policy, warm, global_coeffs, out);
 }
 
 }  // namespace

@@ -108,30 +108,49 @@ def test_per_instance_systems_solve_bit_exact(pkg, oracle, dtype):
     assert stt["iterations"] == int(itn.sum()) and stt["pattern"] == 0
 
 
-def test_tmem_resident_and_global_block_kernels_agree(pkg, monkeypatch):
-    """fp32 systems solve: coefficients resident in tensor memory (default) vs re-read from the global block
-    (TMPC_KERNEL=sys_global) -- identical results, including ragged batch sizes and the refill of single lanes."""
+@pytest.mark.parametrize("S", [333, 40_000])
+def test_systems_kernel_variants_agree(pkg, oracle, monkeypatch, S):
+    """fp32 12/4/10 systems solve, three kernels: row pairs streamed from tensor memory (default, tmpc_kernel_sys.cuh), the first
+    TMEM-resident kernel (TMPC_KERNEL=sys_rows) and coefficients re-read from the global block (sys_global) -- identical results,
+    including ragged batch sizes, the refill of single lanes, the longest-first schedule (large S) and the controls-only
+    output; a sample of the systems is checked against the oracle."""
+    import copy
     import torch
-    S = 333   # not a multiple of the block size
-    base, A, Bm, Q, R, rho = _systems(pkg, S, np.float32)
+    base, A, Bm, Q, R, rho = _systems(pkg, 97, np.float32)   # 97 distinct systems, repeated with different x0
+    idx = np.arange(S) % 97
     x0, xref = pkg.workloads.quadrotor_hover_batch(0, S, mult=0.6)
     dev = torch.device("cuda:0")
     outs = []
-    for variant in (None, "sys_global"):
+    for variant in (None, "sys_rows", "sys_global"):
         if variant:
             monkeypatch.setenv("TMPC_KERNEL", variant)
         s = pkg.capi.Solver(base, dtype=np.float32, policy="parity")
-        sy = pkg.capi.Systems(s, A, Bm, Q, R, rho)
+        sy = pkg.capi.Systems(s, A[idx], Bm[idx], Q[idx], R[idx], rho[idx])
         x = torch.empty((S, 10, 12), device=dev); u = torch.empty((S, 9, 4), device=dev)
         it = torch.empty(S, dtype=torch.int32, device=dev); st = torch.empty(S, dtype=torch.int32, device=dev)
-        sy.solve_raw(torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev), True, x, u, it, st, None)
+        rs = torch.empty((S, 4), device=dev)
+        sy.solve_raw(torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev), True, x, u, it, st, rs)
         torch.cuda.synchronize()
-        outs.append((it.cpu().numpy(), x.cpu().numpy(), u.cpu().numpy()))
+        outs.append((it.cpu().numpy(), st.cpu().numpy(), x.cpu().numpy(), u.cpu().numpy(), rs.cpu().numpy()))
+        if variant is None:
+            K, P, Qi, M = sy.get("Kinf"), sy.get("Pinf"), sy.get("Quu_inv"), sy.get("AmBKt")
         if variant:
             monkeypatch.delenv("TMPC_KERNEL")
-    for a, b, name in zip(outs[0], outs[1], ("iter", "x", "u")):
-        assert_same(a, b, name)
+    for o in outs[1:]:
+        for a, b, name in zip(outs[0], o, ("iter", "status", "x", "u", "resid")):
+            assert_same(a, b, name)
     assert outs[0][0].min() < outs[0][0].max()
+    for sidx in (0, 13, 96):
+        sel = np.nonzero(idx == sidx)[0][:64]
+        p = copy.deepcopy(base)
+        j = sel[0]
+        p.Adyn, p.Bdyn, p.Q, p.rho = A[sidx].astype(np.float64), Bm[sidx].astype(np.float64), Q[sidx].astype(np.float64), float(rho[sidx])
+        p.Kinf, p.Pinf, p.Quu_inv, p.AmBKt = (K[j].astype(np.float64), P[j].astype(np.float64), Qi[j].astype(np.float64), M[j].astype(np.float64))
+        ref = oracle.solve_batch(p, x0[sel], xref, dtype=np.float32, nthreads=4)
+        assert_same(outs[0][0][sel], ref.iter, "iter vs oracle, system %d" % sidx)
+        assert_same(outs[0][2][sel], ref.x, "x vs oracle")
+        assert_same(outs[0][3][sel], ref.u, "u vs oracle")
+        assert_same(outs[0][4][sel], ref.resid, "resid vs oracle")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
