@@ -6,10 +6,10 @@
 namespace tmpc_dispatch {
 namespace {
 
-template <int NH, bool FAST, bool WARM> KernelInfo make_info_sys()
+template <int NH, bool FAST, bool WARM, bool CB> KernelInfo make_info_sys()
 {
     KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_sys<NH, FAST, WARM>;
+    k.fn = (const void *)&tmpc::admm_kernel_sys<NH, FAST, WARM, CB>;
     k.smem = tmpc::sysk::SysSmem<NH>::BYTES;
     k.block = 128;
     k.model_bytes = sizeof(tmpc::Model<float, 12, 4, NH>);
@@ -20,11 +20,16 @@ template <int NH, bool FAST, bool WARM> KernelInfo make_info_sys()
 
 }  // namespace
 
-bool lookup_sys_pairs(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out)
+template <bool CB> KernelInfo pick_pairs(int policy, bool warm)
+{
+    if (policy == TMPC_ORDER_PARITY) return warm ? make_info_sys<10, false, true, CB>() : make_info_sys<10, false, false, CB>();
+    return warm ? make_info_sys<10, true, true, CB>() : make_info_sys<10, true, false, CB>();
+}
+
+bool lookup_sys_pairs(int nx, int nu, int N, int dtype, int policy, bool warm, bool const_bounds, KernelInfo &out)
 {
     if (!(nx == 12 && nu == 4 && N == 10 && dtype == TMPC_F32)) return false;
-    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_sys<10, false, true>() : make_info_sys<10, false, false>();
-    else out = warm ? make_info_sys<10, true, true>() : make_info_sys<10, true, false>();
+    out = const_bounds ? pick_pairs<true>(policy, warm) : pick_pairs<false>(policy, warm);
     return true;
 }
 

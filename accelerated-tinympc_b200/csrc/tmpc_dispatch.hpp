@@ -29,7 +29,7 @@ bool lookup_generic(int nx, int nu, int N, int dtype, int policy, bool warm, int
 // per-instance systems instances of the generic kernel; global_coeffs: re-read the coefficients from global memory
 bool lookup_sys(int nx, int nu, int N, int dtype, int policy, bool warm, bool global_coeffs, KernelInfo &out);
 // fp32 12/4/10 per-instance systems, row-pair kernel (tmpc_kernel_sys.cuh): the default for that shape
-bool lookup_sys_pairs(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out);
+bool lookup_sys_pairs(int nx, int nu, int N, int dtype, int policy, bool warm, bool const_bounds, KernelInfo &out);
 
 // register-resident single-input kernel, fp32 4/1/10 (tmpc_kernel_small.cuh); block = 256, 384 or 512
 bool lookup_small(int block, int policy, bool warm, KernelInfo &out);

@@ -42,22 +42,32 @@ __device__ __forceinline__ void wait16(float *r)
                    "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]) :: "memory");
 }
 
-// tensor-memory image of one system (column = offset): what the FORWARD sweep streams, then what the BACKWARD sweep streams
+// Tensor-memory image of one system = the order in which the sweeps STREAM it, in 16-column groups ("units"): the forward
+// sweep reads units 0..14 of a stage, the backward sweep units 15..30.  The products with only two row-pair chains (Kinf x;
+// Bdyn^T p -> Quu_inv s) are interleaved with the six-chain ones (Adyn x; AmBKt p) so that the scheduler always has independent
+// chains to issue from.  A unit is 16 consecutive coefficients of one matrix in the major that makes row pairs adjacent.
+enum { U_K = 0, U_A = 1, U_B = 2, U_BR = 3, U_QI = 4, U_M = 5, U_KR = 6 };
+struct Unit { int kind, idx; };
 struct TmMap {
-    static constexpr int K = 0, A = 48, B = 192, FWD_END = 240;             // Kinf, Adyn, Bdyn column-major
-    static constexpr int BR = 240, QI = 288, M = 304, KR = 448, END = 496;  // Bdyn row-major, Quu_inv, AmBKt col-major, Kinf row-major
-    static constexpr int GROUPS = END / 16;                                 // 31 x16 groups
+    static constexpr int FWD_UNITS = 15, BWD_UNITS = 16, GROUPS = FWD_UNITS + BWD_UNITS, BWD_COL = 16 * FWD_UNITS;
+    // forward:  A0 K0 A1 K1 A2 K2 A3 .. A8 B0 B1 B2       (Kinf, Adyn, Bdyn column-major)
+    __host__ __device__ static constexpr Unit fwd(int u)
+    {
+        return u < 6 ? ((u & 1) ? Unit{U_K, u >> 1} : Unit{U_A, u >> 1}) : u < 12 ? Unit{U_A, u - 3} : Unit{U_B, u - 12};
+    }
+    // backward: BR0 M0 BR1 M1 BR2 M2 QI M3 .. M8 KR0 KR1 KR2   (Bdyn row-major, AmBKt, Quu_inv column-major, Kinf row-major)
+    __host__ __device__ static constexpr Unit bwd(int u)
+    {
+        return u < 6 ? ((u & 1) ? Unit{U_M, u >> 1} : Unit{U_BR, u >> 1}) : u == 6 ? Unit{U_QI, 0} : u < 13 ? Unit{U_M, u - 4} : Unit{U_KR, u - 13};
+    }
+    static constexpr int FWD_K_DONE = 5, BWD_BR_DONE = 4, BWD_QI_DONE = 6;   // the unit after which Kinf x / B^T p / Quu_inv s are complete
     // block offset (SysBlock<12,4>) of tensor-memory group g
     __host__ __device__ static constexpr int src(int g)
     {
         using SB = SysBlock<12, 4>;
-        return g < 3 ? SB::K + 16 * g
-             : g < 12 ? SB::A + 16 * (g - 3)
-             : g < 15 ? SB::B + 16 * (g - 12)
-             : g < 18 ? SB::Brm + 16 * (g - 15)
-             : g < 19 ? SB::Qi
-             : g < 28 ? SB::M + 16 * (g - 19)
-                      : SB::Krm + 16 * (g - 28);
+        const Unit t = g < FWD_UNITS ? fwd(g) : bwd(g - FWD_UNITS);
+        return (t.kind == U_K ? SB::K : t.kind == U_A ? SB::A : t.kind == U_B ? SB::B : t.kind == U_BR ? SB::Brm
+              : t.kind == U_QI ? SB::Qi : t.kind == U_M ? SB::M : SB::Krm) + 16 * t.idx;
     }
 };
 
@@ -82,7 +92,9 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 #define TMPC_SYS_LOOKAHEAD 1024   // claims ahead of the work counter whose system blocks are prefetched into L2
 #endif
 
-template <int NH, bool FAST, bool WARM>
+// CB: the box bounds are identical at every stage (tmpc_set_model checks the actual rows): fixed constant-bank operands instead
+// of stage-indexed loads
+template <int NH, bool FAST, bool WARM, bool CB>
 __global__ void __launch_bounds__(128, 1)
 admm_kernel_sys(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid_constant__ SolveArgs<float> a)
 {
@@ -330,25 +342,25 @@ admm_kernel_sys(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid_
             float *yo = (WARM && emit && a.wy) ? a.wy + inst * UROW : nullptr;
             auto xs = [&](int k) -> float { return (k & 1) ? x2[k >> 1].y : x2[k >> 1].x; };
 
-            // slack / dual / residuals of the state part of stage i (:48, :59, :70, :95, :96)
-            auto state_part = [&](int i) {
-                float g[NX], v[NX];
-                sg.load(i, g);
-                sv.load(i, v);
-                if (WARM && go) gstore<float, NX>(go + i * NX, g);
-#pragma unroll
-                for (int j = 0; j < HX; ++j) {
-                    const float2 gj = mk2(g[2 * j], g[2 * j + 1]), vj = mk2(v[2 * j], v[2 * j + 1]);
-                    float2 vn = ad2(x2[j], gj);
-                    vn.x = fminf(P.xmax[i * NX + 2 * j], fmaxf(P.xmin[i * NX + 2 * j], vn.x));
-                    vn.y = fminf(P.xmax[i * NX + 2 * j + 1], fmaxf(P.xmin[i * NX + 2 * j + 1], vn.y));
-                    const float2 rp = sb2(x2[j], vn), rd = sb2(vj, vn);
-                    pri_x = fmaxf(pri_x, fmaxf(fabsf(rp.x), fabsf(rp.y)));
-                    dua_x = fmaxf(dua_x, fmaxf(fabsf(rd.x), fabsf(rd.y)));
-                    const float2 gn = sb2(ad2(gj, x2[j]), vn);
-                    g[2 * j] = gn.x; g[2 * j + 1] = gn.y;
-                    v[2 * j] = vn.x; v[2 * j + 1] = vn.y;
-                }
+            // slack / dual / residuals of rows (2j, 2j+1) of the state part of stage i (:48, :59, :70, :95, :96).  The element-wise
+            // work is spread over the coefficient units (one row pair per unit) so that its min / max / constant-bank
+            // instructions issue in the shadow of the packed FMA-pipe instructions instead of in a block of their own.
+            float g[NX], v[NX], d[NU], y[NU], z[NU];
+            auto state_pair = [&](int i, int j) {
+                const int bi = CB ? 0 : i * NX;
+                const float2 gj = mk2(g[2 * j], g[2 * j + 1]), vj = mk2(v[2 * j], v[2 * j + 1]);
+                const float2 xg = ad2(x2[j], gj);
+                float2 vn;
+                vn.x = fminf(P.xmax[bi + 2 * j], fmaxf(P.xmin[bi + 2 * j], xg.x));
+                vn.y = fminf(P.xmax[bi + 2 * j + 1], fmaxf(P.xmin[bi + 2 * j + 1], xg.y));
+                const float2 rp = sb2(x2[j], vn), rd = sb2(vj, vn);
+                pri_x = fmaxf(pri_x, fmaxf(fabsf(rp.x), fabsf(rp.y)));
+                dua_x = fmaxf(dua_x, fmaxf(fabsf(rd.x), fabsf(rd.y)));
+                const float2 gn = sb2(xg, vn);   // (g + x) - vnew: the sum is the one above (addition commutes bit for bit)
+                g[2 * j] = gn.x; g[2 * j + 1] = gn.y;
+                v[2 * j] = vn.x; v[2 * j + 1] = vn.y;
+            };
+            auto state_out = [&](int i) {
                 sg.store(i, g);
                 sv.store(i, v);
                 if (xo) {
@@ -358,55 +370,70 @@ admm_kernel_sys(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid_
                     gstore<float, NX>(xo + i * NX, xx);
                 }
             };
+            // a stage's state is fetched late in the stage before it (the tensor-memory asm statements are memory barriers to the
+            // compiler: it cannot hoist these loads itself), into the registers that stage has finished with
+            sg.load(0, g);
+            sv.load(0, v);
+            sd.load(0, d);
+            sy.load(0, y);
+            sz.load(0, z);
 
 #pragma unroll 1
             for (int i = 0; i < NH - 1; ++i) {
                 float2 kx2[HU], u2[HU], ax2[HX], bu2[HX];
                 auto us = [&](int k) -> float { return (k & 1) ? u2[k >> 1].y : u2[k >> 1].x; };
                 // what the last three slots of this stage fetch: the next stage's first groups, or the backward sweep's
-                const uint32_t nxt = tcol + (i < NH - 2 ? 0u : (uint32_t)TM::BR);
+                const uint32_t nxt = tcol + (i < NH - 2 ? 0u : (uint32_t)TM::BWD_COL);
+                if (WARM && go) gstore<float, NX>(go + i * NX, g);
+                if (WARM && yo) gstore<float, NU>(yo + i * NU, y);
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
-                    if (u < 15) wait16(cb[u & 3]);
-                    if (u + 3 < 15) tm_ld16(tcol + 16 * (u + 3), cb[(u + 3) & 3]);
+                    if (u < TM::FWD_UNITS) wait16(cb[u & 3]);
+                    if (u + 3 < TM::FWD_UNITS) tm_ld16(tcol + 16 * (u + 3), cb[(u + 3) & 3]);
                     else if (u + 3 >= 16) tm_ld16(nxt + 16 * (u + 3 - 16), cb[(u + 3) & 3]);
-                    if (u == 0) state_part(i);
+                    if (u >= 1 && u <= HX) state_pair(i, u - 1);
+                    if (u == HX + 1) state_out(i);
+                    if (u == 12) {   // the next stage's state
+                        sg.load(i + 1, g);
+                        sv.load(i + 1, v);
+                        if (i + 1 < NH - 1) { sd.load(i + 1, d); sy.load(i + 1, y); sz.load(i + 1, z); }
+                    }
+                    if (u < TM::FWD_UNITS) {
+                        const Unit t = TM::fwd(u);
 #pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        const float2 c = mk2(cb[u & 3][e], cb[u & 3][e + 1]);
-                        const int E = 16 * u + e;
-                        if (E < TM::A) {                                   // Kinf x, rows (2h, 2h+1), column k     (:31)
-                            const int k = E / NU, h = (E % NU) / 2;
-                            if (k == 0) kx2[h] = FAST ? ml2(c, xs(0)) : pr2(c, xs(0), Z);
-                            else kx2[h] = FAST ? fm2(c, xs(k), kx2[h]) : ad2(pr2(c, xs(k), Z), kx2[h]);
-                        } else if (E < TM::B) {                            // Adyn x                                (:35)
-                            const int k = (E - TM::A) / NX, j = ((E - TM::A) % NX) / 2;
-                            if (k == 0) ax2[j] = FAST ? ml2(c, xs(0)) : pr2(c, xs(0), Z);
-                            else ax2[j] = FAST ? fm2(c, xs(k), ax2[j]) : ad2(pr2(c, xs(k), Z), ax2[j]);
-                        } else if (E < TM::FWD_END) {                      // Bdyn u                                (:35)
-                            const int k = (E - TM::B) / NX, j = ((E - TM::B) % NX) / 2;
-                            if constexpr (FAST) ax2[j] = fm2(c, us(k), ax2[j]);
-                            else if (k == 0) bu2[j] = pr2(c, us(0), Z);
-                            else bu2[j] = ad2(pr2(c, us(k), Z), bu2[j]);
+                        for (int e = 0; e < 16; e += 2) {
+                            const float2 c = mk2(cb[u & 3][e], cb[u & 3][e + 1]);
+                            const int E = 16 * t.idx + e;
+                            if (t.kind == U_K) {                               // Kinf x, rows (2h, 2h+1), column k     (:31)
+                                const int k = E / NU, h = (E % NU) / 2;
+                                if (k == 0) kx2[h] = FAST ? ml2(c, xs(0)) : pr2(c, xs(0), Z);
+                                else kx2[h] = FAST ? fm2(c, xs(k), kx2[h]) : ad2(pr2(c, xs(k), Z), kx2[h]);
+                            } else if (t.kind == U_A) {                        // Adyn x                                (:35)
+                                const int k = E / NX, j = (E % NX) / 2;
+                                if (k == 0) ax2[j] = FAST ? ml2(c, xs(0)) : pr2(c, xs(0), Z);
+                                else ax2[j] = FAST ? fm2(c, xs(k), ax2[j]) : ad2(pr2(c, xs(k), Z), ax2[j]);
+                            } else {                                           // Bdyn u                                (:35)
+                                const int k = E / NX, j = (E % NX) / 2;
+                                if constexpr (FAST) ax2[j] = fm2(c, us(k), ax2[j]);
+                                else if (k == 0) bu2[j] = pr2(c, us(0), Z);
+                                else bu2[j] = ad2(pr2(c, us(k), Z), bu2[j]);
+                            }
                         }
                     }
-                    if (u == 2) {   // Kinf x complete: input, slack, dual, residuals of stage i
-                        float d[NU], y[NU], z[NU];
-                        sd.load(i, d);
-                        sy.load(i, y);
-                        sz.load(i, z);
-                        if (WARM && yo) gstore<float, NU>(yo + i * NU, y);
+                    if (u == TM::FWD_K_DONE) {   // Kinf x complete: input, slack, dual, residuals of stage i
+                        const int bi = CB ? 0 : i * NU;
 #pragma unroll
                         for (int h = 0; h < HU; ++h) {
                             const float2 dh = mk2(d[2 * h], d[2 * h + 1]), yh = mk2(y[2 * h], y[2 * h + 1]), zh = mk2(z[2 * h], z[2 * h + 1]);
                             u2[h] = sb2(ng2(kx2[h]), dh);                                                        // :31
-                            float2 zn = ad2(u2[h], yh);                                                          // :47
-                            zn.x = fminf(P.umax[i * NU + 2 * h], fmaxf(P.umin[i * NU + 2 * h], zn.x));           // :53
-                            zn.y = fminf(P.umax[i * NU + 2 * h + 1], fmaxf(P.umin[i * NU + 2 * h + 1], zn.y));
+                            const float2 uy = ad2(u2[h], yh);                                                    // :47
+                            float2 zn;
+                            zn.x = fminf(P.umax[bi + 2 * h], fmaxf(P.umin[bi + 2 * h], uy.x));                   // :53
+                            zn.y = fminf(P.umax[bi + 2 * h + 1], fmaxf(P.umin[bi + 2 * h + 1], uy.y));
                             const float2 rp = sb2(u2[h], zn), rd = sb2(zh, zn);
                             pri_u = fmaxf(pri_u, fmaxf(fabsf(rp.x), fabsf(rp.y)));                               // :97
                             dua_u = fmaxf(dua_u, fmaxf(fabsf(rd.x), fabsf(rd.y)));                               // :98
-                            const float2 yn = sb2(ad2(yh, u2[h]), zn);                                           // :69
+                            const float2 yn = sb2(uy, zn);                                                       // :69  (y + u) - znew
                             y[2 * h] = yn.x; y[2 * h + 1] = yn.y;
                             z[2 * h] = zn.x; z[2 * h + 1] = zn.y;
                         }
@@ -424,7 +451,10 @@ admm_kernel_sys(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid_
 #pragma unroll
                 for (int j = 0; j < HX; ++j) x2[j] = FAST ? ax2[j] : ad2(ax2[j], bu2[j]);                       // :35
             }
-            state_part(NH - 1);
+            if (WARM && go) gstore<float, NX>(go + (NH - 1) * NX, g);
+#pragma unroll
+            for (int j = 0; j < HX; ++j) state_pair(NH - 1, j);
+            state_out(NH - 1);
         }
 
         // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
@@ -484,25 +514,34 @@ admm_kernel_sys(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid_
                     else p2[j] = sb2(pj, pp2(rho2, dv, Z));                                                      // :84
                 }
             }
+            // a stage's state and reference row are fetched late in the stage before it (see the forward sweep)
+            float z[NU], y[NU], v[NX], g[NX], xr[NX];
+            sz.load(NH - 2, z);
+            sy.load(NH - 2, y);
+            sv.load(NH - 2, v);
+            sg.load(NH - 2, g);
+            gload<float, NX>(xr_base + (NH - 2) * NX, xr);
 #pragma unroll 1
             for (int i = NH - 2; i >= 0; --i) {
                 float2 r2[HU], q2[HX], s2[HU], d2[HU], mp2[HX], kr2[HX];
                 float2 e0[4][HU], e1[4][HU];          // B^T p: vectorised redux, lane L = k % 4
                 float2 t0[HX], t1[HX], ta[HX], tl[HX];  // AmBKt p: half-split tree over 12 = ((3 + 3) + (3 + 3)), 3 = e + (e + e)
+                float2 k0[HX], k1[HX];                 // Kinf^T r: (e0 + e2) + (e1 + e3)
                 auto rs = [&](int k) -> float { return (k & 1) ? r2[k >> 1].y : r2[k >> 1].x; };
                 auto ss = [&](int k) -> float { return (k & 1) ? s2[k >> 1].y : s2[k >> 1].x; };
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
                     wait16(cb[u & 3]);
-                    if (u + 3 < 16) tm_ld16(tcol + TM::BR + 16 * (u + 3), cb[(u + 3) & 3]);
-                    else if (i > 0) tm_ld16(tcol + TM::BR + 16 * (u + 3 - 16), cb[(u + 3) & 3]);
-                    if (u == 0) {   // r_i, q_i from (z, y, v, g, Xref)
-                        float z[NU], y[NU], v[NX], g[NX], xr[NX];
-                        sz.load(i, z);
-                        sy.load(i, y);
-                        sv.load(i, v);
-                        sg.load(i, g);
-                        gload<float, NX>(xr_base + i * NX, xr);
+                    if (u + 3 < 16) tm_ld16(tcol + TM::BWD_COL + 16 * (u + 3), cb[(u + 3) & 3]);
+                    else if (i > 0) tm_ld16(tcol + TM::BWD_COL + 16 * (u + 3 - 16), cb[(u + 3) & 3]);
+                    if (u == 12 && i > 0) {   // the next stage's state (this one's was consumed at u == 1)
+                        sz.load(i - 1, z);
+                        sy.load(i - 1, y);
+                        sv.load(i - 1, v);
+                        sg.load(i - 1, g);
+                        gload<float, NX>(xr_base + (i - 1) * NX, xr);
+                    }
+                    if (u == 1) {   // r_i, q_i from (z, y, v, g, Xref)
                         if (WARM && wvo) { gstore<float, NX>(wvo + i * NX, v); gstore<float, NU>(wzo + i * NU, z); }
 #pragma unroll
                         for (int h = 0; h < HU; ++h)
@@ -515,12 +554,13 @@ admm_kernel_sys(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid_
                             else q2[j] = sb2(cq, pp2(rho2, dv, Z));                                              // :82
                         }
                     }
+                    const Unit t = TM::bwd(u);
 #pragma unroll
                     for (int e = 0; e < 16; e += 2) {
                         const float2 c = mk2(cb[u & 3][e], cb[u & 3][e + 1]);
-                        const int E = TM::BR + 16 * u + e;
-                        if (E < TM::QI) {                                  // Bdyn^T p, rows (2h, 2h+1), term k       (:19)
-                            const int k = (E - TM::BR) / NU, h = ((E - TM::BR) % NU) / 2;
+                        const int E = 16 * t.idx + e;
+                        if (t.kind == U_BR) {                              // Bdyn^T p, rows (2h, 2h+1), term k       (:19)
+                            const int k = E / NU, h = (E % NU) / 2;
                             if constexpr (FAST) {
                                 s2[h] = k == 0 ? ml2(c, ps(0)) : fm2(c, ps(k), s2[h]);
                             } else {
@@ -530,12 +570,12 @@ admm_kernel_sys(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid_
                                 else if (qk == 1) e1[Lk][h] = pr;
                                 else e0[Lk][h] = ad2(e0[Lk][h], ad2(e1[Lk][h], pr));
                             }
-                        } else if (E < TM::M) {                            // Quu_inv s, column k                      (:19)
-                            const int k = (E - TM::QI) / NU, h = ((E - TM::QI) % NU) / 2;
+                        } else if (t.kind == U_QI) {                       // Quu_inv s, column k                      (:19)
+                            const int k = E / NU, h = (E % NU) / 2;
                             if (k == 0) d2[h] = FAST ? ml2(c, ss(0)) : pr2(c, ss(0), Z);
                             else d2[h] = FAST ? fm2(c, ss(k), d2[h]) : ad2(pr2(c, ss(k), Z), d2[h]);
-                        } else if (E < TM::KR) {                           // AmBKt p, rows (2j, 2j+1), term k         (:20)
-                            const int k = (E - TM::M) / NX, j = ((E - TM::M) % NX) / 2;
+                        } else if (t.kind == U_M) {                        // AmBKt p, rows (2j, 2j+1), term k         (:20)
+                            const int k = E / NX, j = (E % NX) / 2;
                             if constexpr (FAST) {
                                 mp2[j] = k == 0 ? ml2(c, ps(0)) : fm2(c, ps(k), mp2[j]);
                             } else {
@@ -544,34 +584,34 @@ admm_kernel_sys(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid_
                                 if (mk == 0) t0[j] = pr;
                                 else if (mk == 1) t1[j] = pr;
                                 else {
-                                    const float2 t = ad2(t0[j], ad2(t1[j], pr));
-                                    if (qk == 0) ta[j] = t;
-                                    else if (qk == 1) tl[j] = ad2(ta[j], t);
-                                    else if (qk == 2) ta[j] = t;
-                                    else mp2[j] = ad2(tl[j], ad2(ta[j], t));
+                                    const float2 tt = ad2(t0[j], ad2(t1[j], pr));
+                                    if (qk == 0) ta[j] = tt;
+                                    else if (qk == 1) tl[j] = ad2(ta[j], tt);
+                                    else if (qk == 2) ta[j] = tt;
+                                    else mp2[j] = ad2(tl[j], ad2(ta[j], tt));
                                 }
                             }
                         } else {                                           // Kinf^T r, rows (2j, 2j+1), term k        (:20)
-                            const int k = (E - TM::KR) / NX, j = ((E - TM::KR) % NX) / 2;
+                            const int k = E / NX, j = (E % NX) / 2;
                             if constexpr (FAST) {
                                 kr2[j] = k == 0 ? ml2(c, rs(0)) : fm2(c, rs(k), kr2[j]);
                             } else {
                                 const float2 pr = pr2(c, rs(k), Z);
-                                if (k == 0) t0[j] = pr;
-                                else if (k == 1) t1[j] = pr;
-                                else if (k == 2) t0[j] = ad2(t0[j], pr);
-                                else kr2[j] = ad2(t0[j], ad2(t1[j], pr));
+                                if (k == 0) k0[j] = pr;
+                                else if (k == 1) k1[j] = pr;
+                                else if (k == 2) k0[j] = ad2(k0[j], pr);
+                                else kr2[j] = ad2(k0[j], ad2(k1[j], pr));
                             }
                         }
                     }
-                    if (u == 2) {   // B^T p complete
+                    if (u == TM::BWD_BR_DONE) {   // B^T p complete
 #pragma unroll
                         for (int h = 0; h < HU; ++h) {
                             if constexpr (!FAST) s2[h] = ad2(ad2(e0[0][h], e0[2][h]), ad2(e0[1][h], e0[3][h]));
                             s2[h] = ad2(s2[h], r2[h]);
                         }
                     }
-                    if (u == 3) {   // d_i = Quu_inv (B^T p + r)
+                    if (u == TM::BWD_QI_DONE) {   // d_i = Quu_inv (B^T p + r)
                         float d[NU];
 #pragma unroll
                         for (int h = 0; h < HU; ++h) { d[2 * h] = d2[h].x; d[2 * h + 1] = d2[h].y; }

@@ -166,13 +166,13 @@ int sys_stride(int nx, int nu)
     return 0;
 }
 
-bool lookup_kernel_sys(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out)
+bool lookup_kernel_sys(int nx, int nu, int N, int dtype, int policy, bool warm, bool const_bounds, KernelInfo &out)
 {
     // TMPC_KERNEL=sys_global: coefficients re-read from the global block; sys_rows: the first TMEM-resident kernel (row by row);
     // default (fp32 12/4/10): the row-pair kernel of tmpc_kernel_sys.cuh
     const char *e = getenv("TMPC_KERNEL");
     const bool global_coeffs = e && !strcmp(e, "sys_global"), rows = e && !strcmp(e, "sys_rows");
-    if (!global_coeffs && !rows && tmpc_dispatch::lookup_sys_pairs(nx, nu, N, dtype, policy, warm, out)) return true;
+    if (!global_coeffs && !rows && tmpc_dispatch::lookup_sys_pairs(nx, nu, N, dtype, policy, warm, const_bounds, out)) return true;
     return tmpc_dispatch::lookup_sys(nx, nu, N, dtype, policy, warm, global_coeffs, out);
 }
 
@@ -285,7 +285,7 @@ int tmpc_solve_systems(tmpc_ctx *ctx, const tmpc_solve_args *a, const tmpc_syste
         return fail(c, TMPC_ERR_INVALID, "warm state needs all of d, y, g, v, z");
     CUDA_TRY(c, cudaSetDevice(c->device));
     KernelInfo ki;
-    if (!lookup_kernel_sys(c->nx, c->nu, c->N, c->dtype, c->policy, warm, ki)) return fail(c, TMPC_ERR_UNSUPPORTED, "no per-instance-systems kernel for this shape");
+    if (!lookup_kernel_sys(c->nx, c->nu, c->N, c->dtype, c->policy, warm, c->const_bounds, ki)) return fail(c, TMPC_ERR_UNSUPPORTED, "no per-instance-systems kernel for this shape");
     DevArgs da{};
     da.batch = a->batch; da.x0 = a->x0; da.Xref = a->Xref;
     da.xref_stride = a->xref_shared ? 0 : (long long)c->nx * c->N;

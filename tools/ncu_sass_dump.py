@@ -18,6 +18,6 @@ for k, r in enumerate(rows[hdr + 1:]):
     if len(r) != len(h):
         continue
     s = int(float(r[col[samp]] or 0))
-    top = sorted(((int(float(r[col[c]] or 0)), c[6:]) for c in st), reverse=True)[:2]
+    top = sorted(((int(float(r[col[c]] or 0)), c[6:]) for c in st), reverse=True)[:4]
     print("%5d %10d %7d  %-70s %s" % (k, int(float(r[col[inst]] or 0)), s, r[col["Source"]].strip()[:70],
                                       " ".join("%s=%d" % (n, v) for v, n in top if v)))
