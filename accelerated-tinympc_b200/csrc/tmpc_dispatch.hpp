@@ -28,8 +28,9 @@ bool lookup_f32(int policy, bool warm, int pattern, bool const_bounds, int varia
 bool lookup_generic(int nx, int nu, int N, int dtype, int policy, bool warm, int variant, KernelInfo &out);
 // per-instance systems instances of the generic kernel; global_coeffs: re-read the coefficients from global memory
 bool lookup_sys(int nx, int nu, int N, int dtype, int policy, bool warm, bool global_coeffs, KernelInfo &out);
-// fp32 12/4/10 per-instance systems, row-pair kernel (tmpc_kernel_sys.cuh): the default for that shape
-bool lookup_sys_pairs(int nx, int nu, int N, int dtype, int policy, bool warm, bool const_bounds, KernelInfo &out);
+// fp32 12/4/10 per-instance systems, row-pair kernels.  variant 0: two lanes per instance (tmpc_kernel_sysp.cuh, the default for
+// that shape); 1: one thread per instance (tmpc_kernel_sys.cuh)
+bool lookup_sys_pairs(int nx, int nu, int N, int dtype, int policy, bool warm, bool const_bounds, int variant, KernelInfo &out);
 
 // register-resident single-input kernel, fp32 4/1/10 (tmpc_kernel_small.cuh); block = 256, 384 or 512
 bool lookup_small(int block, int policy, bool warm, KernelInfo &out);

@@ -168,11 +168,12 @@ int sys_stride(int nx, int nu)
 
 bool lookup_kernel_sys(int nx, int nu, int N, int dtype, int policy, bool warm, bool const_bounds, KernelInfo &out)
 {
-    // TMPC_KERNEL=sys_global: coefficients re-read from the global block; sys_rows: the first TMEM-resident kernel (row by row);
-    // default (fp32 12/4/10): the row-pair kernel of tmpc_kernel_sys.cuh
+    // fp32 12/4/10 default: two lanes per instance, row pairs streamed from tensor memory (tmpc_kernel_sysp.cuh).  TMPC_KERNEL =
+    // sys_thread: the same with one thread per instance (tmpc_kernel_sys.cuh); sys_rows: the first TMEM-resident kernel (row by
+    // row); sys_global: coefficients re-read from the global block
     const char *e = getenv("TMPC_KERNEL");
-    const bool global_coeffs = e && !strcmp(e, "sys_global"), rows = e && !strcmp(e, "sys_rows");
-    if (!global_coeffs && !rows && tmpc_dispatch::lookup_sys_pairs(nx, nu, N, dtype, policy, warm, const_bounds, out)) return true;
+    const bool global_coeffs = e && !strcmp(e, "sys_global"), rows = e && !strcmp(e, "sys_rows"), thr = e && !strcmp(e, "sys_thread");
+    if (!global_coeffs && !rows && tmpc_dispatch::lookup_sys_pairs(nx, nu, N, dtype, policy, warm, const_bounds, thr ? 1 : 0, out)) return true;
     return tmpc_dispatch::lookup_sys(nx, nu, N, dtype, policy, warm, global_coeffs, out);
 }
 

@@ -110,8 +110,9 @@ def test_per_instance_systems_solve_bit_exact(pkg, oracle, dtype):
 
 @pytest.mark.parametrize("S", [333, 40_000])
 def test_systems_kernel_variants_agree(pkg, oracle, monkeypatch, S):
-    """fp32 12/4/10 systems solve, three kernels: row pairs streamed from tensor memory (default, tmpc_kernel_sys.cuh), the first
-    TMEM-resident kernel (TMPC_KERNEL=sys_rows) and coefficients re-read from the global block (sys_global) -- identical results,
+    """fp32 12/4/10 systems solve, four kernels: two lanes per instance with row pairs streamed from tensor memory (default,
+    tmpc_kernel_sysp.cuh), the same with one thread per instance (TMPC_KERNEL=sys_thread, tmpc_kernel_sys.cuh), the first
+    TMEM-resident kernel (sys_rows) and coefficients re-read from the global block (sys_global) -- identical results,
     including ragged batch sizes, the refill of single lanes, the longest-first schedule (large S) and the controls-only
     output; a sample of the systems is checked against the oracle."""
     import copy
@@ -121,7 +122,7 @@ def test_systems_kernel_variants_agree(pkg, oracle, monkeypatch, S):
     x0, xref = pkg.workloads.quadrotor_hover_batch(0, S, mult=0.6)
     dev = torch.device("cuda:0")
     outs = []
-    for variant in (None, "sys_rows", "sys_global"):
+    for variant in (None, "sys_thread", "sys_rows", "sys_global"):
         if variant:
             monkeypatch.setenv("TMPC_KERNEL", variant)
         s = pkg.capi.Solver(base, dtype=np.float32, policy="parity")
