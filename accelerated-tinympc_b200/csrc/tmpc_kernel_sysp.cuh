@@ -23,33 +23,78 @@
 namespace tmpc {
 namespace sysk {
 
-// per-thread vectors of D floats (D even) per stage in shared memory: 8-byte chunks, [chunk][thread]: conflict-free LDS.64 / STS.64
-template <int D, int STAGES, int BLOCK> struct PVec {
-    static_assert(D % 2 == 0, "pairs");
-    static constexpr size_t BYTES = size_t(D / 2) * STAGES * BLOCK * 8;
-    unsigned char *base;
-    __device__ __forceinline__ PVec(unsigned char *b, int tid) : base(b + tid * 8) {}
-    __device__ __forceinline__ void load(int i, float2 (&o)[D / 2]) const
+// Shared-memory accesses by 32-bit shared-space address (the generic-pointer form makes the compiler rebuild the shared window base
+// -- S2UR SR_CgaCtaId + ULEA, a scoreboard wait each time -- inside the sweeps).  volatile + "memory": they stay where they are written,
+// like the tensor-memory statements around them.
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float2 lo, float2 hi)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(lo.x), "f"(lo.y), "f"(hi.x), "f"(hi.y) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" :: "r"(a), "f"(v.x), "f"(v.y) : "memory"); }
+
+// The thread's own rows of the per-instance state, [chunk][thread] so that every warp access is conflict-free:
+//   g, v : 12 floats per stage = three 16-byte chunks (g0..g3 | g4 g5 v0 v1 | v2..v5)
+//   d, y : one 16-byte chunk per stage;  z : one 8-byte chunk per stage;  p_N seed: three 8-byte chunks
+template <int NH, int BLOCK> struct PairState {
+    static constexpr uint32_t GV = 0, DY = GV + 3u * NH * BLOCK * 16, ZZ = DY + (NH - 1) * BLOCK * 16u, PN = ZZ + (NH - 1) * BLOCK * 8u,
+                              BYTES = PN + 3u * BLOCK * 8;
+    uint32_t gv, dy, zz, pn;
+    __device__ __forceinline__ PairState(unsigned char *smem, int tid)
     {
-#pragma unroll
-        for (int c = 0; c < D / 2; ++c) o[c] = *reinterpret_cast<const float2 *>(base + size_t(i * (D / 2) + c) * BLOCK * 8);
+        const uint32_t b = (uint32_t)__cvta_generic_to_shared(smem);
+        gv = b + GV + tid * 16; dy = b + DY + tid * 16; zz = b + ZZ + tid * 8; pn = b + PN + tid * 8;
     }
-    __device__ __forceinline__ void store(int i, const float2 (&o)[D / 2]) const
+    __device__ __forceinline__ void load_gv(int i, float2 (&o)[6]) const
     {
 #pragma unroll
-        for (int c = 0; c < D / 2; ++c) *reinterpret_cast<float2 *>(base + size_t(i * (D / 2) + c) * BLOCK * 8) = o[c];
+        for (int c = 0; c < 3; ++c) {
+            const float4 t = lds128(gv + (uint32_t)(i * 3 + c) * (BLOCK * 16));
+            o[2 * c] = make_float2(t.x, t.y); o[2 * c + 1] = make_float2(t.z, t.w);
+        }
     }
-    // chunks [c0, c0 + N) of stage i
-    template <int N> __device__ __forceinline__ void load_part(int i, int c0, float2 (&o)[N]) const
+    __device__ __forceinline__ void store_gv(int i, const float2 (&o)[6]) const
     {
 #pragma unroll
-        for (int c = 0; c < N; ++c) o[c] = *reinterpret_cast<const float2 *>(base + size_t(i * (D / 2) + c0 + c) * BLOCK * 8);
+        for (int c = 0; c < 3; ++c) sts128(gv + (uint32_t)(i * 3 + c) * (BLOCK * 16), o[2 * c], o[2 * c + 1]);
     }
-    template <int N> __device__ __forceinline__ void store_part(int i, int c0, const float2 (&o)[N], bool pred = true) const
+    __device__ __forceinline__ void load_dyz(int i, float2 (&o)[3]) const
     {
-        if (!pred) return;
+        const float4 t = lds128(dy + (uint32_t)i * (BLOCK * 16));
+        o[0] = make_float2(t.x, t.y); o[1] = make_float2(t.z, t.w);
+        o[2] = lds64(zz + (uint32_t)i * (BLOCK * 8));
+    }
+    __device__ __forceinline__ void store_dyz(int i, const float2 (&o)[3]) const
+    {
+        sts128(dy + (uint32_t)i * (BLOCK * 16), o[0], o[1]);
+        sts64(zz + (uint32_t)i * (BLOCK * 8), o[2]);
+    }
+    __device__ __forceinline__ void store_yz(int i, float2 y, float2 z) const
+    {
+        sts64(dy + (uint32_t)i * (BLOCK * 16) + 8, y);
+        sts64(zz + (uint32_t)i * (BLOCK * 8), z);
+    }
+    __device__ __forceinline__ void store_d(int i, float2 d, bool pred) const { if (pred) sts64(dy + (uint32_t)i * (BLOCK * 16), d); }
+    __device__ __forceinline__ void load_pn(float2 (&o)[3]) const
+    {
 #pragma unroll
-        for (int c = 0; c < N; ++c) *reinterpret_cast<float2 *>(base + size_t(i * (D / 2) + c0 + c) * BLOCK * 8) = o[c];
+        for (int c = 0; c < 3; ++c) o[c] = lds64(pn + (uint32_t)c * (BLOCK * 8));
+    }
+    __device__ __forceinline__ void store_pn(const float2 (&o)[3]) const
+    {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sts64(pn + (uint32_t)c * (BLOCK * 8), o[c]);
     }
 };
 
@@ -93,12 +138,10 @@ struct SlotMap {
 
 template <int NH> struct SysPSmem {
     static constexpr int BLOCK = 256, WARPS = 8, NSLOT = 2;
-    using GV = PVec<12, NH, BLOCK>;       // own rows of g (3 chunks) and v (3 chunks)
-    using DYZ = PVec<6, NH - 1, BLOCK>;   // own rows of d, y, z (one chunk each)
-    using PN = PVec<6, 1, BLOCK>;
+    using ST = PairState<NH, BLOCK>;
     static constexpr int BLKB = SlotMap::LEN * 4;   // bytes staged per system
     static constexpr int SLOTB = BLKB + 16;
-    static constexpr size_t STATE = GV::BYTES + DYZ::BYTES + PN::BYTES;
+    static constexpr size_t STATE = ST::BYTES;
     static constexpr size_t TMSLOT = STATE, BARS = TMSLOT + 16, STAGE = BARS + WARPS * 8;
     static constexpr size_t BYTES = STAGE + size_t(WARPS) * NSLOT * SLOTB;
     static_assert(BLKB % 16 == 0 && STAGE % 16 == 0, "bulk copies move 16-byte aligned multiples of 16 bytes");
@@ -125,14 +168,11 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
     const unsigned lane = tid & 31;
     const int warp = tid >> 5;
     const int h = lane & 1;                       // which half of the rows this lane owns
-    const unsigned pe = lane & ~1u, po = lane | 1u;   // the pair's even / odd lane
+    const unsigned pe = lane & ~1u;   // the pair's even lane
     constexpr unsigned FULLM = 0xffffffffu, EVEN = 0x55555555u;
     constexpr int XROW = NX * NH, UROW = NU * (NH - 1);
 
-    unsigned char *sp = smem;
-    typename SS::GV sgv(sp, tid); sp += SS::GV::BYTES;
-    typename SS::DYZ sdyz(sp, tid); sp += SS::DYZ::BYTES;
-    typename SS::PN spn(sp, tid);
+    const typename SS::ST st(smem, tid);
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem + SS::BARS + warp * 8);
     unsigned char *stage = smem + SS::STAGE + (size_t)warp * SS::NSLOT * SS::SLOTB;
     uint32_t bar_phase = 0;
@@ -156,17 +196,21 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
     const float nzs = __int_as_float((int)(0x80000000u ^ (unsigned)(a.batch < 0)));   // -0, opaque to the compiler
     const float2 Z = mk2(nzs, nzs);
 
-    auto sh = [&](float vv, unsigned src) -> float { return __shfl_sync(FULLM, vv, src); };
-    // whole vectors from the pair's halves (even lane: low rows, odd lane: high rows)
+    // whole vectors from the pair's halves (even lane: low rows, odd lane: high rows): one butterfly shuffle per float of the
+    // partner's half, then selects (a shuffle costs several issue cycles, a select one)
+    const bool odd = h != 0;
+    auto px = [&](float vv) -> float { return __shfl_xor_sync(FULLM, vv, 1); };
     auto gather12 = [&](const float2 (&own)[OX], float (&full)[NX]) {
 #pragma unroll
         for (int t = 0; t < OX; ++t) {
-            full[2 * t] = sh(own[t].x, pe); full[2 * t + 1] = sh(own[t].y, pe);
-            full[6 + 2 * t] = sh(own[t].x, po); full[6 + 2 * t + 1] = sh(own[t].y, po);
+            const float ox = px(own[t].x), oy = px(own[t].y);
+            full[2 * t] = odd ? ox : own[t].x; full[2 * t + 1] = odd ? oy : own[t].y;
+            full[6 + 2 * t] = odd ? own[t].x : ox; full[6 + 2 * t + 1] = odd ? own[t].y : oy;
         }
     };
     auto gather4 = [&](float2 own, float (&full)[NU]) {
-        full[0] = sh(own.x, pe); full[1] = sh(own.y, pe); full[2] = sh(own.x, po); full[3] = sh(own.y, po);
+        const float ox = px(own.x), oy = px(own.y);
+        full[0] = odd ? ox : own.x; full[1] = odd ? oy : own.y; full[2] = odd ? own.x : ox; full[3] = odd ? own.y : oy;
     };
 
     // CB: the (stage-invariant) box of the lane's own rows lives in registers
@@ -238,7 +282,7 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                             t[0] = __ldg(reinterpret_cast<const float2 *>(a.wd + inst * UROW + i * NU + 2 * h));
                             t[1] = __ldg(reinterpret_cast<const float2 *>(a.wy + inst * UROW + i * NU + 2 * h));
                             t[2] = __ldg(reinterpret_cast<const float2 *>(a.wz + inst * UROW + i * NU + 2 * h));
-                            sdyz.store(i, t);
+                            st.store_dyz(i, t);
                         }
 #pragma unroll 1
                         for (int i = 0; i < NH; ++i) {
@@ -247,7 +291,7 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                             const float2 *vp = reinterpret_cast<const float2 *>(a.wv + inst * XROW + i * NX + 6 * h);
 #pragma unroll
                             for (int j = 0; j < OX; ++j) { t[j] = __ldg(gp + j); t[3 + j] = __ldg(vp + j); }
-                            sgv.store(i, t);
+                            st.store_gv(i, t);
                         }
                     } else {
                         float2 zu[3], zx[6];
@@ -256,9 +300,9 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
 #pragma unroll
                         for (int j = 0; j < 6; ++j) zx[j] = mk2(0.f, 0.f);
 #pragma unroll 1
-                        for (int i = 0; i < NH - 1; ++i) sdyz.store(i, zu);
+                        for (int i = 0; i < NH - 1; ++i) st.store_dyz(i, zu);
 #pragma unroll 1
-                        for (int i = 0; i < NH; ++i) sgv.store(i, zx);
+                        for (int i = 0; i < NH; ++i) st.store_gv(i, zx);
                     }
                 } else {
                     exhausted = true;
@@ -314,7 +358,7 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                             const float vv = -dot<float, O::XtP, NX, FAST>([&](int k) { return c[k]; }, [&](int k) { return xr[k]; });
                             if (j & 1) pn[j >> 1].y = vv; else pn[j >> 1].x = vv;
                         }
-                        spn.store(0, pn);
+                        st.store_pn(pn);
                     }
                 }
                 // tcgen05 is warp-collective: every lane rewrites its 256 columns, lanes that are not being filled with what they hold
@@ -397,14 +441,14 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                 gv[3 + j] = vn;
             };
             auto state_out = [&](int i) {
-                sgv.store(i, gv);
+                st.store_gv(i, gv);
                 if (xo) {
 #pragma unroll
                     for (int j = 0; j < OX; ++j) reinterpret_cast<float2 *>(xo + i * NX)[j] = xo2[j];
                 }
             };
-            sgv.load(0, gv);
-            sdyz.load(0, dyz);
+            st.load_gv(0, gv);
+            st.load_dyz(0, dyz);
 
 #pragma unroll 1
             for (int i = 0; i < NH - 1; ++i) {
@@ -424,8 +468,8 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                     if (u >= 1 && u <= OX) state_pair(i, u - 1);
                     if (u == OX + 1) state_out(i);
                     if (u == 7) {   // the next stage's state, into the registers this stage has finished with
-                        sgv.load(i + 1, gv);
-                        if (i + 1 < NH - 1) sdyz.load(i + 1, dyz);
+                        st.load_gv(i + 1, gv);
+                        if (i + 1 < NH - 1) st.load_dyz(i + 1, dyz);
                     }
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -461,10 +505,7 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                         const float2 rp = sb2(u2o, zn), rd = sb2(dyz[2], zn);
                         pri_u = fmaxf(pri_u, fmaxf(fabsf(rp.x), fabsf(rp.y)));                                   // :97
                         dua_u = fmaxf(dua_u, fmaxf(fabsf(rd.x), fabsf(rd.y)));                                   // :98
-                        float2 yz[2];
-                        yz[0] = sb2(uy, zn);                                                                     // :69
-                        yz[1] = zn;
-                        sdyz.template store_part<2>(i, 1, yz);
+                        st.store_yz(i, sb2(uy, zn), zn);                                                         // :69
                         if (uo) *reinterpret_cast<float2 *>(uo + i * NU) = u2o;
                         if (u0o && i == 0) *reinterpret_cast<float2 *>(u0o) = u2o;
                         gather4(u2o, us);
@@ -535,8 +576,8 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
             float2 gv[6], dyz[3], xr2[OX];
             {
                 float2 pn[OX];
-                sgv.load(NH - 1, gv);
-                spn.load(0, pn);
+                st.load_gv(NH - 1, gv);
+                st.load_pn(pn);
                 if (WARM && wvo) {
 #pragma unroll
                     for (int j = 0; j < OX; ++j) reinterpret_cast<float2 *>(wvo + (NH - 1) * NX)[j] = gv[3 + j];
@@ -549,8 +590,8 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                 }
                 gather12(po2, ps);
             }
-            sgv.load(NH - 2, gv);
-            sdyz.load(NH - 2, dyz);
+            st.load_gv(NH - 2, gv);
+            st.load_dyz(NH - 2, dyz);
 #pragma unroll
             for (int j = 0; j < OX; ++j) xr2[j] = __ldg(reinterpret_cast<const float2 *>(xr_base + (NH - 2) * NX) + j);
 #pragma unroll 1
@@ -582,8 +623,8 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                         }
                     }
                     if (u == 7 && i > 0) {   // the next stage's state (this one's was consumed at u == 1)
-                        sgv.load(i - 1, gv);
-                        sdyz.load(i - 1, dyz);
+                        st.load_gv(i - 1, gv);
+                        st.load_dyz(i - 1, dyz);
 #pragma unroll
                         for (int j = 0; j < OX; ++j) xr2[j] = __ldg(reinterpret_cast<const float2 *>(xr_base + (i - 1) * NX) + j);
                     }
@@ -642,8 +683,7 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                         gather4(s2o, ss);
                     }
                     if (u == PM::BWD_QI_DONE) {   // own rows of d_i = Quu_inv (B^T p + r)
-                        float2 dd[1] = {d2o};
-                        sdyz.template store_part<1>(i, 0, dd, cont);
+                        st.store_d(i, d2o, cont);
                         if (WARM && wdo) *reinterpret_cast<float2 *>(wdo + i * NU) = d2o;
                     }
                 }
