@@ -149,6 +149,10 @@ template <int NH> struct SysPSmem {
 
 }  // namespace sysk
 
+#ifndef TMPC_SPEC_FACTOR_SYS
+#define TMPC_SPEC_FACTOR_SYS 2.0f
+#endif
+
 template <int NH, bool FAST, bool WARM, bool CB>
 __global__ void __launch_bounds__(256, 1)
 admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid_constant__ SolveArgs<float> a)
@@ -236,6 +240,11 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
     const int refill_min = ((a.test_flags >> 8) & 31) ? ((a.test_flags >> 8) & 31) : 2;
     const int defer_max = ((a.test_flags >> 16) & 15) ? ((a.test_flags >> 16) & 15) : 1;
     float res[4] = {0.f, 0.f, 0.f, 0.f};
+    // cold solves: a trip that is likely to be the instance's last (the previous check left every residual within
+    // TMPC_SPEC_FACTOR_SYS of its tolerance, or it is the last allowed iteration) stores x / u as it goes, so that an instance
+    // that does terminate there needs no emission trip.  A wrong guess costs the stores; they are overwritten later.
+    bool spec = false;
+    bool counted = true;   // the completion counter (SolveArgs::done) has been bumped for `inst`
     unsigned long long n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
     float cb[4][16];   // ring of coefficient units: unit u of a sweep stage lands in cb[u & 3]
 
@@ -268,6 +277,8 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                     inst = ci;
                     phase = PH_RUN;
                     it = 0;
+                    spec = !WARM && P.max_iter == 1;
+                    counted = false;
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     blk = a.sys + inst * SB::STRIDE;
                     {
@@ -416,9 +427,10 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
 #pragma unroll
             for (int j = 0; j < OX; ++j) xo2[j] = x0o[j];
             gather12(xo2, xs);
-            float *xo = (emit && a.x) ? a.x + inst * XROW + 6 * h : nullptr;
-            float *uo = (emit && a.u) ? a.u + inst * UROW + 2 * h : nullptr;
-            float *u0o = (emit && a.u0) ? a.u0 + inst * NU + 2 * h : nullptr;
+            const bool wr = emit || (spec && phase == PH_RUN);
+            float *xo = (wr && a.x) ? a.x + inst * XROW + 6 * h : nullptr;
+            float *uo = (wr && a.u) ? a.u + inst * UROW + 2 * h : nullptr;
+            float *u0o = (wr && a.u0) ? a.u0 + inst * NU + 2 * h : nullptr;
             float *go = (WARM && emit && a.wg) ? a.wg + inst * XROW + 6 * h : nullptr;
             float *yo = (WARM && emit && a.wy) ? a.wy + inst * UROW + 2 * h : nullptr;
             float2 gv[6], dyz[3];   // own rows: g (0..2), v (3..5); d, y, z
@@ -550,13 +562,23 @@ admm_kernel_sysp(const __grid_constant__ Model<float, 12, 4, NH> P, const __grid
                     ++n_inst;
                 }
                 final_bwd = !conv;
-                phase = PH_EMIT;
+                phase = spec ? PH_FREE : PH_EMIT;   // (spec: this trip's forward sweep has already written the trajectory)
+            } else if constexpr (!WARM) {
+                constexpr float SF = TMPC_SPEC_FACTOR_SYS;
+                const bool next_chk = ((it + 1) % P.check_term) == 0;
+                spec = (it + 1 >= P.max_iter) ||
+                       (next_chk && res[0] < SF * P.pri_tol && res[2] < SF * P.pri_tol && res[1] < SF * P.dua_tol && res[3] < SF * P.dua_tol);
             }
         } else if (phase == PH_EMIT) {
             phase = PH_FREE;
-            if (a.done) {
+        }
+        if (a.done) {   // every output of the instance is written (by both lanes of its pair): count it once
+            const bool fin = phase == PH_FREE && inst >= 0 && !counted;
+            const unsigned cm = __ballot_sync(FULLM, fin);
+            if (fin) {
+                counted = true;
                 __threadfence();
-                __syncwarp();   // both lanes' stores precede the count
+                __syncwarp(cm);
                 if (h == 0) atomicAdd(a.done + (inst >> a.done_shift), 1u);
             }
         }
