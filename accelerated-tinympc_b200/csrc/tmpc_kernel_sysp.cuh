@@ -55,6 +55,8 @@ template <int NH, int BLOCK> struct PairState {
     {
         const uint32_t b = (uint32_t)__cvta_generic_to_shared(smem);
         gv = b + GV + tid * 16; dy = b + DY + tid * 16; zz = b + ZZ + tid * 8; pn = b + PN + tid * 8;
+        // opaque to the compiler: otherwise it re-derives the shared window base (S2UR SR_CgaCtaId, a scoreboard wait) inside the sweeps
+        asm volatile("" : "+r"(gv), "+r"(dy), "+r"(zz), "+r"(pn));
     }
     __device__ __forceinline__ void load_gv(int i, float2 (&o)[6]) const
     {
