@@ -155,7 +155,9 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
             if (v == 0) return tmpc_dispatch::lookup_generic(nx, nu, N, dtype, policy, warm, 0, out);
             return tmpc_dispatch::lookup_f32(policy, warm, pattern, cb, v, out);   // (v == 3 falls back to 2 where it has no instance)
         }
-        // double: g, v in tensor memory -> 128 instances / SM (TMPC_KERNEL=generic: all state in shared memory, 64 / SM)
+        // double: two lanes per instance, 128 instances / SM (tmpc_kernel_f64p.cuh).  TMPC_KERNEL=f64_thread: one thread per instance,
+        // g, v in tensor memory, 128 / SM; generic: all state in shared memory, 64 / SM
+        if (!generic && !(e && !strcmp(e, "f64_thread")) && tmpc_dispatch::lookup_f64p(nx, nu, N, dtype, policy, warm, out)) return true;
         return tmpc_dispatch::lookup_generic(nx, nu, N, dtype, policy, warm, generic ? 1 : 0, out);
     }
     if (nx == 4 && nu == 1 && N == 10) {

@@ -32,6 +32,9 @@ bool lookup_sys(int nx, int nu, int N, int dtype, int policy, bool warm, bool gl
 // that shape); 1: one thread per instance (tmpc_kernel_sys.cuh)
 bool lookup_sys_pairs(int nx, int nu, int N, int dtype, int policy, bool warm, bool const_bounds, int variant, KernelInfo &out);
 
+// fp64 12/4/10, one shared model, two lanes per instance (tmpc_kernel_f64p.cuh): the default for that shape / dtype
+bool lookup_f64p(int nx, int nu, int N, int dtype, int policy, bool warm, KernelInfo &out);
+
 // register-resident single-input kernel, fp32 4/1/10 (tmpc_kernel_small.cuh); block = 256, 384 or 512
 bool lookup_small(int block, int policy, bool warm, KernelInfo &out);
 // fp32 32/8/50: variant 0 = four instances per warp (tmpc_kernel_warp4.cuh, default); 1 = one instance per warp, g, v in tensor
