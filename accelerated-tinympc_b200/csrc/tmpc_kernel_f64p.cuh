@@ -36,6 +36,16 @@ __device__ __forceinline__ double2 ldc2(uint32_t a)
     return v;
 }
 
+// There is no double-precision min / max instruction: fmin / fmax become a compare plus half a dozen moves and selects each, and a
+// forward stage has 32 of them (a third of its instructions).  For finite data (the only data parity is claimed for) a compare
+// and a select give the same VALUE (only the sign of a zero result can differ, which no later value depends on).
+__device__ __forceinline__ double maxabs(double m, double t) { const double at = fabs(t); return at > m ? at : m; }   // m >= 0
+__device__ __forceinline__ double clampd(double v, double lo, double hi)
+{
+    const double r = lo > v ? lo : v;
+    return hi < r ? hi : r;
+}
+
 // model image in shared memory (doubles)
 struct MdlMap {
     static constexpr int K = 0, A = K + 48, B = A + 144, BR = B + 48, QI = BR + 48, M = QI + 16, KR = M + 144, LEN = KR + 48;
@@ -278,9 +288,9 @@ admm_kernel_f64p(const __grid_constant__ Model<double, 12, 4, NH> P, const __gri
 #pragma unroll
                 for (int j = 0; j < OX; ++j) {
                     const double xg = N::add(xo_[j], gv[j]);
-                    const double vn = N::mn(P.xmax[bi + j], N::mx(P.xmin[bi + j], xg));
-                    pri_x = N::mx(pri_x, N::abs(N::sub(xo_[j], vn)));
-                    dua_x = N::mx(dua_x, N::abs(N::sub(gv[OX + j], vn)));
+                    const double vn = clampd(xg, P.xmin[bi + j], P.xmax[bi + j]);
+                    pri_x = maxabs(pri_x, N::sub(xo_[j], vn));
+                    dua_x = maxabs(dua_x, N::sub(gv[OX + j], vn));
                     gv[j] = N::sub(xg, vn);   // (g + x) - vnew: the sum is the one above (addition commutes bit for bit)
                     gv[OX + j] = vn;
                 }
@@ -320,9 +330,9 @@ admm_kernel_f64p(const __grid_constant__ Model<double, 12, 4, NH> P, const __gri
                     for (int r = 0; r < OU; ++r) {
                         uo_[r] = N::sub(-kx[r], d[r]);                                            // :31
                         const double uy = N::add(uo_[r], y[r]);                                   // :47
-                        zn[r] = N::mn(P.umax[bi + r], N::mx(P.umin[bi + r], uy));                 // :53
-                        pri_u = N::mx(pri_u, N::abs(N::sub(uo_[r], zn[r])));                      // :97
-                        dua_u = N::mx(dua_u, N::abs(N::sub(z[r], zn[r])));                        // :98
+                        zn[r] = clampd(uy, P.umin[bi + r], P.umax[bi + r]);                       // :53
+                        pri_u = maxabs(pri_u, N::sub(uo_[r], zn[r]));                             // :97
+                        dua_u = maxabs(dua_u, N::sub(z[r], zn[r]));                               // :98
                         yn[r] = N::sub(uy, zn[r]);                                                // :69  (y + u) - znew
                     }
                     sts_chunk(i, 1, yn);
@@ -350,10 +360,10 @@ admm_kernel_f64p(const __grid_constant__ Model<double, 12, 4, NH> P, const __gri
             state_part(NH - 1);
             tm_wait_st();   // the backward sweep reads the cells this sweep wrote
         }
-        pri_x = N::mx(pri_x, __shfl_xor_sync(FULLM, pri_x, 1));
-        dua_x = N::mx(dua_x, __shfl_xor_sync(FULLM, dua_x, 1));
-        pri_u = N::mx(pri_u, __shfl_xor_sync(FULLM, pri_u, 1));
-        dua_u = N::mx(dua_u, __shfl_xor_sync(FULLM, dua_u, 1));
+        pri_x = maxabs(pri_x, __shfl_xor_sync(FULLM, pri_x, 1));
+        dua_x = maxabs(dua_x, __shfl_xor_sync(FULLM, dua_x, 1));
+        pri_u = maxabs(pri_u, __shfl_xor_sync(FULLM, pri_u, 1));
+        dua_u = maxabs(dua_u, __shfl_xor_sync(FULLM, dua_u, 1));
 
         // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
         bool final_bwd = false;
