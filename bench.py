@@ -583,9 +583,9 @@ def run_configs(torch, dist, pkg, args, dev, local, rank, world, barrier, allmax
           BYTES_PER_SOLVE["q"], chk, {"executed_flop_per_iteration": exec_flop_of(st.get("pattern"))})
     run.close(); del run; torch.cuda.empty_cache()
 
-    # ---- the reference's SHIPPED scalar type (glob_opts.hpp:3 `typedef double tinytype`): the headline workload in fp64, an eighth
-    #      of the batch per GPU (fp64 runs at half the lane count and half the instances per SM)
-    Bf = max(args.batch // 8 // sc, 1024)
+    # ---- the reference's SHIPPED scalar type (glob_opts.hpp:3 `typedef double tinytype`): the headline workload in fp64, a quarter
+    #      of the batch per GPU (half the instances per SM of the fp32 kernel, a quarter of its arithmetic rate)
+    Bf = max(args.batch // 4 // sc, 1024)
     b0, b1 = pkg.sharding.shard_range(rank, world, per_rank=Bf)
     x0, xref = W.quadrotor_hover_batch(b0, b1, mult=args.mult)
     run = DeviceRun(torch, pkg, quad, dev, local, args.policy, x0, xref, dtype=np.float64)
@@ -596,7 +596,7 @@ def run_configs(torch, dist, pkg, args, dev, local, rank, world, barrier, allmax
     peak64 = prop.multi_processor_count * 64 * 2 * 1965e6 / 1e12
     tf64 = st["iterations"] * FLOP_PER_ITER["q"] / (st["kernel_ms"] * 1e-3) / 1e12
     out["headline_fp64"] = {
-        "workload": "the headline workload in double precision (the reference's shipped tinytype), %d instances per GPU, PARITY" % Bf,
+        "workload": "the headline workload in double precision (the reference's shipped tinytype), %d instances per GPU, PARITY; two lanes per instance, model in shared memory (tmpc_kernel_f64p.cuh)" % Bf,
         "instances_total": Bf * world, "instances_per_gpu": Bf, "value": Bf * world * K / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms / K,
         "kernel_ms_per_launch": allmax(st["kernel_ms"]), "iters_per_s": allsum(st["iterations"]) * K / (ms * 1e-3),
         "mean_iters_per_solve": allsum(st["iterations"]) / (Bf * world), "dtype": "f64",
@@ -606,6 +606,48 @@ def run_configs(torch, dist, pkg, args, dev, local, rank, world, barrier, allmax
         "oracle_check": chk}
     log("configs.headline_fp64: %.3e solves/s, frac %.3f of FP64" % (out["headline_fp64"]["value"], tf64 / peak64))
     run.close(); del run; torch.cuda.empty_cache()
+
+    # ---- per-instance SYSTEMS (every instance its own Adyn, Bdyn, rho and cache), 262,144 in total
+    T = (1 << 18) // sc
+    b0, b1 = pkg.sharding.shard_range(rank, world, total=T)
+    rng = np.random.default_rng(1)
+    off = ~np.eye(12, dtype=bool)
+    sa, sb_, sr = rng.uniform(-1, 1, (T, 1)), rng.uniform(-1, 1, (T, 1, 1)), rng.uniform(-1, 1, T)
+    A = np.repeat(quad.Adyn[None], b1 - b0, 0).copy()
+    A[:, off] *= (1.0 + 0.2 * sa[b0:b1])
+    Bm = quad.Bdyn[None] * (1.0 + 0.3 * sb_[b0:b1])
+    Qs, Rs = np.repeat(quad.Q[None], b1 - b0, 0), np.repeat(quad.R[None], b1 - b0, 0)
+    rhos = 5.0 * (1.0 + 0.4 * sr[b0:b1])
+    x0, xref = W.quadrotor_hover_batch(b0, b1, mult=args.mult)
+    run = DeviceRun(torch, pkg, quad, dev, local, args.policy, x0, xref)
+    sysobj = pkg.capi.Systems(run.solver, A, Bm, Qs, Rs, rhos)
+    run.step = lambda: sysobj.solve_raw(run.x0, run.xref, True, run.x, run.u, run.it, run.st, run.rs, stream=run.stream.cuda_stream)
+    ms, st = run.timed(K, WU, barrier)
+    ms = allmax(ms)
+    chk = None
+    if rank == 0:   # the oracle solves a sample of the systems one by one, each with the cache the device computed for it
+        import copy
+        from oracle.pyoracle import OracleLib
+        orc = OracleLib()
+        t0c = time.perf_counter()
+        Kc, Pc, Qic, Mc = sysobj.get("Kinf"), sysobj.get("Pinf"), sysobj.get("Quu_inv"), sysobj.get("AmBKt")
+        o = outputs_np(run)
+        bad = {"iter": 0, "status": 0, "x": 0, "u": 0}
+        sample = list(range(0, min(b1 - b0, CHECK_PREFIX), max(1, min(b1 - b0, CHECK_PREFIX) // 256)))
+        for j in sample:
+            pj = copy.deepcopy(quad)
+            pj.Adyn, pj.Bdyn, pj.rho = A[j].astype(np.float32).astype(np.float64), Bm[j].astype(np.float32).astype(np.float64), float(np.float32(rhos[j]))
+            pj.Kinf, pj.Pinf, pj.Quu_inv, pj.AmBKt = (Kc[j].astype(np.float64), Pc[j].astype(np.float64), Qic[j].astype(np.float64), Mc[j].astype(np.float64))
+            ref = orc.solve_batch(pj, x0[j:j + 1], xref, dtype=np.float32, nthreads=1)
+            for k in bad:
+                bad[k] += int((np.asarray(o[k][j:j + 1]) != getattr(ref, k)).sum())
+        chk = {"instances": len(sample), "bit_exact": all(v == 0 for v in bad.values()), "mismatching_elements": bad, "compared": list(bad),
+               "oracle_seconds": time.perf_counter() - t0c, "how": "every %d-th system of the first %d, each solved by the oracle with its own model and the cache "
+               "the batched device precompute produced for it" % (max(1, min(b1 - b0, CHECK_PREFIX) // 256), min(b1 - b0, CHECK_PREFIX))}
+    entry("per_instance_systems", "SURVEY 8f row 1: %d perturbed quadrotor systems in total (each instance its own Adyn, Bdyn, rho, cache from the batched "
+          "device precompute), hover batch, cold, tmpc_solve_systems; two lanes per instance, coefficients streamed from tensor memory" % T,
+          "q", run, T, ms, st, BYTES_PER_SOLVE["q"] + 4 * 656, chk, {"kernel": os.environ.get("TMPC_KERNEL", "sys lane pairs (default)")})
+    sysobj.close(); run.close(); del run, sysobj; torch.cuda.empty_cache()
 
     # ---- config 4: cartpole 4/1/10, 16,777,216 instances in total, cold start
     cart = P.cartpole()
