@@ -156,18 +156,58 @@ __device__ __forceinline__ T reduce_products(const E &e)
     }
 }
 
-// sum_k c(k)*x(k) in the named order (PARITY) or as one FMA chain (FAST)
+// sum_k c(k)*x(k) in the named order (PARITY) or as one FMA chain (FAST).  (Spelled out rather than forwarded to reduce_products: with the
+// forwarding form ptxas allocates and schedules the warp-per-instance kernel differently and it runs 8 % slower -- measured, round 2.)
 template <class T, int ORD, int K, bool FAST, class C, class X>
 __device__ __forceinline__ T dot(const C &c, const X &x)
 {
     using N = Num<T>;
+    constexpr int PK = N::PK;
     if constexpr (FAST) {
         T acc = N::mul(c(0), x(0));
 #pragma unroll
         for (int k = 1; k < K; ++k) acc = N::fma(c(k), x(k), acc);
         return acc;
     } else {
-        return reduce_products<T, ORD, K>([&](int k) -> T { return N::mul(c(k), x(k)); });
+        auto e = [&](int k) -> T { return N::mul(c(k), x(k)); };
+        if constexpr (ORD == ORD_SEQ) {
+            T acc = e(0);
+#pragma unroll
+            for (int k = 1; k < K; ++k) acc = N::add(e(k), acc);
+            return acc;
+        } else if constexpr (ORD == ORD_TREE) {
+            return red_tree<T, 0, K>(e);
+        } else if constexpr (ORD == ORD_VECREDUX) {
+            constexpr int NP = K / PK;
+            if constexpr (NP == 0) {
+                return red_tree<T, 0, K>(e);
+            } else {
+                T l[PK];
+                l[0] = red_ptree<T, 0, NP, 0>(e);
+                l[1] = red_ptree<T, 0, NP, 1>(e);
+                if constexpr (PK == 4) {
+                    l[2] = red_ptree<T, 0, NP, 2>(e);
+                    l[3] = red_ptree<T, 0, NP, 3>(e);
+                }
+                T r = predux<T>(l);
+                if constexpr (NP * PK != K) r = N::add(r, red_tree<T, NP * PK, K - NP * PK>(e));
+                return r;
+            }
+        } else {  // ORD_GEMV_ROW
+            constexpr int FULL = (K / PK) * PK;
+            static_assert(FULL > 0, "row-major GEMV order needs K >= packet");
+            T l[PK];
+            l[0] = red_lane_seq<T, K, 0>(e);
+            l[1] = red_lane_seq<T, K, 1>(e);
+            if constexpr (PK == 4) {
+                l[2] = red_lane_seq<T, K, 2>(e);
+                l[3] = red_lane_seq<T, K, 3>(e);
+            }
+            T r = predux<T>(l);
+#pragma unroll
+            for (int j = FULL; j < K; ++j) r = N::add(r, e(j));
+            return r;
+        }
     }
 }
 
