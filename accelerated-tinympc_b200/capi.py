@@ -493,10 +493,11 @@ class Systems:
         s._check(self.lib.tmpc_systems_get(self._p, SYS[what], out.ctypes.data), "tmpc_systems_get")
         return np.transpose(out, (0, 2, 1)) if what in shape else out
 
-    def solve_raw(self, x0, Xref, xref_shared, x=None, u=None, it=None, status=None, resid=None, warm=None, stream=None):
+    def solve_raw(self, x0, Xref, xref_shared, x=None, u=None, it=None, status=None, resid=None, warm=None, stream=None, u0=None):
         """Device buffers (torch tensors / addresses) only."""
         args = TmpcSolveArgs()
         args.batch = self.B
+        args.u0 = _addr(u0)
         args.x0, args.Xref = _addr(x0), _addr(Xref)
         args.xref_shared = 1 if xref_shared else 0
         args.mem = TMPC_MEM_DEVICE

@@ -1019,7 +1019,7 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
     // and is claimed in index order.  Simulated on the hover workload's real iteration counts: makespan 1.018 x the mean
     // lane load with a quarter of the batch ranked, 1.013 with half (index order 1.075, fully sorted 1.013).
     //   late (default): the persistent kernel is launched on all SMs BUT TWO as soon as a first small chunk of the
-    //     index-ordered part is in; the ranked segment (half the batch) goes over LAST and its key kernel + radix sort run
+    //     index-ordered part is in; the ranked segment (a quarter of the batch) goes over LAST and its key kernel + radix sort run
     //     beside the solver on the two free SMs (a full grid leaves them no register file); the lanes reach those claims
     //     milliseconds after the ranking is done (gate[2]).  Nothing but 32,768 instances of H2D precedes the launch.
     //     Used when the caller wants neither x nor u back (controls-only: u0 / iter / status): measured 10.77 ms per 1M-instance
@@ -1037,8 +1037,13 @@ int solve_host_gated(tmpc_ctx_impl *c, const tmpc_solve_args *a)
         const bool off = e && !strcmp(e, "0");
         if (!off && overlap && a->xref_shared && !c->ib_batch && c->d_kinf && nch >= 8 &&
             lookup_kernel(c->nx, c->nu, c->N, c->dtype, c->policy, false, ki, c->pattern | (c->const_bounds ? 0x100 : 0)) &&
-            B >= 2 * (int64_t)ki.per_block * c->sm_count && B >= 16384)
-            T0 = ((B / (late ? 2 : 4) + CH - 1) / CH) * CH;
+            B >= 2 * (int64_t)ki.per_block * c->sm_count && B >= 16384) {
+            int div = 4;   // share of the batch that is ranked: 1 / div  (TMPC_TAIL_DIV: tuning; measured in late mode, one GPU, 1M hover
+                           // instances, controls-only: 2 -> 10.80 ms, 3 -> 10.78, 4 -> 10.71, 8 -> 10.95; the ranked segment's
+                           // read-back trails the kernel, which costs eight ranks sharing one host D2H path more than one)
+            if (const char *dv = getenv("TMPC_TAIL_DIV")) div = std::max(2, std::min(64, atoi(dv)));
+            T0 = ((B / div + CH - 1) / CH) * CH;
+        }
     }
     const int64_t ICH = overlap ? 131072 : B;
     const bool gate_stall_test = getenv("TMPC_TEST_GATE_STALL") != nullptr;

@@ -130,9 +130,17 @@ def test_systems_kernel_variants_agree(pkg, oracle, monkeypatch, S):
         x = torch.empty((S, 10, 12), device=dev); u = torch.empty((S, 9, 4), device=dev)
         it = torch.empty(S, dtype=torch.int32, device=dev); st = torch.empty(S, dtype=torch.int32, device=dev)
         rs = torch.empty((S, 4), device=dev)
-        sy.solve_raw(torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev), True, x, u, it, st, rs)
+        u0 = torch.empty((S, 4), device=dev)
+        sy.solve_raw(torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev), True, x, u, it, st, rs, u0=u0)
         torch.cuda.synchronize()
         outs.append((it.cpu().numpy(), st.cpu().numpy(), x.cpu().numpy(), u.cpu().numpy(), rs.cpu().numpy()))
+        assert_same(u0.cpu().numpy(), outs[-1][3][:, 0, :], "u0 next to the full outputs (%s)" % variant)
+        # controls-only output mask: no trajectories, same u0 / iter
+        u0b = torch.zeros((S, 4), device=dev); itb = torch.zeros(S, dtype=torch.int32, device=dev)
+        sy.solve_raw(torch.from_numpy(x0).to(dev), torch.from_numpy(xref).to(dev), True, None, None, itb, None, None, u0=u0b)
+        torch.cuda.synchronize()
+        assert_same(u0b.cpu().numpy(), outs[-1][3][:, 0, :], "u0, controls-only (%s)" % variant)
+        assert_same(itb.cpu().numpy(), outs[-1][0], "iter, controls-only (%s)" % variant)
         if variant is None:
             K, P, Qi, M = sy.get("Kinf"), sy.get("Pinf"), sy.get("Quu_inv"), sy.get("AmBKt")
         if variant:
