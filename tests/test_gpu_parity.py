@@ -158,3 +158,39 @@ def test_longest_first_schedule_is_result_neutral(pkg, oracle, monkeypatch):
         assert_same(o1[k], o0[k], "scheduled vs index order " + k)
         assert_same(o1[k], getattr(ref, k), "scheduled vs oracle " + k)
     assert st1["trips"] <= st0["trips"]
+
+
+@pytest.mark.parametrize("variant", ["", "f64_thread", "generic"])
+def test_fp64_kernel_variants(pkg, oracle, monkeypatch, variant):
+    """fp64 12/4/10, three kernels: two lanes per instance with the model in shared memory (default, tmpc_kernel_f64p.cuh), one
+    thread per instance with g, v in tensor memory (TMPC_KERNEL=f64_thread) and with all state in shared memory (generic).  A ragged
+    batch several times the resident instances (so every lane pair refills), cold with every output, the warm state written back,
+    a warm-started re-solve from it, and the controls-only mask -- all bit-exact against the oracle."""
+    if variant:
+        monkeypatch.setenv("TMPC_KERNEL", variant)
+    keys = ("d", "y", "g", "v", "z")
+    prob = pkg.problems.quadrotor(20)
+    B = 41003
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.3)
+    r1 = oracle.solve_batch(prob, x0, xref, dtype=np.float64, want_state=True, nthreads=8)
+    assert (r1.status == 1).any() and (r1.status == 11).any()
+    s = pkg.capi.Solver(prob, dtype=np.float64, policy="parity")
+    cold = s.solve(x0, xref, outputs=("x", "u", "u0", "iter", "status", "resid"))
+    for k in ("iter", "status", "resid", "x", "u"):
+        assert_same(cold[k], getattr(r1, k), "%s cold %s" % (variant, k))
+    assert_same(cold["u0"], r1.u[:, 0, :], "%s cold u0" % variant)
+    only = s.solve(x0, xref, outputs=("u0", "iter", "status"))
+    assert_same(only["u0"], r1.u[:, 0, :], "%s controls-only u0" % variant)
+    assert_same(only["iter"], r1.iter, "%s controls-only iter" % variant)
+    zw = {k: np.zeros((B, 9, 4) if k in "dyz" else (B, 10, 12), np.float64) for k in keys}
+    o1 = s.solve(x0, xref, warm=zw)
+    for k in keys:
+        assert_same(o1["warm"][k], r1.state[k], "%s warm.%s" % (variant, k))
+    x1 = pkg.workloads.perturb_x0(x0, 0)
+    r2 = oracle.solve_batch(prob, x1, xref, dtype=np.float64, warm={k: r1.state[k] for k in keys}, want_state=True, nthreads=8)
+    o2 = s.solve(x1, xref, warm=o1["warm"])
+    for k in ("iter", "status", "resid", "x", "u"):
+        assert_same(o2[k], getattr(r2, k), "%s re-solve %s" % (variant, k))
+    for k in keys:
+        assert_same(o2["warm"][k], r2.state[k], "%s re-solve warm.%s" % (variant, k))
+    s.close()
