@@ -108,8 +108,8 @@ def test_per_instance_systems_solve_bit_exact(pkg, oracle, dtype):
     assert stt["iterations"] == int(itn.sum()) and stt["pattern"] == 0
 
 
-@pytest.mark.parametrize("S", [333, 40_000])
-def test_systems_kernel_variants_agree(pkg, oracle, monkeypatch, S):
+@pytest.mark.parametrize("S,const_bounds", [(333, True), (40_000, True), (2_000, False)])
+def test_systems_kernel_variants_agree(pkg, oracle, monkeypatch, S, const_bounds):
     """fp32 12/4/10 systems solve, four kernels: two lanes per instance with row pairs streamed from tensor memory (default,
     tmpc_kernel_sysp.cuh), the same with one thread per instance (TMPC_KERNEL=sys_thread, tmpc_kernel_sys.cuh), the first
     TMEM-resident kernel (sys_rows) and coefficients re-read from the global block (sys_global) -- identical results,
@@ -117,6 +117,8 @@ def test_systems_kernel_variants_agree(pkg, oracle, monkeypatch, S):
     output; a sample of the systems is checked against the oracle."""
     import copy
     import torch
+    if not const_bounds:   # the instances of the kernels that read stage-indexed bounds (the examples' boxes are the same at every stage)
+        monkeypatch.setenv("TMPC_NO_CONST_BOUNDS", "1")
     base, A, Bm, Q, R, rho = _systems(pkg, 97, np.float32)   # 97 distinct systems, repeated with different x0
     idx = np.arange(S) % 97
     x0, xref = pkg.workloads.quadrotor_hover_batch(0, S, mult=0.6)
