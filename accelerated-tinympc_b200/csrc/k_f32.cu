@@ -6,12 +6,12 @@
 namespace tmpc_dispatch {
 namespace {
 
-template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT, bool CB, bool IB = false, bool CSM = false>
+template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT, bool CB, bool IB = false, bool CSM = false, bool ROLL = false>
 KernelInfo make_info_f32()
 {
     KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM, PAT, CB, IB, CSM>;
-    k.smem = CSM ? tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES_CSM : tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES;
+    k.fn = (const void *)&tmpc::admm_kernel_f32<NX, NU, NH, BLOCK, FAST, WARM, TM, PAT, CB, IB, CSM, ROLL>;
+    k.smem = CSM ? tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES_CSM : ROLL ? tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES_ROLL : tmpc::SmemLayoutF32<NX, NU, NH, BLOCK, TM>::BYTES;
     k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::ModelF32<NX, NU, NH>);
     k.model_kind = 1;
@@ -53,6 +53,18 @@ bool lookup_f32(int policy, bool warm, int pattern, bool cb, int variant, Kernel
         return cb ? pick_f32<12, 4, 10, 256, true, tmpc::PatDense<12>, true>(policy, warm, out)
                   : pick_f32<12, 4, 10, 256, true, tmpc::PatDense<12>, false>(policy, warm, out);
     return pick_f32<12, 4, 10, 128, false>(policy, warm, out);                     // all state in shared memory
+}
+
+// fused closed loop (ROLL instances): warm, tensor-memory variant, shared box, PARITY order
+bool lookup_f32_roll(int pattern, bool cb, KernelInfo &out)
+{
+    if (pattern == tmpc::PatQuadrotor::id)
+        out = cb ? make_info_f32<12, 4, 10, 256, false, true, true, tmpc::PatQuadrotor, true, false, false, true>()
+                 : make_info_f32<12, 4, 10, 256, false, true, true, tmpc::PatQuadrotor, false, false, false, true>();
+    else
+        out = cb ? make_info_f32<12, 4, 10, 256, false, true, true, tmpc::PatDense<12>, true, false, false, true>()
+                 : make_info_f32<12, 4, 10, 256, false, true, true, tmpc::PatDense<12>, false, false, false, true>();
+    return true;
 }
 
 }  // namespace tmpc_dispatch

@@ -558,6 +558,9 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     const void *ixmin, *ixmax, *iumin, *iumax;
     const void *model_g;
     long long gate_split;
+    int roll_steps, roll_pad;
+    void *roll_x, *roll_u0;
+    int *roll_iter, *roll_status;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
@@ -645,7 +648,7 @@ int plan_lane_scratch(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, long 
         CUDA_TRY(c, cudaMemcpyAsync(c->d_model_f32, c->model_f32.data(), c->model_f32.size(), cudaMemcpyHostToDevice, s));
         da.model_g = c->d_model_f32;
     }
-    if (const char *e = getenv("TMPC_TEST_MIRROR")) da.test_flags = atoi(e) & 3;
+    if (const char *e = getenv("TMPC_TEST_MIRROR")) da.test_flags = atoi(e) & 11;   // (8: fused closed loop, exact hand-over at every step)
     if (c->duals_zero_next && da.wd) da.test_flags |= 4;
     c->duals_zero_next = false;
     using SM = tmpc::ScratchMap<12, 4, 10>;
@@ -655,7 +658,7 @@ int plan_lane_scratch(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, long 
         if (c->en_state) { da.ixmin = c->d_ib[0]; da.ixmax = c->d_ib[1]; }
         if (c->en_input) { da.iumin = c->d_ib[2]; da.iumax = c->d_ib[3]; }
     }
-    if (da.wd) { da.sc_wm = chunks; chunks += SM::WM_CHUNKS; }
+    if (da.wd) { da.sc_wm = chunks; chunks += SM::WM_CHUNKS * (da.roll_steps > 1 ? 2 : 1); }   // (a fused closed loop keeps two mirror areas)
     da.sc_chunks = chunks;
     if (!chunks) return TMPC_OK;
     const size_t need = (size_t)blocks * ki.block * chunks * 16;
@@ -768,7 +771,8 @@ bool lpt_wanted(const tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da)
     // Warm starts stream 2.9 KB of state per instance in and out of [instance]-major buffers; with thread-per-instance
     // kernels the permuted order turns that into scattered 144..480-byte rows (measured: device rollout of 1M hover instances
     // 7.85 -> 9.65 ms per MPC step).  The warp-per-instance kernel moves 17 KB contiguous per instance and gains (19.7 -> 18.0 ms).
-    if (da.wd && ki.model_kind != 2) return false;
+    // (a fused closed loop streams the state once per `roll_steps` solves and its claims are that much longer: there the order pays)
+    if (da.wd && ki.model_kind != 2 && da.roll_steps <= 1) return false;
     const long long lanes = (long long)ki.per_block * c->sm_count;
     return da.batch >= 2 * lanes && da.batch >= 16384;
 }
@@ -858,11 +862,25 @@ int lpt_from_keys(tmpc_ctx_impl *c, DevArgs &da, cudaStream_t s, const unsigned 
     return TMPC_OK;
 }
 
+// Fused closed loop (ROLL instances of the fp32 12/4/10 kernel): PARITY order, tensor-memory variant, one box for the batch.
+// TMPC_ROLL=0 keeps one launch per MPC step.
+bool roll_supported(const tmpc_ctx_impl *c)
+{
+    const char *e = getenv("TMPC_ROLL");
+    if (e && !strcmp(e, "0")) return false;
+    return c->nx == 12 && c->nu == 4 && c->N == 10 && c->dtype == TMPC_F32 && c->policy == TMPC_ORDER_PARITY && kernel_variant() == 2 && !force_rt() &&
+           !c->ib_batch;
+}
+
 int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
 {
     KernelInfo ki;
     const bool ib_f32 = c->ib_batch && ib_on_f32_kernel(c);
-    if (ib_f32) {
+    if (da.roll_steps > 1) {
+        // fused closed loop (tmpc_batch_rollout): the caller has checked roll_supported()
+        if (!warm || !da.wd || c->ib_batch || da.sys || !tmpc_dispatch::lookup_f32_roll(c->pattern, c->const_bounds, ki))
+            return fail(c, TMPC_ERR_UNSUPPORTED, "fused closed loop: no kernel");
+    } else if (ib_f32) {
         // per-instance bounds on the specialised fp32 12/4/10 kernel: each lane copies its instance's box into its coalesced
         // scratch rows at refill and projects onto it (IB instances of the kernel)
         if (da.sys) return fail(c, TMPC_ERR_UNSUPPORTED, "per-instance bounds with per-instance systems");

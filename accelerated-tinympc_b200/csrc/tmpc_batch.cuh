@@ -167,7 +167,10 @@ int batch_copy_out(tmpc_batch_impl *b, void *dst, const void *src, size_t bytes,
 // for batches that keep the GPU busy for several rounds of lanes; TMPC_LPT=0 turns it off.
 // controls_only: neither x nor u is written (nothing can read them before the next solve overwrites them: the steps of a rollout
 // but the last); u(:,0) goes to b->u0, which is all the plant step needs -- and all the kernels then skip their emission work
-int batch_solve_async(tmpc_batch_impl *b, bool controls_only = false)
+// roll_steps > 1: ONE launch runs that many MPC steps per instance (fused closed loop, tmpc_kernel_f32.cuh ROLL); rx / ru / ri / rs
+// receive the histories of the steps before the last (SolveArgs::roll_*), the last step's outputs land where a plain solve's do
+int batch_solve_async(tmpc_batch_impl *b, bool controls_only = false, int roll_steps = 0, void *rx = nullptr, void *ru = nullptr, int *ri = nullptr,
+                      int *rs = nullptr)
 {
     tmpc_ctx_impl *c = b->c;
     DevArgs da{};
@@ -180,6 +183,7 @@ int batch_solve_async(tmpc_batch_impl *b, bool controls_only = false)
         da.x = nullptr; da.u = nullptr; da.u0 = b->u0;
         b->plant_u = b->u0; b->plant_u_stride = c->nu;
     }
+    if (roll_steps > 1) { da.roll_steps = roll_steps; da.roll_x = rx; da.roll_u0 = ru; da.roll_iter = ri; da.roll_status = rs; }
     c->stats.instances = b->B;
     c->stats.launches = 0;
     const char *e = getenv("TMPC_LPT");
@@ -386,7 +390,22 @@ int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void 
     float kernel_ms = 0.f;
     BCUDA_TRY(b, cudaEventRecord(r0, s));
     int rc = TMPC_OK;
-    for (int k = 0; k < steps && rc == TMPC_OK; ++k) {
+    int k0 = 0;
+    if (steps >= 2 && reset_duals && !b->table && roll_supported(c) && !getenv("TMPC_ROLLOUT_FULL_OUTPUTS")) {
+        // Fused closed loop: every lane of ONE persistent launch takes an instance through all `steps` solves (plant step, dual reset and
+        // the warm d / v / z hand-over stay on chip); only the last step's plant update is left to the loop below
+        c->duals_zero_next = true;
+        rc = batch_solve_async(b, false, steps, dx ? dx + nxb : nullptr, du, di, ds);
+        if (rc == TMPC_OK) {
+            k0 = steps - 1;
+            e = dispatch_plant(c, b, dx ? dx + nxb * steps : nullptr, du ? du + nub * k0 : nullptr, di ? di + (size_t)B * k0 : nullptr,
+                               ds ? ds + (size_t)B * k0 : nullptr, s);
+            if (e != cudaSuccess) rc = bfail(b, TMPC_ERR_CUDA, std::string("plant step: ") + cudaGetErrorString(e));
+            b->steps_done += steps;
+            k0 = steps;
+        }
+    }
+    for (int k = k0; k < steps && rc == TMPC_OK; ++k) {
         if (b->table) {   // 2. reference window (tracking.cpp:101)
             const long long n = (long long)B * c->nx * c->N;
             const unsigned blocks = (unsigned)((n + 255) / 256);
@@ -431,7 +450,7 @@ int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void 
     cudaEventDestroy(r1);
     cleanup();
     if (rc == TMPC_OK) {
-        c->stats.launches = steps * (2 + (b->table ? 1 : 0));
+        c->stats.launches = k0 ? 2 : steps * (2 + (b->table ? 1 : 0));
         c->rollout_ms = kernel_ms;
     }
     return rc;

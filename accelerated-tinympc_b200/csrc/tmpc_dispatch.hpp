@@ -23,6 +23,10 @@ struct KernelInfo {
 // per_instance_bounds: the IB instances (variant 2 only; boxes read from the lane's scratch rows)
 bool lookup_f32(int policy, bool warm, int pattern, bool const_bounds, int variant, KernelInfo &out, bool per_instance_bounds = false);
 
+// the same kernel running a whole closed loop per claimed instance (SolveArgs::roll_steps MPC steps, state kept on the lane between
+// them): warm PARITY solves with a shared box on the tensor-memory variant
+bool lookup_f32_roll(int pattern, bool const_bounds, KernelInfo &out);
+
 // generic shared-memory kernel (tmpc_kernel.cuh): fp64 shapes and the development variants of the fp32 shapes.
 // variant 0: default for the shape / dtype; 1: all state in shared memory; 2: horizon loops unrolled (4/1/10 fp32 only)
 bool lookup_generic(int nx, int nu, int N, int dtype, int policy, bool warm, int variant, KernelInfo &out);

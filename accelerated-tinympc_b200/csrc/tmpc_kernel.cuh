@@ -294,13 +294,21 @@ template <class T> struct SolveArgs {
     int sc_ib, sc_wm, sc_chunks;
     int test_flags;                           // 1, 2: tests only (1 = never predict the mirror: every early exit takes the re-solve
                                               // fall-back; 2 = mirror in every backward sweep); 4 = the warm duals y, g are ZERO
-                                              // (closed loop with reset duals, quadrotor_hovering.cpp:100-101): not read at all
+                                              // (closed loop with reset duals, quadrotor_hovering.cpp:100-101): not read at all;
+                                              // 8: tests only, fused closed loop: exact hand-over at every step (no lazy first iteration)
     const T *ixmin, *ixmax, *iumin, *iumax;   // per-instance boxes [instance][N][nx] / [instance][N-1][nu]; a null pair = unbounded
     const void *model_g;                      // device copy of the kernel's model image (CSM instances of the fp32 kernel: staged
                                               // into shared memory by one TMA bulk copy per CTA), else null
     long long gate_split;                     // host pipeline, 0 or T: instances [0, T) are the tail segment -- transferred LAST, ranked on
                                               // the SMs the launch leaves free, claimed last (claims batch-T .. batch-1); gate[2] != 0 once
                                               // they have arrived and order[] holds their ranking.  gate[0] then covers [T, batch) only.
+    // Fused closed loop (ROLL instances of the fp32 12/4/10 kernel, tmpc_kernel_f32.cuh): roll_steps > 1 MPC steps per instance in ONE
+    // launch -- solve, plant step x0 <- x_1 of the solve, y = g = 0, warm d / v / z carried on chip -- for steps 0 .. roll_steps-2,
+    // then the last step as a plain warm solve (outputs, state written back).  Histories of the steps the kernel completes
+    // itself (each nullable): roll_x[k] = the state after step k, roll_u0[k] = the control applied, roll_iter / roll_status[k].
+    int roll_steps, roll_pad;
+    T *roll_x, *roll_u0;          // [roll_steps-1][batch][nx] / [..][nu]
+    int *roll_iter, *roll_status; // [roll_steps-1][batch]
 };
 
 // instance solved by the idx-th claim of the work counter

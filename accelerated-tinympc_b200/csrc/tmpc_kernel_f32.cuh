@@ -398,6 +398,8 @@ template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
     static constexpr size_t BYTES = 3 * SU::BYTES + SP::BYTES + XBYTES + 16;
     // CSM instances: + the model image (128-byte aligned) and its mbarrier
     static constexpr size_t BYTES_CSM = (BYTES + 127) / 128 * 128 + sizeof(ModelF32<NX, NU, NH>) + 16;
+    // ROLL instances (TM): + two x rows per lane, the step's measurement and the plant's next state
+    static constexpr size_t BYTES_ROLL = BYTES + 2 * SP::BYTES;
 };
 
 // CB: the bounds are the same at every horizon stage (the usual box constraints, e.g. every example of the reference):
@@ -411,7 +413,7 @@ template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
 // instead of a constant-bank operand folded into the FMUL.  Measured against the default (profiles/r02_cache_smem_ab.md):
 // kept as TMPC_KERNEL=f32_tma_cache, not the default.
 template <int NX, int NU, int NH, int BLOCK, bool FAST, bool WARM, bool TM, class PAT = PatDense<NX>, bool CB = false, bool IB = false,
-          bool CSM = false>
+          bool CSM = false, bool ROLL = false>
 __global__ void __launch_bounds__(BLOCK, 1)
 admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_constant__ SolveArgs<float> a)
 {
@@ -463,6 +465,10 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
     typename L::SU sy(sp, tid); sp += L::SU::BYTES;
     typename L::SU sz(sp, tid); sp += L::SU::BYTES;
     typename L::SP spn(sp, tid); sp += L::SP::BYTES;
+    // ROLL (TM instances: nothing else lives past spn): x_1 of the latest forward sweep, and the step's x0 -- registers are what keeps
+    // the coefficient pairs of the backward sweep out of the loop (profiles/r02_ncu_fused_loop.md)
+    typename L::SP sx1(sp, tid);
+    typename L::SP sx0(sp + L::SP::BYTES, tid);
 
     uint32_t tmem_base = 0;
     if constexpr (TM) {
@@ -496,9 +502,34 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                          // expected to terminate in it (residuals within SPEC_FACTOR of tolerance, or last iteration)
     float x0[NX];
     float res[4] = {0.f, 0.f, 0.f, 0.f};
-    unsigned long long n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
+    using cnt_t = typename std::conditional<ROLL, unsigned, unsigned long long>::type;   // (per lane: far below 2^32 either way)
+    cnt_t n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
 #pragma unroll
     for (int j = 0; j < NX; ++j) x0[j] = 0.f;
+    // ROLL -- the examples' closed loop (quadrotor_hovering.cpp:90-114) for this lane's instance WITHOUT leaving the lane: when step
+    // rs < S-1 ends, the next step starts from the state on chip (x0 <- x_1 of the solve = the plant step, y = g = 0, d / v / z as the
+    // reference carries them) instead of a write-back, a re-launch and a refill; the last step is a plain warm solve.  The warm
+    // state the reference leaves after an early exit is one iteration behind (see the backward section): it comes from the mirror
+    // rows, of which a ROLL launch has two sets: `area` receives this step's mirrors, area ^ 1 holds the state the step started from
+    // (the previous step's last mirror), which is also what a step is solved again from when its mirror was not predicted.
+    // LAZY first iteration.  After an early exit the chip holds v, z of the terminating iteration; the reference's (one behind) differ
+    // from them in ONE place of the next step: the dual residuals of its first iteration (admm.cpp:96,98), i.e. only in whether that
+    // iteration may terminate.  So the next step starts on the on-chip v, z -- no reload.  Its first dual residuals are then measured
+    // against v, z that are off by exactly what the previous step's LAST dual residuals measured (dprev, each below the tolerance):
+    // when one of them exceeds (dprev + tolerance) by a margin, or a primal residual fails, the exact test fails as well (triangle
+    // inequality; the 0.1 % margin covers the roundings) and the step simply goes on.  Otherwise -- the first iteration MIGHT end the
+    // step -- the step is taken again from the exact state in the mirror rows (pend 3).  Every result stays bit-exact; in the hover
+    // closed loop the first dual residual of a step is 10-100 tolerances, so the second path is for nearly stationary instances.
+    static_assert(!ROLL || (WARM && TM && !IB && !CSM), "fused closed loop: warm, tensor-memory instance, shared box");
+    const int S = ROLL ? a.roll_steps : 1;
+    int rs = 0;           // MPC step of `inst` being solved
+    int pend = 0;         // what the top of the next trip does: 1 next step after an early exit, 2 after a max_iter exit, 3 same step again
+    int area = 0, varea = 0, farea = 0;
+    bool gzero = false;   // this trip's forward sweep reads g as zero (reset duals; g lives in tensor memory, written collectively)
+    bool vprev = false;   // this trip's forward sweep takes v from the mirror rows `varea` (v one iteration behind)
+    bool lazy = false;    // this step's first iteration ran on the on-chip v, z (see above)
+    float dprev_x = 0.f, dprev_u = 0.f;   // rho-scaled dual residuals of the iteration that ended the previous step
+    auto wm = [&](int ar) -> int { return a.sc_wm + (ROLL ? ar * SM::WM_CHUNKS : 0); };
 
     // p_N seed: -(Xref_{N-1}^T Pinf)  (admm.cpp:83).  It depends on the reference trajectory only, so with one Xref shared by the
     // batch it is computed once per lane here instead of at every refill: the refill section runs at warp level nearly every
@@ -520,6 +551,60 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
     if (shared_xref) seed_pn(a.Xref + (NH - 1) * NX);
 
     for (;;) {
+        if constexpr (ROLL) {
+            // ------------------------------------------------------------------ next MPC step (or the same one again) on this lane
+            if (pend) {
+                // where the state the coming run starts from (d, v, z) is: this step's last mirror after an early exit past the first
+                // iteration or a max_iter exit (whose backward sweep mirrored what it left on chip); otherwise the step's own start state
+                const int src = (pend == 3 || (pend == 1 && it == 1)) ? (area ^ 1) : area;
+                // exact hand-over (reload z, v read from the mirror rows in the sweep): a step taken again, and after a step that ended
+                // at its first iteration (the next one probably does too); otherwise lazy
+                const bool exact = pend == 3 || (pend == 1 && (it == 1 || (a.test_flags & 8)));
+                lazy = (pend == 1) && !exact;
+                dprev_x = res[1]; dprev_u = res[3];
+                if (exact) {
+                    // z (and for a repeated step d) of the reference's state: the forward sweeps have overwritten them on chip
+                    float4 tz[NH - 1], td[NH - 1];
+#pragma unroll
+                    for (int i = 0; i < NH - 1; ++i) {
+                        tz[i] = sc.ld(wm(src) + SM::WM_STAGE * i + SM::CX);
+                        if (pend == 3) td[i] = sc.ld(wm(src) + SM::WM_STAGE * i + SM::CX + SM::CU);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NH - 1; ++i) {
+                        const float t[NU] = {tz[i].x, tz[i].y, tz[i].z, tz[i].w};
+                        sz.store(i, t);
+                        if (pend == 3) { const float t2[NU] = {td[i].x, td[i].y, td[i].z, td[i].w}; sd.store(i, t2); }
+                    }
+                    vprev = true; varea = src;
+                }
+                {   // y = 0 (hovering.cpp:100); g = 0 is applied by the next forward sweep
+                    float zu[NU];
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) zu[j] = 0.f;
+#pragma unroll 1
+                    for (int i = 0; i < NH - 1; ++i) sy.store(i, zu);
+                }
+                gzero = true;
+                if (pend != 3) {
+                    // plant step (hovering.cpp:108): x1 = Adyn x0 + Bdyn u0 is stage 1 of the solve's last forward sweep, which left it in
+                    // the lane's shared-memory row; the instance's x0 row follows (the measurement the LAST step starts from is what the
+                    // caller's plant step needs after the launch)
+                    sx1.load(0, x0);
+                    sx0.store(0, x0);
+                    gstore<float, NX>(const_cast<float *>(a.x0) + inst * NX, x0);
+                    if (a.roll_x) gstore<float, NX>(a.roll_x + ((long long)rs * a.batch + inst) * NX, x0);
+                    rs += 1;
+                    area = src ^ 1;
+                    force_mirror = (a.test_flags & 2) != 0;
+                } else {
+                    force_mirror = true;
+                }
+                it = 0; mirrored = false; pend = 0;
+                res[0] = res[1] = res[2] = res[3] = 0.f;
+                spec = (rs >= S - 1) && (P.max_iter <= 1);
+            }
+        }
         // ------------------------------------------------------------------ lane refill (warp-uniform branch)
         const bool need = (phase == PH_FREE) && !exhausted;
         unsigned m = __ballot_sync(FULLM, need);
@@ -546,23 +631,24 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 if (flush) {
                     // y of the terminating iteration (still in shared memory); d, v, z of the iteration before it from the scratch
                     // rows, fetched in two batches so that their L2 latency is paid twice, not once per row
-                    float *wyo = a.wy + finst * UROW;
+                    const long long fi = ROLL ? inst : finst;   // (a ROLL lane flushes before its refill below replaces inst)
+                    float *wyo = a.wy + fi * UROW;
 #pragma unroll
                     for (int i = 0; i < NH - 1; ++i) { float t[NU]; sy.load(i, t); gstore<float, NU>(wyo + i * NU, t); }
                     if (flush == 2) {
-                        float *wvo = a.wv + finst * XROW, *wzo = a.wz + finst * UROW, *wdo = a.wd + finst * UROW;
+                        float *wvo = a.wv + fi * XROW, *wzo = a.wz + fi * UROW, *wdo = a.wd + fi * UROW;
                         float4 tv[NH * SM::CX];
 #pragma unroll
                         for (int i = 0; i < NH; ++i)
 #pragma unroll
-                            for (int c = 0; c < SM::CX; ++c) tv[i * SM::CX + c] = sc.ld(a.sc_wm + SM::WM_STAGE * i + c);
+                            for (int c = 0; c < SM::CX; ++c) tv[i * SM::CX + c] = sc.ld(wm(farea) + SM::WM_STAGE * i + c);
 #pragma unroll
                         for (int i = 0; i < NH; ++i)
 #pragma unroll
                             for (int c = 0; c < SM::CX; ++c) reinterpret_cast<float4 *>(wvo + i * NX)[c] = tv[i * SM::CX + c];
                         float4 tz[NH - 1], td[NH - 1];
 #pragma unroll
-                        for (int i = 0; i < NH - 1; ++i) { tz[i] = sc.ld(a.sc_wm + SM::WM_STAGE * i + SM::CX); td[i] = sc.ld(a.sc_wm + SM::WM_STAGE * i + SM::CX + SM::CU); }
+                        for (int i = 0; i < NH - 1; ++i) { tz[i] = sc.ld(wm(farea) + SM::WM_STAGE * i + SM::CX); td[i] = sc.ld(wm(farea) + SM::WM_STAGE * i + SM::CX + SM::CU); }
 #pragma unroll
                         for (int i = 0; i < NH - 1; ++i) { reinterpret_cast<float4 *>(wzo)[i] = tz[i]; reinterpret_cast<float4 *>(wdo)[i] = td[i]; }
                     }
@@ -577,9 +663,11 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 if (ni >= 0) {
                     inst = ni; phase = PH_RUN; it = 0; fill = true;
                     force_mirror = (redo >= 0) || (a.test_flags & 2); redo = -1; mirrored = false;
-                    spec = (P.max_iter <= 1) && !u0only;
+                    spec = (P.max_iter <= 1) && !u0only && !(ROLL && S > 1);
+                    if constexpr (ROLL) { rs = 0; pend = 0; area = 0; gzero = false; vprev = false; lazy = false; }
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);
+                    if constexpr (ROLL) sx0.store(0, x0);
                     if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
                     if constexpr (IB) {
                         // the instance's own box -> the lane's scratch rows (a missing / disabled family = +-inf).  Loads are issued
@@ -646,6 +734,13 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                         }
 #pragma unroll
                         for (int i = 0; i < NH - 1; ++i) { sd.store(i, td[i]); sy.store(i, ty[i]); sz.store(i, tz[i]); }
+                        if constexpr (ROLL) {   // the state step 0 starts from -> mirror rows 1
+#pragma unroll
+                            for (int i = 0; i < NH - 1; ++i) {
+                                sc.stv<NU>(wm(1) + SM::WM_STAGE * i + SM::CX + SM::CU, td[i]);
+                                sc.stv<NU>(wm(1) + SM::WM_STAGE * i + SM::CX, tz[i]);
+                            }
+                        }
                     } else {
                         float zu[NU];
 #pragma unroll
@@ -663,7 +758,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
             // converged instance stores the g it reads before anything overwrites it.
             const bool wfill = WARM && a.wd;
             constexpr int RB = WARM ? 5 : 2;
-            float *wgo = (WARM && flush) ? a.wg + finst * XROW : nullptr;
+            float *wgo = (WARM && flush) ? a.wg + (ROLL ? inst : finst) * XROW : nullptr;
             auto refill_batch = [&](int i0, auto nb_tag) {
                 constexpr int NB = decltype(nb_tag)::value;
                 float gv[NB][2 * NX];
@@ -686,6 +781,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                                 for (int j = 0; j < NX; ++j) gv[q][j] = 0.f;
                             } else gload<float, NX>(a.wg + inst * XROW + (i0 + q) * NX, *reinterpret_cast<float(*)[NX]>(gv[q]));
                             gload<float, NX>(a.wv + inst * XROW + (i0 + q) * NX, *reinterpret_cast<float(*)[NX]>(gv[q] + NX));
+                            if constexpr (ROLL) sc.stv<NX>(wm(1) + SM::WM_STAGE * (i0 + q), *reinterpret_cast<float(*)[NX]>(gv[q] + NX));
                         }
                     } else {
 #pragma unroll
@@ -738,15 +834,29 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
         float pri_x = 0.f, dua_x = 0.f, pri_u = 0.f, dua_u = 0.f;
         {
             float x[NX];
+            if constexpr (ROLL) sx0.load(0, x);
+            else {
 #pragma unroll
-            for (int j = 0; j < NX; ++j) x[j] = x0[j];
+                for (int j = 0; j < NX; ++j) x[j] = x0[j];
+            }
             const bool wr = emit || (spec && phase == PH_RUN);
             float *xo = (wr && a.x) ? a.x + inst * XROW : nullptr;
             float *uo = (wr && a.u) ? a.u + inst * UROW : nullptr;
+            const bool any_vprev = ROLL && __any_sync(FULLM, vprev);
 
-            auto xpart = [&](int i, float (&gv)[2 * NX], const float (&bxl)[NX], const float (&bxh)[NX]) {
+            auto xpart = [&](int i, float (&gv)[2 * NX], const float (&bxl)[NX], const float (&bxh)[NX], const float (&vsub)[NX]) {
                 // state slack / dual / residuals for stage i (uses x_i)
                 xs.wait(gv);
+                if constexpr (ROLL) {   // first sweep of a step on this lane: g = 0; exact hand-over: v from the mirror rows
+#pragma unroll
+                    for (int j = 0; j < NX; ++j)
+                        if (gzero) gv[j] = 0.f;
+                    if (any_vprev) {
+#pragma unroll
+                        for (int j = 0; j < NX; ++j)
+                            if (vprev) gv[NX + j] = vsub[j];
+                    }
+                }
                 float g[NX], vn[NX];
 #pragma unroll
                 for (int j = 0; j < NX; j += 2) {
@@ -774,6 +884,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
             for (int i = 0; i < NH - 1; ++i) {
                 float gv[2 * NX];
                 xs.load_issue(i, gv);
+                float vsub[NX];
+                if constexpr (ROLL) { if (any_vprev && vprev) sc.ldv<NX>(wm(varea) + SM::WM_STAGE * i, vsub); }
                 // the instance's own box for this stage: 8 coalesced 16-byte loads from the lane's scratch rows, in flight
                 // behind the mat-vecs below
                 float bxl[NX], bxh[NX], bul[NU], buh[NU];
@@ -835,7 +947,10 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 // u(:,0): with the trajectory outputs it is written by the emitting trip; a controls-only solve stores it in EVERY
                 // trip (16 bytes per lane, the terminating trip's value is the last one written) -- cheaper than keeping it in
                 // four registers across the sweep (measured: 10.21 -> 10.10 ms per 1M-instance launch)
-                if (i == 0 && a.u0 && (u0only ? phase == PH_RUN : wr)) gstore<float, NU>(a.u0 + inst * NU, u);
+                if (i == 0 && a.u0 && (!ROLL || rs >= S - 1) && (u0only ? phase == PH_RUN : wr)) gstore<float, NU>(a.u0 + inst * NU, u);
+                if constexpr (ROLL) {   // a step the lane continues from: the control applied, every trip (the last one written counts)
+                    if (i == 0 && rs < S - 1 && phase == PH_RUN && a.roll_u0) gstore<float, NU>(a.roll_u0 + ((long long)rs * a.batch + inst) * NU, u);
+                }
                 // x_{i+1} = A x_i + B u_i                                                            :35
                 float2 xn[NX / 2];
                 if constexpr (FAST) {
@@ -852,9 +967,12 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
 #pragma unroll
                     for (int j = 0; j < NX / 2; ++j) xn[j] = add2(ka[NU / 2 + j], bu[j]);
                 }
-                xpart(i, gv, bxl, bxh);
+                xpart(i, gv, bxl, bxh, vsub);
 #pragma unroll
                 for (int j = 0; j < NX / 2; ++j) { x[2 * j] = xn[j].x; x[2 * j + 1] = xn[j].y; }
+                if constexpr (ROLL) {   // x_1 = Adyn x0 + Bdyn u0: the plant's next state if this trip ends the step
+                    if (i == 0 && rs < S - 1 && phase == PH_RUN) sx1.store(0, x);
+                }
             }
             {
                 float gv[2 * NX];
@@ -864,9 +982,12 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                     sc.ldv<NX>(a.sc_ib + SM::IB_STAGE * (NH - 1), bxl);
                     sc.ldv<NX>(a.sc_ib + SM::IB_STAGE * (NH - 1) + SM::CX, bxh);
                 }
-                xpart(NH - 1, gv, bxl, bxh);
+                float vsub[NX];
+                if constexpr (ROLL) { if (any_vprev && vprev) sc.ldv<NX>(wm(varea) + SM::WM_STAGE * (NH - 1), vsub); }
+                xpart(NH - 1, gv, bxl, bxh, vsub);
             }
             xs.fence_st();
+            if constexpr (ROLL) { gzero = false; vprev = false; }
         }
 
         // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
@@ -880,7 +1001,22 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 res[0] = pri_x; res[1] = __fmul_rn(dua_x, P.rho); res[2] = pri_u; res[3] = __fmul_rn(dua_u, P.rho);
             }
             const bool conv = chk && res[0] < P.pri_tol && res[2] < P.pri_tol && res[1] < P.dua_tol && res[3] < P.dua_tol;
-            if (WARM && a.wd && conv && it > 1 && !mirrored) {
+            bool rolled = false;
+            if constexpr (ROLL) {
+                if (lazy && it == 1 && chk && res[0] < P.pri_tol && res[2] < P.pri_tol &&
+                    !(res[1] > __fmul_rn(__fadd_rn(dprev_x, P.dua_tol), 1.001f) || res[3] > __fmul_rn(__fadd_rn(dprev_u, P.dua_tol), 1.001f))) {
+                    pend = 3; rolled = true;   // the lazy first iteration might end the step: again, from the exact state
+                } else if (conv && it > 1 && !mirrored) {
+                    pend = 3; rolled = true;   // early exit without the mirror: the step again, from its start state, mirror forced
+                } else if (rs < S - 1 && (conv || it >= P.max_iter)) {
+                    if (a.roll_iter) a.roll_iter[(long long)rs * a.batch + inst] = it;
+                    if (a.roll_status) a.roll_status[(long long)rs * a.batch + inst] = conv ? 1 : 11;
+                    n_iter += (unsigned)it; n_solved += conv ? 1u : 0u; ++n_inst;
+                    pend = conv ? 1 : 2; rolled = true;   // (2: this trip's backward sweep still runs, admm.cpp:141-144, and mirrors)
+                }
+            }
+            if (rolled) {
+            } else if (!ROLL && WARM && a.wd && conv && it > 1 && !mirrored) {
                 // Converged, but the previous backward sweep did not mirror d / v / z (the predicate below did not see it coming:
                 // not observed in 150,000 hover / closed-loop solves at factor 4, but nothing guarantees it).  Nothing of this
                 // instance has touched the caller's warm buffers yet: solve it again from there with the mirror forced on.
@@ -891,12 +1027,18 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 if (a.resid) *reinterpret_cast<float4 *>(a.resid + inst * 4) = make_float4(res[0], res[1], res[2], res[3]);
                 n_iter += (unsigned)it; n_solved += conv ? 1u : 0u; ++n_inst;
                 final_bwd = !conv;
-                if (WARM && conv && a.wd) { flush = it > 1 ? 2 : 1; finst = inst; }   // written back at the top of the next trip
+                if constexpr (!ROLL) {
+                    if (WARM && conv && a.wd) { flush = it > 1 ? 2 : 1; finst = inst; }   // written back at the top of the next trip
+                } else {
+                    // the caller's d, v, z are those of step 0: always written, from the mirror rows that hold the reference's state -- after
+                    // a max_iter exit the ones this trip's backward sweep is about to fill (no direct write-back path in these instances)
+                    flush = 2; farea = (!conv || it > 1) ? area : (area ^ 1);
+                }
                 if (u0only) { phase = PH_FREE; finished = true; }   // u(:,0) of this very trip is already in the output
                 else if (spec) { phase = PH_FREE; finished = true; }   // x,u of this very trip are already in the output
                 else phase = PH_EMIT;
                 spec = false;
-            } else if (!u0only) {
+            } else if (!u0only && !(ROLL && rs < S - 1)) {
                 // predict termination in the next trip: last allowed iteration, or every residual within 25 % of its
                 // tolerance at a check (ADMM crawls across the threshold); a wrong guess only costs stores
                 constexpr float SF = TMPC_SPEC_FACTOR;
@@ -911,7 +1053,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
 
         // ------------------------------------------------------------------ backward sweep
         // update_linear_cost (admm.cpp:77-85) recomputed per stage + backward_pass_grad (:15-22)
-        const bool cont = (phase == PH_RUN);
+        const bool cont = (phase == PH_RUN) && !(ROLL && (pend == 1 || pend == 3));
         // Warm start: the caller's buffers must end up as the reference leaves its workspace (SURVEY 8a note W):
         //   max_iter exit (wfbw): this trip's backward still runs (admm.cpp:141-144): d, v = vnew, z = znew, g, y of this iteration;
         //   early exit  (flush): g, y of this iteration, but d, v, z of the iteration BEFORE (admm.cpp:135-138) -- which the forward
@@ -921,16 +1063,17 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
         //                        largest ratio seen one iteration before convergence is 3.0; a miss is caught above and the
         //                        instance is solved again).  That is 3-5 mirrored sweeps per solve instead of 14-34, and the
         //                        caller's buffers are written exactly once, at the top of the trip after the instance ends.
-        const bool wfbw = WARM && final_bwd && a.wd;
+        const bool wfbw = !ROLL && WARM && final_bwd && a.wd;
+        const bool rfbw = ROLL && final_bwd;   // fused loop: the last step's max_iter exit mirrors instead
         bool wmir = false;
         if constexpr (WARM) {
             constexpr float MF = TMPC_MIRROR_FACTOR;
             const bool next_chk = ((it + 1) % P.check_term) == 0;
             const bool near = !chk_now || (res[0] < MF * P.pri_tol && res[2] < MF * P.pri_tol && res[1] < MF * P.dua_tol && res[3] < MF * P.dua_tol);
-            wmir = cont && a.wd && (force_mirror || (next_chk && near && !(a.test_flags & 1)));
+            wmir = (cont || rfbw) && a.wd && (force_mirror || (ROLL && (pend == 2 || rfbw)) || (next_chk && near && !(a.test_flags & 1)));
             if (cont) mirrored = wmir;
         }
-        if (__any_sync(FULLM, cont || wfbw)) {
+        if (__any_sync(FULLM, cont || wfbw || rfbw)) {
             float p[NX];
             const float *xr_base = a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
             float *wdo = wfbw ? a.wd + inst * UROW : nullptr;
@@ -947,7 +1090,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                     if (wfbw) {
                         gstore<float, NX>(wgo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv));
                         gstore<float, NX>(wvo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
-                    } else if (wmir) sc.stv<NX>(a.sc_wm + SM::WM_STAGE * (NH - 1), *reinterpret_cast<float(*)[NX]>(gv + NX));
+                    } else if (wmir) sc.stv<NX>(wm(area) + SM::WM_STAGE * (NH - 1), *reinterpret_cast<float(*)[NX]>(gv + NX));
                 }
 #pragma unroll
                 for (int j = 0; j < NX; ++j) {
@@ -1016,7 +1159,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 sd.store(i, d, cont);
                 if constexpr (WARM) {
                     if (wfbw) gstore<float, NU>(wdo + i * NU, d);
-                    else if (wmir) { sc.stv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX + SM::CU, d); sc.stv<NU>(a.sc_wm + SM::WM_STAGE * i + SM::CX, z); }
+                    else if (wmir) { sc.stv<NU>(wm(area) + SM::WM_STAGE * i + SM::CX + SM::CU, d); sc.stv<NU>(wm(area) + SM::WM_STAGE * i + SM::CX, z); }
                 }
                 float2 kr[NX / 2];
                 matvec2<O::Ktr, NX, NU, NX, 0, FAST>(P.Kr, r, kr, Z);
@@ -1028,7 +1171,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                         gstore<float, NX>(wvo + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
                         gstore<float, NU>(wzo + i * NU, z);
                     } else if (wmir) {
-                        sc.stv<NX>(a.sc_wm + SM::WM_STAGE * i, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                        sc.stv<NX>(wm(area) + SM::WM_STAGE * i, *reinterpret_cast<float(*)[NX]>(gv + NX));
                     }
                 }
 #pragma unroll
@@ -1048,18 +1191,19 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
     }
 
     if (a.stats) {
+        unsigned long long t_iter = n_iter, t_solved = n_solved, t_trips = n_trips, t_inst = n_inst;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            n_iter += __shfl_down_sync(FULLM, n_iter, o);
-            n_solved += __shfl_down_sync(FULLM, n_solved, o);
-            n_trips += __shfl_down_sync(FULLM, n_trips, o);
-            n_inst += __shfl_down_sync(FULLM, n_inst, o);
+            t_iter += __shfl_down_sync(FULLM, t_iter, o);
+            t_solved += __shfl_down_sync(FULLM, t_solved, o);
+            t_trips += __shfl_down_sync(FULLM, t_trips, o);
+            t_inst += __shfl_down_sync(FULLM, t_inst, o);
         }
         if (lane == 0) {
-            atomicAdd(a.stats + 0, n_iter);
-            atomicAdd(a.stats + 1, n_solved);
-            atomicAdd(a.stats + 2, n_trips);
-            atomicAdd(a.stats + 3, n_inst);
+            atomicAdd(a.stats + 0, t_iter);
+            atomicAdd(a.stats + 1, t_solved);
+            atomicAdd(a.stats + 2, t_trips);
+            atomicAdd(a.stats + 3, t_inst);
         }
     }
     if constexpr (TM) {

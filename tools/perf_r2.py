@@ -77,7 +77,7 @@ if "warm" in which:
             del os.environ[k]
 if "rollout" in which:
     x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
-    for env in ({}, {"TMPC_NO_WM_SCRATCH": "1"}):
+    for env in ({}, {"TMPC_ROLL": "0"}, {"TMPC_TEST_MIRROR": "8"}):
         os.environ.update(env)
         s = capi.Solver(prob, dtype=np.float32, policy="parity")
         b = capi.Batch(s, B)
@@ -90,8 +90,10 @@ if "rollout" in which:
             if best is None or ms < best[0]:
                 best = (ms, int(ith.sum().item()))
         ms, iters = best
-        print("rollout hover 10 steps %r: %.3f ms  %.3e MPC steps/s  %.3e it/s  mean it/step %.2f  frac %.3f" %
-              (env, ms, B * steps / ms * 1e3, iters / ms * 1e3, iters / (B * steps), iters * 11918 / (ms * 1e-3) / PEAK), flush=True)
+        q = s.stats()
+        print("rollout hover 10 steps %r: %.3f ms  %.3e MPC steps/s  %.3e it/s  mean it/step %.2f  frac %.3f  trips/it (last launch) %.3f" %
+              (env, ms, B * steps / ms * 1e3, iters / ms * 1e3, iters / (B * steps), iters * 11918 / (ms * 1e-3) / PEAK,
+               q["trips"] / max(1, q["iterations"])), flush=True)
         b.close(); s.close()
         for k in env:
             del os.environ[k]
