@@ -378,6 +378,13 @@ struct LaneScratch {
 #pragma unroll
         for (int k = 0; k < D / 4; ++k) st(c + k, make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
     }
+    // the same through a row pointer the caller steps itself (chunk offsets become immediates of the stores)
+    __device__ __forceinline__ float4 *row(int c) const { return base + (long long)c * 32; }
+    template <int D> __device__ static __forceinline__ void stp(float4 *p, const float (&o)[D])
+    {
+#pragma unroll
+        for (int k = 0; k < D / 4; ++k) __stcg(p + k * 32, make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+    }
 };
 // chunk maps (NX = 12, NU = 4): per-instance box of stage i = 8 chunks [xmin(3) xmax(3) umin(1) umax(1)]; warm mirror of
 // stage i = 5 chunks [v(3) z(1) d(1)] (last stage: v only)
@@ -398,8 +405,8 @@ template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
     static constexpr size_t BYTES = 3 * SU::BYTES + SP::BYTES + XBYTES + 16;
     // CSM instances: + the model image (128-byte aligned) and its mbarrier
     static constexpr size_t BYTES_CSM = (BYTES + 127) / 128 * 128 + sizeof(ModelF32<NX, NU, NH>) + 16;
-    // ROLL instances (TM): + two x rows per lane, the step's measurement and the plant's next state
-    static constexpr size_t BYTES_ROLL = BYTES + 2 * SP::BYTES;
+    // ROLL instances (TM): + two x rows per lane, the step's measurement and the plant's next state, and the control applied
+    static constexpr size_t BYTES_ROLL = BYTES + 2 * SP::BYTES + SVec<float, NU, 1, BLOCK>::BYTES;
 };
 
 // CB: the bounds are the same at every horizon stage (the usual box constraints, e.g. every example of the reference):
@@ -469,6 +476,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
     // the coefficient pairs of the backward sweep out of the loop (profiles/r02_ncu_fused_loop.md)
     typename L::SP sx1(sp, tid);
     typename L::SP sx0(sp + L::SP::BYTES, tid);
+    SVec<float, NU, 1, BLOCK> su0(sp + 2 * L::SP::BYTES, tid);   // u(:,0) of the latest forward sweep
 
     uint32_t tmem_base = 0;
     if constexpr (TM) {
@@ -526,7 +534,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
     int pend = 0;         // what the top of the next trip does: 1 next step after an early exit, 2 after a max_iter exit, 3 same step again
     int area = 0, varea = 0, farea = 0;
     bool gzero = false;   // this trip's forward sweep reads g as zero (reset duals; g lives in tensor memory, written collectively)
-    bool vprev = false;   // this trip's forward sweep takes v from the mirror rows `varea` (v one iteration behind)
+    bool vprev = false;   // exact hand-over: before this trip's forward sweep v is replaced by the mirror rows `varea` (one iteration behind)
     bool lazy = false;    // this step's first iteration ran on the on-chip v, z (see above)
     float dprev_x = 0.f, dprev_u = 0.f;   // rho-scaled dual residuals of the iteration that ended the previous step
     auto wm = [&](int ar) -> int { return a.sc_wm + (ROLL ? ar * SM::WM_CHUNKS : 0); };
@@ -594,6 +602,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                     sx0.store(0, x0);
                     gstore<float, NX>(const_cast<float *>(a.x0) + inst * NX, x0);
                     if (a.roll_x) gstore<float, NX>(a.roll_x + ((long long)rs * a.batch + inst) * NX, x0);
+                    if (a.roll_u0) { float t[NU]; su0.load(0, t); gstore<float, NU>(a.roll_u0 + ((long long)rs * a.batch + inst) * NU, t); }
                     rs += 1;
                     area = src ^ 1;
                     force_mirror = (a.test_flags & 2) != 0;
@@ -603,6 +612,23 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 it = 0; mirrored = false; pend = 0;
                 res[0] = res[1] = res[2] = res[3] = 0.f;
                 spec = (rs >= S - 1) && (P.max_iter <= 1);
+            }
+            // exact hand-over: v of the reference's state into tensor memory (collective: the other lanes write back what they read).
+            // Off the common path -- a lazy step never gets here
+            if (__any_sync(FULLM, vprev)) {
+#pragma unroll 1
+                for (int i = 0; i < NH; ++i) {
+                    float gv[2 * NX], vsub[NX];
+                    xs.load_issue(i, gv);
+                    if (vprev) sc.ldv<NX>(wm(varea) + SM::WM_STAGE * i, vsub);
+                    xs.wait(gv);
+#pragma unroll
+                    for (int j = 0; j < NX; ++j)
+                        if (vprev) gv[NX + j] = vsub[j];
+                    xs.store(i, *reinterpret_cast<float(*)[NX]>(gv), *reinterpret_cast<float(*)[NX]>(gv + NX));
+                }
+                xs.fence_st();
+                vprev = false;
             }
         }
         // ------------------------------------------------------------------ lane refill (warp-uniform branch)
@@ -842,20 +868,15 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
             const bool wr = emit || (spec && phase == PH_RUN);
             float *xo = (wr && a.x) ? a.x + inst * XROW : nullptr;
             float *uo = (wr && a.u) ? a.u + inst * UROW : nullptr;
-            const bool any_vprev = ROLL && __any_sync(FULLM, vprev);
+            const bool stash = ROLL && rs < S - 1 && phase == PH_RUN;   // a step the lane continues from: u(:,0) and x_1 kept on chip
 
-            auto xpart = [&](int i, float (&gv)[2 * NX], const float (&bxl)[NX], const float (&bxh)[NX], const float (&vsub)[NX]) {
+            auto xpart = [&](int i, float (&gv)[2 * NX], const float (&bxl)[NX], const float (&bxh)[NX]) {
                 // state slack / dual / residuals for stage i (uses x_i)
                 xs.wait(gv);
-                if constexpr (ROLL) {   // first sweep of a step on this lane: g = 0; exact hand-over: v from the mirror rows
+                if constexpr (ROLL) {   // first sweep of a step on this lane: g = 0
 #pragma unroll
                     for (int j = 0; j < NX; ++j)
                         if (gzero) gv[j] = 0.f;
-                    if (any_vprev) {
-#pragma unroll
-                        for (int j = 0; j < NX; ++j)
-                            if (vprev) gv[NX + j] = vsub[j];
-                    }
                 }
                 float g[NX], vn[NX];
 #pragma unroll
@@ -884,8 +905,6 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
             for (int i = 0; i < NH - 1; ++i) {
                 float gv[2 * NX];
                 xs.load_issue(i, gv);
-                float vsub[NX];
-                if constexpr (ROLL) { if (any_vprev && vprev) sc.ldv<NX>(wm(varea) + SM::WM_STAGE * i, vsub); }
                 // the instance's own box for this stage: 8 coalesced 16-byte loads from the lane's scratch rows, in flight
                 // behind the mat-vecs below
                 float bxl[NX], bxh[NX], bul[NU], buh[NU];
@@ -947,9 +966,11 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 // u(:,0): with the trajectory outputs it is written by the emitting trip; a controls-only solve stores it in EVERY
                 // trip (16 bytes per lane, the terminating trip's value is the last one written) -- cheaper than keeping it in
                 // four registers across the sweep (measured: 10.21 -> 10.10 ms per 1M-instance launch)
-                if (i == 0 && a.u0 && (!ROLL || rs >= S - 1) && (u0only ? phase == PH_RUN : wr)) gstore<float, NU>(a.u0 + inst * NU, u);
-                if constexpr (ROLL) {   // a step the lane continues from: the control applied, every trip (the last one written counts)
-                    if (i == 0 && rs < S - 1 && phase == PH_RUN && a.roll_u0) gstore<float, NU>(a.roll_u0 + ((long long)rs * a.batch + inst) * NU, u);
+                if constexpr (!ROLL) {
+                    if (i == 0 && a.u0 && (u0only ? phase == PH_RUN : wr)) gstore<float, NU>(a.u0 + inst * NU, u);
+                } else {
+                    if (i == 0 && !stash && a.u0 && (u0only ? phase == PH_RUN : wr)) gstore<float, NU>(a.u0 + inst * NU, u);
+                    if (i == 0 && stash) su0.store(0, u);   // every trip: the last one written counts
                 }
                 // x_{i+1} = A x_i + B u_i                                                            :35
                 float2 xn[NX / 2];
@@ -967,11 +988,11 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
 #pragma unroll
                     for (int j = 0; j < NX / 2; ++j) xn[j] = add2(ka[NU / 2 + j], bu[j]);
                 }
-                xpart(i, gv, bxl, bxh, vsub);
+                xpart(i, gv, bxl, bxh);
 #pragma unroll
                 for (int j = 0; j < NX / 2; ++j) { x[2 * j] = xn[j].x; x[2 * j + 1] = xn[j].y; }
                 if constexpr (ROLL) {   // x_1 = Adyn x0 + Bdyn u0: the plant's next state if this trip ends the step
-                    if (i == 0 && rs < S - 1 && phase == PH_RUN) sx1.store(0, x);
+                    if (i == 0 && stash) sx1.store(0, x);
                 }
             }
             {
@@ -982,12 +1003,10 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                     sc.ldv<NX>(a.sc_ib + SM::IB_STAGE * (NH - 1), bxl);
                     sc.ldv<NX>(a.sc_ib + SM::IB_STAGE * (NH - 1) + SM::CX, bxh);
                 }
-                float vsub[NX];
-                if constexpr (ROLL) { if (any_vprev && vprev) sc.ldv<NX>(wm(varea) + SM::WM_STAGE * (NH - 1), vsub); }
-                xpart(NH - 1, gv, bxl, bxh, vsub);
+                xpart(NH - 1, gv, bxl, bxh);
             }
             xs.fence_st();
-            if constexpr (ROLL) { gzero = false; vprev = false; }
+            if constexpr (ROLL) gzero = false;
         }
 
         // ------------------------------------------------------------------ termination (admm.cpp:91-109, :135-138)
@@ -1081,6 +1100,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
             float *wzo = wfbw ? a.wz + inst * UROW : nullptr;
             float *wgo = wfbw ? a.wg + inst * XROW : nullptr;
             float *wyo = wfbw ? a.wy + inst * UROW : nullptr;
+            float4 *mrow = nullptr;   // this sweep's mirror rows, stage by stage (only dereferenced under wmir)
+            if constexpr (WARM) mrow = sc.row(wm(area) + SM::WM_STAGE * (NH - 1));
             {
                 float gv[2 * NX], pn[NX];
                 xs.load_issue(NH - 1, gv);
@@ -1090,7 +1111,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                     if (wfbw) {
                         gstore<float, NX>(wgo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv));
                         gstore<float, NX>(wvo + (NH - 1) * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
-                    } else if (wmir) sc.stv<NX>(wm(area) + SM::WM_STAGE * (NH - 1), *reinterpret_cast<float(*)[NX]>(gv + NX));
+                    } else if (wmir) LaneScratch::stp<NX>(mrow, *reinterpret_cast<float(*)[NX]>(gv + NX));
                 }
 #pragma unroll
                 for (int j = 0; j < NX; ++j) {
@@ -1103,6 +1124,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
             for (int i = NH - 2; i >= 0; --i) {
                 float gv[2 * NX];
                 xs.load_issue(i, gv);
+                if constexpr (WARM) mrow -= SM::WM_STAGE * 32;
                 float z[NU], y[NU], r[NU], xr[NX];
                 sz.load(i, z);
                 sy.load(i, y);
@@ -1159,7 +1181,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                 sd.store(i, d, cont);
                 if constexpr (WARM) {
                     if (wfbw) gstore<float, NU>(wdo + i * NU, d);
-                    else if (wmir) { sc.stv<NU>(wm(area) + SM::WM_STAGE * i + SM::CX + SM::CU, d); sc.stv<NU>(wm(area) + SM::WM_STAGE * i + SM::CX, z); }
+                    else if (wmir) { LaneScratch::stp<NU>(mrow + (SM::CX + SM::CU) * 32, d); LaneScratch::stp<NU>(mrow + SM::CX * 32, z); }
                 }
                 float2 kr[NX / 2];
                 matvec2<O::Ktr, NX, NU, NX, 0, FAST>(P.Kr, r, kr, Z);
@@ -1171,7 +1193,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                         gstore<float, NX>(wvo + i * NX, *reinterpret_cast<float(*)[NX]>(gv + NX));
                         gstore<float, NU>(wzo + i * NU, z);
                     } else if (wmir) {
-                        sc.stv<NX>(wm(area) + SM::WM_STAGE * i, *reinterpret_cast<float(*)[NX]>(gv + NX));
+                        LaneScratch::stp<NX>(mrow, *reinterpret_cast<float(*)[NX]>(gv + NX));
                     }
                 }
 #pragma unroll

@@ -583,6 +583,68 @@ def run_configs(torch, dist, pkg, args, dev, local, rank, world, barrier, allmax
           BYTES_PER_SOLVE["q"], chk, {"executed_flop_per_iteration": exec_flop_of(st.get("pattern"))})
     run.close(); del run; torch.cuda.empty_cache()
 
+    # ---- the examples' closed loop (quadrotor_hovering.cpp:90-114) on the device: 10 MPC steps per instance from the cold start
+    #      (reset duals, warm d / v / z, plant step x <- Adyn x + Bdyn u0); fp32 12/4/10 runs it as ONE persistent launch
+    try:
+        Bh = args.batch // sc
+        b0, b1 = pkg.sharding.shard_range(rank, world, per_rank=Bh)
+        x0, xref = W.quadrotor_hover_batch(b0, b1, mult=args.mult)
+        s = pkg.capi.Solver(quad, dtype=np.float32, policy=args.policy, device=local)
+        bt = pkg.capi.Batch(s, Bh)
+        steps_h = 10
+        ith = torch.empty((steps_h, Bh), dtype=torch.int32, device=dev)
+        sth = torch.empty((steps_h, Bh), dtype=torch.int32, device=dev)
+        u0h = torch.empty((steps_h, Bh, 4), dtype=torch.float32, device=dev)
+        x0h = torch.empty((steps_h + 1, Bh, 12), dtype=torch.float32, device=dev)
+        reps_ms = []
+        for rep in range(3):     # (each repetition restarts the loop from the cold workspace; the first one also allocates)
+            bt.reset(); bt.set_x0(x0); bt.set_xref(xref)
+            barrier()
+            s._check(s.lib.tmpc_batch_rollout(bt._b, steps_h, 1, x0h.data_ptr(), u0h.data_ptr(), ith.data_ptr(), sth.data_ptr(),
+                                              pkg.capi.TMPC_MEM_DEVICE), "rollout")
+            reps_ms.append(allmax(bt.last_rollout_ms()))
+        ms_h = min(reps_ms[1:])
+        launches_h = s.stats()["launches"]
+        iters_h = allsum(float(ith.sum().item()))
+        chk = None
+        if rank == 0:
+            from oracle.pyoracle import OracleLib
+            orc = OracleLib()
+            t0c = time.perf_counter()
+            n = min(CHECK_PREFIX // 4, Bh)
+            xc, warm, bad = x0[:n].copy(), None, {"iter": 0, "status": 0, "u0": 0, "plant_state": 0}
+            for k in range(steps_h):
+                r = orc.solve_batch(quad, xc, xref, dtype=np.float32, warm=warm, want_state=True, nthreads=os.cpu_count() or 1)
+                bad["iter"] += int((ith[k, :n].cpu().numpy() != r.iter).sum())
+                bad["status"] += int((sth[k, :n].cpu().numpy() != r.status).sum())
+                bad["u0"] += int((u0h[k, :n].cpu().numpy() != r.u[:, 0, :]).sum())
+                xc = orc.plant_step(quad, xc, r.u[:, 0, :], dtype=np.float32)
+                bad["plant_state"] += int((x0h[k + 1, :n].cpu().numpy() != xc).sum())
+                warm = {q: r.state[q].copy() for q in ("d", "y", "g", "v", "z")}
+                warm["y"][:] = 0
+                warm["g"][:] = 0
+            chk = {"instances": n, "mpc_steps": steps_h, "bit_exact": all(v == 0 for v in bad.values()), "mismatching_elements": bad,
+                   "compared": list(bad), "oracle_seconds": time.perf_counter() - t0c,
+                   "how": "the oracle's closed loop (solve, its own plant step, duals reset) for the first %d instances, every step" % n}
+        tf = iters_h / world * FLOP_PER_ITER["q"] / (ms_h * 1e-3) / 1e12
+        out["closed_loop_rollout_hover"] = {
+            "workload": "the hovering example's closed loop (quadrotor_hovering.cpp:90-114) for every instance of the headline batch, on the device: "
+                        "%d MPC steps from the cold start, duals reset every step, warm d / v / z, plant step; histories of x, u0, iter, status "
+                        "written to HBM; tmpc_batch_rollout" % steps_h,
+            "instances_total": Bh * world, "instances_per_gpu": Bh, "mpc_steps": steps_h, "value": Bh * world * steps_h / (ms_h * 1e-3),
+            "unit": "MPC steps/s (= solves/s)", "ms_per_rollout": ms_h, "ms_per_rollout_all_repetitions": reps_ms, "ms_per_mpc_step": ms_h / steps_h, "launches_per_rollout": launches_h,
+            "fused": os.environ.get("TMPC_ROLL", "1") != "0",
+            "iters_per_s": iters_h / (ms_h * 1e-3), "mean_iters_per_solve": iters_h / (Bh * world * steps_h),
+            "roofline": {"bound": "fp32", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                         "algorithmic_flop_per_iteration": FLOP_PER_ITER["q"], "traffic": None},
+            "oracle_check": chk}
+        log("configs.closed_loop_rollout_hover: %.3e MPC steps/s, %.2f ms per %d-step rollout, frac %.3f" %
+            (out["closed_loop_rollout_hover"]["value"], ms_h, steps_h, tf / peak_tf))
+        bt.close(); s.close(); del ith, sth, u0h, x0h
+    except Exception as e:   # additional evidence: a failure here must not void the headline line
+        out["closed_loop_rollout_hover"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+
     # ---- the reference's SHIPPED scalar type (glob_opts.hpp:3 `typedef double tinytype`): the headline workload in fp64, a quarter
     #      of the batch per GPU (half the instances per SM of the fp32 kernel, a quarter of its arithmetic rate)
     Bf = max(args.batch // 4 // sc, 1024)

@@ -162,7 +162,15 @@ def test_large_rollout_uses_iteration_history_schedule(pkg, oracle):
     b = pkg.capi.Batch(s, B)
     b.set_x0(x0)
     b.set_xref(xref)
-    h = b.rollout(steps, reset_duals=True)
+    old = os.environ.get("TMPC_ROLL")
+    os.environ["TMPC_ROLL"] = "0"      # one launch per MPC step (the fused loop has its own tests, test_gpu_roll.py)
+    try:
+        h = b.rollout(steps, reset_duals=True)
+    finally:
+        if old is None:
+            del os.environ["TMPC_ROLL"]
+        else:
+            os.environ["TMPC_ROLL"] = old
     assert s.stats()["scheduled"] == 2
     xc, warm = x0[:n].copy(), None
     for k in range(steps):
