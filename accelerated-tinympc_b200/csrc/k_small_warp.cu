@@ -54,6 +54,20 @@ bool pick_warp(int policy, bool warm, KernelInfo &out)
 
 }  // namespace
 
+// fused closed loop at 4/1/10 (admm_kernel_small_roll): PARITY, warm buffers; block 256 (three generations of v in registers) or 384
+bool lookup_small_roll(int block, KernelInfo &out)
+{
+    KernelInfo k;
+    k.fn = block == 384 ? (const void *)&tmpc::admm_kernel_small_roll<4, 10, 384> : (const void *)&tmpc::admm_kernel_small_roll<4, 10, 256>;
+    k.smem = 0;
+    k.block = block == 384 ? 384 : 256;
+    k.model_bytes = sizeof(tmpc::Model<float, 4, 1, 10>);
+    k.model_kind = 0;
+    k.per_block = k.block;
+    out = k;
+    return true;
+}
+
 bool lookup_small(int block, int policy, bool warm, KernelInfo &out)
 {
     if (block == 256) return pick_small<4, 10, 256>(policy, warm, out);

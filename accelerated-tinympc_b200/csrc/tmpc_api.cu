@@ -773,6 +773,7 @@ bool lpt_wanted(const tmpc_ctx_impl *c, const KernelInfo &ki, const DevArgs &da)
     // 7.85 -> 9.65 ms per MPC step).  The warp-per-instance kernel moves 17 KB contiguous per instance and gains (19.7 -> 18.0 ms).
     // (a fused closed loop streams the state once per `roll_steps` solves and its claims are that much longer: there the order pays)
     if (da.wd && ki.model_kind != 2 && da.roll_steps <= 1) return false;
+    if (da.roll_steps > 1 && ki.model_kind != 1) return false;   // (4/1/10 closed loops: a handful of iterations per step, uniform claims)
     const long long lanes = (long long)ki.per_block * c->sm_count;
     return da.batch >= 2 * lanes && da.batch >= 16384;
 }
@@ -868,8 +869,13 @@ bool roll_supported(const tmpc_ctx_impl *c)
 {
     const char *e = getenv("TMPC_ROLL");
     if (e && !strcmp(e, "0")) return false;
-    return c->nx == 12 && c->nu == 4 && c->N == 10 && c->dtype == TMPC_F32 && c->policy == TMPC_ORDER_PARITY && kernel_variant() == 2 && !force_rt() &&
-           !c->ib_batch;
+    if (c->dtype != TMPC_F32 || c->policy != TMPC_ORDER_PARITY || force_rt() || c->ib_batch) return false;
+    if (c->nx == 12 && c->nu == 4 && c->N == 10) return kernel_variant() == 2;
+    if (c->nx == 4 && c->nu == 1 && c->N == 10) {   // register-resident kernel (tmpc_kernel_small.cuh), not with the generic development variants
+        const char *k = getenv("TMPC_KERNEL");
+        return !k || !strncmp(k, "small", 5);
+    }
+    return false;
 }
 
 int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool time_it)
@@ -878,8 +884,12 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
     const bool ib_f32 = c->ib_batch && ib_on_f32_kernel(c);
     if (da.roll_steps > 1) {
         // fused closed loop (tmpc_batch_rollout): the caller has checked roll_supported()
-        if (!warm || !da.wd || c->ib_batch || da.sys || !tmpc_dispatch::lookup_f32_roll(c->pattern, c->const_bounds, ki))
-            return fail(c, TMPC_ERR_UNSUPPORTED, "fused closed loop: no kernel");
+        bool ok = warm && da.wd && !c->ib_batch && !da.sys;
+        if (ok && c->nx == 4) {
+            const char *k = getenv("TMPC_KERNEL");
+            ok = tmpc_dispatch::lookup_small_roll(k && !strcmp(k, "small384") ? 384 : 256, ki);
+        } else if (ok) ok = tmpc_dispatch::lookup_f32_roll(c->pattern, c->const_bounds, ki);
+        if (!ok) return fail(c, TMPC_ERR_UNSUPPORTED, "fused closed loop: no kernel");
     } else if (ib_f32) {
         // per-instance bounds on the specialised fp32 12/4/10 kernel: each lane copies its instance's box into its coalesced
         // scratch rows at refill and projects onto it (IB instances of the kernel)

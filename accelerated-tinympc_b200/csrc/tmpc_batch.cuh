@@ -187,7 +187,8 @@ int batch_solve_async(tmpc_batch_impl *b, bool controls_only = false, int roll_s
     c->stats.instances = b->B;
     c->stats.launches = 0;
     const char *e = getenv("TMPC_LPT");
-    if (b->iter_valid && !(e && !strcmp(e, "0")) && !c->ib_batch && b->B >= 4LL * 256 * c->sm_count && b->B < (1LL << 31)) {
+    const bool uniform_claims = roll_steps > 1 && c->nx == 4;   // fused 4/1/10 loops: every claim is a few iterations per step, index order keeps the rows coalesced
+    if (b->iter_valid && !uniform_claims && !(e && !strcmp(e, "0")) && !c->ib_batch && b->B >= 4LL * 256 * c->sm_count && b->B < (1LL << 31)) {
         int rc = order_after_previous(c, c->stream);
         int bits = 1;
         while ((1 << bits) <= c->max_iter && bits < 31) ++bits;

@@ -41,6 +41,8 @@ bool lookup_f64p(int nx, int nu, int N, int dtype, int policy, bool warm, Kernel
 
 // register-resident single-input kernel, fp32 4/1/10 (tmpc_kernel_small.cuh); block = 256, 384 or 512
 bool lookup_small(int block, int policy, bool warm, KernelInfo &out);
+// the same shape running a whole closed loop per claimed instance in registers (SolveArgs::roll_steps MPC steps); block = 256 or 384
+bool lookup_small_roll(int block, KernelInfo &out);
 // fp32 32/8/50: variant 0 = four instances per warp (tmpc_kernel_warp4.cuh, default); 1 = one instance per warp, g, v in tensor
 // memory (tmpc_kernel_warp.cuh, 16 instances / SM); 2 = one instance per warp, all state in shared memory (12 / SM)
 bool lookup_warp(int variant, int policy, bool warm, KernelInfo &out);

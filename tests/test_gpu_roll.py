@@ -152,3 +152,23 @@ def test_fused_loop_continues_a_previous_rollout(pkg, oracle):
             assert_same(b.get(k)[:n], r.state[k], "B %d final workspace %s" % (B, k))
         b.close()
         s.close()
+
+
+@pytest.mark.parametrize("scale,max_iter,check", [(0.2, 100, 1), (1.0, 30, 1), (0.2, 2, 1), (0.5, 100, 2), (0.2, 1, 1)])
+def test_fused_loop_cartpole_registers(pkg, oracle, scale, max_iter, check):
+    """4/1/10 (codegen_cartpole.cpp:75-122): the register-resident fused loop (tmpc_kernel_small.cuh admm_kernel_small_roll) keeps both
+    generations of v, z, so the hand-over after an early exit is the reference's state by construction.  Steps of 1-4 iterations
+    (scale 0.2), instances pinned at max_iter (scale 1.0 / max_iter 2 / 1), check_termination 2."""
+    prob = dataclasses.replace(pkg.problems.cartpole(max_iter=max_iter), check_termination=check)
+    B, steps, n = 120_000, 6, 3_000
+    x0, xref = pkg.workloads.cartpole_batch(0, B)
+    x0 = (scale * x0).astype(np.float32)
+    fused = _run(pkg, prob, x0, xref, steps)
+    assert fused[2]["launches"] == 2
+    ho, r = _oracle_loop(oracle, prob, x0[:n], xref, steps)
+    _check(fused[0], fused[1], ho, r, n, "cartpole scale %g max_iter %d check %d" % (scale, max_iter, check))
+    if scale == 0.2 and max_iter == 100:
+        assert (ho["iter"] == 1).any() and (ho["iter"] == 2).any()
+    if max_iter <= 30:
+        assert (ho["status"] == 11).any()
+    _same_runs(fused, _run(pkg, prob, x0, xref, steps, TMPC_ROLL=0), "fused vs one launch per step")
