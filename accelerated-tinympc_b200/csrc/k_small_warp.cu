@@ -54,17 +54,21 @@ bool pick_warp(int policy, bool warm, KernelInfo &out)
 
 }  // namespace
 
-// fused closed loop at 4/1/10 (admm_kernel_small_roll): PARITY, warm buffers; block 256 (three generations of v in registers) or 384
-bool lookup_small_roll(int block, KernelInfo &out)
+// fused closed loop at 4/1/10 (admm_kernel_small_roll): PARITY, warm buffers; v of the reference in shared memory (160 B per lane)
+template <int BLOCK> KernelInfo make_info_small_roll()
 {
     KernelInfo k;
-    k.fn = block == 384 ? (const void *)&tmpc::admm_kernel_small_roll<4, 10, 384> : (const void *)&tmpc::admm_kernel_small_roll<4, 10, 256>;
-    k.smem = 0;
-    k.block = block == 384 ? 384 : 256;
+    k.fn = (const void *)&tmpc::admm_kernel_small_roll<4, 10, BLOCK>;
+    k.smem = tmpc::SVec<float, 4, 10, BLOCK>::BYTES;
+    k.block = BLOCK;
     k.model_bytes = sizeof(tmpc::Model<float, 4, 1, 10>);
     k.model_kind = 0;
-    k.per_block = k.block;
-    out = k;
+    k.per_block = BLOCK;
+    return k;
+}
+bool lookup_small_roll(int block, KernelInfo &out)
+{
+    out = block == 256 ? make_info_small_roll<256>() : block == 512 ? make_info_small_roll<512>() : make_info_small_roll<384>();
     return true;
 }
 

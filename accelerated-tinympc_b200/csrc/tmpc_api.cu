@@ -887,7 +887,7 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
         bool ok = warm && da.wd && !c->ib_batch && !da.sys;
         if (ok && c->nx == 4) {
             const char *k = getenv("TMPC_KERNEL");
-            ok = tmpc_dispatch::lookup_small_roll(k && !strcmp(k, "small384") ? 384 : 256, ki);
+            ok = tmpc_dispatch::lookup_small_roll(k && !strcmp(k, "small256") ? 256 : k && !strcmp(k, "small512") ? 512 : 384, ki);
         } else if (ok) ok = tmpc_dispatch::lookup_f32_roll(c->pattern, c->const_bounds, ki);
         if (!ok) return fail(c, TMPC_ERR_UNSUPPORTED, "fused closed loop: no kernel");
     } else if (ib_f32) {

@@ -289,8 +289,9 @@ admm_kernel_small(const __grid_constant__ Model<float, NX, 1, NH> P, const __gri
 // At this shape a closed-loop step takes 1-4 iterations, so the per-step path is bound by moving 1.1 KB of state through HBM for
 // ~3,500 FLOP; here that traffic is paid once per roll_steps steps.
 // The reference leaves v, z one iteration behind after an early exit (admm.cpp:135-138: the exit comes before v = vnew, z = znew).
-// The kernel keeps BOTH generations in registers -- the forward sweep writes vn, zn; v, z advance only when the iteration does not
-// end the step by convergence -- so the hand-over to the next step is the reference's state with no copy and no special case.
+// The kernel keeps BOTH generations on chip -- the forward sweep writes vn, zn (registers); v (shared memory, one 16-byte row per
+// stage and lane) and z advance only when the iteration does not end the step by convergence -- so the hand-over to the next step is
+// the reference's state with no special case.  (v in registers as well costs 40 more of them: 256 instead of 384 lanes per SM.)
 // PARITY order, warm buffers required (they receive the workspace the loop leaves: d, v, z, y, g of the last step).
 template <int NX, int NH, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1)
@@ -307,14 +308,16 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
     const unsigned lane = threadIdx.x & 31;
     const int S = a.roll_steps;
 
-    float2 g[NH][H], v[NH][H], vn[NH][H], pn[H];
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SVec<float, NX, NH, BLOCK> sv(smem, threadIdx.x);   // v as the reference holds it (one iteration behind vn until it advances)
+    float2 g[NH][H], vn[NH][H], pn[H];
     float d[NH - 1], y[NH - 1], z[NH - 1], zn[NH - 1];
     float x0[NX], x1[NX];
     float u0r = 0.f;
 #pragma unroll
     for (int i = 0; i < NH; ++i)
 #pragma unroll
-        for (int j = 0; j < H; ++j) g[i][j] = v[i][j] = vn[i][j] = f2(0.f, 0.f);
+        for (int j = 0; j < H; ++j) g[i][j] = vn[i][j] = f2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NH - 1; ++i) d[i] = y[i] = z[i] = zn[i] = 0.f;
 #pragma unroll
@@ -365,8 +368,9 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                     for (int i = 0; i < NH; ++i) {
                         float tv[NX];
                         gload<float, NX>(a.wv + inst * XROW + i * NX, tv);
+                        sv.store(i, tv);
 #pragma unroll
-                        for (int j = 0; j < H; ++j) { g[i][j] = f2(0.f, 0.f); v[i][j] = f2(tv[2 * j], tv[2 * j + 1]); }
+                        for (int j = 0; j < H; ++j) g[i][j] = f2(0.f, 0.f);
                     }
                 } else {
                     exhausted = true;
@@ -427,6 +431,8 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                     }
                 }
                 // state slack / dual / residuals of stage i
+                float vo[NX];
+                sv.load(i, vo);
                 if (go && emit) {
                     float t[NX];
 #pragma unroll
@@ -439,7 +445,7 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                     float2 t = add2(x2, g[i][j]);                                                    // :48
                     t.x = fminf(P.xmax[i * NX + 2 * j], fmaxf(P.xmin[i * NX + 2 * j], t.x));         // :59
                     t.y = fminf(P.xmax[i * NX + 2 * j + 1], fmaxf(P.xmin[i * NX + 2 * j + 1], t.y));
-                    const float2 rp = sub2(x2, t), rd = sub2(v[i][j], t);
+                    const float2 rp = sub2(x2, t), rd = sub2(f2(vo[2 * j], vo[2 * j + 1]), t);
                     pri_x = fmaxf(pri_x, fmaxf(fabsf(rp.x), fabsf(rp.y)));                           // :95
                     dua_x = fmaxf(dua_x, fmaxf(fabsf(rd.x), fabsf(rd.y)));                           // :96
                     g[i][j] = sub2(add2(g[i][j], x2), t);                                            // :70
@@ -492,8 +498,7 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
 #pragma unroll
                         for (int i = 0; i < NH; ++i) {
                             float t[NX];
-#pragma unroll
-                            for (int j = 0; j < H; ++j) { t[2 * j] = v[i][j].x; t[2 * j + 1] = v[i][j].y; }
+                            sv.load(i, t);
                             gstore<float, NX>(a.wv + inst * XROW + i * NX, t);
                         }
                     }
@@ -515,9 +520,12 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
 #pragma unroll
             for (int i = 0; i < NH - 1; ++i) z[i] = zn[i];
 #pragma unroll
-            for (int i = 0; i < NH; ++i)
+            for (int i = 0; i < NH; ++i) {
+                float t[NX];
 #pragma unroll
-                for (int j = 0; j < H; ++j) v[i][j] = vn[i][j];
+                for (int j = 0; j < H; ++j) { t[2 * j] = vn[i][j].x; t[2 * j + 1] = vn[i][j].y; }
+                sv.store(i, t);
+            }
         }
 
         // ------------------------------------------------------------------ backward sweep
@@ -533,13 +541,13 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
             auto store_v = [&](int i) {
                 float t[NX];
 #pragma unroll
-                for (int j = 0; j < H; ++j) { t[2 * j] = v[i][j].x; t[2 * j + 1] = v[i][j].y; }
+                for (int j = 0; j < H; ++j) { t[2 * j] = vn[i][j].x; t[2 * j + 1] = vn[i][j].y; }   // (= v: the lane has advanced)
                 gstore<float, NX>(wvo + i * NX, t);
             };
             if (wvo) store_v(NH - 1);
 #pragma unroll
             for (int j = 0; j < H; ++j) {
-                const float2 dvg = sub2(v[NH - 1][j], g[NH - 1][j]);
+                const float2 dvg = sub2(vn[NH - 1][j], g[NH - 1][j]);
                 const float2 t = sub2(pn[j], f2(__fmul_rn(P.rho, dvg.x), __fmul_rn(P.rho, dvg.y)));  // :84
                 p[2 * j] = t.x; p[2 * j + 1] = t.y;
             }
@@ -560,7 +568,7 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
 #pragma unroll
                 for (int j = 0; j < H; ++j) {
                     const float2 cq = neg2(f2(__fmul_rn(xr[2 * j], P.Qd[2 * j]), __fmul_rn(xr[2 * j + 1], P.Qd[2 * j + 1])));   // :81
-                    const float2 dvg = sub2(v[i][j], g[i][j]);
+                    const float2 dvg = sub2(vn[i][j], g[i][j]);
                     const float2 q = sub2(cq, f2(__fmul_rn(P.rho, dvg.x), __fmul_rn(P.rho, dvg.y)));  // :82
                     const float2 kr = f2(__fmul_rn(P.K[2 * j], r), __fmul_rn(P.K[2 * j + 1], r));
                     const float2 t = sub2(add2(q, mp[j]), kr);
