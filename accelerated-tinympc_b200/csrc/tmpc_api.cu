@@ -558,9 +558,12 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     const void *ixmin, *ixmax, *iumin, *iumax;
     const void *model_g;
     long long gate_split;
-    int roll_steps, roll_pad;
+    int roll_steps, roll_step0;
     void *roll_x, *roll_u0;
     int *roll_iter, *roll_status;
+    const void *roll_table;
+    long long roll_rows;
+    const int *roll_start;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");

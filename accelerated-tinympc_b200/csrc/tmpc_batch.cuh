@@ -183,7 +183,10 @@ int batch_solve_async(tmpc_batch_impl *b, bool controls_only = false, int roll_s
         da.x = nullptr; da.u = nullptr; da.u0 = b->u0;
         b->plant_u = b->u0; b->plant_u_stride = c->nu;
     }
-    if (roll_steps > 1) { da.roll_steps = roll_steps; da.roll_x = rx; da.roll_u0 = ru; da.roll_iter = ri; da.roll_status = rs; }
+    if (roll_steps > 1) {
+        da.roll_steps = roll_steps; da.roll_x = rx; da.roll_u0 = ru; da.roll_iter = ri; da.roll_status = rs;
+        if (b->table) { da.roll_table = b->table; da.roll_rows = b->table_rows; da.roll_start = b->start; da.roll_step0 = (int)b->steps_done; }
+    }
     c->stats.instances = b->B;
     c->stats.launches = 0;
     const char *e = getenv("TMPC_LPT");
@@ -392,11 +395,18 @@ int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void 
     BCUDA_TRY(b, cudaEventRecord(r0, s));
     int rc = TMPC_OK;
     int k0 = 0;
-    if (steps >= 2 && reset_duals && !b->table && roll_supported(c) && !getenv("TMPC_ROLLOUT_FULL_OUTPUTS")) {
+    if (steps >= 2 && reset_duals && roll_supported(c) && !getenv("TMPC_ROLLOUT_FULL_OUTPUTS")) {
         // Fused closed loop: every lane of ONE persistent launch takes an instance through all `steps` solves (plant step, dual reset and
         // the warm d / v / z hand-over stay on chip); only the last step's plant update is left to the loop below
         c->duals_zero_next = true;
         rc = batch_solve_async(b, false, steps, dx ? dx + nxb : nullptr, du, di, ds);
+        if (rc == TMPC_OK && b->table) {
+            // the lanes read their windows from the table themselves; the batch's Xref buffer is left as the per-step path leaves it
+            // (the last step's window), for a wrapper-style solve that may follow
+            const long long n = (long long)B * c->nx * c->N;
+            tmpc::xref_window_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(B, c->nx, c->N, (const float *)b->table, b->table_rows, b->start,
+                                                                                     (int)(b->steps_done + steps - 1), (float *)b->xref);
+        }
         if (rc == TMPC_OK) {
             k0 = steps - 1;
             e = dispatch_plant(c, b, dx ? dx + nxb * steps : nullptr, du ? du + nub * k0 : nullptr, di ? di + (size_t)B * k0 : nullptr,

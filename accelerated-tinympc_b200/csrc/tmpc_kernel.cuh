@@ -306,9 +306,14 @@ template <class T> struct SolveArgs {
     // launch -- solve, plant step x0 <- x_1 of the solve, y = g = 0, warm d / v / z carried on chip -- for steps 0 .. roll_steps-2,
     // then the last step as a plain warm solve (outputs, state written back).  Histories of the steps the kernel completes
     // itself (each nullable): roll_x[k] = the state after step k, roll_u0[k] = the control applied, roll_iter / roll_status[k].
-    int roll_steps, roll_pad;
+    int roll_steps, roll_step0;
     T *roll_x, *roll_u0;          // [roll_steps-1][batch][nx] / [..][nu]
     int *roll_iter, *roll_status; // [roll_steps-1][batch]
+    // ... tracking a reference TABLE (quadrotor_tracking.cpp:101): step k of instance b follows rows w0 .. w0+N-1 of roll_table
+    // [roll_rows][nx], w0 = min(roll_start[b] (null = 0) + roll_step0 + k, roll_rows - N); null table = the fixed Xref above
+    const T *roll_table;
+    long long roll_rows;
+    const int *roll_start;
 };
 
 // instance solved by the idx-th claim of the work counter

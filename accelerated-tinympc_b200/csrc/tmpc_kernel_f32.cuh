@@ -551,6 +551,13 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
         spn.store(0, pn);
     };
     const bool shared_xref = (a.xref_stride == 0);
+    // ROLL with a reference table: the window of MPC step `step` of this lane's instance (tmpc.h tmpc_batch_set_xref_table)
+    const bool tab = ROLL && a.roll_table != nullptr;
+    auto window = [&](int step) -> const float * {
+        long long w0 = (long long)(a.roll_start ? __ldg(a.roll_start + (inst < 0 ? 0 : inst)) : 0) + a.roll_step0 + step;
+        if (w0 > a.roll_rows - NH) w0 = a.roll_rows - NH;
+        return a.roll_table + w0 * NX;
+    };
     // Controls-only callers (x = u = NULL, u0 given: what an MPC loop applies, quadrotor_hovering.cpp:110): u(:,0) is stored by
     // every trip's stage 0, so the trip in which the lane terminates has already delivered it and neither an emission trip
     // nor a speculative one is needed -- warm starts included (their state is written back by the flush at the next trip).
@@ -604,6 +611,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                     if (a.roll_x) gstore<float, NX>(a.roll_x + ((long long)rs * a.batch + inst) * NX, x0);
                     if (a.roll_u0) { float t[NU]; su0.load(0, t); gstore<float, NU>(a.roll_u0 + ((long long)rs * a.batch + inst) * NU, t); }
                     rs += 1;
+                    if (tab) seed_pn(window(rs) + (NH - 1) * NX);   // the window moves on: p_N seed of the new step
                     area = src ^ 1;
                     force_mirror = (a.test_flags & 2) != 0;
                 } else {
@@ -694,7 +702,8 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);
                     if constexpr (ROLL) sx0.store(0, x0);
-                    if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
+                    if (tab) seed_pn(window(0) + (NH - 1) * NX);
+                    else if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
                     if constexpr (IB) {
                         // the instance's own box -> the lane's scratch rows (a missing / disabled family = +-inf).  Loads are issued
                         // half a horizon at a time, so the copy costs a handful of memory round trips instead of one per stage
@@ -1094,7 +1103,7 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
         }
         if (__any_sync(FULLM, cont || wfbw || rfbw)) {
             float p[NX];
-            const float *xr_base = a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
+            const float *xr_base = tab ? window(rs) : a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
             float *wdo = wfbw ? a.wd + inst * UROW : nullptr;
             float *wvo = wfbw ? a.wv + inst * XROW : nullptr;
             float *wzo = wfbw ? a.wz + inst * UROW : nullptr;

@@ -327,6 +327,22 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
 
     long long inst = -1;
     int it = 0, rs = 0;
+    // tracking a reference table: the window of MPC step `step` of this lane's instance (SolveArgs::roll_table)
+    const bool tab = a.roll_table != nullptr;
+    auto window = [&](int step) -> const float * {
+        long long w0 = (long long)(a.roll_start ? __ldg(a.roll_start + (inst < 0 ? 0 : inst)) : 0) + a.roll_step0 + step;
+        if (w0 > a.roll_rows - NH) w0 = a.roll_rows - NH;
+        return a.roll_table + w0 * NX;
+    };
+    auto seed_pn = [&](const float *xl) {   // p_N seed: -(Xref_{N-1}^T Pinf)  (admm.cpp:83)
+        float xr[NX];
+        gload<float, NX>(xl, xr);
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            const float t = -dot<float, O::XtP, NX, FAST>([&](int k) { return P.Pf[k + j * NX]; }, [&](int k) { return xr[k]; });
+            if (j & 1) pn[j / 2].y = t; else pn[j / 2].x = t;
+        }
+    };
     int phase = PH_FREE;
     bool exhausted = false;
     bool spec = false;
@@ -350,13 +366,7 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                     spec = (S <= 1) && (P.max_iter <= 1);
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);
-                    float xr[NX];
-                    gload<float, NX>(a.Xref + inst * a.xref_stride + (NH - 1) * NX, xr);
-#pragma unroll
-                    for (int j = 0; j < NX; ++j) {   // p_N seed: -(Xref_{N-1}^T Pinf)  (admm.cpp:83)
-                        const float t = -dot<float, O::XtP, NX, FAST>([&](int k) { return P.Pf[k + j * NX]; }, [&](int k) { return xr[k]; });
-                        if (j & 1) pn[j / 2].y = t; else pn[j / 2].x = t;
-                    }
+                    seed_pn((tab ? window(0) : a.Xref + inst * a.xref_stride) + (NH - 1) * NX);
                     // warm d, v, z of the caller's workspace; the duals start from zero (the loop resets them every step)
 #pragma unroll
                     for (int i = 0; i < NH - 1; ++i) {
@@ -534,7 +544,7 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
         const bool wout = final_bwd;
         if (__any_sync(FULLM, cont)) {
             float p[NX];
-            const float *xr_base = a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
+            const float *xr_base = tab ? window(rs) : a.Xref + (inst < 0 ? 0 : inst) * a.xref_stride;
             float *wdo = wout ? a.wd + inst * UROW : nullptr;
             float *wvo = wout ? a.wv + inst * XROW : nullptr;
             float *wzo = wout ? a.wz + inst * UROW : nullptr;
@@ -587,6 +597,7 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
 #pragma unroll
                 for (int j = 0; j < H; ++j) g[i][j] = f2(0.f, 0.f);                                  // :101
             ++rs; it = 0;
+            if (tab) seed_pn(window(rs) + (NH - 1) * NX);   // the window moves on
             res[0] = res[1] = res[2] = res[3] = 0.f;
             spec = (rs >= S - 1) && (P.max_iter <= 1);
             // the measurement the LAST step starts from: the caller's plant step reads it after the launch

@@ -172,3 +172,50 @@ def test_fused_loop_cartpole_registers(pkg, oracle, scale, max_iter, check):
     if max_iter <= 30:
         assert (ho["status"] == 11).any()
     _same_runs(fused, _run(pkg, prob, x0, xref, steps, TMPC_ROLL=0), "fused vs one launch per step")
+
+
+def test_fused_loop_tracks_a_reference_table(pkg, oracle):
+    """quadrotor_tracking.cpp:93-118 fused: every lane reads the window of its instance's current step from the table itself
+    (w0 = min(start + k, rows - N): starts up to the end of the table exercise the clamp).  Against the oracle's loop with the
+    windows gathered on the host, and against the one-launch-per-step path on the whole batch -- twice in a row, so the second
+    rollout continues from the first one's step count."""
+    prob = pkg.problems.quadrotor(20)
+    table = np.ascontiguousarray(pkg.problems.quadrotor_trajectory().T).astype(np.float32)     # [301, 12]
+    B, n = 50_000, 1_200
+    rng = np.random.default_rng(11)
+    starts = rng.integers(0, table.shape[0] - 4, B).astype(np.int32)
+    x0 = (table[np.minimum(starts, table.shape[0] - prob.N)] + 0.05 * rng.standard_normal((B, 12))).astype(np.float32)
+
+    def run(**env):
+        with _env(**env):
+            s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+            b = pkg.capi.Batch(s, B)
+            b.set_x0(x0)
+            b.set_xref_table(table, starts)
+            h1 = b.rollout(4, reset_duals=True)
+            l1 = s.stats()["launches"]
+            h2 = b.rollout(3, reset_duals=True)
+            h = {k: np.concatenate([h1[k], h2[k][1:] if k == "x0" else h2[k]]) for k in h1}
+            out = {k: b.get(k) for k in ("x", "u", "iter", "status", "resid", "x0", "d", "y", "g", "v", "z")}
+            b.close(); s.close()
+        return h, out, l1
+
+    fused, stepwise = run(), run(TMPC_ROLL=0)
+    assert fused[2] == 2 and stepwise[2] == 3 * 4
+    _same_runs(fused, stepwise, "fused vs one launch per step (table)")
+    xc, warm = x0[:n].copy(), None
+    for k in range(7):
+        w0 = np.minimum(starts[:n].astype(np.int64) + k, table.shape[0] - prob.N)
+        xref = table[w0[:, None] + np.arange(prob.N)[None, :]]
+        r = oracle.solve_batch(prob, xc, xref, dtype=np.float32, warm=warm, want_state=True, nthreads=8)
+        assert_same(fused[0]["iter"][k, :n], r.iter, "step %d iter" % k)
+        assert_same(fused[0]["u0"][k, :n], r.u[:, 0, :], "step %d u0" % k)
+        xc = oracle.plant_step(prob, xc, r.u[:, 0, :], dtype=np.float32)
+        assert_same(fused[0]["x0"][k + 1, :n], xc, "step %d plant state" % k)
+        warm = {q: r.state[q].copy() for q in ("d", "y", "g", "v", "z")}
+        warm["y"][:] = 0
+        warm["g"][:] = 0
+    for q in ("x", "u", "iter"):
+        assert_same(fused[1][q][:n], getattr(r, q), "last step " + q)
+    for q in ("d", "v", "z", "y", "g"):
+        assert_same(fused[1][q][:n], r.state[q], "final workspace " + q)
