@@ -741,20 +741,56 @@ def run_configs(torch, dist, pkg, args, dev, local, rank, world, barrier, allmax
         ms_cl = allmax(bt.last_rollout_ms())
         iters_cl = allsum(float(ith.sum().item()))
         hist = torch.bincount(ith.flatten().to(torch.int64), minlength=8)[:8].cpu().numpy().tolist()
+        chk_cl = None
+        if rank == 0:     # the oracle runs the same 4 + STEPS steps for a prefix: iteration counts of the timed steps and the final plant state
+            from oracle.pyoracle import OracleLib
+            orc = OracleLib()
+            t0c = time.perf_counter()
+            n = min(CHECK_PREFIX, Bc)
+            xc, warm, bad = (0.2 * x0[:n]).astype(np.float32), None, {"iter": 0, "plant_state": 0}
+            ith_h = ith[:, :n].cpu().numpy()
+            for k in range(4 + steps_cl):
+                r = orc.solve_batch(cart, xc, xref, dtype=np.float32, warm=warm, want_state=True, nthreads=os.cpu_count() or 1)
+                if k >= 4:
+                    bad["iter"] += int((ith_h[k - 4] != r.iter).sum())
+                xc = orc.plant_step(cart, xc, r.u[:, 0, :], dtype=np.float32)
+                warm = {q: r.state[q].copy() for q in ("d", "y", "g", "v", "z")}
+                warm["y"][:] = 0
+                warm["g"][:] = 0
+            bad["plant_state"] = int((bt.get("x0")[:n] != xc).sum())
+            chk_cl = {"instances": n, "mpc_steps": 4 + steps_cl, "bit_exact": all(v == 0 for v in bad.values()), "mismatching_elements": bad,
+                      "compared": list(bad), "oracle_seconds": time.perf_counter() - t0c,
+                      "how": "the oracle's closed loop (solve, its own plant step, duals reset) over all the steps for the first instances: iteration "
+                             "counts of the timed steps and the final plant state (which every applied control went into)"}
         nx, nu, N = 4, 1, 10
+        fused = s.stats()["launches"] == 2      # one persistent launch for all the steps + the last plant step (tmpc_kernel_small.cuh)
         state = 4 * (3 * nu * (N - 1) + 2 * nx * N)                    # d y z g v
-        per_step = (4 * nx + state) + state + 4 * (nx * N + nu * (N - 1)) + 8 + 16 + 4 * nx    # in + out + x,u,iter,status,resid + new x0
+        per_step_unfused = (4 * nx + state) + state + 4 * (nx * N + nu * (N - 1)) + 8 + 16 + 4 * nx    # in + out + x,u,iter,status,resid + new x0
+        # fused: per INSTANCE and rollout x0, d, v, z in; workspace, x, u, iter, status, resid, x0 out; per step the iteration history
+        per_rollout = (4 * nx + 4 * (2 * nu * (N - 1) + nx * N)) + state + 4 * (nx * N + nu * (N - 1)) + 8 + 16 + 2 * 4 * nx
+        per_step = per_rollout / steps_cl + 4 if fused else per_step_unfused
         gbs = Bc * steps_cl * per_step / (ms_cl * 1e-3) / 1e9
+        tf = iters_cl / world * FLOP_PER_ITER["c"] / (ms_cl * 1e-3) / 1e12
+        bound = "hbm" if gbs / hbm_peak > tf / peak_tf else "fp32"
         out["config4_cartpole_closed_loop"] = {
             "workload": "the reference's cartpole closed loop (codegen_cartpole.cpp:75-122) for every instance, on the device: reset duals, "
                         "warm-started solve, plant step; x0 = 0.2 x the cold recipe's spread (|theta| <= 0.04 rad ...); %d MPC steps timed after 4 untimed ones" % steps_cl,
             "instances_total": T, "instances_per_gpu": Bc, "value": T * steps_cl / (ms_cl * 1e-3), "unit": "MPC steps/s (= solves/s)",
             "ms_per_mpc_step": ms_cl / steps_cl, "mean_iters_per_solve": iters_cl / (T * steps_cl), "iter_hist_0_to_7": hist,
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "algorithmic_bytes_per_mpc_step": per_step, "peak_source": hbm_src, "traffic": None,
-                         "bytes": "x0 + warm state d,y,z,g,v in (%d B), warm state out (%d B), x,u,iter,status,resid out (%d B), plant state out (%d B)"
-                                  % (4 * nx + state, state, 4 * (nx * N + nu * (N - 1)) + 24, 4 * nx)}}
-        log("configs.config4_cartpole_closed_loop: %.3e MPC steps/s, HBM frac %.3f" % (T * steps_cl / (ms_cl * 1e-3), gbs / hbm_peak))
+            "fused": fused, "launches_per_rollout": s.stats()["launches"],
+            "roofline": {"bound": bound, "achieved": gbs if bound == "hbm" else tf, "peak": hbm_peak if bound == "hbm" else peak_tf,
+                         "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": gbs / hbm_peak if bound == "hbm" else tf / peak_tf,
+                         "fp32": {"achieved_tflops": tf, "peak": peak_tf, "frac": tf / peak_tf, "algorithmic_flop_per_iteration": FLOP_PER_ITER["c"],
+                                  "note": "FLOP of full iterations; the iteration that ends a step runs no backward sweep (admm.cpp:135-138)"},
+                         "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": gbs / hbm_peak, "algorithmic_bytes_per_mpc_step": per_step,
+                                 "algorithmic_bytes_per_mpc_step_one_launch_per_step": per_step_unfused, "peak_source": hbm_src,
+                                 "bytes": "fused: the state stays in registers between the steps of a rollout, so per instance x0 + d, v, z in, workspace + "
+                                          "x, u, iter, status, resid + x0 out ONCE per rollout (%d B / %d steps) + 4 B of iteration history per step; "
+                                          "one launch per step (TMPC_ROLL=0): %d B per step" % (per_rollout, steps_cl, per_step_unfused)},
+                         "traffic": None},
+            "oracle_check": chk_cl}
+        log("configs.config4_cartpole_closed_loop: %.3e MPC steps/s, frac %.3f (%s)%s" % (T * steps_cl / (ms_cl * 1e-3),
+            out["config4_cartpole_closed_loop"]["roofline"]["frac"], bound, " fused" if fused else ""))
         bt.close(); s.close(); del ith
     except Exception as e:   # the entry is additional evidence: a failure here must not void the headline line
         out["config4_cartpole_closed_loop"] = {"error": repr(e)}
