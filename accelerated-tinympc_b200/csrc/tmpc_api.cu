@@ -692,6 +692,7 @@ int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cuda
         int rc = plan_launch(c, ki, da, s, blocks);
         if (rc == TMPC_OK) rc = plan_lane_scratch(c, ki, da, blocks, c->ib_batch != 0 && !da.sys, s);
         if (rc != TMPC_OK) return rc;
+        if (da.roll_steps > 1 && ki.model_kind == 0 && getenv("TMPC_ROLL_ASYNC_REFILL")) da.test_flags |= 16;   // A/B of admm_kernel_small_roll
         if (da.sys) {   // refill policy of the row-pair systems kernel (tmpc_kernel_sys.cuh), tuning only
             if (const char *e = getenv("TMPC_SYS_REFILL_MIN")) da.test_flags |= (atoi(e) & 31) << 8;
             if (const char *e = getenv("TMPC_SYS_DEFER_MAX")) da.test_flags |= (atoi(e) & 15) << 16;
@@ -890,7 +891,9 @@ int launch_device(tmpc_ctx_impl *c, DevArgs &da, bool warm, cudaStream_t s, bool
         bool ok = warm && da.wd && !c->ib_batch && !da.sys;
         if (ok && c->nx == 4) {
             const char *k = getenv("TMPC_KERNEL");
-            ok = tmpc_dispatch::lookup_small_roll(k && !strcmp(k, "small256") ? 256 : k && !strcmp(k, "small512") ? 512 : 384, ki);
+            // 256 lanes per SM: the only size at which the unrolled sweeps keep every register (measured: 16.7 ms per 8 steps x 16.7M
+            // instances; 384 lanes spill 450 B: 19.6 ms)
+            ok = tmpc_dispatch::lookup_small_roll(k && !strcmp(k, "small384") ? 384 : k && !strcmp(k, "small512") ? 512 : 256, ki);
         } else if (ok) ok = tmpc_dispatch::lookup_f32_roll(c->pattern, c->const_bounds, ki);
         if (!ok) return fail(c, TMPC_ERR_UNSUPPORTED, "fused closed loop: no kernel");
     } else if (ib_f32) {

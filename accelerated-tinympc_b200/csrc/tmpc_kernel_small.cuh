@@ -291,7 +291,10 @@ admm_kernel_small(const __grid_constant__ Model<float, NX, 1, NH> P, const __gri
 // The reference leaves v, z one iteration behind after an early exit (admm.cpp:135-138: the exit comes before v = vnew, z = znew).
 // The kernel keeps BOTH generations on chip -- the forward sweep writes vn, zn (registers); v (shared memory, one 16-byte row per
 // stage and lane) and z advance only when the iteration does not end the step by convergence -- so the hand-over to the next step is
-// the reference's state with no special case.  (v in registers as well costs 40 more of them: 256 instead of 384 lanes per SM.)
+// the reference's state with no special case.
+// The sweeps are fully unrolled (the state is indexed statically), so the loop body is ~40 KB of code that every warp streams once
+// per trip: code size is a first-order cost here.  The forward sweep therefore carries NO output code; the last step's x, u are
+// written by a separate emission pass (the forward pass alone, evaluated again) in the trip that ends the rollout.
 // PARITY order, warm buffers required (they receive the workspace the loop leaves: d, v, z, y, g of the last step).
 template <int NX, int NH, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1)
@@ -345,14 +348,18 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
     };
     int phase = PH_FREE;
     bool exhausted = false;
-    bool spec = false;
     float res[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned n_iter = 0, n_solved = 0, n_trips = 0, n_inst = 0;
 
     for (;;) {
         // ------------------------------------------------------------------ lane refill
+        // Refills are WARP-SYNCHRONOUS: the warp claims 32 instances when its last lane has finished.  A lane idles for the trip or two
+        // by which its rollout was shorter than the longest of the warp, but the refill's memory latency (claim, 250 B of rows per lane,
+        // p_N seed) is paid once per rollout instead of in nearly every trip, and the lanes' last steps -- the only trips that run the
+        // emission pass -- coincide.  (test_flags bit 4: every lane refills on its own, for the A/B: 29.1 vs 16.7 ms)
         const bool need = (phase == PH_FREE) && !exhausted;
-        const unsigned m = __ballot_sync(FULLM, need);
+        unsigned m = __ballot_sync(FULLM, need);
+        if (!(a.test_flags & 16) && __any_sync(FULLM, phase != PH_FREE)) m = 0;
         if (m) {
             const int leader = __ffs(m) - 1;
             unsigned long long base = 0;
@@ -363,7 +370,6 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                 const long long ci = idx < a.batch ? claim_instance(a, idx) : -1;
                 if (ci >= 0) {
                     inst = ci; phase = PH_RUN; it = 0; rs = 0;
-                    spec = (S <= 1) && (P.max_iter <= 1);
                     res[0] = res[1] = res[2] = res[3] = 0.f;
                     gload<float, NX>(a.x0 + inst * NX, x0);
                     seed_pn((tab ? window(0) : a.Xref + inst * a.xref_stride) + (NH - 1) * NX);
@@ -390,23 +396,17 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
         if (__all_sync(FULLM, phase == PH_FREE)) break;
         ++n_trips;
 
-        const bool emit = (phase == PH_EMIT);
         if (phase == PH_RUN) ++it;
         const bool last = rs >= S - 1;   // the step whose outputs and workspace the caller gets
 
         // ------------------------------------------------------------------ forward sweep
-        // forward_pass (admm.cpp:27-37) + update_slack (:45-61) + update_dual (:67-71) + residual maxima (:95-98)
+        // forward_pass (admm.cpp:27-37) + update_slack (:45-61) + update_dual (:67-71) + residual maxima (:95-98).  No output code in
+        // here: the trajectories of the last step are written by the emission pass below, in the trip that ends it
         float pri_x = 0.f, dua_x = 0.f, pri_u = 0.f, dua_u = 0.f;
         {
             float x[NX];
 #pragma unroll
             for (int j = 0; j < NX; ++j) x[j] = x0[j];
-            const bool wr = emit || (spec && phase == PH_RUN);
-            float *xo = (wr && a.x) ? a.x + inst * XROW : nullptr;
-            float *uo = (wr && a.u) ? a.u + inst * UROW : nullptr;
-            float *go = wr ? a.wg + inst * XROW : nullptr;
-            float *yo = wr ? a.wy + inst * UROW : nullptr;
-
 #pragma unroll
             for (int i = 0; i < NH; ++i) {
                 float2 xn[H];
@@ -414,19 +414,13 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                     // u_i = -(Kinf x_i) - d_i                                                        :31
                     const float kx = dot<float, O::Kx, NX, FAST>([&](int k) { return P.K[k]; }, [&](int k) { return x[k]; });
                     const float u = __fsub_rn(-kx, d[i]);
-                    if (yo && emit) yo[i] = y[i];
                     float t = __fadd_rn(u, y[i]);                                                    // :47
                     t = fminf(P.umax[i], fmaxf(P.umin[i], t));                                       // :53
                     pri_u = fmaxf(pri_u, fabsf(__fsub_rn(u, t)));                                    // :97
                     dua_u = fmaxf(dua_u, fabsf(__fsub_rn(z[i], t)));                                 // :98
                     y[i] = __fsub_rn(__fadd_rn(y[i], u), t);                                         // :69
                     zn[i] = t;
-                    if (yo && !emit) yo[i] = y[i];
-                    if (uo) uo[i] = u;
-                    if (i == 0) {
-                        u0r = u;
-                        if (wr && a.u0) a.u0[inst] = u;
-                    }
+                    if (i == 0) u0r = u;
                     // x_{i+1} = A x_i + B u_i                                                        :35
                     float2 ax[H];
                     matvec2<ORD_SEQ, NX, NX, NX, 0, FAST>(P.A, x, ax, Z);
@@ -443,12 +437,6 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                 // state slack / dual / residuals of stage i
                 float vo[NX];
                 sv.load(i, vo);
-                if (go && emit) {
-                    float t[NX];
-#pragma unroll
-                    for (int j = 0; j < H; ++j) { t[2 * j] = g[i][j].x; t[2 * j + 1] = g[i][j].y; }
-                    gstore<float, NX>(go + i * NX, t);
-                }
 #pragma unroll
                 for (int j = 0; j < H; ++j) {
                     const float2 x2 = f2(x[2 * j], x[2 * j + 1]);
@@ -461,13 +449,6 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                     g[i][j] = sub2(add2(g[i][j], x2), t);                                            // :70
                     vn[i][j] = t;
                 }
-                if (go && !emit) {
-                    float t[NX];
-#pragma unroll
-                    for (int j = 0; j < H; ++j) { t[2 * j] = g[i][j].x; t[2 * j + 1] = g[i][j].y; }
-                    gstore<float, NX>(go + i * NX, t);
-                }
-                if (xo) gstore<float, NX>(xo + i * NX, x);
                 if (i < NH - 1) {
 #pragma unroll
                     for (int j = 0; j < H; ++j) { x[2 * j] = xn[j].x; x[2 * j + 1] = xn[j].y; }
@@ -479,6 +460,7 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
         bool final_bwd = false;   // last step, max_iter exit: this trip's backward sweep still runs and writes the workspace
         bool step_end = false;    // a step before the last ended in this trip: the next one starts after the backward section
         bool finished = false;
+        bool fin = false;         // the last step of this lane's instance ended in this trip
         bool advance = false;     // v = vnew, z = znew (admm.cpp:141-142): every iteration that does not end its step by convergence
         if (phase == PH_RUN) {
             const bool chk = (it % P.check_term) == 0;
@@ -501,6 +483,7 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                     if (a.status) a.status[inst] = conv ? 1 : 11;
                     if (a.resid) *reinterpret_cast<float4 *>(a.resid + inst * 4) = make_float4(res[0], res[1], res[2], res[3]);
                     final_bwd = !conv;
+                    fin = true;
                     if (conv) {
                         // the workspace an early exit leaves: d, v, z as they entered this iteration (y, g go out with the trajectories)
 #pragma unroll
@@ -512,19 +495,46 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
                             gstore<float, NX>(a.wv + inst * XROW + i * NX, t);
                         }
                     }
-                    if (spec) { phase = PH_FREE; finished = true; }   // x, u, y, g of this very trip are already in the output
-                    else phase = PH_EMIT;
-                    spec = false;
+                    phase = PH_FREE; finished = true;
                 }
-            } else if (last) {
-                constexpr float SF = TMPC_SPEC_FACTOR;
-                const bool next_chk = ((it + 1) % P.check_term) == 0;
-                spec = (it + 1 >= P.max_iter) ||
-                       (next_chk && res[0] < SF * P.pri_tol && res[2] < SF * P.pri_tol && res[1] < SF * P.dua_tol && res[3] < SF * P.dua_tol);
             }
-        } else if (phase == PH_EMIT) {
-            phase = PH_FREE;
-            finished = true;
+        }
+        // ------------------------------------------------------------------ emission: the rollout of this lane ends in this trip
+        // x, u of the solve = its last forward pass (admm.cpp:27-37 with the d that pass used: BEFORE the backward sweep of a max_iter
+        // exit), evaluated again without the slack / dual work; y, g as the terminating iteration left them
+        if (__any_sync(FULLM, fin)) {
+            if (fin) {
+                float *xo = a.x ? a.x + inst * XROW : nullptr;
+                float *uo = a.u ? a.u + inst * UROW : nullptr;
+                float x[NX];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) x[j] = x0[j];
+#pragma unroll
+                for (int i = 0; i < NH; ++i) {
+                    if (xo) gstore<float, NX>(xo + i * NX, x);
+                    {
+                        float t[NX];
+#pragma unroll
+                        for (int j = 0; j < H; ++j) { t[2 * j] = g[i][j].x; t[2 * j + 1] = g[i][j].y; }
+                        gstore<float, NX>(a.wg + inst * XROW + i * NX, t);
+                    }
+                    if (i < NH - 1) {
+                        const float kx = dot<float, O::Kx, NX, FAST>([&](int k) { return P.K[k]; }, [&](int k) { return x[k]; });
+                        const float u = __fsub_rn(-kx, d[i]);
+                        if (uo) uo[i] = u;
+                        if (i == 0 && a.u0) a.u0[inst] = u;
+                        a.wy[inst * UROW + i] = y[i];
+                        float2 ax[H];
+                        matvec2<ORD_SEQ, NX, NX, NX, 0, FAST>(P.A, x, ax, Z);
+#pragma unroll
+                        for (int j = 0; j < H; ++j) {
+                            const float2 b2 = f2(P.B[2 * j], P.B[2 * j + 1]);
+                            const float2 xn = add2(ax[j], f2(__fmul_rn(b2.x, u), __fmul_rn(b2.y, u)));
+                            x[2 * j] = xn.x; x[2 * j + 1] = xn.y;
+                        }
+                    }
+                }
+            }
         }
         if (advance) {
 #pragma unroll
@@ -599,7 +609,6 @@ admm_kernel_small_roll(const __grid_constant__ Model<float, NX, 1, NH> P, const 
             ++rs; it = 0;
             if (tab) seed_pn(window(rs) + (NH - 1) * NX);   // the window moves on
             res[0] = res[1] = res[2] = res[3] = 0.f;
-            spec = (rs >= S - 1) && (P.max_iter <= 1);
             // the measurement the LAST step starts from: the caller's plant step reads it after the launch
             if (rs >= S - 1) gstore<float, NX>(const_cast<float *>(a.x0) + inst * NX, x0);
         }

@@ -14,7 +14,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 prob = pkg.problems.cartpole()
 x0, xref = pkg.workloads.cartpole_batch(0, B)
 x0 = (0.2 * x0).astype(np.float32)
-for env in ({}, {"TMPC_ROLL": "0"}, {"TMPC_KERNEL": "small256"}, {"TMPC_KERNEL": "small512"}):
+for env in ({}, {"TMPC_ROLL": "0"}, {"TMPC_ROLL_ASYNC_REFILL": "1"}, {"TMPC_KERNEL": "small384"}):
     os.environ.update(env)
     s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
     b = pkg.capi.Batch(s, B)
