@@ -644,7 +644,7 @@ int plan_lane_scratch(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, long 
     da.scratch = nullptr; da.sc_ib = da.sc_wm = -1; da.sc_chunks = 0; da.test_flags = 0;
     da.ixmin = da.ixmax = da.iumin = da.iumax = nullptr;
     da.model_g = nullptr;
-    if (ki.model_kind != 1) return TMPC_OK;
+    if (ki.model_kind != 1) { c->duals_zero_next = false; return TMPC_OK; }   // (the other kernels take their duals from the caller's buffers)
     if (kernel_variant() == 3) {
         // (re-uploaded per launch: 3.9 KB on the launch stream, ordered before the kernel; the A/B variant is not tuned for launch cost)
         if (!c->d_model_f32) CUDA_TRY(c, cudaMalloc(&c->d_model_f32, c->model_f32.size()));

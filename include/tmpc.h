@@ -198,7 +198,10 @@ int tmpc_batch_get(tmpc_batch *b, int32_t what, void *dst, int32_t mem);
  * entirely on the device: [reference window from the table] -> [y = g = 0 if reset_duals] -> tiny_solve ->
  * x0 <- Adyn x0 + Bdyn u(:,0) (the examples' plant step, same evaluation order).  Histories are optional (NULL):
  * x0_hist [steps+1][batch][nx] (entry 0 = the initial state), u0_hist [steps][batch][nu], iter_hist / status_hist
- * [steps][batch].  Synchronous. */
+ * [steps][batch].  Synchronous.
+ * With reset_duals != 0 on an fp32 PARITY context of the 12/4/10 or 4/1/10 shape (shared bounds) the whole rollout is ONE
+ * persistent launch: every lane takes its instance through all the steps with the state on chip (same results bit for bit;
+ * the environment switch TMPC_ROLL=0 keeps one launch per step). */
 int tmpc_batch_rollout(tmpc_batch *b, int32_t steps, int32_t reset_duals, void *x0_hist, void *u0_hist, int32_t *iter_hist,
                        int32_t *status_hist, int32_t mem);
 float tmpc_batch_last_rollout_ms(const tmpc_batch *b);   /* device time of the last rollout (CUDA events on the ctx stream) */
