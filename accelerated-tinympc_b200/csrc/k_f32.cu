@@ -55,6 +55,11 @@ bool lookup_f32(int policy, bool warm, int pattern, bool cb, int variant, Kernel
     return pick_f32<12, 4, 10, 128, false>(policy, warm, out);                     // all state in shared memory
 }
 
+const void *lookup_f32_pn_seed(int policy)
+{
+    return policy == TMPC_ORDER_PARITY ? (const void *)&tmpc::pn_seed_kernel<12, 4, 10, false> : (const void *)&tmpc::pn_seed_kernel<12, 4, 10, true>;
+}
+
 // fused closed loop (ROLL instances): warm, tensor-memory variant, shared box, PARITY order
 bool lookup_f32_roll(int pattern, bool cb, KernelInfo &out)
 {

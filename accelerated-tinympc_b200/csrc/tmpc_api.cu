@@ -60,6 +60,8 @@ struct tmpc_ctx_impl {
     // per-lane coalesced scratch of the fp32 12/4/10 kernel (SolveArgs::scratch)
     void *d_lane_scratch = nullptr;
     size_t d_lane_scratch_bytes = 0;
+    void *d_pn_seed = nullptr;     // p_N seeds of a batch with per-instance Xref (pre-pass of the fp32 12/4/10 kernel)
+    size_t d_pn_seed_bytes = 0;
     int reserve_sms_next = 0;      // host pipeline: the next launch leaves this many SMs to the ranking kernels that run beside it
     bool duals_zero_next = false;  // tmpc_batch rollout with reset duals: the next launch of the fp32 12/4/10 kernel zero-fills y, g itself
     void *d_model_f32 = nullptr;   // device copy of model_f32 (TMPC_KERNEL=f32_tma_cache: the kernel stages it into shared memory by TMA)
@@ -564,6 +566,7 @@ struct DevArgs {  // type-erased tmpc::SolveArgs<T> (identical layout for float/
     const void *roll_table;
     long long roll_rows;
     const int *roll_start;
+    const void *pn_seed;
 };
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<float>), "arg layout");
 static_assert(sizeof(DevArgs) == sizeof(tmpc::SolveArgs<double>), "arg layout");
@@ -700,6 +703,25 @@ int launch_kernel_info(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, cuda
     }
     void *params[2] = {model_param(c, ki), &da};
     if (time_it && !ev0_done) CUDA_TRY(c, cudaEventRecord(c->ev0, s));
+    da.pn_seed = nullptr;
+    if (ki.model_kind == 1 && da.xref_stride != 0 && !da.gate && !da.roll_table && da.batch >= 8192 && !getenv("TMPC_NO_PN_PREPASS")) {
+        // per-instance reference trajectories, inputs resident: the p_N seeds in one coalesced pre-pass (part of the solve: inside the events)
+        const size_t need = (size_t)da.batch * c->nx * sizeof(float);
+        if (c->d_pn_seed_bytes < need) {
+            CUDA_TRY(c, cudaDeviceSynchronize());
+            if (c->d_pn_seed) cudaFree(c->d_pn_seed);
+            c->d_pn_seed = nullptr; c->d_pn_seed_bytes = 0;
+            CUDA_TRY(c, cudaMalloc(&c->d_pn_seed, need));
+            c->d_pn_seed_bytes = need;
+        }
+        const void *xr = da.Xref;
+        long long stride = da.xref_stride, nb = da.batch;
+        void *out = c->d_pn_seed;
+        void *pp[5] = {c->model_f32.data(), (void *)&xr, &stride, &nb, &out};
+        CUDA_TRY(c, cudaLaunchKernel(tmpc_dispatch::lookup_f32_pn_seed(c->policy), dim3((unsigned)((nb + 127) / 128)), dim3(128), pp, 0, s));
+        da.pn_seed = c->d_pn_seed;
+        c->stats.launches += 1;
+    }
     CUDA_TRY(c, cudaLaunchKernel(ki.fn, dim3((unsigned)blocks), dim3(ki.block), params, ki.smem, s));
     if (time_it) CUDA_TRY(c, cudaEventRecord(c->ev1, s));
     {
@@ -1299,6 +1321,7 @@ int tmpc_destroy(tmpc_ctx *ctx)
     if (c->d_model_w) cudaFree(c->d_model_w);
     if (c->d_model_rt) cudaFree(c->d_model_rt);
     if (c->d_rt_scratch) cudaFree(c->d_rt_scratch);
+    if (c->d_pn_seed) cudaFree(c->d_pn_seed);
     if (c->d_lane_scratch) cudaFree(c->d_lane_scratch);
     if (c->d_model_f32) cudaFree(c->d_model_f32);
     for (void *p : c->d_ib) if (p) cudaFree(p);

@@ -23,6 +23,8 @@ struct KernelInfo {
 // per_instance_bounds: the IB instances (variant 2 only; boxes read from the lane's scratch rows)
 bool lookup_f32(int policy, bool warm, int pattern, bool const_bounds, int variant, KernelInfo &out, bool per_instance_bounds = false);
 
+// pre-pass of that kernel for per-instance reference trajectories: (ModelF32, Xref, stride, batch, out [batch][12])
+const void *lookup_f32_pn_seed(int policy);
 // the same kernel running a whole closed loop per claimed instance (SolveArgs::roll_steps MPC steps, state kept on the lane between
 // them): warm PARITY solves with a shared box on the tensor-memory variant
 bool lookup_f32_roll(int pattern, bool const_bounds, KernelInfo &out);

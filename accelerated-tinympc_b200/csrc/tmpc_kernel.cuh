@@ -314,6 +314,8 @@ template <class T> struct SolveArgs {
     const T *roll_table;
     long long roll_rows;
     const int *roll_start;
+    // fp32 12/4/10 kernel, per-instance Xref: p_N seeds -(Xref_{N-1}^T Pinf) [batch][nx] computed by a pre-pass (null = by the lanes)
+    const T *pn_seed;
 };
 
 // instance solved by the idx-th claim of the work counter

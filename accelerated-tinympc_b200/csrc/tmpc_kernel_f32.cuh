@@ -398,6 +398,23 @@ template <int NX, int NU, int NH> struct ScratchMap {
                                   // residual is within this factor of its tolerance (see the kernel's backward section)
 #endif
 
+// Pre-pass for batches with per-instance reference trajectories: the p_N seed -(Xref_{N-1}^T Pinf) (admm.cpp:83) of every instance,
+// one thread each, same evaluation order as the kernel's own seed_pn.
+template <int NX, int NU, int NH, bool FAST>
+__global__ void pn_seed_kernel(const __grid_constant__ ModelF32<NX, NU, NH> P, const float *__restrict__ Xref, long long stride, long long batch,
+                               float *__restrict__ out)
+{
+    using O = Orders<float, NX, NU>;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    float xr[NX], pn[NX];
+    gload<float, NX>(Xref + b * stride + (NH - 1) * NX, xr);
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+        pn[j] = -dot<float, O::XtP, NX, FAST>([&](int k) { return P.Pt[k * NX + j]; }, [&](int k) { return xr[k]; });
+    gstore<float, NX>(out + b * NX, pn);
+}
+
 template <int NX, int NU, int NH, int BLOCK, bool TM> struct SmemLayoutF32 {
     using SU = SVec<float, NU, NH - 1, BLOCK>;
     using SP = SVec<float, NX, 1, BLOCK>;
@@ -703,7 +720,11 @@ admm_kernel_f32(const __grid_constant__ ModelF32<NX, NU, NH> Pc, const __grid_co
                     gload<float, NX>(a.x0 + inst * NX, x0);
                     if constexpr (ROLL) sx0.store(0, x0);
                     if (tab) seed_pn(window(0) + (NH - 1) * NX);
-                    else if (!shared_xref) seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
+                    else if (!shared_xref) {
+                        // (the refill section is warp-level code: with the seeds from the pre-pass it issues three loads instead of a 12 x 12 product)
+                        if (a.pn_seed) { float pn[NX]; gload<float, NX>(a.pn_seed + inst * NX, pn); spn.store(0, pn); }
+                        else seed_pn(a.Xref + inst * a.xref_stride + (NH - 1) * NX);
+                    }
                     if constexpr (IB) {
                         // the instance's own box -> the lane's scratch rows (a missing / disabled family = +-inf).  Loads are issued
                         // half a horizon at a time, so the copy costs a handful of memory round trips instead of one per stage
