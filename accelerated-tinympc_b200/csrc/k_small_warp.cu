@@ -79,26 +79,33 @@ bool lookup_small(int block, int policy, bool warm, KernelInfo &out)
     return pick_small<4, 10, 384>(policy, warm, out);
 }
 
-template <int NH, bool FAST, bool WARM>
+template <int NH, bool FAST, bool WARM, int WARPS>
 KernelInfo make_info_warp4()
 {
-    static_assert(tmpc::Warp4Smem<NH>::total_bytes(4) <= 232448, "per-block shared memory limit of sm_100");
+    static_assert(tmpc::Warp4Smem<NH>::total_bytes(WARPS) <= 232448, "per-block shared memory limit of sm_100");
     KernelInfo k;
-    k.fn = (const void *)&tmpc::admm_kernel_warp4<NH, FAST, WARM>;
-    k.smem = tmpc::Warp4Smem<NH>::total_bytes(4);
-    k.block = 128;
+    k.fn = (const void *)&tmpc::admm_kernel_warp4<NH, FAST, WARM, WARPS>;
+    k.smem = tmpc::Warp4Smem<NH>::total_bytes(WARPS);
+    k.block = WARPS * 32;
     k.model_bytes = sizeof(tmpc::ModelWarp);
     k.model_kind = 2;
-    k.per_block = 16;   // 4 warps x 4 slots
+    k.per_block = WARPS * 4;   // four slots per warp
+    // eight warps: g, v of two slots per warp in the L2-resident scratch (rows of 128 B)
+    k.scratch_per_block = WARPS == 8 ? size_t(WARPS) * 2 * 2 * NH * 128 : 0;
     return k;
+}
+template <int WARPS> void pick_warp4(int policy, bool warm, KernelInfo &out)
+{
+    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_warp4<50, false, true, WARPS>() : make_info_warp4<50, false, false, WARPS>();
+    else out = warm ? make_info_warp4<50, true, true, WARPS>() : make_info_warp4<50, true, false, WARPS>();
 }
 
 bool lookup_warp(int variant, int policy, bool warm, KernelInfo &out)
 {
     if (variant == 1) return pick_warp<50, 16, true>(policy, warm, out);
     if (variant == 2) return pick_warp<50, 12, false>(policy, warm, out);
-    if (policy == TMPC_ORDER_PARITY) out = warm ? make_info_warp4<50, false, true>() : make_info_warp4<50, false, false>();
-    else out = warm ? make_info_warp4<50, true, true>() : make_info_warp4<50, true, false>();
+    if (variant == 3) pick_warp4<8>(policy, warm, out);   // two warps per scheduler
+    else pick_warp4<4>(policy, warm, out);
     return true;
 }
 

@@ -177,7 +177,7 @@ bool lookup_kernel(int nx, int nu, int N, int dtype, int policy, bool warm, Kern
     // large shape: one warp per instance.  g,v in tensor memory -> 16 instances / SM (TMPC_KERNEL=warp_smem: all state in
     // shared memory, 17.8 KB each -> 12 instances / SM)
     if (nx == 32 && nu == 8 && N == 50 && dtype == TMPC_F32)
-        return tmpc_dispatch::lookup_warp(e && !strcmp(e, "warp_smem") ? 2 : e && !strcmp(e, "warp4") ? 0 : 1, policy, warm, out);
+        return tmpc_dispatch::lookup_warp(e && !strcmp(e, "warp_smem") ? 2 : e && !strcmp(e, "warp4") ? 0 : e && !strcmp(e, "warp4x2") ? 3 : 1, policy, warm, out);
     return lookup_kernel_rt(nx, nu, N, dtype, policy, out);
 }
 
@@ -647,7 +647,21 @@ int plan_lane_scratch(tmpc_ctx_impl *c, const KernelInfo &ki, DevArgs &da, long 
     da.scratch = nullptr; da.sc_ib = da.sc_wm = -1; da.sc_chunks = 0; da.test_flags = 0;
     da.ixmin = da.ixmax = da.iumin = da.iumax = nullptr;
     da.model_g = nullptr;
-    if (ki.model_kind != 1) { c->duals_zero_next = false; return TMPC_OK; }   // (the other kernels take their duals from the caller's buffers)
+    if (ki.model_kind != 1) {
+        c->duals_zero_next = false;   // (the other kernels take their duals from the caller's buffers)
+        if (ki.scratch_per_block) {   // eight-warp 32/8/50 kernel: g, v rows of two slots per warp
+            const size_t need = (size_t)blocks * ki.scratch_per_block;
+            if (c->d_lane_scratch_bytes < need) {
+                CUDA_TRY(c, cudaDeviceSynchronize());
+                if (c->d_lane_scratch) cudaFree(c->d_lane_scratch);
+                c->d_lane_scratch = nullptr; c->d_lane_scratch_bytes = 0;
+                CUDA_TRY(c, cudaMalloc(&c->d_lane_scratch, need));
+                c->d_lane_scratch_bytes = need;
+            }
+            da.scratch = c->d_lane_scratch;
+        }
+        return TMPC_OK;
+    }
     if (kernel_variant() == 3) {
         // (re-uploaded per launch: 3.9 KB on the launch stream, ordered before the kernel; the A/B variant is not tuned for launch cost)
         if (!c->d_model_f32) CUDA_TRY(c, cudaMalloc(&c->d_model_f32, c->model_f32.size()));

@@ -15,6 +15,7 @@ struct KernelInfo {
                      // 2: tmpc::ModelWarp (warp-per-instance kernel; pointers into the ctx's device model image)
                      // 3: tmpc::ModelRT<T> (run-time-shape kernel; pointers into the ctx's device model image + scratch)
     int per_block;   // instances resident per block (threads for the thread-per-instance kernels, warps for kind 2)
+    size_t scratch_per_block = 0;   // bytes of SolveArgs::scratch per block (kind 2, eight-warp four-slot kernel)
 };
 
 // fp32 12/4/10 production kernel (tmpc_kernel_f32.cuh).  variant 2: g, v in tensor memory, 256 instances / SM (default);
@@ -46,7 +47,8 @@ bool lookup_small(int block, int policy, bool warm, KernelInfo &out);
 // the same shape running a whole closed loop per claimed instance in registers (SolveArgs::roll_steps MPC steps); block = 256 or 384
 bool lookup_small_roll(int block, KernelInfo &out);
 // fp32 32/8/50: variant 0 = four instances per warp (tmpc_kernel_warp4.cuh, default); 1 = one instance per warp, g, v in tensor
-// memory (tmpc_kernel_warp.cuh, 16 instances / SM); 2 = one instance per warp, all state in shared memory (12 / SM)
+// memory (tmpc_kernel_warp.cuh, 16 instances / SM); 2 = one instance per warp, all state in shared memory (12 / SM);
+// 3 = four instances per warp, eight warps (32 instances / SM; g, v of two slots per warp in L2-resident scratch)
 bool lookup_warp(int variant, int policy, bool warm, KernelInfo &out);
 
 }  // namespace tmpc_dispatch

@@ -34,14 +34,21 @@ template <int NH> struct Warp4Smem {
     static constexpr size_t total_bytes(int warps) { return size_t(SH::SH_FLOATS) * 4 + size_t(FLOATS) * 4 * warps; }
 };
 
-template <int NH, bool FAST, bool WARM>
-__global__ void __launch_bounds__(128, 1)
+// WARPS = 8 (TMPC_KERNEL=warp4x2): TWO warps per scheduler.  Tensor memory decides the residency of the four-warp kernel (400 of a lane
+// quadrant's 512 columns per warp); shared memory has room for eight warps (197 KB).  So each warp keeps g, v of slots 0 and 1 in
+// tensor memory (200 columns; two warps per quadrant) and g, v of slots 2 and 3 in its rows of the L2-resident scratch
+// (SolveArgs::scratch: [warp][2 slots][g | v][NH] rows of 128 B, one float per lane, read and written by the owning lane only, one
+// stage ahead of their use like the tensor-memory columns).  32 instances per SM.
+template <int NH, bool FAST, bool WARM, int WARPS = 4>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ SolveArgs<float> a)
 {
     using S = Warp4Smem<NH>;
     using SH = typename S::SH;
-    constexpr int NS = S::NS, WARPS = 4;
-    static_assert(NS * 2 * NH <= 512, "four slots x (g, v) x NH columns in one TMEM lane quadrant");
+    constexpr int NS = S::NS;
+    static_assert(WARPS == 4 || WARPS == 8, "one or two warps per scheduler");
+    constexpr int TS = WARPS == 4 ? NS : 2;   // slots whose g, v live in tensor memory
+    static_assert((WARPS / 4) * TS * 2 * NH <= 512, "slots x (g, v) x NH columns of the warps that share a TMEM lane quadrant");
     constexpr unsigned FULLM = 0xffffffffu;
     constexpr int XROW = WNX * NH, UROW = WNU * (NH - 1);
     extern __shared__ __align__(16) unsigned char smem[];
@@ -76,12 +83,20 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tbase = *slot_addr + ((uint32_t)(warp * 32) << 16);     // this warp's lane quadrant, column 0
+    // this warp's lane quadrant (warp % 4) and its column range in it
+    const uint32_t tbase = *slot_addr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TS * 2 * NH);
+    float *scr = nullptr;                                                  // this lane's column of the warp's scratch rows
+    if constexpr (TS < NS) scr = reinterpret_cast<float *>(a.scratch) + ((size_t)blockIdx.x * WARPS + warp) * ((NS - TS) * 2 * NH) * 32 + lane;
     const float4 *fwd4 = reinterpret_cast<const float4 *>(shr + SH::SH_FWD), *bwd4 = reinterpret_cast<const float4 *>(shr + SH::SH_BWD);
     const float *bxmin = shr + SH::SH_XMIN, *bxmax = shr + SH::SH_XMAX, *bumin = shr + SH::SH_UMIN, *bumax = shr + SH::SH_UMAX;
     // slot e, stage i: g at column e*2*NH + i, v at + NH
     auto gcol = [&](int e, int i) -> uint32_t { return tbase + (uint32_t)(e * 2 * NH + i); };
     auto vcol = [&](int e, int i) -> uint32_t { return tbase + (uint32_t)(e * 2 * NH + NH + i); };
+    // g / v of (slot e, stage i): tensor-memory column or scratch row (e is a compile-time constant wherever these are called)
+    auto ldg_ = [&](int e, int i, float &r) { if (e < TS) tm_ld1(gcol(e, i), r); else r = __ldcg(scr + ((e - TS) * 2 * NH + i) * 32); };
+    auto ldv_ = [&](int e, int i, float &r) { if (e < TS) tm_ld1(vcol(e, i), r); else r = __ldcg(scr + ((e - TS) * 2 * NH + NH + i) * 32); };
+    auto stg_ = [&](int e, int i, float r) { if (e < TS) tm_st1(gcol(e, i), r); else __stcg(scr + ((e - TS) * 2 * NH + i) * 32, r); };
+    auto stv_ = [&](int e, int i, float r) { if (e < TS) tm_st1(vcol(e, i), r); else __stcg(scr + ((e - TS) * 2 * NH + NH + i) * 32, r); };
 
     // ---- per-slot state (warp-uniform unless noted)
     long long inst[NS];
@@ -104,7 +119,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
 #pragma unroll 5
             for (int i = 0; i < NH; ++i) {
                 float g;
-                tm_ld1(gcol(e, i), g);
+                ldg_(e, i, g);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(g) :: "memory");
                 gg[i * WNX + lane] = g;
             }
@@ -151,11 +166,11 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                 const float *gg = a.wg + ni * XROW, *gv = a.wv + ni * XROW;
                 for (int k = lane; k < UROW; k += 32) { se[S::D + k] = gd[k]; se[S::Y + k] = gy[k]; se[S::Z + k] = gz[k]; }
 #pragma unroll 5
-                for (int i = 0; i < NH; ++i) { tm_st1(gcol(e, i), gg[i * WNX + lane]); tm_st1(vcol(e, i), gv[i * WNX + lane]); }
+                for (int i = 0; i < NH; ++i) { stg_(e, i, gg[i * WNX + lane]); stv_(e, i, gv[i * WNX + lane]); }
             } else {
                 for (int k = lane; k < UROW; k += 32) { se[S::D + k] = 0.f; se[S::Y + k] = 0.f; se[S::Z + k] = 0.f; }
 #pragma unroll 5
-                for (int i = 0; i < NH; ++i) { tm_st1(gcol(e, i), 0.f); tm_st1(vcol(e, i), 0.f); }
+                for (int i = 0; i < NH; ++i) { stg_(e, i, 0.f); stv_(e, i, 0.f); }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
@@ -192,7 +207,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
             };
             float x[NS], g[NS], v[NS];
 #pragma unroll
-            for (int e = 0; e < NS; ++e) { x[e] = x0[e]; tm_ld1(gcol(e, 0), g[e]); tm_ld1(vcol(e, 0), v[e]); }
+            for (int e = 0; e < NS; ++e) { x[e] = x0[e]; ldg_(e, 0, g[e]); ldv_(e, 0, v[e]); }
             float xmn = bxmin[lane], xmx = bxmax[lane], umn = bumin[ur], umx = bumax[ur];
             float d = myd[ur], y = myy[ur], z = myz[ur];
             float *uo = (urun && a.u) ? a.u + uinst * UROW + ur : nullptr;
@@ -275,8 +290,8 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                     pri_x[h] = fmaxf(pri_x[h], fabsf(rp.x)); pri_x[h + 1] = fmaxf(pri_x[h + 1], fabsf(rp.y));   // :95
                     dua_x[h] = fmaxf(dua_x[h], fabsf(rd.x)); dua_x[h + 1] = fmaxf(dua_x[h + 1], fabsf(rd.y));   // :96
                     const float2 gn = sub2(add2(g2, x2), t);                                           // :70
-                    tm_st1(gcol(h, i), gn.x); tm_st1(vcol(h, i), t.x);
-                    tm_st1(gcol(h + 1, i), gn.y); tm_st1(vcol(h + 1, i), t.y);
+                    stg_(h, i, gn.x); stv_(h, i, t.x);
+                    stg_(h + 1, i, gn.y); stv_(h + 1, i, t.y);
                 }
                 __syncwarp();
                 {   // operands of stage i+1 (the nu-rows of the last stage do not exist: re-read stage i's)
@@ -284,7 +299,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                     xmn = bxmin[in * WNX + lane]; xmx = bxmax[in * WNX + lane];
                     umn = bumin[iu * WNU + ur]; umx = bumax[iu * WNU + ur];
 #pragma unroll
-                    for (int e = 0; e < NS; ++e) { tm_ld1(gcol(e, in), g[e]); tm_ld1(vcol(e, in), v[e]); }
+                    for (int e = 0; e < NS; ++e) { ldg_(e, in, g[e]); ldv_(e, in, v[e]); }
                     d = myd[iu * WNU + ur]; y = myy[iu * WNU + ur]; z = myz[iu * WNU + ur];
                 }
                 // x_{i+1} = Adyn x_i + Bdyn u_i                                                         :35
@@ -324,7 +339,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                     t = fminf(xmx, fmaxf(xmn, t));
                     pri_x[e] = fmaxf(pri_x[e], fabsf(__fsub_rn(x[e], t)));
                     dua_x[e] = fmaxf(dua_x[e], fabsf(__fsub_rn(v[e], t)));
-                    tm_st1(gcol(e, i), __fsub_rn(__fadd_rn(g[e], x[e]), t)); tm_st1(vcol(e, i), t);
+                    stg_(e, i, __fsub_rn(__fadd_rn(g[e], x[e]), t)); stv_(e, i, t);
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
@@ -389,7 +404,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
             {
                 float g[NS], v[NS];
 #pragma unroll
-                for (int e = 0; e < NS; ++e) { tm_ld1(gcol(e, NH - 1), g[e]); tm_ld1(vcol(e, NH - 1), v[e]); }
+                for (int e = 0; e < NS; ++e) { ldg_(e, NH - 1, g[e]); ldv_(e, NH - 1, v[e]); }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(g[0]), "+f"(g[1]), "+f"(g[2]), "+f"(g[3]), "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory");
 #pragma unroll
                 for (int e = 0; e < NS; ++e) {
@@ -404,7 +419,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
             float z = myz[(NH - 2) * WNU + ur], y = myy[(NH - 2) * WNU + ur];
             float v[NS], g[NS], xr[NS];
 #pragma unroll
-            for (int e = 0; e < NS; ++e) { tm_ld1(gcol(e, NH - 2), g[e]); tm_ld1(vcol(e, NH - 2), v[e]); xr[e] = __ldg(xrf[e] + (NH - 2) * WNX + lane); }
+            for (int e = 0; e < NS; ++e) { ldg_(e, NH - 2, g[e]); ldv_(e, NH - 2, v[e]); xr[e] = __ldg(xrf[e] + (NH - 2) * WNX + lane); }
 #pragma unroll 1
             for (int i = NH - 2; i >= 0; --i) {
                 const float r = __fmul_rn(nrho, __fsub_rn(z, y));                                    // :80  (slot sl, row ur)
@@ -526,7 +541,7 @@ admm_kernel_warp4(const __grid_constant__ ModelWarp P, const __grid_constant__ S
                     const int ip = (i > 0) ? i - 1 : 0;
                     z = myz[ip * WNU + ur]; y = myy[ip * WNU + ur];
 #pragma unroll
-                    for (int e = 0; e < NS; ++e) { tm_ld1(gcol(e, ip), g[e]); tm_ld1(vcol(e, ip), v[e]); xr[e] = __ldg(xrf[e] + ip * WNX + lane); }
+                    for (int e = 0; e < NS; ++e) { ldg_(e, ip, g[e]); ldv_(e, ip, v[e]); xr[e] = __ldg(xrf[e] + ip * WNX + lane); }
                 }
                 // d_i = Quu_inv (Bdyn^T p_{i+1} + r_i)                                                  :19  (slot sl, row ur)
                 {

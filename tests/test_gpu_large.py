@@ -120,7 +120,7 @@ def test_large_step_functions(pkg, oracle):
                 assert term[b] == rc
 
 
-@pytest.mark.parametrize("variant", ["", "warp4", "warp_smem"])
+@pytest.mark.parametrize("variant", ["", "warp4", "warp4x2", "warp_smem"])
 def test_large_kernel_variants_and_slot_refill(pkg, oracle, monkeypatch, variant):
     """Default = four instances per warp (tmpc_kernel_warp4.cuh); TMPC_KERNEL=warp1 / warp_smem = the one-instance-per-warp
     kernels.  1,100 instances on a 3-block grid cap would be too few to refill slots, so the batch is several times the resident
