@@ -318,6 +318,34 @@ int tiny_precompute_raw(int nx, int nu, const tinytype *Adyn, const tinytype *Bd
     return sweeps;
 }
 
+int tiny_rollout_batch(TinySolver *s, const TinyRolloutIn *in, TinyRolloutOut *out)
+{
+    if (!s || !in || !out) return fail("tiny_rollout_batch: null argument");
+    if (in->batch < 1 || in->steps < 1 || !in->x0) return fail("tiny_rollout_batch: batch, steps >= 1 and x0 are required");
+    if (!in->table && !in->Xref) return fail("tiny_rollout_batch: a fixed Xref or a reference table is required");
+    if (in->table && in->table_rows < s->N) return fail("tiny_rollout_batch: the reference table needs at least N rows");
+    Backend *b = backend(s);
+    if (b->ib_batch) return fail("tiny_rollout_batch: per-instance bounds are set (tiny_set_instance_bounds): clear them first");
+    if (sync_model(s) != 0) return -1;
+    tmpc_batch *bt = nullptr;
+    if (tmpc_batch_create(b->ctx, in->batch, &bt) != TMPC_OK) return fail(std::string("tmpc_batch_create: ") + tmpc_last_error(b->ctx));
+    auto bail = [&](const char *what) {
+        g_err = std::string(what) + ": " + tmpc_batch_last_error(bt);
+        tmpc_batch_destroy(bt);
+        return -1;
+    };
+    if (tmpc_batch_set_x0(bt, in->x0, TMPC_MEM_HOST) != TMPC_OK) return bail("tmpc_batch_set_x0");
+    if (in->table) {
+        if (tmpc_batch_set_xref_table(bt, in->table, in->table_rows, in->start, TMPC_MEM_HOST) != TMPC_OK) return bail("tmpc_batch_set_xref_table");
+    } else if (tmpc_batch_set_xref(bt, in->Xref, in->xref_shared ? 1 : 0, TMPC_MEM_HOST) != TMPC_OK) return bail("tmpc_batch_set_xref");
+    if (tmpc_batch_rollout(bt, in->steps, in->reset_duals ? 1 : 0, out->x_hist, out->u0_hist, out->iter_hist, out->status_hist, TMPC_MEM_HOST) != TMPC_OK)
+        return bail("tmpc_batch_rollout");
+    if (out->x && tmpc_batch_get(bt, TMPC_GET_X, out->x, TMPC_MEM_HOST) != TMPC_OK) return bail("tmpc_batch_get(x)");
+    if (out->u && tmpc_batch_get(bt, TMPC_GET_U, out->u, TMPC_MEM_HOST) != TMPC_OK) return bail("tmpc_batch_get(u)");
+    tmpc_batch_destroy(bt);
+    return 0;
+}
+
 int tiny_set_order_policy(TinySolver *s, int policy)
 {
     if (!s || (policy != TMPC_ORDER_PARITY && policy != TMPC_ORDER_FAST)) return fail("tiny_set_order_policy: bad argument");

@@ -53,6 +53,34 @@ typedef struct {
  * (instances that stop at max_iter have status 11), negative = error. */
 int tiny_solve_batch(TinySolver *solver, const TinyBatchIn *in, TinyBatchOut *out);
 
+/* The closed loop every example of the reference runs around tiny_solve (quadrotor_hovering.cpp:90-114, quadrotor_tracking.cpp:93-118,
+ * codegen_cartpole.cpp:75-122), for `batch` instances and `steps` MPC steps in ONE call, entirely on the device:
+ *     [Xref = rows w0 .. w0+N-1 of `table`, w0 = min(start[b] + k, rows - N)]  ->  [y = g = 0 if reset_duals]  ->  tiny_solve
+ *     (warm: d, v, z carried from step to step)  ->  x0 <- Adyn x0 + Bdyn u(:,0)
+ * starting from the cold workspace the examples zero.  Host pointers.  Forwards to tmpc_batch_* (include/tmpc.h); with reset_duals
+ * on a float build of the 12/4/10 or 4/1/10 shape the whole loop is one persistent kernel launch. */
+typedef struct {
+    int64_t batch;
+    int32_t steps;
+    int32_t reset_duals;
+    const tinytype *x0;      /* [batch][nx] initial measurements */
+    const tinytype *Xref;    /* fixed reference: [N][nx] if xref_shared, else [batch][N][nx]; ignored when table != NULL */
+    int32_t xref_shared;
+    const tinytype *table;   /* reference table [table_rows][nx] (Xref_total transposed), or NULL */
+    int64_t table_rows;
+    const int32_t *start;    /* [batch] first row of each instance's window at step 0; NULL = 0 */
+} TinyRolloutIn;
+
+typedef struct {             /* every pointer may be NULL (= not wanted) */
+    tinytype *x_hist;        /* [steps+1][batch][nx]: the measurement each step started from; entry `steps` = the final plant state */
+    tinytype *u0_hist;       /* [steps][batch][nu]: the control applied */
+    int32_t *iter_hist;      /* [steps][batch] */
+    int32_t *status_hist;    /* [steps][batch] */
+    tinytype *x, *u;         /* trajectories of the LAST solve: [batch][N][nx], [batch][N-1][nu] */
+} TinyRolloutOut;
+
+int tiny_rollout_batch(TinySolver *solver, const TinyRolloutIn *in, TinyRolloutOut *out);
+
 /* One box per instance for tiny_solve_batch: the wrapper's set_xmin / set_xmax / set_umin / set_umax
  * (tiny_wrapper.cpp:43-129) with a leading batch dimension.  x_min, x_max [batch][N][nx], u_min, u_max [batch][N-1][nu]
  * (host arrays, or device arrays when on_device != 0); copied.  While set, tiny_solve_batch must be called with exactly

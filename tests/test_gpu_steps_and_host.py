@@ -141,3 +141,14 @@ def test_host_api_batch_over_devices_and_controls_only(tag):
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "batch_devices ok" in p.stdout
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_host_api_rollout_batch(tag):
+    """tiny_rollout_batch (the examples' closed loop for a batch in one call; fused into one persistent launch in the float build)
+    against a step-by-step loop of tiny_solve_batch with the warm state carried in host arrays (host/examples/rollout_batch.cpp,
+    self-checking): controls, iteration counts, status of every step and the last trajectories agree bit for bit."""
+    p = subprocess.run([os.path.join(BIN, "rollout_batch_" + tag), DATA, "50000" if tag == "f32" else "12000", "6"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "rollout batch ok" in p.stdout
