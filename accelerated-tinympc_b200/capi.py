@@ -25,7 +25,7 @@ EXPORTS = ["tmpc_create", "tmpc_destroy", "tmpc_set_model", "tmpc_set_settings",
            "tmpc_batch_last_rollout_ms", "tmpc_batch_last_error",
            "tmpc_systems_precompute", "tmpc_systems_destroy", "tmpc_systems_get", "tmpc_solve_systems",
            "tmpc_multi_create", "tmpc_multi_destroy", "tmpc_multi_device_count", "tmpc_multi_ctx", "tmpc_multi_set_model",
-           "tmpc_multi_set_settings", "tmpc_multi_set_instance_bounds", "tmpc_multi_solve", "tmpc_multi_get_stats",
+           "tmpc_multi_set_settings", "tmpc_multi_set_instance_bounds", "tmpc_multi_solve", "tmpc_multi_rollout", "tmpc_multi_get_stats",
            "tmpc_multi_last_error", "tmpc_device_count"]
 
 SYS = {"Kinf": 0, "Pinf": 1, "Quu_inv": 2, "AmBKt": 3, "Adyn": 4, "Bdyn": 5, "Q": 6, "rho": 7, "sweeps": 8}
@@ -134,6 +134,8 @@ def load():
     lib.tmpc_multi_set_instance_bounds.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4
     lib.tmpc_multi_solve.restype = C.c_int
     lib.tmpc_multi_solve.argtypes = [C.c_void_p, C.POINTER(TmpcSolveArgs)]
+    lib.tmpc_multi_rollout.restype = C.c_int
+    lib.tmpc_multi_rollout.argtypes = [C.c_void_p, C.c_void_p]
     lib.tmpc_multi_get_stats.restype = C.c_int
     lib.tmpc_multi_get_stats.argtypes = [C.c_void_p, C.POINTER(TmpcStats), C.c_void_p]
     lib.tmpc_multi_last_error.restype = C.c_char_p
@@ -293,6 +295,14 @@ class Solver:
             pass
 
 
+class RolloutArgs(C.Structure):
+    """tmpc_rollout_args (include/tmpc.h)."""
+    _fields_ = [("batch", C.c_int64), ("steps", C.c_int32), ("reset_duals", C.c_int32), ("x0", C.c_void_p), ("Xref", C.c_void_p),
+                ("xref_shared", C.c_int32), ("table", C.c_void_p), ("table_rows", C.c_int64), ("start", C.POINTER(C.c_int32)),
+                ("x0_hist", C.c_void_p), ("u0_hist", C.c_void_p), ("iter_hist", C.POINTER(C.c_int32)), ("status_hist", C.POINTER(C.c_int32)),
+                ("x", C.c_void_p), ("u", C.c_void_p)]
+
+
 class Multi:
     """tmpc_multi: one host batch over several devices from one process (one ctx + one host worker thread per device,
     contiguous instance ranges, no inter-device traffic).  devices: None = every visible device, an int n = the first n,
@@ -350,6 +360,38 @@ class Multi:
         self.solve_raw(x0.shape[0], x0, Xref, shared, out.get("x"), out.get("u"), out.get("iter"), out.get("status"),
                        out.get("resid"), warm=warm, u0=out.get("u0"))
         return out
+
+    def rollout(self, x0, steps, xref=None, table=None, start=None, reset_duals=True, last=False):
+        """tmpc_multi_rollout: the closed loop of every instance on the device that owns its index range.  Returns the histories
+        (x0 [steps+1,B,nx], u0 [steps,B,nu], iter, status [steps,B]) and, with last=True, x / u of the last solve."""
+        x0 = np.ascontiguousarray(x0, dtype=self.dtype)
+        B = x0.shape[0]
+        r = RolloutArgs()
+        keep = [x0]
+        r.batch, r.steps, r.reset_duals, r.x0 = B, steps, 1 if reset_duals else 0, _addr(x0)
+        if table is not None:
+            t = np.ascontiguousarray(table, dtype=self.dtype).reshape(-1, self.nx)
+            keep.append(t)
+            r.table, r.table_rows = _addr(t), t.shape[0]
+            if start is not None:
+                st = np.ascontiguousarray(start, dtype=np.int32).reshape(B)
+                keep.append(st)
+                r.start = st.ctypes.data_as(C.POINTER(C.c_int32))
+        else:
+            xr = np.ascontiguousarray(xref, dtype=self.dtype)
+            keep.append(xr)
+            r.Xref, r.xref_shared = _addr(xr), 1 if xr.ndim == 2 else 0
+        h = {"x0": np.empty((steps + 1, B, self.nx), self.dtype), "u0": np.empty((steps, B, self.nu), self.dtype),
+             "iter": np.empty((steps, B), np.int32), "status": np.empty((steps, B), np.int32)}
+        r.x0_hist, r.u0_hist = _addr(h["x0"]), _addr(h["u0"])
+        r.iter_hist = h["iter"].ctypes.data_as(C.POINTER(C.c_int32))
+        r.status_hist = h["status"].ctypes.data_as(C.POINTER(C.c_int32))
+        if last:
+            h["x"] = np.empty((B, self.N, self.nx), self.dtype)
+            h["u"] = np.empty((B, self.N - 1, self.nu), self.dtype)
+            r.x, r.u = _addr(h["x"]), _addr(h["u"])
+        self._check(self.lib.tmpc_multi_rollout(self._m, C.byref(r)), "tmpc_multi_rollout")
+        return h
 
     def stats(self):
         n = self.device_count

@@ -354,8 +354,12 @@ int tmpc_batch_get(tmpc_batch *bt, int32_t what, void *dst, int32_t mem)
     return batch_copy_out(b, dst, src, (size_t)b->B * per, mem);
 }
 
-int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void *x0_hist, void *u0_hist, int32_t *iter_hist,
-                       int32_t *status_hist, int32_t mem)
+}  // extern "C"
+
+// hist_stride: instances per step row of the caller's HOST history arrays (>= batch; tmpc_multi_rollout: the whole job's batch, this
+// device's range starting at the pointers passed) -- device histories are always dense
+int batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void *x0_hist, void *u0_hist, int32_t *iter_hist,
+                  int32_t *status_hist, int32_t mem, int64_t hist_stride)
 {
     if (!bt) return TMPC_ERR_INVALID;
     tmpc_batch_impl *b = BAT(bt);
@@ -448,10 +452,12 @@ int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void 
     if (rc == TMPC_OK) {
         cudaEventRecord(r1, s);
         if (host) {
-            if (dx) cudaMemcpyAsync(x0_hist, dx, nxb * (steps + 1), cudaMemcpyDeviceToHost, s);
-            if (du) cudaMemcpyAsync(u0_hist, du, nub * steps, cudaMemcpyDeviceToHost, s);
-            if (di) cudaMemcpyAsync(iter_hist, di, ib * steps, cudaMemcpyDeviceToHost, s);
-            if (ds) cudaMemcpyAsync(status_hist, ds, ib * steps, cudaMemcpyDeviceToHost, s);
+            // one row of `batch` instances per step; the caller's rows are hist_stride instances apart
+            const size_t hs = (size_t)(hist_stride > 0 ? hist_stride : B);
+            if (dx) cudaMemcpy2DAsync(x0_hist, hs * c->nx * es, dx, nxb, nxb, (size_t)steps + 1, cudaMemcpyDeviceToHost, s);
+            if (du) cudaMemcpy2DAsync(u0_hist, hs * c->nu * es, du, nub, nub, (size_t)steps, cudaMemcpyDeviceToHost, s);
+            if (di) cudaMemcpy2DAsync(iter_hist, hs * 4, di, ib, ib, (size_t)steps, cudaMemcpyDeviceToHost, s);
+            if (ds) cudaMemcpy2DAsync(status_hist, hs * 4, ds, ib, ib, (size_t)steps, cudaMemcpyDeviceToHost, s);
         }
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) rc = bfail(b, TMPC_ERR_CUDA, std::string("tmpc_batch_rollout: ") + cudaGetErrorString(e));
@@ -465,6 +471,14 @@ int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void 
         c->rollout_ms = kernel_ms;
     }
     return rc;
+}
+
+extern "C" {
+
+int tmpc_batch_rollout(tmpc_batch *bt, int32_t steps, int32_t reset_duals, void *x0_hist, void *u0_hist, int32_t *iter_hist,
+                       int32_t *status_hist, int32_t mem)
+{
+    return batch_rollout(bt, steps, reset_duals, x0_hist, u0_hist, iter_hist, status_hist, mem, 0);
 }
 
 float tmpc_batch_last_rollout_ms(const tmpc_batch *bt) { return bt ? reinterpret_cast<const tmpc_batch_impl *>(bt)->c->rollout_ms : 0.f; }

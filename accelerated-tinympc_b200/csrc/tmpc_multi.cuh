@@ -249,6 +249,43 @@ int tmpc_multi_solve(tmpc_multi *mm, const tmpc_solve_args *a)
     });
 }
 
+int tmpc_multi_rollout(tmpc_multi *mm, const tmpc_rollout_args *a)
+{
+    if (!mm || !a) return TMPC_ERR_INVALID;
+    tmpc_multi_impl *m = MULTI(mm);
+    if (a->batch < 1 || a->steps < 1 || !a->x0 || (!a->table && !a->Xref)) return mfail(m, TMPC_ERR_INVALID, "tmpc_multi_rollout: batch, steps >= 1, x0 and a reference are required");
+    if (m->ib_batch) return mfail(m, TMPC_ERR_UNSUPPORTED, "tmpc_multi_rollout with per-instance bounds");
+    const int64_t B = a->batch;
+    const int G = devices_for(m, B);
+    m->used = G;
+    const size_t es = m->dtype == TMPC_F32 ? 4 : 8;
+    const size_t xrow = (size_t)m->nx * m->N * es, urow = (size_t)m->nu * (m->N - 1) * es, x0b = (size_t)m->nx * es, u0b = (size_t)m->nu * es;
+    const tmpc_rollout_args r = *a;
+    return run_all(m, G, [=](int i) {
+        MultiWorker *w = m->w[i].get();
+        const int64_t b0 = B * i / G, b1 = B * (i + 1) / G;
+        w->b0 = b0; w->n = b1 - b0;
+        auto at = [&](const void *p, size_t per) -> void * { return p ? (void *)((const char *)p + (size_t)b0 * per) : nullptr; };
+        tmpc_batch *bt = nullptr;
+        int rc = tmpc_batch_create(w->ctx, b1 - b0, &bt);
+        if (rc != TMPC_OK) return rc;
+        rc = tmpc_batch_set_x0(bt, at(r.x0, x0b), TMPC_MEM_HOST);
+        if (rc == TMPC_OK) {
+            if (r.table) rc = tmpc_batch_set_xref_table(bt, r.table, r.table_rows, r.start ? r.start + b0 : nullptr, TMPC_MEM_HOST);
+            else rc = tmpc_batch_set_xref(bt, r.xref_shared ? r.Xref : at(r.Xref, xrow), r.xref_shared ? 1 : 0, TMPC_MEM_HOST);
+        }
+        // the histories are [step][batch][...]: this device's columns start at instance b0 of every step row
+        if (rc == TMPC_OK)
+            rc = batch_rollout(bt, r.steps, r.reset_duals, at(r.x0_hist, x0b), at(r.u0_hist, u0b), (int32_t *)at(r.iter_hist, 4),
+                               (int32_t *)at(r.status_hist, 4), TMPC_MEM_HOST, B);
+        if (rc == TMPC_OK && r.x) rc = tmpc_batch_get(bt, TMPC_GET_X, at(r.x, xrow), TMPC_MEM_HOST);
+        if (rc == TMPC_OK && r.u) rc = tmpc_batch_get(bt, TMPC_GET_U, at(r.u, urow), TMPC_MEM_HOST);
+        if (rc == TMPC_OK) rc = tmpc_get_stats(w->ctx, &w->stats);
+        tmpc_batch_destroy(bt);   // (keeps the ctx's last error text when something failed above)
+        return rc;
+    });
+}
+
 int tmpc_multi_get_stats(tmpc_multi *mm, tmpc_stats *total, tmpc_stats *per_device)
 {
     if (!mm || !total) return TMPC_ERR_INVALID;

@@ -42,7 +42,7 @@ int main(int argc, char **argv)
         std::memcpy(s->cache->Quu_inv.data(), Qi.data(), sizeof(tinytype) * Qi.size());
         std::memcpy(s->cache->AmBKt.data(), M.data(), sizeof(tinytype) * M.size());
     }
-    tiny_set_devices(s, 1);
+    // (every visible device takes part: tiny_rollout_batch and tiny_solve_batch split host batches of >= 32,768 instances)
     const double scale[12] = {2, 2, 2, .2, .2, .2, .5, .5, .5, .5, .5, .5}, hover[12] = {0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<tinytype> x0((size_t)Bn * nx), xref((size_t)N * nx, 0);
     for (int i = 0; i < N; ++i) xref[(size_t)i * nx + 2] = 2;

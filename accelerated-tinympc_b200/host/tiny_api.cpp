@@ -326,6 +326,19 @@ int tiny_rollout_batch(TinySolver *s, const TinyRolloutIn *in, TinyRolloutOut *o
     if (in->table && in->table_rows < s->N) return fail("tiny_rollout_batch: the reference table needs at least N rows");
     Backend *b = backend(s);
     if (b->ib_batch) return fail("tiny_rollout_batch: per-instance bounds are set (tiny_set_instance_bounds): clear them first");
+    if (in->batch >= 32768 && (b->devices ? b->devices : tmpc_device_count()) > 1) {
+        // every selected device runs the loop of its contiguous instance range (tmpc_multi_rollout)
+        if (sync_multi(s) != 0) return -1;
+        tmpc_rollout_args r;
+        std::memset(&r, 0, sizeof r);
+        r.batch = in->batch; r.steps = in->steps; r.reset_duals = in->reset_duals ? 1 : 0;
+        r.x0 = in->x0; r.Xref = in->Xref; r.xref_shared = in->xref_shared ? 1 : 0;
+        r.table = in->table; r.table_rows = in->table_rows; r.start = in->start;
+        r.x0_hist = out->x_hist; r.u0_hist = out->u0_hist; r.iter_hist = out->iter_hist; r.status_hist = out->status_hist;
+        r.x = out->x; r.u = out->u;
+        if (tmpc_multi_rollout(b->multi, &r) != TMPC_OK) return fail(std::string("tmpc_multi_rollout: ") + tmpc_multi_last_error(b->multi));
+        return 0;
+    }
     if (sync_model(s) != 0) return -1;
     tmpc_batch *bt = nullptr;
     if (tmpc_batch_create(b->ctx, in->batch, &bt) != TMPC_OK) return fail(std::string("tmpc_batch_create: ") + tmpc_last_error(b->ctx));

@@ -58,7 +58,8 @@ int tiny_solve_batch(TinySolver *solver, const TinyBatchIn *in, TinyBatchOut *ou
  *     [Xref = rows w0 .. w0+N-1 of `table`, w0 = min(start[b] + k, rows - N)]  ->  [y = g = 0 if reset_duals]  ->  tiny_solve
  *     (warm: d, v, z carried from step to step)  ->  x0 <- Adyn x0 + Bdyn u(:,0)
  * starting from the cold workspace the examples zero.  Host pointers.  Forwards to tmpc_batch_* (include/tmpc.h); with reset_duals
- * on a float build of the 12/4/10 or 4/1/10 shape the whole loop is one persistent kernel launch. */
+ * on a float build of the 12/4/10 or 4/1/10 shape the whole loop is one persistent kernel launch.  Batches of at least 32,768
+ * instances are spread over the devices tiny_set_devices selects (contiguous instance ranges, tmpc_multi_rollout). */
 typedef struct {
     int64_t batch;
     int32_t steps;

@@ -256,6 +256,24 @@ int tmpc_multi_set_settings(tmpc_multi *m, double abs_pri_tol, double abs_dua_to
 int tmpc_multi_set_instance_bounds(tmpc_multi *m, int64_t batch, const void *x_min, const void *x_max, const void *u_min,
                                    const void *u_max);
 int tmpc_multi_solve(tmpc_multi *m, const tmpc_solve_args *args);   /* args->mem must be TMPC_MEM_HOST; args->stream ignored */
+/* tmpc_batch_rollout for one HOST batch spread over the devices: every device runs the closed loop of its contiguous instance range
+ * (from the cold workspace) and writes its slices of the histories.  Pointers as in tmpc_batch_set_x0 / set_xref / set_xref_table /
+ * rollout / get; x0 and one of (Xref, table) are required, every output may be NULL. */
+typedef struct {
+    int64_t batch;
+    int32_t steps, reset_duals;
+    const void *x0;          /* [batch][nx] */
+    const void *Xref;        /* [N][nx] if xref_shared, else [batch][N][nx]; ignored when table != NULL */
+    int32_t xref_shared;
+    const void *table;       /* [table_rows][nx] or NULL */
+    int64_t table_rows;
+    const int32_t *start;    /* [batch] or NULL */
+    void *x0_hist;           /* [steps+1][batch][nx] */
+    void *u0_hist;           /* [steps][batch][nu] */
+    int32_t *iter_hist, *status_hist;   /* [steps][batch] */
+    void *x, *u;             /* last step's trajectories [batch][N][nx] / [batch][N-1][nu] */
+} tmpc_rollout_args;
+int tmpc_multi_rollout(tmpc_multi *m, const tmpc_rollout_args *args);
 /* totals over the devices of the last tmpc_multi_solve (kernel_ms = the slowest device's); per_device: NULL or an array of
  * tmpc_multi_device_count() entries */
 int tmpc_multi_get_stats(tmpc_multi *m, tmpc_stats *total, tmpc_stats *per_device);

@@ -221,3 +221,37 @@ def test_multi_device_solve_equals_single_device(pkg, oracle, ndev):
     assert_same(outs["iter"], ref.iter[:1000], "small")
     assert sum(1 for d in m.stats()["per_device"] if d["instances"]) == 1
     m.close()
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_multi_rollout_matches_single_device_batch(pkg, ndev):
+    """tmpc_multi_rollout: the closed loop of one host batch over `ndev` devices (contiguous instance ranges, strided history
+    slices) equals tmpc_batch_rollout of the whole batch on one device, element for element -- fixed Xref (fused loop) and a
+    reference table with per-instance window starts."""
+    import torch
+    if torch.cuda.device_count() < ndev:
+        pytest.skip("needs %d devices" % ndev)
+    prob = pkg.problems.quadrotor(20)
+    B, steps = 70_001, 5
+    x0, xref = pkg.workloads.quadrotor_hover_batch(0, B, mult=0.25)
+    table = np.ascontiguousarray(pkg.problems.quadrotor_trajectory().T).astype(np.float32)
+    starts = (np.arange(B) % 295).astype(np.int32)
+    m = pkg.capi.Multi(prob, dtype=np.float32, policy="parity", devices=ndev)
+    s = pkg.capi.Solver(prob, dtype=np.float32, policy="parity")
+    for use_table in (False, True):
+        hm = m.rollout(x0, steps, xref=None if use_table else xref, table=table if use_table else None,
+                       start=starts if use_table else None, last=True)
+        assert len([d for d in m.stats()["per_device"] if d["instances"]]) == ndev
+        b = pkg.capi.Batch(s, B)
+        b.set_x0(x0)
+        if use_table:
+            b.set_xref_table(table, starts)
+        else:
+            b.set_xref(xref)
+        h1 = b.rollout(steps, reset_duals=True)
+        for k in ("x0", "u0", "iter", "status"):
+            assert_same(hm[k], h1[k], "table %s history %s" % (use_table, k))
+        assert_same(hm["x"], b.get("x"), "last x")
+        assert_same(hm["u"], b.get("u"), "last u")
+        b.close()
+    s.close()
