@@ -122,8 +122,9 @@ def test_large_step_functions(pkg, oracle):
 
 @pytest.mark.parametrize("variant", ["", "warp4", "warp4x2", "warp_smem"])
 def test_large_kernel_variants_and_slot_refill(pkg, oracle, monkeypatch, variant):
-    """Default = four instances per warp (tmpc_kernel_warp4.cuh); TMPC_KERNEL=warp1 / warp_smem = the one-instance-per-warp
-    kernels.  1,100 instances on a 3-block grid cap would be too few to refill slots, so the batch is several times the resident
+    """Default = one instance per warp, g / v in tensor memory (tmpc_kernel_warp.cuh); TMPC_KERNEL=warp4 = four instances per warp
+    (tmpc_kernel_warp4.cuh), warp4x2 = the same with eight warps per SM (g / v of two slots per warp in L2-resident scratch),
+    warp_smem = one instance per warp with all state in shared memory.  1,100 instances on a 3-block grid cap would be too few to refill slots, so the batch is several times the resident
     slots of the test GPU only in the sense that every slot is refilled many times in index order (148 SMs x 16 = 2,368 resident:
     use a ragged 5,003 with a short max_iter so that the oracle stays cheap), cold and warm, state included."""
     if variant:
